@@ -1,0 +1,152 @@
+/* chips_b200.h — C ABI of the B200-native CHIPS detection hot path.
+ *
+ * The reference (shibaji7/pyCHIPS) has no FFI layer: its hot path is Python calling
+ * numpy / scipy.signal / OpenCV directly.  Each entry point below
+ * replaces one of those call sites; the citation after "replaces:" is the reference
+ * line(s) a maintainer would rebind (see INTEGRATION.md for the ctypes stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless it is named h_*;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - all calls only ENQUEUE work on `stream` and never synchronise;
+ *   - return value: 0 = OK, negative = CHIPS_E_* ; nothing throws across the ABI;
+ *   - images are row-major [H][W]; `elem` is 4 (float32) or 8 (float64) bytes;
+ *   - disk geometry: pixel (x,y) is on-disk iff (x-cx)^2+(y-cy)^2 <= r^2 in integers,
+ *     which is exactly filled cv2.circle (chips.py:186-192); r < 0 means "no mask"
+ *     (the synoptic variant, syn_chips.py).
+ */
+#ifndef CHIPS_B200_H
+#define CHIPS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHIPS_OK 0
+#define CHIPS_E_ARG (-1)      /* bad argument (k even, k too large, T too large, ...) */
+#define CHIPS_E_CUDA (-2)     /* a CUDA runtime call / launch failed                  */
+#define CHIPS_E_WS (-3)       /* workspace too small                                  */
+
+#define CHIPS_MAX_T 64        /* max number of thresholds per detection               */
+#define CHIPS_MAX_K 75        /* max median kernel size of the tiled fast path        */
+#define CHIPS_PROB_BINS 20    /* chips.py:445 np.linspace(0,1,21)                     */
+
+/* Per-image result record written by the device epilogues (one per detection). */
+typedef struct chips_result {
+  double first_edge;          /* histogram range = min / max of the filtered on-disk data */
+  double last_edge;
+  double h_thresh;            /* chips.py:240-241 (sticky: in = NaN means "compute")      */
+  double limit_0;             /* chips.py:356 peaks[0]                                    */
+  double limits[CHIPS_MAX_T]; /* chips.py:357 np.round(limit_0 + arange, 4)               */
+  double probs[CHIPS_MAX_T];  /* chips.py:378 / :432-450                                  */
+  int64_t n_samples;          /* number of histogrammed pixels                            */
+  int32_t n_peaks;            /* len(find_peaks(...)) ; 0 => no regions (chips.py:355)    */
+  int32_t n_thresholds;       /* T                                                        */
+  int32_t n_kept[CHIPS_MAX_T];/* kept top-level components per threshold                  */
+  int32_t n_comp[CHIPS_MAX_T];/* top-level components per threshold before the area cut   */
+  int32_t median_errors;      /* internal consistency counter of the median (must be 0)  */
+  int32_t pad_;
+} chips_result;
+
+/* Byte offsets of every buffer inside one workspace blob (all 256-byte aligned). */
+typedef struct chips_plan {
+  int32_t H, W, k, h_bins, T, elem, masked, pad_;
+  int32_t roi_x0, roi_y0, roi_w, roi_h;   /* bounding box of the disk (whole image if unmasked) */
+  int32_t bp_pitch, bp_rows;              /* padded bucket image geometry                 */
+  size_t off_bounds;     /* 256 bucket boundaries (ordered keys, 8 B each)                */
+  size_t off_bucket;     /* u8  [bp_rows][bp_pitch]   padded bucket image                 */
+  size_t off_bstar;      /* u8  [H][W]   median bucket per pixel                          */
+  size_t off_rres;       /* u16 [H][W]   residual rank inside that bucket                 */
+  size_t off_filt;       /* elem[H][W]   masked median (filt_disk)                        */
+  size_t off_minmax;     /* 2 ordered keys (8 B each)                                     */
+  size_t off_counts;     /* i64 [h_bins]                                                  */
+  size_t off_density;    /* f64 [h_bins]   hbase                                          */
+  size_t off_edges;      /* f64 [h_bins+1] hbins                                          */
+  size_t off_bound;      /* f64 [h_bins]   bound                                          */
+  size_t off_peaks;      /* i32 [h_bins]   peak indices (first n_peaks valid)             */
+  size_t off_result;     /* chips_result                                                  */
+  size_t off_level;      /* u8  [H][W]   first threshold index with v<=lim (T = none)     */
+  size_t off_fill;       /* u8  [H][W]   hole-filled level W                              */
+  size_t off_keep;       /* u8  [H][W]   first threshold at which the pixel is in the final map */
+  size_t off_probtab;    /* u32 [T+1][20]                                                 */
+  size_t off_parent_b;   /* u32 [roi_h*roi_w + 1]   background union-find                 */
+  size_t off_parent_c;   /* u32 [T][roi_h*roi_w]    per-threshold union-find              */
+  size_t off_area;       /* u32 [T][roi_h*roi_w]    2*area accumulators at roots          */
+  size_t bytes;          /* total workspace size                                          */
+} chips_plan;
+
+int chips_version(void);
+
+/* Fill `plan` for one image geometry.  cx,cy,r as in the conventions (r<0: unmasked). */
+int chips_plan_init(chips_plan* plan, int H, int W, int k, int h_bins, int T, int elem,
+                    int cx, int cy, int r);
+
+/* ---- row C  replaces: cv2.circle canvas + NaN/1 assigns, chips.py:183-200 ---------- */
+int chips_disk_mask(void* n_mask, void* i_mask, int H, int W, int elem, int cx, int cy,
+                    int r, void* stream);
+
+/* ---- row D  replaces: i_mask * scipy.signal.medfilt2d(normalized, k), chips.py:214-216;
+ *             scipy.signal.medfilt2d(raw, k), syn_chips.py:106.
+ * Zero-padded k x k median (rank (k*k-1)/2), bit-exact; with r >= 0 the output is the
+ * median on-disk and 0 off-disk, and min/max keys of the on-disk output are left at
+ * plan->off_minmax.  `out` may be ws + plan->off_filt. */
+int chips_medfilt2d(const void* in, void* out, const chips_plan* plan, int cx, int cy, int r,
+                    void* ws, void* stream);
+/* brute-force radix-select reference of the same filter (tests / at-scale checker) */
+int chips_medfilt2d_bruteforce(const void* in, void* out, int H, int W, int k, int elem,
+                               int cx, int cy, int r, void* stream);
+
+/* ---- row E  replaces: np.histogram(h_data[~isnan], bins=h_bins), chips.py:235-239 --- */
+int chips_minmax(const void* filt, const chips_plan* plan, int cx, int cy, int r, void* ws,
+                 void* stream);
+int chips_histogram(const void* filt, const chips_plan* plan, int cx, int cy, int r, void* ws,
+                    void* stream);
+/* replaces: density, h_thresh, scipy.signal.find_peaks, bound, peaks, limits
+ *           chips.py:239-244, :356-357.  h_thresh_in: NaN = compute max(h)/ratio. */
+int chips_select_threshold(const chips_plan* plan, double ht_peak_ratio, double h_thresh_in,
+                           int t0, int t1, void* ws, void* stream);
+
+/* ---- rows F+G  replaces: the `for lim in limits` mask assigns chips.py:360-375 and
+ *                calculate_prob chips.py:378,432-450 (all T in one pass) ------------- */
+int chips_threshold_prob(const void* filt, const chips_plan* plan, int cx, int cy, int r,
+                         double porb_threshold, void* ws, void* stream);
+
+/* ---- row H  replaces: cv2.findContours + clean_small_scale_structures
+ *             chips.py:382-389, :405-430 (hole fill + 8-conn CCL + bit-quad area) ---- */
+int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, double disk_area,
+                  double area_threshold, void* ws, void* stream);
+
+/* Expand the level-encoded result into T uint8 maps [T][H][W] (map_t = keep <= t), or
+ * the raw threshold masks when which = 1 (level <= t), or filled masks which = 2. */
+int chips_expand_maps(const chips_plan* plan, int which, uint8_t* maps, void* ws, void* stream);
+/* One float64/float32 map (the reference's `dxmap/255`, chips.py:430) for threshold t. */
+int chips_expand_map(const chips_plan* plan, int which, int t, void* out, int out_elem,
+                     void* ws, void* stream);
+/* Root image of the per-threshold labelling: roots[y][x] = ROI-local index of the first
+ * pixel (raster order) of the pixel's filled top-level component at threshold t, -1 for
+ * background; twice_area (optional) = 2*contourArea of that component.  Numbering the
+ * distinct roots in ascending order gives the canonical label image
+ * (== scipy.ndimage.label(filled, ones((3,3)))). */
+int chips_roots(const chips_plan* plan, int cx, int cy, int r, int t, int32_t* roots,
+                uint32_t* twice_area, void* ws, void* stream);
+
+/* ---- row J  replaces: probability-map stack plots.py:305-322 ---------------------- */
+int chips_prob_stack(const chips_plan* plan, double lower_lim, void* out, int out_elem,
+                     int accumulate, void* ws, void* stream);
+
+/* ---- rows B..I fused: one full detection enqueued on `stream` --------------------- */
+int chips_detect(const void* image, const chips_plan* plan, int cx, int cy, int r,
+                 double ht_peak_ratio, double h_thresh_in, int t0, int t1,
+                 double porb_threshold, double area_threshold, uint8_t* maps_or_null,
+                 void* ws, void* stream);
+
+/* helper: f64 -> f32 demotion with an exactness flag (1 = every value representable) */
+int chips_demote_f64(const double* in, float* out, size_t n, int32_t* all_exact, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHIPS_B200_H */

@@ -1,0 +1,87 @@
+"""ctypes binding of the C-ABI library (`include/chips_b200.h`).
+
+There is deliberately NO fallback: if `libchips_b200.so` is missing the import of the
+product path fails loudly (build it with `python -m pychips_b200.build`)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB
+
+MAX_T = 64
+PROB_BINS = 20
+
+
+class Result(C.Structure):
+    """Mirror of `chips_result`."""
+    _fields_ = [
+        ("first_edge", C.c_double), ("last_edge", C.c_double), ("h_thresh", C.c_double),
+        ("limit_0", C.c_double), ("limits", C.c_double * MAX_T), ("probs", C.c_double * MAX_T),
+        ("n_samples", C.c_int64), ("n_peaks", C.c_int32), ("n_thresholds", C.c_int32),
+        ("n_kept", C.c_int32 * MAX_T), ("n_comp", C.c_int32 * MAX_T),
+        ("median_errors", C.c_int32), ("pad_", C.c_int32),
+    ]
+
+
+class Plan(C.Structure):
+    """Mirror of `chips_plan`."""
+    _fields_ = [(n, C.c_int32) for n in
+                ("H", "W", "k", "h_bins", "T", "elem", "masked", "pad_",
+                 "roi_x0", "roi_y0", "roi_w", "roi_h", "bp_pitch", "bp_rows")] + \
+               [(n, C.c_size_t) for n in
+                ("off_bounds", "off_bucket", "off_bstar", "off_rres", "off_filt", "off_minmax",
+                 "off_counts", "off_density", "off_edges", "off_bound", "off_peaks",
+                 "off_result", "off_level", "off_fill", "off_keep", "off_probtab",
+                 "off_parent_b", "off_parent_c", "off_area", "bytes")]
+
+
+_vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
+_PP = C.POINTER(Plan)
+
+SIGNATURES = {
+    "chips_version": ([], C.c_int),
+    "chips_plan_init": ([_PP, _i, _i, _i, _i, _i, _i, _i, _i, _i], C.c_int),
+    "chips_disk_mask": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
+    "chips_medfilt2d": ([_vp, _vp, _PP, _i, _i, _i, _vp, _vp], C.c_int),
+    "chips_medfilt2d_bruteforce": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
+    "chips_minmax": ([_vp, _PP, _i, _i, _i, _vp, _vp], C.c_int),
+    "chips_histogram": ([_vp, _PP, _i, _i, _i, _vp, _vp], C.c_int),
+    "chips_select_threshold": ([_PP, _d, _d, _i, _i, _vp, _vp], C.c_int),
+    "chips_threshold_prob": ([_vp, _PP, _i, _i, _i, _d, _vp, _vp], C.c_int),
+    "chips_cleanup": ([_PP, _i, _i, _i, _d, _d, _vp, _vp], C.c_int),
+    "chips_expand_maps": ([_PP, _i, _vp, _vp, _vp], C.c_int),
+    "chips_expand_map": ([_PP, _i, _i, _vp, _i, _vp, _vp], C.c_int),
+    "chips_roots": ([_PP, _i, _i, _i, _i, _vp, _vp, _vp, _vp], C.c_int),
+    "chips_prob_stack": ([_PP, _d, _vp, _i, _i, _vp, _vp], C.c_int),
+    "chips_detect": ([_vp, _PP, _i, _i, _i, _d, _d, _i, _i, _d, _d, _vp, _vp, _vp], C.c_int),
+    "chips_demote_f64": ([_vp, _vp, _sz, _vp, _vp], C.c_int),
+}
+
+_lib = None
+
+
+class ChipsNativeError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            raise ChipsNativeError(
+                f"{LIB} not found: the CUDA extension is required (no CPU fallback). "
+                "Build it with `python -m pychips_b200.build`.")
+        lib = C.CDLL(LIB)
+        for name, (args, ret) in SIGNATURES.items():
+            fn = getattr(lib, name)          # AttributeError if a declared symbol is missing
+            fn.argtypes = args
+            fn.restype = ret
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise ChipsNativeError(f"{what} failed with code {rc} "
+                               "(-1 bad argument, -2 CUDA error, -3 workspace)")

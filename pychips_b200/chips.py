@@ -1,0 +1,305 @@
+"""`Chips` — drop-in for `chips.chips.Chips` of the reference on the detection hot path.
+
+Same constructor signature and defaults (`/root/reference/chips/chips.py:47-61`), same entry
+point `run_CHIPS(wavelength, resolution, clear_prev_runs)` (`:110-150`), same stage methods
+(`:173, :202, :223, :341`), same result attributes written on the caller's `disk` object
+(`solar_mask`, `solar_filter`, `histogram`, `solar_ch_regions`) with the `hasattr`
+memoisation and the sticky `h_thresh` of the reference.  All arithmetic runs in the sm_100a
+kernels behind `libchips_b200.so`; result arrays are materialised from device memory lazily
+on first attribute access.  There is no CPU fallback.
+
+Out of scope: plotting (`plot_diagonestics`), `to_netcdf`, filament cleanup
+(`run_fl_cleanup=True` raises), `compute_similarity_measures`.
+"""
+from __future__ import annotations
+
+import os
+from argparse import Namespace
+from typing import List
+
+import numpy as np
+import torch
+
+from . import engine
+from .engine import Detector, Geometry
+
+try:                                    # logging is optional
+    from loguru import logger
+except Exception:                       # pragma: no cover
+    import logging
+    logger = logging.getLogger("pychips_b200")
+
+
+class LazyNamespace(Namespace):
+    """`argparse.Namespace` whose listed attributes are produced on first access
+    (device -> host copies happen only for what the caller actually reads)."""
+
+    def __init__(self, _lazy=None, **kw):
+        super().__init__(**kw)
+        object.__setattr__(self, "_lazy", dict(_lazy or {}))
+
+    def __getattr__(self, name):         # only called when normal lookup fails
+        lazy = object.__getattribute__(self, "_lazy")
+        if name in lazy:
+            value = lazy.pop(name)()
+            setattr(self, name, value)
+            return value
+        raise AttributeError(name)
+
+    def __contains__(self, key):
+        return key in self.__dict__ or key in object.__getattribute__(self, "_lazy")
+
+
+class Chips(object):
+    r"""CHIPS on a full-disk image, B200-native.  Parameters as in the reference."""
+
+    def __init__(
+        self,
+        aia,
+        base_folder: str = "tmp/chips_dataset/",
+        medfilt_kernel: int = 51,
+        h_bins: int = 500,
+        h_thresh: float = None,
+        ht_peak_ratio: int = 5,
+        hist_xsplit: int = 2,
+        hist_ysplit: int = 2,
+        threshold_range: List[float] = [0, 20],
+        porb_threshold: float = 0.8,
+        area_threshold: float = 1e-3,
+        run_fl_cleanup: bool = False,
+        device=None,
+        make_folder: bool = True,
+    ) -> None:
+        self.aia = aia
+        self.base_folder = base_folder
+        self.medfilt_kernel = medfilt_kernel
+        self.h_bins = h_bins
+        self.h_thresh = h_thresh
+        self.ht_peak_ratio = ht_peak_ratio
+        self.hist_xsplit = hist_xsplit
+        self.hist_ysplit = hist_ysplit
+        self.threshold_range = threshold_range
+        self.porb_threshold = porb_threshold
+        self.area_threshold = area_threshold
+        self.run_fl_cleanup = run_fl_cleanup
+        if run_fl_cleanup:
+            raise NotImplementedError(
+                "run_fl_cleanup=True (chips/cleanup.py CHIMERA candidates) is outside the "
+                "accelerated path; see DESIGN.md 'out of scope'.")
+        self.device = engine.require_cuda(device)
+        self._det = {}                   # id(disk) -> Detector
+        self._img = {}                   # id(disk) -> device image
+        if make_folder:
+            self.get_base_folder()
+
+    # ---- chips.py:78-88
+    def get_base_folder(self) -> None:
+        self.folder = self.base_folder + self.aia.date.strftime("%Y.%m.%d")
+        os.makedirs(self.folder, exist_ok=True)
+
+    # ---- chips.py:90-108
+    def clear_run_results(self, disk):
+        for key in ("solar_mask", "solar_filter", "histogram", "histograms", "solar_ch_regions"):
+            if hasattr(disk, key):
+                delattr(disk, key)
+        self._det.pop(id(disk), None)
+        self._img.pop(id(disk), None)
+
+    # ---- chips.py:110-150
+    def run_CHIPS(self, wavelength: int = None, resolution: int = None,
+                  clear_prev_runs: bool = False) -> None:
+        resolution = self.aia.resolution if resolution is None else resolution
+        if (wavelength is not None) and (resolution is not None):
+            if (wavelength in self.aia.wavelengths) and (resolution == self.aia.resolution):
+                logger.info(f"Singleton: Running CHIPS for {wavelength}/{resolution}")
+                disk = self.aia.datasets[wavelength][resolution]
+                self.process_CHIPS(disk, clear_prev_runs)
+            else:
+                logger.error(f"No entry for {wavelength} and {resolution}!!!")
+        else:
+            for wavelength in self.aia.wavelengths:
+                if (wavelength in self.aia.wavelengths) and (resolution is self.aia.resolution):
+                    logger.info(f"Multiton: Running CHIPS for {wavelength}/{resolution}")
+                    disk = self.aia.datasets[wavelength][resolution]
+                    self.process_CHIPS(disk, clear_prev_runs)
+                else:
+                    logger.error(f"No entry for {wavelength} and {resolution}!!!")
+        return
+
+    # ---- chips.py:152-171 (the plotter call at :170 is presentation, not detection)
+    def process_CHIPS(self, disk, clear_prev_runs) -> None:
+        if clear_prev_runs:
+            self.clear_run_results(disk)
+        self.extract_solar_masks(disk)
+        self.run_filters(disk)
+        self.extract_histogram(disk)
+        self.extract_CHs_CHBs(disk)
+        return
+
+    # ------------------------------------------------------------------ device plumbing
+    def _geometry(self, disk) -> Geometry:
+        H, W = disk.normalized.data.shape
+        c = int(disk.resolution / 2)             # chips.py:188
+        return Geometry(int(H), int(W), c, c, int(disk.pixel_radius))
+
+    def _out_dtype(self, disk):
+        # np.zeros_like(raw.data) * np.nan: float32 stays float32, everything else -> float64
+        return np.float32 if np.asarray(disk.raw.data).dtype == np.float32 else np.float64
+
+    def _detector(self, disk) -> Detector:
+        det = self._det.get(id(disk))
+        if det is None:
+            with torch.cuda.device(self.device):
+                img, elem = engine.to_device_image(np.asarray(disk.normalized.data), self.device)
+                tr = np.arange(self.threshold_range[0], self.threshold_range[1])
+                if len(tr) < 1:
+                    raise ValueError("threshold_range selects no threshold")
+                t0 = int(tr[0])
+                if not np.array_equal(tr, t0 + np.arange(len(tr))):
+                    raise ValueError("threshold_range must produce unit-spaced integer offsets")
+                det = Detector(self._geometry(disk), self.medfilt_kernel, self.h_bins, t0,
+                               t0 + len(tr), elem, self.device)
+                det.state = set()
+            self._det[id(disk)] = det
+            self._img[id(disk)] = img
+        return det
+
+    def _ensure_filt(self, disk, det) -> None:
+        """`disk.solar_filter` may have been memoised by an earlier `Chips` object
+        (chips.py:212 `hasattr` guard): reload it instead of recomputing."""
+        if "filt" not in det.state:
+            host = np.ascontiguousarray(disk.solar_filter.filt_disk)
+            det.filt.copy_(torch.from_numpy(host).to(self.device).to(det.dtype))
+            engine._lib.check(det.lib.chips_minmax(
+                engine._ptr(det.filt), det._pp, *det._g(), engine._ptr(det.ws),
+                engine._stream_ptr()), "chips_minmax")
+            det.state.add("filt")
+
+    # ---- chips.py:173-200
+    def extract_solar_masks(self, disk) -> None:
+        logger.info(f"Create solar mask for {disk.wavelength}/{disk.resolution}")
+        if not hasattr(disk, "solar_mask"):
+            self.disk_area = np.pi * disk.pixel_radius ** 2
+            g = self._geometry(disk)
+            dt = self._out_dtype(disk)
+            tdt = torch.float32 if dt == np.float32 else torch.float64
+
+            def both():
+                with torch.cuda.device(self.device):
+                    n = torch.empty((g.H, g.W), dtype=tdt, device=self.device)
+                    i = torch.empty((g.H, g.W), dtype=tdt, device=self.device)
+                    lib = engine._lib.load()
+                    engine._lib.check(lib.chips_disk_mask(
+                        engine._ptr(n), engine._ptr(i), g.H, g.W, n.element_size(), g.cx, g.cy, g.r,
+                        engine._stream_ptr()), "chips_disk_mask")
+                    return n.cpu().numpy(), i.cpu().numpy()
+
+            cache = {}
+
+            def get(idx):
+                if "v" not in cache:
+                    cache["v"] = both()
+                return cache["v"][idx]
+
+            disk.set_value("solar_mask", LazyNamespace(
+                _lazy=dict(n_mask=lambda: get(0), i_mask=lambda: get(1))))
+        return
+
+    # ---- chips.py:202-221
+    def run_filters(self, disk) -> None:
+        logger.info(f"Running solar filters for {disk.wavelength}/{disk.resolution}")
+        if not hasattr(disk, "solar_filter"):
+            det = self._detector(disk)
+            img = self._img[id(disk)]
+            dt = self._out_dtype(disk)
+            with torch.cuda.device(self.device):
+                det.medfilt(img)
+            det.state.add("filt")
+
+            def filt_disk():
+                return det.filt.cpu().numpy().astype(dt, copy=False)
+
+            def solar_disk():
+                i_mask = disk.solar_mask.i_mask
+                return np.asarray(disk.normalized.data) * i_mask
+
+            disk.set_value("solar_filter", LazyNamespace(
+                _lazy=dict(solar_disk=solar_disk, filt_disk=filt_disk)))
+        return
+
+    # ---- chips.py:223-258
+    def extract_histogram(self, disk) -> None:
+        logger.info(f"Extract solar histogram {disk.wavelength}/{disk.resolution}")
+        if not hasattr(disk, "histogram"):
+            det = self._detector(disk)
+            with torch.cuda.device(self.device):
+                self._ensure_filt(disk, det)
+                det.histogram()
+                det.select_threshold(self.ht_peak_ratio, self.h_thresh)
+                det.state.add("hist")
+                res = det.result()
+                if self.h_thresh is None:
+                    self.h_thresh = np.float64(res.h_thresh)       # sticky, chips.py:240-241
+                npk = int(res.n_peaks)
+                pidx = det.peak_index[:npk].cpu().numpy()
+                bound = det.bound.cpu().numpy()
+            peaks = [bound[p] for p in pidx]
+            disk.set_value("histogram", LazyNamespace(
+                _lazy=dict(hbase=lambda: det.density.cpu().numpy(),
+                           hbins=lambda: det.edges.cpu().numpy(),
+                           counts=lambda: det.counts.cpu().numpy()),
+                peaks=peaks, bound=bound, h_thresh=self.h_thresh, h_bins=self.h_bins,
+                peak_indexs=pidx))
+        return
+
+    # ---- chips.py:341-403
+    def extract_CHs_CHBs(self, disk) -> None:
+        logger.info(f"Extract CHs and CHBs for different regions {disk.wavelength}/{disk.resolution}")
+        if not hasattr(disk, "solar_ch_regions"):
+            if len(disk.histogram.peaks) > 0:
+                det = self._detector(disk)
+                dt = self._out_dtype(disk)
+                with torch.cuda.device(self.device):
+                    if "hist" not in det.state:      # results memoised on `disk` by another object
+                        self._ensure_filt(disk, det)
+                        det.histogram()
+                        det.select_threshold(self.ht_peak_ratio, disk.histogram.h_thresh)
+                        det.state.add("hist")
+                    det.threshold_prob(self.porb_threshold)
+                    det.cleanup(self.area_threshold)
+                    res = det.result()
+                if res.median_errors:
+                    raise engine._lib.ChipsNativeError(
+                        f"median filter self-check failed for {res.median_errors} pixels")
+                limit_0 = np.float64(res.limit_0)
+                dtmp_map = {}
+                for t in range(det.T):
+                    lim = np.float64(res.limits[t])
+
+                    def _map(t=t, which=0):
+                        with torch.cuda.device(self.device):
+                            return det.expand_map(t, which).cpu().numpy().astype(dt, copy=False)
+
+                    dtmp_map[str(lim)] = LazyNamespace(
+                        _lazy=dict(map=_map, raw_map=lambda t=t: _map(t, 1),
+                                   filled_map=lambda t=t: _map(t, 2)),
+                        lim=lim, limit_0=limit_0, prob=np.float64(res.probs[t]),
+                        n_components=int(res.n_comp[t]), n_kept=int(res.n_kept[t]),
+                        contours=None, hierarchy=None, contour_ids=None, index=t)
+                    logger.info(f"Estimated prob.({res.probs[t]}) at lim({lim})")
+                disk.set_value("solar_ch_regions", Namespace(**dtmp_map))
+        return
+
+    # ---- plots.py:305-322 (the arithmetic only)
+    def probability_map(self, disk, prob_lower_lim: float = 0.0) -> np.ndarray:
+        det = self._detector(disk)
+        with torch.cuda.device(self.device):
+            return det.prob_stack(prob_lower_lim).cpu().numpy()
+
+    def labels(self, disk, lim_index: int):
+        """Canonical component labels (raster order of first pixel) of the hole-filled mask
+        at threshold `lim_index`, and 2*contourArea per label."""
+        return self._detector(disk).labels(lim_index)
+
+    def plot_diagonestics(self, *a, **k) -> None:
+        raise NotImplementedError("plotting is outside the accelerated path (SURVEY.md §2 row 6)")

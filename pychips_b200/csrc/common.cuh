@@ -1,0 +1,82 @@
+// common.cuh — shared device helpers for the CHIPS sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/chips_b200.h"
+
+#define CHIPS_CHECK_LAUNCH()                                   \
+  do {                                                         \
+    cudaError_t e__ = cudaGetLastError();                      \
+    if (e__ != cudaSuccess) return CHIPS_E_CUDA;               \
+  } while (0)
+
+#define CHIPS_CUDA(call)                                       \
+  do {                                                         \
+    cudaError_t e__ = (call);                                  \
+    if (e__ != cudaSuccess) return CHIPS_E_CUDA;               \
+  } while (0)
+
+namespace chips {
+
+constexpr int kNumSM = 148;   // B200: 2 dies x 74 SMs
+
+// ---- order-preserving integer keys of IEEE floats (NaN-free input assumed) ----------
+template <typename T> struct Key;
+template <> struct Key<float> {
+  using type = uint32_t;
+  static __device__ __forceinline__ uint32_t enc(float v) {
+    uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  }
+  static __device__ __forceinline__ float dec(uint32_t k) {
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    return __uint_as_float(u);
+  }
+  static constexpr uint32_t kMax = 0xFFFFFFFFu;
+};
+template <> struct Key<double> {
+  using type = uint64_t;
+  static __device__ __forceinline__ uint64_t enc(double v) {
+    uint64_t u = (uint64_t)__double_as_longlong(v);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+  }
+  static __device__ __forceinline__ double dec(uint64_t k) {
+    uint64_t u = (k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    return __longlong_as_double((long long)u);
+  }
+  static constexpr uint64_t kMax = 0xFFFFFFFFFFFFFFFFull;
+};
+
+// filled cv2.circle == integer test
+__device__ __forceinline__ bool on_disk(int x, int y, int cx, int cy, int r) {
+  if (r < 0) return true;
+  long long dx = x - cx, dy = y - cy;
+  return dx * dx + dy * dy <= (long long)r * (long long)r;
+}
+
+// np.linspace edge i (fp64, multiply THEN add, never fused), last edge forced to `last`
+__device__ __forceinline__ double linspace_edge(int i, int nbins, double first, double last,
+                                                double step) {
+  if (i >= nbins) return last;
+  if (step == 0.0) {   // numpy's denormal branch: (i / div) * delta + start
+    double t = __ddiv_rn((double)i, (double)nbins);
+    t = __dmul_rn(t, __dsub_rn(last, first));
+    return __dadd_rn(t, first);
+  }
+  return __dadd_rn(__dmul_rn((double)i, step), first);
+}
+
+__device__ __forceinline__ void atomic_min_key(uint32_t* p, uint32_t v) { atomicMin(p, v); }
+__device__ __forceinline__ void atomic_max_key(uint32_t* p, uint32_t v) { atomicMax(p, v); }
+__device__ __forceinline__ void atomic_min_key(uint64_t* p, uint64_t v) {
+  atomicMin(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+__device__ __forceinline__ void atomic_max_key(uint64_t* p, uint64_t v) {
+  atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+
+template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace chips

@@ -1,0 +1,96 @@
+// pipeline.cu — workspace plan and the fused per-image detection (rows B..I of
+// SURVEY.md §8(a)): every stage is enqueued on one stream, all intermediate scalars
+// (histogram range, h_thresh, limit_0, limits, probabilities) stay in device memory, so a
+// detection is a fixed launch sequence with no host round trip (CUDA-graph capturable).
+#include "common.cuh"
+
+using namespace chips;
+
+extern "C" int chips_version(void) { return 100; }
+
+extern "C" int chips_plan_init(chips_plan* p, int H, int W, int k, int h_bins, int T, int elem,
+                               int cx, int cy, int r) {
+  if (!p || H < 1 || W < 1 || k < 1 || !(k & 1) || k > CHIPS_MAX_K) return CHIPS_E_ARG;
+  if (h_bins < 1 || T < 1 || T > CHIPS_MAX_T || (elem != 4 && elem != 8)) return CHIPS_E_ARG;
+  if ((long long)H * W >= (1LL << 31)) return CHIPS_E_ARG;
+  p->H = H; p->W = W; p->k = k; p->h_bins = h_bins; p->T = T; p->elem = elem;
+  p->masked = r >= 0; p->pad_ = 0;
+  if (r >= 0) {
+    int x0 = cx - r, x1 = cx + r + 1, y0 = cy - r, y1 = cy + r + 1;
+    if (x0 < 0) x0 = 0;
+    if (y0 < 0) y0 = 0;
+    if (x1 > W) x1 = W;
+    if (y1 > H) y1 = H;
+    if (x1 <= x0 || y1 <= y0) return CHIPS_E_ARG;
+    p->roi_x0 = x0; p->roi_y0 = y0; p->roi_w = x1 - x0; p->roi_h = y1 - y0;
+  } else {
+    p->roi_x0 = 0; p->roi_y0 = 0; p->roi_w = W; p->roi_h = H;
+  }
+  const int half = k >> 1;
+  p->bp_pitch = (int)align_up((size_t)W + 2 * half + 16, 16);
+  p->bp_rows = H + 2 * half;
+  const size_t n = (size_t)H * W, nr = (size_t)p->roi_w * p->roi_h;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  p->off_bounds = take(256 * 8);
+  p->off_bucket = take((size_t)p->bp_pitch * p->bp_rows);
+  p->off_bstar = take(n);
+  p->off_rres = take(n * 2);
+  p->off_filt = take(n * elem);
+  p->off_minmax = take(16);
+  p->off_counts = take((size_t)h_bins * 8);
+  p->off_density = take((size_t)h_bins * 8);
+  p->off_edges = take((size_t)(h_bins + 1) * 8);
+  p->off_bound = take((size_t)h_bins * 8);
+  p->off_peaks = take((size_t)h_bins * 4);
+  p->off_result = take(sizeof(chips_result));
+  p->off_level = take(n);
+  p->off_fill = take(n);
+  p->off_keep = take(n);
+  p->off_probtab = take((size_t)(T + 1) * CHIPS_PROB_BINS * 4);
+  if (p->masked) {
+    p->off_parent_b = take((nr + 1) * 4);
+    p->off_parent_c = take(nr * 4 * T);
+    p->off_area = take(nr * 4 * T);
+  } else {   // the synoptic variant has no contour/cleanup step (syn_chips.py:237-251)
+    p->off_parent_b = p->off_parent_c = p->off_area = off;
+  }
+  p->bytes = off;
+  return CHIPS_OK;
+}
+
+__global__ void k_copy_level_to_keep(const uint8_t* __restrict__ lev, uint8_t* __restrict__ keep,
+                                     size_t n) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i + 16 <= n) {
+    *reinterpret_cast<uint4*>(keep + i) = *reinterpret_cast<const uint4*>(lev + i);
+  } else {
+    for (; i < n; ++i) keep[i] = lev[i];
+  }
+}
+
+extern "C" int chips_detect(const void* image, const chips_plan* plan, int cx, int cy, int r,
+                            double ht_peak_ratio, double h_thresh_in, int t0, int t1,
+                            double porb_threshold, double area_threshold, uint8_t* maps_or_null,
+                            void* ws, void* stream) {
+  if (!image || !plan || !ws) return CHIPS_E_ARG;
+  unsigned char* w = (unsigned char*)ws;
+  void* filt = w + plan->off_filt;
+  int rc;
+  if ((rc = chips_medfilt2d(image, filt, plan, cx, cy, r, ws, stream))) return rc;
+  if (plan->k == 1 && (rc = chips_minmax(filt, plan, cx, cy, r, ws, stream))) return rc;
+  if ((rc = chips_histogram(filt, plan, cx, cy, r, ws, stream))) return rc;
+  if ((rc = chips_select_threshold(plan, ht_peak_ratio, h_thresh_in, t0, t1, ws, stream))) return rc;
+  if ((rc = chips_threshold_prob(filt, plan, cx, cy, r, porb_threshold, ws, stream))) return rc;
+  if (plan->masked) {
+    double disk_area = 3.141592653589793 * (double)((long long)r * r);   // np.pi * r**2
+    if ((rc = chips_cleanup(plan, cx, cy, r, disk_area, area_threshold, ws, stream))) return rc;
+  } else {
+    size_t n = (size_t)plan->H * plan->W;
+    k_copy_level_to_keep<<<(unsigned)((n / 16 + 256) / 256), 256, 0, (cudaStream_t)stream>>>(
+        w + plan->off_level, w + plan->off_keep, n);
+    CHIPS_CHECK_LAUNCH();
+  }
+  if (maps_or_null && (rc = chips_expand_maps(plan, 0, maps_or_null, ws, stream))) return rc;
+  return CHIPS_OK;
+}

@@ -1,0 +1,461 @@
+// stats.cu — histogram, threshold selection, per-threshold levels and probabilities.
+//
+//   k_minmax / k_hist      np.histogram(bins=h_bins) of the on-disk filtered image
+//                          (/root/reference/chips/chips.py:235-239): numpy's uniform-bin
+//                          index formula in fp64 with its +-1 edge correction, counts kept
+//                          in warp-private shared-memory sub-histograms.
+//   k_select               density, sticky h_thresh, scipy.signal.find_peaks(height=) with
+//                          the plateau-midpoint rule, bound, limit_0 and the rounded limits
+//                          (chips.py:239-244, :356-357) — one CTA, fp64, no host round trip.
+//   k_threshold_prob       one pass over the filtered image produces the level image
+//                          (first threshold each pixel satisfies == all T masks of
+//                          chips.py:360-375) and the [T+1][20] table behind all T
+//                          calculate_prob results (chips.py:432-450).
+//   k_prob_epilogue        Σ_{b>x_tau} b·h / Σ b·h in numpy's pairwise-sum order, rounded.
+#include <math.h>
+#include "common.cuh"
+
+namespace chips {
+
+// ------------------------------------------------------------------ min / max
+template <typename T>
+__global__ void k_minmax_init(typename Key<T>::type* minmax) {
+  minmax[0] = Key<T>::kMax;
+  minmax[1] = 0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_minmax(const T* __restrict__ filt, int W, int rx0, int ry0,
+                                                int rw, int rh, int cx, int cy, int r,
+                                                typename Key<T>::type* __restrict__ minmax) {
+  using K = typename Key<T>::type;
+  K kmin = Key<T>::kMax, kmax = 0;
+  for (int y = ry0 + blockIdx.x; y < ry0 + rh; y += gridDim.x) {
+    for (int x = rx0 + threadIdx.x; x < rx0 + rw; x += blockDim.x) {
+      if (!on_disk(x, y, cx, cy, r)) continue;
+      K key = Key<T>::enc(filt[(size_t)y * W + x]);
+      kmin = key < kmin ? key : kmin;
+      kmax = key > kmax ? key : kmax;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    K a = __shfl_xor_sync(0xFFFFFFFFu, kmin, o);
+    K b = __shfl_xor_sync(0xFFFFFFFFu, kmax, o);
+    kmin = a < kmin ? a : kmin;
+    kmax = b > kmax ? b : kmax;
+  }
+  if ((threadIdx.x & 31) == 0 && kmin <= kmax) {
+    atomic_min_key(&minmax[0], kmin);
+    atomic_max_key(&minmax[1], kmax);
+  }
+}
+
+// ------------------------------------------------------------------ histogram
+template <typename T>
+__global__ void __launch_bounds__(256) k_hist(const T* __restrict__ filt, int W, int rx0, int ry0,
+                                              int rw, int rh, int cx, int cy, int r,
+                                              const typename Key<T>::type* __restrict__ minmax,
+                                              int nbins, int copies,
+                                              unsigned long long* __restrict__ counts,
+                                              chips_result* __restrict__ res) {
+  extern __shared__ __align__(16) uint32_t sh[];
+  for (int i = threadIdx.x; i < copies * nbins; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  double first, last;
+  {
+    typename Key<T>::type k0 = minmax[0], k1 = minmax[1];
+    if (k0 > k1) {          // empty selection: np.histogram uses the range (0, 1)
+      first = 0.0;
+      last = 1.0;
+    } else {
+      first = (double)Key<T>::dec(k0);
+      last = (double)Key<T>::dec(k1);
+    }
+    if (first == last) {
+      first = first - 0.5;
+      last = last + 0.5;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    res->first_edge = first;
+    res->last_edge = last;
+  }
+  const double denom = __dsub_rn(last, first);
+  const double step = __ddiv_rn(denom, (double)nbins);
+  uint32_t* mine = sh + ((threadIdx.x >> 5) % copies) * nbins;
+  for (int y = ry0 + blockIdx.x; y < ry0 + rh; y += gridDim.x) {
+    for (int x = rx0 + threadIdx.x; x < rx0 + rw; x += blockDim.x) {
+      if (!on_disk(x, y, cx, cy, r)) continue;
+      double v = (double)filt[(size_t)y * W + x];
+      double f = __dmul_rn(__ddiv_rn(__dsub_rn(v, first), denom), (double)nbins);
+      int idx = (int)f;                       // astype(intp): truncation
+      if (idx == nbins) idx -= 1;
+      if (v < linspace_edge(idx, nbins, first, last, step)) idx -= 1;
+      if (idx != nbins - 1 && v >= linspace_edge(idx + 1, nbins, first, last, step)) idx += 1;
+      atomicAdd(&mine[idx], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
+    unsigned long long s = 0;
+    for (int c = 0; c < copies; ++c) s += sh[c * nbins + i];
+    if (s) atomicAdd(&counts[i], s);
+  }
+}
+
+// ------------------------------------------------------------------ threshold selection
+__global__ void __launch_bounds__(1024) k_select(const long long* __restrict__ counts, int nbins,
+                                                 double ratio, double h_thresh_in, int t0, int T,
+                                                 double* __restrict__ density,
+                                                 double* __restrict__ edges,
+                                                 double* __restrict__ bound, int* __restrict__ peaks,
+                                                 chips_result* __restrict__ res) {
+  __shared__ long long s_ll[32];
+  __shared__ double s_d[32];
+  __shared__ int s_cnt[1024];
+  __shared__ long long total_s;
+  __shared__ double hthr_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double first = res->first_edge, last = res->last_edge;
+  const double step = __ddiv_rn(__dsub_rn(last, first), (double)nbins);
+
+  long long part = 0;
+  for (int i = tid; i < nbins; i += blockDim.x) part += counts[i];
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+  if (lane == 0) s_ll[warp] = part;
+  __syncthreads();
+  if (tid == 0) {
+    long long t = 0;
+    for (int w = 0; w < 32; ++w) t += s_ll[w];
+    total_s = t;
+  }
+  __syncthreads();
+  const double total = (double)total_s;
+
+  double dmax = -INFINITY;
+  for (int i = tid; i <= nbins; i += blockDim.x) {
+    double e0 = linspace_edge(i, nbins, first, last, step);
+    edges[i] = e0;
+    if (i < nbins) {
+      double e1 = linspace_edge(i + 1, nbins, first, last, step);
+      double db = __dsub_rn(e1, e0);
+      double d = __ddiv_rn(__ddiv_rn((double)counts[i], db), total);   // n / db / n.sum()
+      density[i] = d;
+      bound[i] = __dadd_rn(e0, db);                                     // be[:-1] + diff(be)
+      dmax = fmax(dmax, d);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xFFFFFFFFu, dmax, o));
+  if (lane == 0) s_d[warp] = dmax;
+  __syncthreads();
+  if (tid == 0) {
+    double m = -INFINITY;
+    for (int w = 0; w < 32; ++w) m = fmax(m, s_d[w]);
+    hthr_s = isnan(h_thresh_in) ? __ddiv_rn(m, ratio) : h_thresh_in;
+  }
+  __syncthreads();
+  const double hthr = hthr_s;
+
+  // find_peaks(height=hthr): contiguous chunk per thread keeps the output ordered
+  const int chunk = (nbins + blockDim.x - 1) / blockDim.x;
+  const int lo = tid * chunk, hi = min(lo + chunk, nbins);
+  auto peak_at = [&](int i) -> int {     // returns peak index started by rising edge at i, or -1
+    if (i < 1 || i >= nbins - 1) return -1;
+    double di = density[i];
+    if (!(density[i - 1] < di)) return -1;
+    int ia = i + 1;
+    while (ia < nbins - 1 && density[ia] == di) ++ia;
+    if (density[ia] < di) {
+      int p = (i + ia - 1) / 2;
+      return (density[p] >= hthr) ? p : -1;
+    }
+    return -1;
+  };
+  int c = 0;
+  for (int i = lo; i < hi; ++i) c += (peak_at(i) >= 0);
+  s_cnt[tid] = c;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int t = 0; t < (int)blockDim.x; ++t) {
+      int v = s_cnt[t];
+      s_cnt[t] = run;
+      run += v;
+    }
+    res->n_peaks = run;
+    res->n_thresholds = T;
+    res->n_samples = total_s;
+    res->h_thresh = hthr;
+  }
+  __syncthreads();
+  int o = s_cnt[tid];
+  for (int i = lo; i < hi; ++i) {
+    int p = peak_at(i);
+    if (p >= 0) peaks[o++] = p;
+  }
+  __syncthreads();
+  if (tid < T) {
+    if (res->n_peaks > 0) {
+      double l0 = bound[peaks[0]];
+      if (tid == 0) res->limit_0 = l0;
+      // np.round(limit_0 + arange(t0,t1), 4) = rint(x * 1e4) / 1e4
+      double xv = __dadd_rn(l0, (double)(t0 + tid));
+      res->limits[tid] = __ddiv_rn(rint(__dmul_rn(xv, 10000.0)), 10000.0);
+    } else {
+      if (tid == 0) res->limit_0 = nan("");
+      res->limits[tid] = nan("");
+    }
+  }
+}
+
+// ------------------------------------------------------------------ levels + prob table
+// d-space cut points of calculate_prob's 20 bins: bin(d) = #{j=1..19 : d <= kProbCut[j]}
+// (largest float64 d with rint(exp(d)*1e4) <= k_j, k_j the largest integer whose
+// ps = 1/(1+k/1e4) still lies in bin >= j; generated and re-checked against numpy by
+// tests/test_first_principles.py::test_prob_cut_constants).
+__constant__ double kProbCut[20] = {
+    0.0, 0x1.78e376738f1eep+1, 0x1.193ed6453eac1p+1, 0x1.bc0e9f3c39428p+0,
+    0x1.62e501a66511cp+0, 0x1.193fbf4901473p+0, 0x1.b1d1f61d1fc89p-1, 0x1.3cf336143d45fp-1,
+    0x1.9f3afbb8bc957p-2, 0x1.9b052730799f3p-3, 0x1.a36b7f85c4e5fp-15, -0x1.9b0da0803bfd9p-3,
+    -0x1.9f38cc8a12b56p-2, -0x1.3cf5840e17938p-1, -0x1.b1d79434228fap-1, -0x1.193b60d3d1253p+0,
+    -0x1.62d714d4115dep+0, -0x1.bc1676093fb01p+0, -0x1.1933302b0a04ap+1, -0x1.78d7e8e08506cp+1};
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_threshold_prob(const T* __restrict__ filt, int W, int rx0,
+                                                        int ry0, int rw, int rh, int cx, int cy,
+                                                        int r, const chips_result* __restrict__ res,
+                                                        uint8_t* __restrict__ lev,
+                                                        uint32_t* __restrict__ probtab) {
+  __shared__ double slim[CHIPS_MAX_T];
+  __shared__ uint32_t tab[(CHIPS_MAX_T + 1) * CHIPS_PROB_BINS];
+  const int nT = res->n_thresholds;
+  const bool have = res->n_peaks > 0;
+  for (int i = threadIdx.x; i < nT; i += blockDim.x) slim[i] = res->limits[i];
+  for (int i = threadIdx.x; i < (nT + 1) * CHIPS_PROB_BINS; i += blockDim.x) tab[i] = 0;
+  __syncthreads();
+  int t_inv = 0;                     // limits ascend: the ones < -1 are a prefix
+  for (int t = 0; t < nT; ++t) t_inv += (slim[t] < -1.0) ? 1 : 0;
+  const double limit_0 = res->limit_0;
+  const double top = have ? slim[nT - 1] : 0.0;
+  for (int y = ry0 + blockIdx.x; y < ry0 + rh; y += gridDim.x) {
+    for (int x = rx0 + threadIdx.x; x < rx0 + rw; x += blockDim.x) {
+      int level = nT;
+      if (have && on_disk(x, y, cx, cy, r)) {
+        double v = (double)filt[(size_t)y * W + x];
+        if (v <= top) {
+          level = 0;
+          for (int t = 0; t < nT; ++t) level += (slim[t] < v) ? 1 : 0;   // first t with v <= lim_t
+          double d = __dsub_rn(v, limit_0);
+          int bin = 0;
+#pragma unroll
+          for (int j = 1; j < CHIPS_PROB_BINS; ++j) bin += (d <= kProbCut[j]) ? 1 : 0;
+          atomicAdd(&tab[level * CHIPS_PROB_BINS + bin], 1u);
+          level = max(level, t_inv);             // chips.py:372-374: lim < -1 wipes the mask
+        }
+      }
+      lev[(size_t)y * W + x] = (uint8_t)level;
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nT * CHIPS_PROB_BINS; i += blockDim.x)
+    if (tab[i]) atomicAdd(&probtab[i], tab[i]);
+}
+
+__device__ double pairwise_sum20(const double* a, int n) {
+  // numpy add.reduce for a contiguous float64 run with n < 128
+  if (n < 8) {
+    double res = 0.0;
+    for (int i = 0; i < n; ++i) res = __dadd_rn(res, a[i]);
+    return res;
+  }
+  double r[8];
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+  return res;
+}
+
+__global__ void k_prob_epilogue(const uint32_t* __restrict__ probtab, double porb_threshold,
+                                chips_result* __restrict__ res) {
+  const int T = res->n_thresholds;
+  const int t = threadIdx.x;
+  if (t >= T) return;
+  if (res->n_peaks <= 0) {
+    res->probs[t] = nan("");
+    return;
+  }
+  // b = (e + diff(e)[0]/2)[:-1], e = np.linspace(0, 1, 21)
+  const double stepe = __ddiv_rn(1.0, 20.0);
+  const double halfw = __ddiv_rn(__dsub_rn(__dadd_rn(__dmul_rn(1.0, stepe), 0.0), 0.0), 2.0);
+  double all[CHIPS_PROB_BINS], sel[CHIPS_PROB_BINS];
+  int nsel = 0;
+  for (int j = 0; j < CHIPS_PROB_BINS; ++j) {
+    long long h = 0;
+    for (int l = 0; l <= t; ++l) h += probtab[l * CHIPS_PROB_BINS + j];
+    double e = (j == 20) ? 1.0 : __dadd_rn(__dmul_rn((double)j, stepe), 0.0);
+    double b = __dadd_rn(e, halfw);
+    double bh = __dmul_rn(b, (double)h);
+    all[j] = bh;
+    if (b > porb_threshold) sel[nsel++] = bh;
+  }
+  double p = __ddiv_rn(pairwise_sum20(sel, nsel), pairwise_sum20(all, CHIPS_PROB_BINS));
+  res->probs[t] = __ddiv_rn(rint(__dmul_rn(p, 10000.0)), 10000.0);
+}
+
+// ------------------------------------------------------------------ f64 -> f32 demotion
+__global__ void k_demote(const double* __restrict__ in, float* __restrict__ out, size_t n,
+                         int* __restrict__ all_exact) {
+  bool ok = true;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    double v = in[i];
+    float f = (float)v;
+    out[i] = f;
+    ok = ok && ((double)f == v);
+  }
+  if (!__all_sync(0xFFFFFFFFu, ok) && (threadIdx.x & 31) == 0) atomicAnd(all_exact, 0);
+}
+
+__global__ void k_set_int(int* p, int v) { *p = v; }
+
+template <typename T>
+__global__ void k_disk_mask(T* __restrict__ n_mask, T* __restrict__ i_mask, int H, int W, int cx,
+                            int cy, int r) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)H * W) return;
+  int y = (int)(i / W), x = (int)(i % W);
+  bool on = on_disk(x, y, cx, cy, r);
+  if (n_mask) n_mask[i] = on ? (T)1 : (T)NAN;
+  if (i_mask) i_mask[i] = on ? (T)1 : (T)0;
+}
+
+static int hist_copies(int nbins) {
+  int c = 65536 / (nbins * 4);
+  if (c < 1) c = 1;
+  if (c > 8) c = 8;
+  return c;
+}
+
+template <typename T>
+static int minmax_impl(const T* filt, const chips_plan* p, int cx, int cy, int r, unsigned char* ws,
+                       cudaStream_t st) {
+  using K = typename Key<T>::type;
+  K* mm = reinterpret_cast<K*>(ws + p->off_minmax);
+  k_minmax_init<T><<<1, 1, 0, st>>>(mm);
+  CHIPS_CHECK_LAUNCH();
+  int grid = min(p->roi_h, 4 * kNumSM);
+  k_minmax<T><<<grid, 256, 0, st>>>(filt, p->W, p->roi_x0, p->roi_y0, p->roi_w, p->roi_h, cx, cy, r, mm);
+  CHIPS_CHECK_LAUNCH();
+  return CHIPS_OK;
+}
+
+template <typename T>
+static int hist_impl(const T* filt, const chips_plan* p, int cx, int cy, int r, unsigned char* ws,
+                     cudaStream_t st) {
+  using K = typename Key<T>::type;
+  const int nbins = p->h_bins;
+  int copies = hist_copies(nbins);
+  size_t smem = (size_t)copies * nbins * sizeof(uint32_t);
+  if (smem > 200 * 1024) return CHIPS_E_ARG;
+  unsigned long long* counts = reinterpret_cast<unsigned long long*>(ws + p->off_counts);
+  CHIPS_CUDA(cudaMemsetAsync(counts, 0, (size_t)nbins * sizeof(long long), st));
+  CHIPS_CUDA(cudaFuncSetAttribute(k_hist<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = smem > 100 * 1024 ? 1 : (smem > 56 * 1024 ? 2 : 4);
+  int grid = min(p->roi_h, per_sm * kNumSM);
+  k_hist<T><<<grid, 256, smem, st>>>(filt, p->W, p->roi_x0, p->roi_y0, p->roi_w, p->roi_h, cx, cy, r,
+                                     reinterpret_cast<const K*>(ws + p->off_minmax), nbins, copies,
+                                     counts, reinterpret_cast<chips_result*>(ws + p->off_result));
+  CHIPS_CHECK_LAUNCH();
+  return CHIPS_OK;
+}
+
+template <typename T>
+static int thr_impl(const T* filt, const chips_plan* p, int cx, int cy, int r, double porb,
+                    unsigned char* ws, cudaStream_t st) {
+  uint8_t* lev = ws + p->off_level;
+  uint32_t* tab = reinterpret_cast<uint32_t*>(ws + p->off_probtab);
+  chips_result* res = reinterpret_cast<chips_result*>(ws + p->off_result);
+  CHIPS_CUDA(cudaMemsetAsync(lev, p->T, (size_t)p->H * p->W, st));
+  CHIPS_CUDA(cudaMemsetAsync(tab, 0, (size_t)(p->T + 1) * CHIPS_PROB_BINS * sizeof(uint32_t), st));
+  int grid = min(p->roi_h, 8 * kNumSM);
+  k_threshold_prob<T><<<grid, 256, 0, st>>>(filt, p->W, p->roi_x0, p->roi_y0, p->roi_w, p->roi_h, cx,
+                                            cy, r, res, lev, tab);
+  CHIPS_CHECK_LAUNCH();
+  k_prob_epilogue<<<1, CHIPS_MAX_T, 0, st>>>(tab, porb, res);
+  CHIPS_CHECK_LAUNCH();
+  return CHIPS_OK;
+}
+
+}  // namespace chips
+
+using namespace chips;
+
+extern "C" int chips_minmax(const void* filt, const chips_plan* plan, int cx, int cy, int r,
+                            void* ws, void* stream) {
+  if (!filt || !plan || !ws) return CHIPS_E_ARG;
+  if (plan->elem == 4) return minmax_impl<float>((const float*)filt, plan, cx, cy, r, (unsigned char*)ws, (cudaStream_t)stream);
+  if (plan->elem == 8) return minmax_impl<double>((const double*)filt, plan, cx, cy, r, (unsigned char*)ws, (cudaStream_t)stream);
+  return CHIPS_E_ARG;
+}
+
+extern "C" int chips_histogram(const void* filt, const chips_plan* plan, int cx, int cy, int r,
+                               void* ws, void* stream) {
+  if (!filt || !plan || !ws || plan->h_bins < 1) return CHIPS_E_ARG;
+  if (plan->elem == 4) return hist_impl<float>((const float*)filt, plan, cx, cy, r, (unsigned char*)ws, (cudaStream_t)stream);
+  if (plan->elem == 8) return hist_impl<double>((const double*)filt, plan, cx, cy, r, (unsigned char*)ws, (cudaStream_t)stream);
+  return CHIPS_E_ARG;
+}
+
+extern "C" int chips_select_threshold(const chips_plan* plan, double ht_peak_ratio,
+                                      double h_thresh_in, int t0, int t1, void* ws, void* stream) {
+  if (!plan || !ws) return CHIPS_E_ARG;
+  int T = t1 - t0;
+  if (T < 0) T = 0;
+  if (T != plan->T || T > CHIPS_MAX_T) return CHIPS_E_ARG;
+  unsigned char* w = (unsigned char*)ws;
+  k_select<<<1, 1024, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long*>(w + plan->off_counts), plan->h_bins, ht_peak_ratio,
+      h_thresh_in, t0, T, reinterpret_cast<double*>(w + plan->off_density),
+      reinterpret_cast<double*>(w + plan->off_edges), reinterpret_cast<double*>(w + plan->off_bound),
+      reinterpret_cast<int*>(w + plan->off_peaks), reinterpret_cast<chips_result*>(w + plan->off_result));
+  CHIPS_CHECK_LAUNCH();
+  return CHIPS_OK;
+}
+
+extern "C" int chips_threshold_prob(const void* filt, const chips_plan* plan, int cx, int cy, int r,
+                                    double porb_threshold, void* ws, void* stream) {
+  if (!filt || !plan || !ws) return CHIPS_E_ARG;
+  if (plan->elem == 4) return thr_impl<float>((const float*)filt, plan, cx, cy, r, porb_threshold, (unsigned char*)ws, (cudaStream_t)stream);
+  if (plan->elem == 8) return thr_impl<double>((const double*)filt, plan, cx, cy, r, porb_threshold, (unsigned char*)ws, (cudaStream_t)stream);
+  return CHIPS_E_ARG;
+}
+
+extern "C" int chips_disk_mask(void* n_mask, void* i_mask, int H, int W, int elem, int cx, int cy,
+                               int r, void* stream) {
+  size_t n = (size_t)H * W;
+  unsigned grid = (unsigned)((n + 255) / 256);
+  if (elem == 4)
+    k_disk_mask<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)n_mask, (float*)i_mask, H, W, cx, cy, r);
+  else if (elem == 8)
+    k_disk_mask<double><<<grid, 256, 0, (cudaStream_t)stream>>>((double*)n_mask, (double*)i_mask, H, W, cx, cy, r);
+  else
+    return CHIPS_E_ARG;
+  CHIPS_CHECK_LAUNCH();
+  return CHIPS_OK;
+}
+
+extern "C" int chips_demote_f64(const double* in, float* out, size_t n, int32_t* all_exact,
+                                void* stream) {
+  if (!in || !out || !all_exact) return CHIPS_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  k_set_int<<<1, 1, 0, st>>>(all_exact, 1);
+  CHIPS_CHECK_LAUNCH();
+  k_demote<<<8 * kNumSM, 256, 0, st>>>(in, out, n, all_exact);
+  CHIPS_CHECK_LAUNCH();
+  return CHIPS_OK;
+}

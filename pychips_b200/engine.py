@@ -1,0 +1,251 @@
+"""Device-side driver of one CHIPS detection: plan + workspace + C-ABI calls.
+
+PyTorch is used only as plumbing here (device memory, streams, host<->device copies); every
+compute step is a hand-written sm_100a kernel reached through `libchips_b200.so`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Plan, Result
+
+_NP2T = {np.dtype("float32"): torch.float32, np.dtype("float64"): torch.float64}
+
+
+def _stream_ptr(stream=None) -> C.c_void_p:
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def _ptr(t: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.ChipsNativeError(
+            "pychips_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback.")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+@dataclass
+class Geometry:
+    H: int
+    W: int
+    cx: int
+    cy: int
+    r: int            # < 0: unmasked (synoptic)
+
+    @property
+    def disk_area(self) -> float:
+        return float(np.pi * self.r ** 2)      # chips.py:185
+
+
+class Detector:
+    """Plan + workspace for one (geometry, k, h_bins, T, elem) and the stage calls.
+
+    Stage methods mirror the C ABI one to one; `detect` is the fused sequence
+    (`chips_detect`).  All calls only enqueue on the current torch stream.
+    """
+
+    def __init__(self, geom: Geometry, k: int, h_bins: int, t0: int, t1: int, elem: int = 4,
+                 device=None):
+        self.lib = _lib.load()
+        self.device = require_cuda(device)
+        self.geom = geom
+        self.k, self.h_bins, self.t0, self.t1, self.elem = int(k), int(h_bins), int(t0), int(t1), elem
+        self.T = max(0, self.t1 - self.t0)
+        if self.T < 1:
+            raise ValueError("threshold_range must span at least one threshold")
+        self.plan = Plan()
+        _lib.check(self.lib.chips_plan_init(C.byref(self.plan), geom.H, geom.W, self.k, self.h_bins,
+                                            self.T, elem, geom.cx, geom.cy, geom.r), "chips_plan_init")
+        with torch.cuda.device(self.device):
+            self.ws = torch.empty(int(self.plan.bytes), dtype=torch.uint8, device=self.device)
+        self._pp = C.byref(self.plan)
+        self.dtype = torch.float32 if elem == 4 else torch.float64
+
+    # ------------------------------------------------------------------ workspace views
+    def view(self, name: str, dtype, shape) -> torch.Tensor:
+        off = int(getattr(self.plan, "off_" + name))
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        return self.ws[off:off + n].view(dtype).reshape(shape)
+
+    @property
+    def filt(self):
+        return self.view("filt", self.dtype, (self.geom.H, self.geom.W))
+
+    @property
+    def level(self):
+        return self.view("level", torch.uint8, (self.geom.H, self.geom.W))
+
+    @property
+    def fill(self):
+        return self.view("fill", torch.uint8, (self.geom.H, self.geom.W))
+
+    @property
+    def keep(self):
+        return self.view("keep", torch.uint8, (self.geom.H, self.geom.W))
+
+    @property
+    def counts(self):
+        return self.view("counts", torch.int64, (self.h_bins,))
+
+    @property
+    def density(self):
+        return self.view("density", torch.float64, (self.h_bins,))
+
+    @property
+    def edges(self):
+        return self.view("edges", torch.float64, (self.h_bins + 1,))
+
+    @property
+    def bound(self):
+        return self.view("bound", torch.float64, (self.h_bins,))
+
+    @property
+    def peak_index(self):
+        return self.view("peaks", torch.int32, (self.h_bins,))
+
+    @property
+    def probtab(self):
+        return self.view("probtab", torch.int32, (self.T + 1, _lib.PROB_BINS))
+
+    def result_bytes(self) -> torch.Tensor:
+        off = int(self.plan.off_result)
+        return self.ws[off:off + C.sizeof(Result)]
+
+    def result(self) -> Result:
+        """Device -> host read of the per-image record (synchronises the current stream)."""
+        host = self.result_bytes().cpu().numpy().tobytes()
+        return Result.from_buffer_copy(host)
+
+    # ------------------------------------------------------------------ stages
+    def _g(self):
+        return self.geom.cx, self.geom.cy, self.geom.r
+
+    def medfilt(self, image: torch.Tensor, out: torch.Tensor | None = None):
+        out = self.filt if out is None else out
+        _lib.check(self.lib.chips_medfilt2d(_ptr(image), _ptr(out), self._pp, *self._g(),
+                                            _ptr(self.ws), _stream_ptr()), "chips_medfilt2d")
+        if self.k == 1:
+            _lib.check(self.lib.chips_minmax(_ptr(out), self._pp, *self._g(), _ptr(self.ws),
+                                             _stream_ptr()), "chips_minmax")
+        return out
+
+    def histogram(self, filt: torch.Tensor | None = None, recompute_minmax: bool = False):
+        filt = self.filt if filt is None else filt
+        if recompute_minmax:
+            _lib.check(self.lib.chips_minmax(_ptr(filt), self._pp, *self._g(), _ptr(self.ws),
+                                             _stream_ptr()), "chips_minmax")
+        _lib.check(self.lib.chips_histogram(_ptr(filt), self._pp, *self._g(), _ptr(self.ws),
+                                            _stream_ptr()), "chips_histogram")
+
+    def select_threshold(self, ht_peak_ratio: float, h_thresh):
+        h_in = float("nan") if h_thresh is None else float(h_thresh)
+        _lib.check(self.lib.chips_select_threshold(self._pp, float(ht_peak_ratio), h_in, self.t0,
+                                                   self.t1, _ptr(self.ws), _stream_ptr()),
+                   "chips_select_threshold")
+
+    def threshold_prob(self, porb_threshold: float, filt: torch.Tensor | None = None):
+        filt = self.filt if filt is None else filt
+        _lib.check(self.lib.chips_threshold_prob(_ptr(filt), self._pp, *self._g(),
+                                                 float(porb_threshold), _ptr(self.ws), _stream_ptr()),
+                   "chips_threshold_prob")
+
+    def cleanup(self, area_threshold: float):
+        if self.geom.r < 0:
+            self.keep.copy_(self.level)      # synoptic: map = raw threshold mask
+            return
+        _lib.check(self.lib.chips_cleanup(self._pp, *self._g(), self.geom.disk_area,
+                                          float(area_threshold), _ptr(self.ws), _stream_ptr()),
+                   "chips_cleanup")
+
+    def detect(self, image: torch.Tensor, ht_peak_ratio=5, h_thresh=None, porb_threshold=0.8,
+               area_threshold=1e-3, maps: torch.Tensor | None = None):
+        h_in = float("nan") if h_thresh is None else float(h_thresh)
+        _lib.check(self.lib.chips_detect(_ptr(image), self._pp, *self._g(), float(ht_peak_ratio),
+                                         h_in, self.t0, self.t1, float(porb_threshold),
+                                         float(area_threshold), _ptr(maps), _ptr(self.ws),
+                                         _stream_ptr()), "chips_detect")
+
+    # ------------------------------------------------------------------ outputs
+    def expand_maps(self, which: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+        """uint8 [T,H,W]: which=0 final maps, 1 raw threshold masks, 2 hole-filled masks."""
+        if out is None:
+            out = torch.empty((self.T, self.geom.H, self.geom.W), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.chips_expand_maps(self._pp, which, _ptr(out), _ptr(self.ws),
+                                              _stream_ptr()), "chips_expand_maps")
+        return out
+
+    def expand_map(self, t: int, which: int = 0, dtype=torch.float64) -> torch.Tensor:
+        out = torch.empty((self.geom.H, self.geom.W), dtype=dtype, device=self.device)
+        _lib.check(self.lib.chips_expand_map(self._pp, which, int(t), _ptr(out), out.element_size(),
+                                             _ptr(self.ws), _stream_ptr()), "chips_expand_map")
+        return out
+
+    def roots(self, t: int):
+        roots = torch.empty((self.geom.H, self.geom.W), dtype=torch.int32, device=self.device)
+        area2 = torch.empty((self.geom.H, self.geom.W), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.chips_roots(self._pp, *self._g(), int(t), _ptr(roots), _ptr(area2),
+                                        _ptr(self.ws), _stream_ptr()), "chips_roots")
+        return roots, area2
+
+    def labels(self, t: int):
+        """Canonical label image (raster order of first pixel) and 2*area per label (host)."""
+        roots, area2 = self.roots(t)
+        r = roots.cpu().numpy()
+        a = area2.cpu().numpy()
+        fg = r >= 0
+        uniq, first, inv = np.unique(r[fg], return_index=True, return_inverse=True)
+        lab = np.zeros(r.shape, dtype=np.int32)
+        lab[fg] = inv.astype(np.int32) + 1
+        return lab, a[fg][first].astype(np.int64)
+
+    def prob_stack(self, lower_lim: float = 0.0, out: torch.Tensor | None = None,
+                   accumulate: bool = False, dtype=torch.float64) -> torch.Tensor:
+        if out is None:
+            out = torch.zeros((self.geom.H, self.geom.W), dtype=dtype, device=self.device)
+        _lib.check(self.lib.chips_prob_stack(self._pp, float(lower_lim), _ptr(out), out.element_size(),
+                                             int(accumulate), _ptr(self.ws), _stream_ptr()),
+                   "chips_prob_stack")
+        return out
+
+
+def to_device_image(data: np.ndarray, device, allow_demote: bool = True):
+    """Host array -> (device tensor, elem).  float64 input whose values are all exactly
+    float32-representable is stored as float32 (half the HBM traffic; every comparison the
+    reference makes in float64 is done on the widened value, so results are identical)."""
+    lib = _lib.load()
+    arr = np.ascontiguousarray(data)
+    if arr.dtype == np.float32:
+        return torch.from_numpy(arr).to(device, non_blocking=False), 4
+    if arr.dtype != np.float64:
+        arr = arr.astype(np.float64)
+    t64 = torch.from_numpy(arr).to(device)
+    if not allow_demote:
+        return t64, 8
+    t32 = torch.empty(arr.shape, dtype=torch.float32, device=device)
+    flag = torch.ones(1, dtype=torch.int32, device=device)
+    _lib.check(lib.chips_demote_f64(_ptr(t64), _ptr(t32), t64.numel(), _ptr(flag), _stream_ptr()),
+               "chips_demote_f64")
+    if int(flag.item()) == 1:
+        return t32, 4
+    return t64, 8
+
+
+def medfilt2d(data: np.ndarray, k: int, device=None) -> np.ndarray:
+    """`scipy.signal.medfilt2d(data, k)` on the GPU (zero padded, exact)."""
+    device = require_cuda(device)
+    img, elem = to_device_image(data, device, allow_demote=False)
+    H, W = data.shape
+    det = Detector(Geometry(H, W, 0, 0, -1), k, 1, 0, 1, elem, device)
+    out = torch.empty_like(img)
+    det.medfilt(img, out)
+    return out.cpu().numpy()

@@ -1,0 +1,158 @@
+"""`SynopticChips` — drop-in for `syn_chips.SynopticChips` of the reference
+(`/root/reference/chips/syn_chips.py:24-274`): same constructor defaults (`:40-52`),
+`run_CHIPS()` (`:79-93`) and stage methods; no disk mask and no contour/cleanup step — the
+per-threshold map is the raw threshold mask (`:237-251`).  NaN-free maps are assumed (the
+reference's own median is order-dependent on NaNs)."""
+from __future__ import annotations
+
+import os
+from argparse import Namespace
+from typing import List
+
+import numpy as np
+import torch
+
+from . import engine
+from .chips import LazyNamespace, logger
+from .engine import Detector, Geometry
+
+
+class SynopticChips(object):
+    def __init__(
+        self,
+        synoptic_map,
+        base_folder: str = "tmp/chips_dataset/",
+        medfilt_kernel: int = 3,
+        h_bins: int = 5000,
+        h_thresh: float = None,
+        ht_peak_ratio: int = 5,
+        hist_xsplit: int = 2,
+        hist_ysplit: int = 2,
+        threshold_range: List[float] = [-5, 20],
+        porb_threshold: float = 0.8,
+        device=None,
+        make_folder: bool = True,
+    ) -> None:
+        self.synoptic_map = synoptic_map
+        self.base_folder = base_folder
+        self.medfilt_kernel = medfilt_kernel
+        self.h_bins = h_bins
+        self.h_thresh = h_thresh
+        self.ht_peak_ratio = ht_peak_ratio
+        self.hist_xsplit = hist_xsplit
+        self.hist_ysplit = hist_ysplit
+        self.threshold_range = threshold_range
+        self.porb_threshold = porb_threshold
+        self.device = engine.require_cuda(device)
+        self._det = None
+        self._img = None
+        if make_folder:
+            self.get_base_folder()
+
+    # ---- syn_chips.py:67-77
+    def get_base_folder(self) -> None:
+        self.folder = self.base_folder + self.synoptic_map.date.strftime("%Y.%m.%d")
+        os.makedirs(self.folder, exist_ok=True)
+
+    # ---- syn_chips.py:79-93 (plotter call excluded)
+    def run_CHIPS(self) -> None:
+        self.run_filters(self.synoptic_map)
+        self.extract_histogram(self.synoptic_map)
+        self.extract_CHs_CHBs(self.synoptic_map)
+        return
+
+    def _detector(self, syn) -> Detector:
+        if self._det is None:
+            data = np.asarray(syn.raw.data)
+            with torch.cuda.device(self.device):
+                img, elem = engine.to_device_image(data, self.device)
+                tr = np.arange(self.threshold_range[0], self.threshold_range[1])
+                t0 = int(tr[0])
+                H, W = data.shape
+                self._det = Detector(Geometry(int(H), int(W), 0, 0, -1), self.medfilt_kernel,
+                                     self.h_bins, t0, t0 + len(tr), elem, self.device)
+                self._det.state = set()
+            self._img = img
+        return self._det
+
+    def _out_dtype(self, syn):
+        return np.float32 if np.asarray(syn.raw.data).dtype == np.float32 else np.float64
+
+    # ---- syn_chips.py:95-108
+    def run_filters(self, synoptic_map) -> None:
+        logger.info(f"Running solar filters for {synoptic_map.wavelength}")
+        if not hasattr(synoptic_map, "solar_filter"):
+            det = self._detector(synoptic_map)
+            with torch.cuda.device(self.device):
+                det.medfilt(self._img)
+                det.state.add("filt")
+                filt = det.filt.cpu().numpy().astype(self._out_dtype(synoptic_map), copy=False)
+            synoptic_map.set_value("solar_filter", filt)     # a bare ndarray, as in the reference
+        return
+
+    # ---- syn_chips.py:110-144
+    def extract_histogram(self, synoptic_map) -> None:
+        logger.info(f"Extract solar histogram {synoptic_map.wavelength}")
+        if not hasattr(synoptic_map, "histogram"):
+            det = self._detector(synoptic_map)
+            with torch.cuda.device(self.device):
+                if "filt" not in det.state:
+                    host = np.ascontiguousarray(synoptic_map.solar_filter)
+                    det.filt.copy_(torch.from_numpy(host).to(self.device).to(det.dtype))
+                    det.state.add("filt")
+                    det.histogram(recompute_minmax=True)
+                else:
+                    det.histogram()
+                det.select_threshold(self.ht_peak_ratio, self.h_thresh)
+                det.state.add("hist")
+                res = det.result()
+                if self.h_thresh is None:
+                    self.h_thresh = np.float64(res.h_thresh)
+                npk = int(res.n_peaks)
+                pidx = det.peak_index[:npk].cpu().numpy()
+                bound = det.bound.cpu().numpy()
+            peaks = [bound[p] for p in pidx]
+            synoptic_map.set_value("histogram", LazyNamespace(
+                _lazy=dict(hbase=lambda: det.density.cpu().numpy(),
+                           counts=lambda: det.counts.cpu().numpy()),
+                peaks=peaks, bound=bound, h_thresh=self.h_thresh, h_bins=self.h_bins,
+                peak_indexs=pidx))
+        return
+
+    # ---- syn_chips.py:218-254
+    def extract_CHs_CHBs(self, synoptic_map) -> None:
+        logger.info(f"Extract CHs and CHBs for different regions {synoptic_map.wavelength}")
+        if not hasattr(synoptic_map, "solar_ch_regions"):
+            if len(synoptic_map.histogram.peaks) > 0:
+                det = self._detector(synoptic_map)
+                dt = self._out_dtype(synoptic_map)
+                with torch.cuda.device(self.device):
+                    det.threshold_prob(self.porb_threshold)
+                    det.cleanup(0.0)
+                    res = det.result()
+                if res.median_errors:
+                    raise engine._lib.ChipsNativeError(
+                        f"median filter self-check failed for {res.median_errors} pixels")
+                limit_0 = np.float64(res.limit_0)
+                dtmp_map = {}
+                for t in range(det.T):
+                    lim = np.float64(res.limits[t])
+
+                    def _map(t=t):
+                        with torch.cuda.device(self.device):
+                            return det.expand_map(t, 1).cpu().numpy().astype(dt, copy=False)
+
+                    dtmp_map[str(lim)] = LazyNamespace(
+                        _lazy=dict(map=_map), lim=lim, limit_0=limit_0,
+                        prob=np.float64(res.probs[t]), index=t)
+                    logger.info(f"Estimated prob.({res.probs[t]}) at lim({lim})")
+                synoptic_map.set_value("solar_ch_regions", Namespace(**dtmp_map))
+        return
+
+    # ---- plots.py:624-641 (the arithmetic only)
+    def probability_map(self, prob_lower_lim: float = 0.0) -> np.ndarray:
+        with torch.cuda.device(self.device):
+            return self._det.prob_stack(prob_lower_lim).cpu().numpy()
+
+    def plot_diagonestics(self, *a, **k) -> None:
+        raise NotImplementedError("plotting is outside the accelerated path (SURVEY.md §2 row 6)")

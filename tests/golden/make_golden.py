@@ -1,0 +1,121 @@
+"""Generate the committed golden fixtures (run in the BUILD container, where the reference
+tree exists).  For every case: run the UNMODIFIED reference (oracle/ref_harness.py), run the
+oracle restatement (oracle/chips_oracle.py) on the same input, assert they agree on every
+stage output, and store the reference's outputs.
+
+    python tests/golden/make_golden.py
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import chips_oracle as co            # noqa: E402
+from oracle import ref_harness as rh             # noqa: E402
+from pychips_b200 import synth                   # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+DISK_CASES = {
+    # name: (N, seed, scale, kwargs)
+    "disk_n256_k11": (256, 0, 1.0, dict(medfilt_kernel=11, h_bins=500, threshold_range=[0, 20])),
+    "disk_n256_k31_211": (256, 1, 1.0, dict(medfilt_kernel=31, h_bins=1000, threshold_range=[-3, 11])),
+    "disk_n192_k51": (192, 2, 1.0, dict(medfilt_kernel=51, h_bins=500, threshold_range=[0, 20])),
+    "disk_n256_k5_t28": (256, 3, 1.0, dict(medfilt_kernel=5, h_bins=5000, threshold_range=[-3, 25])),
+    "disk_n200_k7_wiped": (200, 4, 0.02, dict(medfilt_kernel=7, h_bins=500, threshold_range=[-3, 5])),
+}
+SYN_CASES = {
+    "syn_180x360_k3": (180, 360, 0, dict(medfilt_kernel=3, h_bins=5000, threshold_range=[-5, 20])),
+    "syn_96x240_k11": (96, 240, 1, dict(medfilt_kernel=11, h_bins=500, threshold_range=[-5, 20])),
+}
+
+
+def _same(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+def make_disk(name, n, seed, scale, kw):
+    img, r = synth.synthetic_disk(n, seed)
+    img = (img * np.float32(scale)).astype(np.float32)
+    d_ref = synth.FakeDisk(img.astype(np.float64), r)
+    rh.run_disk(d_ref, synth.FakeAIA(d_ref), **kw)
+    d_or = synth.FakeDisk(img.astype(np.float64), r)
+    co.OracleChips(**kw).run(d_or)
+    assert _same(d_ref.solar_mask.n_mask, d_or.solar_mask.n_mask)
+    assert _same(d_ref.solar_filter.filt_disk, d_or.solar_filter.filt_disk)
+    assert _same(d_ref.solar_filter.solar_disk, d_or.solar_filter.solar_disk)
+    for f in ("hbase", "hbins", "bound", "h_thresh"):
+        assert _same(getattr(d_ref.histogram, f), getattr(d_or.histogram, f)), f
+    assert _same(d_ref.histogram.peaks, d_or.histogram.peaks)
+    out = dict(image=img, pixel_radius=r, i_mask=np.packbits(d_ref.solar_mask.i_mask.astype(np.uint8)),
+               filt_disk=d_ref.solar_filter.filt_disk.astype(np.float32),
+               hbase=d_ref.histogram.hbase, hbins=d_ref.histogram.hbins,
+               bound=d_ref.histogram.bound, h_thresh=d_ref.histogram.h_thresh,
+               peaks=np.array(d_ref.histogram.peaks, dtype=np.float64),
+               kw_medfilt_kernel=kw["medfilt_kernel"], kw_h_bins=kw["h_bins"],
+               kw_threshold_range=np.array(kw["threshold_range"]))
+    assert _same(out["filt_disk"].astype(np.float64), d_ref.solar_filter.filt_disk)
+    has = hasattr(d_ref, "solar_ch_regions")
+    assert has == hasattr(d_or, "solar_ch_regions")
+    if has:
+        keys = list(d_ref.solar_ch_regions.__dict__.keys())
+        assert keys == list(d_or.solar_ch_regions.__dict__.keys())
+        maps, probs, lims, ncont = [], [], [], []
+        for k in keys:
+            a, b = d_ref.solar_ch_regions.__dict__[k], d_or.solar_ch_regions.__dict__[k]
+            assert _same(a.map, b.map) and _same(a.prob, b.prob) and a.lim == b.lim, k
+            assert len(a.contours) == len(b.contours)
+            maps.append(a.map.astype(np.uint8))
+            probs.append(a.prob)
+            lims.append(a.lim)
+            ncont.append(len(a.contours))
+        out.update(keys=np.array(keys), limits=np.array(lims), probs=np.array(probs),
+                   n_contours=np.array(ncont), limit_0=d_ref.solar_ch_regions.__dict__[keys[0]].limit_0,
+                   maps=np.packbits(np.array(maps)), raw_maps=np.packbits(
+                       np.array([d_or.solar_ch_regions.__dict__[k].raw_map.astype(np.uint8) for k in keys])))
+        try:       # plots.py:314 raises on an all-NaN probability list (nothing to stack)
+            st, npb = co.prob_stack([d_ref.solar_ch_regions.__dict__[k].map for k in keys], probs)
+            out.update(stack=st.astype(np.float64))
+        except ValueError:
+            pass
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "peaks", len(out["peaks"]), "regions", has, "T", len(out.get("limits", [])))
+
+
+def make_syn(name, h, w, seed, kw):
+    img = synth.synthetic_synoptic(h, w, seed)
+    s_ref = synth.FakeSynoptic(img.astype(np.float64))
+    rh.run_synoptic(s_ref, **kw)
+    s_or = synth.FakeSynoptic(img.astype(np.float64))
+    co.OracleSynopticChips(**kw).run(s_or)
+    assert _same(s_ref.solar_filter, s_or.solar_filter)
+    for f in ("hbase", "bound", "h_thresh"):
+        assert _same(getattr(s_ref.histogram, f), getattr(s_or.histogram, f)), f
+    assert _same(s_ref.histogram.peaks, s_or.histogram.peaks)
+    keys = list(s_ref.solar_ch_regions.__dict__.keys())
+    maps, probs, lims = [], [], []
+    for k in keys:
+        a, b = s_ref.solar_ch_regions.__dict__[k], s_or.solar_ch_regions.__dict__[k]
+        assert _same(a.map, b.map) and _same(a.prob, b.prob), k
+        maps.append(a.map.astype(np.uint8)); probs.append(a.prob); lims.append(a.lim)
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"), image=img, solar_filter=s_ref.solar_filter.astype(np.float32),
+        hbase=s_ref.histogram.hbase, bound=s_ref.histogram.bound, h_thresh=s_ref.histogram.h_thresh,
+        peaks=np.array(s_ref.histogram.peaks), keys=np.array(keys), limits=np.array(lims),
+        probs=np.array(probs), limit_0=s_ref.solar_ch_regions.__dict__[keys[0]].limit_0,
+        maps=np.packbits(np.array(maps)), kw_medfilt_kernel=kw["medfilt_kernel"],
+        kw_h_bins=kw["h_bins"], kw_threshold_range=np.array(kw["threshold_range"]))
+    print(name, "peaks", len(s_ref.histogram.peaks), "T", len(keys))
+
+
+if __name__ == "__main__":
+    assert rh.available(), "reference tree missing"
+    for name, (n, seed, scale, kw) in DISK_CASES.items():
+        make_disk(name, n, seed, scale, kw)
+    for name, (h, w, seed, kw) in SYN_CASES.items():
+        make_syn(name, h, w, seed, kw)
