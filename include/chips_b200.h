@@ -79,6 +79,8 @@ typedef struct chips_plan {
 } chips_plan;
 
 int chips_version(void);
+/* kernels launched by this library so far (process-wide counter) */
+long long chips_launch_count(void);
 
 /* Fill `plan` for one image geometry.  cx,cy,r as in the conventions (r<0: unmasked). */
 int chips_plan_init(chips_plan* plan, int H, int W, int k, int h_bins, int T, int elem,
@@ -95,6 +97,10 @@ int chips_disk_mask(void* n_mask, void* i_mask, int H, int W, int elem, int cx, 
  * plan->off_minmax.  `out` may be ws + plan->off_filt. */
 int chips_medfilt2d(const void* in, void* out, const chips_plan* plan, int cx, int cy, int r,
                     void* ws, void* stream);
+/* the same, restricted to a subset of its four kernels (bit 0 boundaries, 1 bucket image,
+ * 2 tier-1 sliding histograms, 3 tier-2 tile refine) so a caller can time each one */
+int chips_medfilt2d_stages(const void* in, void* out, const chips_plan* plan, int cx, int cy,
+                           int r, void* ws, void* stream, int stages);
 /* brute-force radix-select reference of the same filter (tests / at-scale checker) */
 int chips_medfilt2d_bruteforce(const void* in, void* out, int H, int W, int k, int elem,
                                int cx, int cy, int r, void* stream);

@@ -41,6 +41,8 @@ _PP = C.POINTER(Plan)
 
 SIGNATURES = {
     "chips_version": ([], C.c_int),
+    "chips_launch_count": ([], C.c_longlong),
+    "chips_medfilt2d_stages": ([_vp, _vp, _PP, _i, _i, _i, _vp, _vp, _i], C.c_int),
     "chips_plan_init": ([_PP, _i, _i, _i, _i, _i, _i, _i, _i, _i], C.c_int),
     "chips_disk_mask": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
     "chips_medfilt2d": ([_vp, _vp, _PP, _i, _i, _i, _vp, _vp], C.c_int),

@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) k_expand_all(const uint8_t* __restrict__ 
   // 4 pixels per thread, one 32-bit store per plane
   size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= n) return;
-  if (i4 + 4 <= n) {
+  if (i4 + 4 <= n && (n & 3) == 0) {      // plane stride n keeps the 32-bit stores aligned
     uint32_t v = *reinterpret_cast<const uint32_t*>(src + i4);
     for (int t = 0; t < T; ++t) {
       uint32_t o = 0;
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256) k_expand_all(const uint8_t* __restrict__ 
       *reinterpret_cast<uint32_t*>(maps + (size_t)t * n + i4) = o;
     }
   } else {
-    for (size_t i = i4; i < n; ++i)
+    for (size_t i = i4; i < n && i < i4 + 4; ++i)
       for (int t = 0; t < T; ++t) maps[(size_t)t * n + i] = src[i] <= t;
   }
 }
@@ -418,6 +418,7 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
   k_ccl_stats<<<gridz, blk, 0, st>>>(g, Wimg, parent_c, area, disk_area, area_threshold, res);
   k_ccl_keep<<<grid, blk, 0, st>>>(g, Wimg, T, parent_c, area, disk_area, area_threshold, keep);
   CHIPS_CHECK_LAUNCH();
+  count_launch(10 + 2 * (T - 1));
   return CHIPS_OK;
 }
 
@@ -433,6 +434,7 @@ extern "C" int chips_expand_maps(const chips_plan* plan, int which, uint8_t* map
   k_expand_all<<<grid, 256, 0, (cudaStream_t)stream>>>(pick_src(plan, which, (unsigned char*)ws), n,
                                                        plan->T, maps);
   CHIPS_CHECK_LAUNCH();
+  count_launch();
   return CHIPS_OK;
 }
 
@@ -448,6 +450,7 @@ extern "C" int chips_expand_map(const chips_plan* plan, int which, int t, void* 
   else if (out_elem == 8) k_expand_one<double><<<grid, 256, 0, st>>>(src, n, t, (double*)out);
   else return CHIPS_E_ARG;
   CHIPS_CHECK_LAUNCH();
+  count_launch();
   return CHIPS_OK;
 }
 
@@ -461,6 +464,7 @@ extern "C" int chips_roots(const chips_plan* plan, int cx, int cy, int r, int t,
       g, w + plan->off_fill, t, reinterpret_cast<uint32_t*>(w + plan->off_parent_c),
       reinterpret_cast<const uint32_t*>(w + plan->off_area), roots, twice_area);
   CHIPS_CHECK_LAUNCH();
+  count_launch();
   return CHIPS_OK;
 }
 
@@ -477,5 +481,6 @@ extern "C" int chips_prob_stack(const chips_plan* plan, double lower_lim, void* 
   else if (out_elem == 8) k_prob_stack<double><<<grid, 256, 0, st>>>(keep, n, res, lower_lim, accumulate, (double*)out);
   else return CHIPS_E_ARG;
   CHIPS_CHECK_LAUNCH();
+  count_launch();
   return CHIPS_OK;
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include "../../include/chips_b200.h"
 
 #define CHIPS_CHECK_LAUNCH()                                   \
@@ -17,6 +18,10 @@
   } while (0)
 
 namespace chips {
+
+// number of kernels this library has launched (bench.py reports it as gpu_launches)
+extern std::atomic<long long> g_launches;
+static inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 constexpr int kNumSM = 148;   // B200: 2 dies x 74 SMs
 

@@ -402,7 +402,7 @@ static int refine_cap(int k) {
 
 template <typename T>
 static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy, int r,
-                        unsigned char* ws, cudaStream_t st) {
+                        unsigned char* ws, cudaStream_t st, int stages) {
   using K = typename Key<T>::type;
   const int H = p->H, W = p->W, k = p->k, half = k >> 1;
   K* bounds = reinterpret_cast<K*>(ws + p->off_bounds);
@@ -413,20 +413,24 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
   int* err = &reinterpret_cast<chips_result*>(ws + p->off_result)->median_errors;
   const int rx0 = p->roi_x0, ry0 = p->roi_y0, rw = p->roi_w, rh = p->roi_h;
 
-  CHIPS_CUDA(cudaMemsetAsync(out, 0, (size_t)H * W * sizeof(T), st));
-  CHIPS_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
-  CHIPS_CUDA(cudaFuncSetAttribute(k_bounds<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(kSamples * sizeof(K))));
-  k_bounds<T><<<1, 1024, kSamples * sizeof(K), st>>>(in, W, rx0, ry0, rw, rh, bounds, minmax);
-  CHIPS_CHECK_LAUNCH();
+  if (stages & 1) {
+    CHIPS_CUDA(cudaMemsetAsync(out, 0, (size_t)H * W * sizeof(T), st));
+    CHIPS_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+    CHIPS_CUDA(cudaFuncSetAttribute(k_bounds<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(kSamples * sizeof(K))));
+    k_bounds<T><<<1, 1024, kSamples * sizeof(K), st>>>(in, W, rx0, ry0, rw, rh, bounds, minmax);
+    CHIPS_CHECK_LAUNCH();
+    count_launch();
+  }
   if (k == 1) {
     // medfilt2d with a 1x1 kernel is the identity (then masked); min/max via k_minmax later
     size_t n = (size_t)H * W;
     k_copy_masked<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, H, W, cx, cy, r);
     CHIPS_CHECK_LAUNCH();
+    count_launch();
     return CHIPS_OK;
   }
-  {  // bucket image over the ROI expanded by the halo (padded coordinates)
+  if (stages & 2) {  // bucket image over the ROI expanded by the halo (padded coordinates)
     int prow0 = ry0, prow1 = ry0 + rh + 2 * half;            // padded rows [ry0, ry0+rh+2h)
     int pcol0_w = rx0 / 4;
     int pcol1_w = (rx0 + rw + 2 * half + 8 + 3) / 4;         // + slack for the funnel loads
@@ -436,8 +440,9 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
     k_bucketize<T><<<grid, 256, 0, st>>>(in, H, W, half, p->bp_pitch, prow0, pcol0_w, ncol_w,
                                          bounds, Bp);
     CHIPS_CHECK_LAUNCH();
+    count_launch();
   }
-  {  // tier 1
+  if (stages & 4) {  // tier 1
     // run length: aim at >= 4 CTAs per SM worth of work, but keep the (k-1)-row warm-up
     // of every run amortised (L >= 2k).
     int nbx = (rw + kHuangThreads - 1) / kHuangThreads;
@@ -450,8 +455,9 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
     k_huang<<<grid, kHuangThreads, smem, st>>>(Bp, p->bp_pitch, half, k, W, rx0, ry0, rw, rh, L, cx,
                                                cy, r, bstar, rres);
     CHIPS_CHECK_LAUNCH();
+    count_launch();
   }
-  {  // tier 2
+  if (stages & 8) {  // tier 2
     int cap = refine_cap(k);
     size_t smem = (size_t)cap * (sizeof(K) + sizeof(uint16_t));
     CHIPS_CUDA(cudaFuncSetAttribute(k_refine<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -460,23 +466,32 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
                                                    half, rx0, ry0, rw, rh, cx, cy, r, cap, out,
                                                    minmax, err);
     CHIPS_CHECK_LAUNCH();
+    count_launch();
   }
   return CHIPS_OK;
 }
 
 }  // namespace chips
 
+extern "C" int chips_medfilt2d_stages(const void* in, void* out, const chips_plan* plan, int cx,
+                                      int cy, int r, void* ws, void* stream, int stages);
+
 extern "C" int chips_medfilt2d(const void* in, void* out, const chips_plan* plan, int cx, int cy,
                                int r, void* ws, void* stream) {
+  return chips_medfilt2d_stages(in, out, plan, cx, cy, r, ws, stream, 15);
+}
+
+extern "C" int chips_medfilt2d_stages(const void* in, void* out, const chips_plan* plan, int cx,
+                                      int cy, int r, void* ws, void* stream, int stages) {
   if (!in || !out || !plan || !ws) return CHIPS_E_ARG;
   if (plan->k < 1 || !(plan->k & 1) || plan->k > CHIPS_MAX_K) return CHIPS_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->elem == 4)
     return chips::medfilt_impl<float>((const float*)in, (float*)out, plan, cx, cy, r,
-                                      (unsigned char*)ws, st);
+                                      (unsigned char*)ws, st, stages);
   if (plan->elem == 8)
     return chips::medfilt_impl<double>((const double*)in, (double*)out, plan, cx, cy, r,
-                                       (unsigned char*)ws, st);
+                                       (unsigned char*)ws, st, stages);
   return CHIPS_E_ARG;
 }
 
@@ -500,5 +515,6 @@ extern "C" int chips_medfilt2d_bruteforce(const void* in, void* out, int H, int 
     return CHIPS_E_ARG;
   }
   CHIPS_CHECK_LAUNCH();
+  chips::count_launch();
   return CHIPS_OK;
 }

@@ -6,6 +6,12 @@
 
 using namespace chips;
 
+namespace chips {
+std::atomic<long long> g_launches{0};
+}
+
+extern "C" long long chips_launch_count(void) { return g_launches.load(); }
+
 extern "C" int chips_version(void) { return 100; }
 
 extern "C" int chips_plan_init(chips_plan* p, int H, int W, int k, int h_bins, int T, int elem,
@@ -90,6 +96,7 @@ extern "C" int chips_detect(const void* image, const chips_plan* plan, int cx, i
     k_copy_level_to_keep<<<(unsigned)((n / 16 + 256) / 256), 256, 0, (cudaStream_t)stream>>>(
         w + plan->off_level, w + plan->off_keep, n);
     CHIPS_CHECK_LAUNCH();
+    count_launch();
   }
   if (maps_or_null && (rc = chips_expand_maps(plan, 0, maps_or_null, ws, stream))) return rc;
   return CHIPS_OK;

@@ -351,6 +351,7 @@ static int minmax_impl(const T* filt, const chips_plan* p, int cx, int cy, int r
   int grid = min(p->roi_h, 4 * kNumSM);
   k_minmax<T><<<grid, 256, 0, st>>>(filt, p->W, p->roi_x0, p->roi_y0, p->roi_w, p->roi_h, cx, cy, r, mm);
   CHIPS_CHECK_LAUNCH();
+  count_launch(2);
   return CHIPS_OK;
 }
 
@@ -371,6 +372,7 @@ static int hist_impl(const T* filt, const chips_plan* p, int cx, int cy, int r, 
                                      reinterpret_cast<const K*>(ws + p->off_minmax), nbins, copies,
                                      counts, reinterpret_cast<chips_result*>(ws + p->off_result));
   CHIPS_CHECK_LAUNCH();
+  count_launch();
   return CHIPS_OK;
 }
 
@@ -388,6 +390,7 @@ static int thr_impl(const T* filt, const chips_plan* p, int cx, int cy, int r, d
   CHIPS_CHECK_LAUNCH();
   k_prob_epilogue<<<1, CHIPS_MAX_T, 0, st>>>(tab, porb, res);
   CHIPS_CHECK_LAUNCH();
+  count_launch(2);
   return CHIPS_OK;
 }
 
@@ -424,6 +427,7 @@ extern "C" int chips_select_threshold(const chips_plan* plan, double ht_peak_rat
       reinterpret_cast<double*>(w + plan->off_edges), reinterpret_cast<double*>(w + plan->off_bound),
       reinterpret_cast<int*>(w + plan->off_peaks), reinterpret_cast<chips_result*>(w + plan->off_result));
   CHIPS_CHECK_LAUNCH();
+  count_launch();
   return CHIPS_OK;
 }
 
@@ -446,6 +450,7 @@ extern "C" int chips_disk_mask(void* n_mask, void* i_mask, int H, int W, int ele
   else
     return CHIPS_E_ARG;
   CHIPS_CHECK_LAUNCH();
+  count_launch();
   return CHIPS_OK;
 }
 
@@ -457,5 +462,6 @@ extern "C" int chips_demote_f64(const double* in, float* out, size_t n, int32_t*
   CHIPS_CHECK_LAUNCH();
   k_demote<<<8 * kNumSM, 256, 0, st>>>(in, out, n, all_exact);
   CHIPS_CHECK_LAUNCH();
+  count_launch(2);
   return CHIPS_OK;
 }

@@ -1,0 +1,169 @@
+"""Time series / batch detection: one full-disk image per detection, images sharded
+round-robin across ranks (one process per GPU), each rank double-buffered over two CUDA
+streams so the host->device copy of image i+1 overlaps the kernels of image i.
+
+The reference has no batch API (one `Chips` per `RegisterAIA`, `/root/reference/chips/chips.py:
+110-150`); this is the multi-image driver SURVEY.md §8(e) asks for.  The only exchange step is
+at the end of a batch: `all_gather` of the per-image statistics and one `all_reduce(sum)` of the
+per-rank accumulated probability map (plots.py:305-322 arithmetic) for the uncertainty estimate.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+from .engine import Detector, Geometry
+
+STAT_FIELDS = 4          # limit_0, h_thresh, n_peaks, median_errors  (+ 2*T lims/probs, + T kept)
+
+
+def shard_indices(n_items: int, rank: int, world: int) -> list[int]:
+    """Round-robin partition of a batch (image i -> rank i % world)."""
+    return list(range(rank, n_items, world))
+
+
+@dataclass
+class SeriesResult:
+    indices: list
+    limit_0: np.ndarray            # [n]
+    h_thresh: np.ndarray           # [n]
+    n_peaks: np.ndarray            # [n]
+    limits: np.ndarray             # [n, T]
+    probs: np.ndarray              # [n, T]
+    n_kept: np.ndarray             # [n, T]
+    keep: list = field(default_factory=list)   # per image uint8 [H,W] level-encoded maps (host)
+    prob_map_sum: torch.Tensor | None = None   # device fp32 [H,W], summed over the batch
+
+
+class SeriesRunner:
+    """Runs `chips_detect` over a list of host images on ONE GPU with `n_streams` in flight."""
+
+    def __init__(self, H: int, W: int, medfilt_kernel: int = 51, h_bins: int = 500,
+                 threshold_range=(0, 20), ht_peak_ratio=5, porb_threshold=0.8,
+                 area_threshold=1e-3, masked: bool = True, device=None, n_streams: int = 2,
+                 elem: int = 4, want_keep: bool = True, want_prob_map: bool = True,
+                 want_maps: bool = False):
+        self.device = engine.require_cuda(device)
+        self.H, self.W = int(H), int(W)
+        self.k, self.h_bins = int(medfilt_kernel), int(h_bins)
+        self.t0, self.t1 = int(threshold_range[0]), int(threshold_range[1])
+        self.T = self.t1 - self.t0
+        self.ratio, self.porb, self.area_thr = ht_peak_ratio, porb_threshold, area_threshold
+        self.masked = masked
+        self.elem = elem
+        self.want_keep, self.want_prob_map, self.want_maps = want_keep, want_prob_map, want_maps
+        self.dtype = torch.float32 if elem == 4 else torch.float64
+        self.n_streams = n_streams
+        self._slots = {}
+        with torch.cuda.device(self.device):
+            self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
+            self.dev_in = [torch.empty((self.H, self.W), dtype=self.dtype, device=self.device)
+                           for _ in range(n_streams)]
+            self.maps = [torch.empty((self.T, self.H, self.W), dtype=torch.uint8, device=self.device)
+                         if want_maps else None for _ in range(n_streams)]
+            self.prob_sum = torch.zeros((self.H, self.W), dtype=torch.float32, device=self.device)
+
+    def _detector(self, slot: int, r: int) -> Detector:
+        key = (slot, r)
+        det = self._slots.get(key)
+        if det is None:
+            # one workspace per (stream slot, radius); a jittered series reuses a handful
+            c = int(self.H / 2)
+            g = Geometry(self.H, self.W, c, c, int(r) if self.masked else -1)
+            det = Detector(g, self.k, self.h_bins, self.t0, self.t1, self.elem, self.device)
+            self._slots[key] = det
+        return det
+
+    def run(self, images, radii, indices=None, h_thresh=None) -> SeriesResult:
+        """images: list of host arrays (pinned torch tensors or numpy, dtype matching `elem`);
+        radii: per-image pixel_radius.  Copies each image to the device, runs the fused
+        detection, copies the record (and the level-encoded map) back."""
+        n = len(images)
+        indices = list(range(n)) if indices is None else list(indices)
+        rec_bytes = C.sizeof(_lib.Result)
+        if getattr(self, "_host_n", -1) != n:          # pinned result buffers are reused
+            self._rec_host = torch.empty((n, rec_bytes), dtype=torch.uint8).pin_memory()
+            self._keep_host = [torch.empty((self.H, self.W), dtype=torch.uint8).pin_memory()
+                               for _ in range(n)] if self.want_keep else []
+            self._host_n = n
+        rec_host, keep_host = self._rec_host, self._keep_host
+        with torch.cuda.device(self.device):
+            cur = torch.cuda.current_stream()
+            for s in self.streams:
+                s.wait_stream(cur)
+            for i in range(n):
+                slot = i % self.n_streams
+                st = self.streams[slot]
+                det = self._detector(slot, radii[i])
+                src = images[i]
+                if isinstance(src, np.ndarray):
+                    src = torch.from_numpy(src)
+                with torch.cuda.stream(st):
+                    self.dev_in[slot].copy_(src, non_blocking=True)
+                    det.detect(self.dev_in[slot], self.ratio, h_thresh, self.porb, self.area_thr,
+                               self.maps[slot])
+                    if self.want_prob_map:
+                        det.prob_stack(0.0, self.prob_sum, accumulate=True)
+                    rec_host[i].copy_(det.result_bytes(), non_blocking=True)
+                    if self.want_keep:
+                        keep_host[i].copy_(det.keep, non_blocking=True)
+            for s in self.streams:
+                cur.wait_stream(s)
+            cur.synchronize()
+        recs = [_lib.Result.from_buffer_copy(rec_host[i].numpy().tobytes()) for i in range(n)]
+        T = self.T
+        for rc in recs:
+            if rc.median_errors:
+                raise _lib.ChipsNativeError("median self-check failed")
+        return SeriesResult(
+            indices=indices,
+            limit_0=np.array([rc.limit_0 for rc in recs]),
+            h_thresh=np.array([rc.h_thresh for rc in recs]),
+            n_peaks=np.array([rc.n_peaks for rc in recs]),
+            limits=np.array([[rc.limits[t] for t in range(T)] for rc in recs]).reshape(n, T),
+            probs=np.array([[rc.probs[t] for t in range(T)] for rc in recs]).reshape(n, T),
+            n_kept=np.array([[rc.n_kept[t] for t in range(T)] for rc in recs]).reshape(n, T),
+            keep=[k.numpy() for k in keep_host],
+            prob_map_sum=self.prob_sum if self.want_prob_map else None,
+        )
+
+
+def pack_stats(res: SeriesResult, T: int) -> torch.Tensor:
+    """[n, 3 + 3T] float64: image index, limit_0, n_peaks, limits, probs, n_kept."""
+    n = len(res.indices)
+    out = np.zeros((n, 3 + 3 * T), dtype=np.float64)
+    if n:
+        out[:, 0] = res.indices
+        out[:, 1] = res.limit_0
+        out[:, 2] = res.n_peaks
+        out[:, 3:3 + T] = res.limits
+        out[:, 3 + T:3 + 2 * T] = res.probs
+        out[:, 3 + 2 * T:] = res.n_kept
+    return torch.from_numpy(out)
+
+
+def gather_series(stats: torch.Tensor, prob_sum: torch.Tensor | None, n_total: int, T: int,
+                  group=None):
+    """The one exchange step of a batch: all_gather of the per-image statistics (padded to the
+    largest shard) and all_reduce(sum) of the probability map.  Works on NCCL (device tensors)
+    and on gloo (CPU tensors; used by the world_size-2 CPU tests)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    per = (n_total + world - 1) // world
+    dev = prob_sum.device if prob_sum is not None else stats.device
+    if dist.get_backend(group) == "nccl":
+        stats = stats.to(dev)
+    pad = torch.full((per, 3 + 3 * T), float("nan"), dtype=torch.float64, device=stats.device)
+    pad[:stats.shape[0]] = stats
+    bucket = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bucket, pad, group=group)
+    if prob_sum is not None:
+        dist.all_reduce(prob_sum, op=dist.ReduceOp.SUM, group=group)
+    allstats = torch.cat(bucket).cpu().numpy()
+    allstats = allstats[~np.isnan(allstats[:, 0])]
+    order = np.argsort(allstats[:, 0], kind="stable")
+    return allstats[order], prob_sum

@@ -1,0 +1,361 @@
+"""GPU parity tests: the CUDA path (through the C ABI / the drop-in classes) against the
+oracle, the committed reference goldens and, at full size, an independent brute-force GPU
+selection plus size-independent properties.  Bit-exact for medians, counts, masks, labels;
+1e-5 relative for thresholds / probabilities (they are in fact compared exactly too)."""
+import numpy as np
+import pytest
+import torch
+from scipy import ndimage, signal
+
+from conftest import load_golden
+from oracle import chips_oracle as co
+from oracle import first_principles as fp
+from pychips_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+def _engine():
+    from pychips_b200 import engine
+    return engine
+
+
+def gpu_medfilt(img, k, cx=0, cy=0, r=-1, brute=False):
+    eng = _engine()
+    from pychips_b200 import _lib
+    dev = eng.require_cuda()
+    t = torch.from_numpy(np.ascontiguousarray(img)).to(dev)
+    out = torch.full_like(t, -777.0)
+    H, W = img.shape
+    if brute:
+        lib = _lib.load()
+        _lib.check(lib.chips_medfilt2d_bruteforce(eng._ptr(t), eng._ptr(out), H, W, k,
+                                                  t.element_size(), cx, cy, r, eng._stream_ptr()),
+                   "brute")
+        return out.cpu().numpy(), None
+    det = eng.Detector(eng.Geometry(H, W, cx, cy, r), k, 8, 0, 1, t.element_size(), dev)
+    det.medfilt(t, out)
+    res = det.result()
+    return out.cpu().numpy(), res
+
+
+# ----------------------------------------------------------------------------- median
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("k", [3, 5, 11, 31, 51])
+def test_median_bruteforce_kernel_vs_scipy(k, dtype):
+    rng = np.random.default_rng(k)
+    img = rng.gamma(2.0, 30.0, size=(70, 93)).astype(dtype)
+    img[10:14, 20:50] = 0.0
+    img[30:33, :] = -2.5
+    got, _ = gpu_medfilt(img, k, brute=True)
+    assert np.array_equal(got, signal.medfilt2d(img, k))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("k", [1, 3, 5, 7, 11, 31, 51, 71])
+def test_median_fast_vs_scipy_unmasked(k, dtype):
+    rng = np.random.default_rng(100 + k)
+    img = rng.gamma(2.0, 30.0, size=(150, 203)).astype(dtype)
+    img[10:40, 20:90] = 0.0                 # ties with the zero padding
+    img[60:64, :] = -2.5                    # negatives
+    img[100:140, 100:160] = 7.25            # constant block
+    got, res = gpu_medfilt(img, k)
+    assert res.median_errors == 0
+    ref = signal.medfilt2d(img, k)
+    bad = np.argwhere(got != ref)
+    assert bad.size == 0, (len(bad), bad[:5], got[tuple(bad[0])], ref[tuple(bad[0])])
+
+
+@pytest.mark.parametrize("shape,k", [((20, 20), 31), ((9, 300), 11), ((300, 9), 11), ((1, 1), 3),
+                                     ((64, 64), 51), ((17, 33), 5)])
+def test_median_fast_ragged_shapes(shape, k):
+    rng = np.random.default_rng(shape[0] * 7 + k)
+    img = rng.normal(50, 20, size=shape).astype(np.float32)
+    got, res = gpu_medfilt(img, k)
+    assert res.median_errors == 0
+    assert np.array_equal(got, signal.medfilt2d(img, k))
+
+
+def test_median_fast_degenerate_values():
+    for img in (np.zeros((90, 90), np.float32), np.full((90, 90), 3.5, np.float32),
+                np.tile(np.arange(90, dtype=np.float32), (90, 1)),
+                (np.arange(8100).reshape(90, 90) % 2).astype(np.float32)):
+        got, res = gpu_medfilt(img, 11)
+        assert res.median_errors == 0
+        assert np.array_equal(got, signal.medfilt2d(img, 11))
+
+
+@pytest.mark.parametrize("n,k", [(256, 11), (256, 51), (200, 31)])
+def test_median_fast_masked_vs_oracle(n, k):
+    img, r = synth.synthetic_disk(n, 5)
+    c = int(n / 2)
+    got, res = gpu_medfilt(img, k, c, c, r)
+    assert res.median_errors == 0
+    _, i_mask = co.solar_masks(img.astype(np.float64), n, r)
+    _, ref = co.run_filters(img.astype(np.float64), i_mask, k)
+    assert np.array_equal(got.astype(np.float64), ref)
+
+
+@pytest.mark.parametrize("n,k", [(1024, 51), (4096, 11), (4096, 51)])
+def test_median_fast_vs_bruteforce_full_size(n, k):
+    img, r = synth.synthetic_disk(n, 1)
+    c = int(n / 2)
+    fast, res = gpu_medfilt(img, k, c, c, r)
+    assert res.median_errors == 0
+    slow, _ = gpu_medfilt(img, k, c, c, r, brute=True)
+    assert np.array_equal(fast, slow), int((fast != slow).sum())
+    # spot-check 64 windows against a plain numpy median of the zero-padded window
+    rng = np.random.default_rng(0)
+    h = k // 2
+    pad = np.pad(img, h)
+    on = fp.circle_mask(n, n, c, c, r)
+    ys, xs = np.nonzero(on)
+    for i in rng.integers(0, len(ys), 64):
+        y, x = ys[i], xs[i]
+        w = np.sort(pad[y:y + k, x:x + k].ravel())
+        assert fast[y, x] == w[(k * k - 1) // 2]
+    assert np.all(fast[~on] == 0)
+
+
+# ----------------------------------------------------------------------------- full pipeline
+def run_gpu_disk(img, r, dtype=np.float64, **kw):
+    from pychips_b200 import Chips
+    d = synth.FakeDisk(img.astype(dtype), r)
+    c = Chips(synth.FakeAIA(d), base_folder="/tmp/chips_b200_test/", **kw)
+    c.run_CHIPS()
+    return c, d
+
+
+def compare_disk(d, g_filt, g_hbase, g_hbins, g_bound, g_peaks, g_lims, g_probs, g_raw, g_maps,
+                 g_stack=None, chips=None):
+    assert np.array_equal(d.solar_filter.filt_disk, g_filt)
+    assert np.array_equal(d.histogram.hbase, g_hbase)
+    assert np.array_equal(d.histogram.hbins, g_hbins)
+    assert np.array_equal(d.histogram.bound, g_bound)
+    assert np.allclose(np.array(d.histogram.peaks), g_peaks, rtol=REL, atol=0)
+    assert np.array_equal(np.array(d.histogram.peaks), g_peaks)
+    if g_lims is None:
+        assert not hasattr(d, "solar_ch_regions")
+        return
+    keys = list(d.solar_ch_regions.__dict__.keys())
+    assert keys == [str(l) for l in g_lims]
+    for t, k in enumerate(keys):
+        reg = d.solar_ch_regions.__dict__[k]
+        assert reg.lim == g_lims[t]
+        gp = g_probs[t]
+        assert (np.isnan(gp) and np.isnan(reg.prob)) or abs(reg.prob - gp) <= REL * abs(gp), (t, reg.prob, gp)
+        assert np.array_equal(reg.raw_map.astype(np.uint8), g_raw[t]), ("raw", t)
+        assert np.array_equal(reg.map.astype(np.uint8), g_maps[t]), ("map", t, int((reg.map != g_maps[t]).sum()))
+    if g_stack is not None and chips is not None:
+        st = chips.probability_map(d)
+        assert np.allclose(st, g_stack, rtol=REL, atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["disk_n256_k11", "disk_n256_k31_211", "disk_n192_k51",
+                                  "disk_n256_k5_t28", "disk_n200_k7_wiped"])
+def test_disk_pipeline_vs_reference_golden(name):
+    g = load_golden(name)
+    n = g["image"].shape[0]
+    c, d = run_gpu_disk(g["image"], int(g["pixel_radius"]),
+                        medfilt_kernel=int(g["kw_medfilt_kernel"]), h_bins=int(g["kw_h_bins"]),
+                        threshold_range=[int(v) for v in g["kw_threshold_range"]])
+    T = len(g["limits"])
+    maps = np.unpackbits(g["maps"])[:T * n * n].reshape(T, n, n)
+    raw = np.unpackbits(g["raw_maps"])[:T * n * n].reshape(T, n, n)
+    assert np.array_equal(d.solar_mask.i_mask.astype(np.uint8),
+                          np.unpackbits(g["i_mask"])[:n * n].reshape(n, n))
+    assert np.isnan(d.solar_mask.n_mask[0, 0]) and d.solar_mask.n_mask[n // 2, n // 2] == 1.0
+    compare_disk(d, g["filt_disk"].astype(np.float64), g["hbase"], g["hbins"], g["bound"], g["peaks"],
+                 g["limits"], g["probs"], raw, maps, g.get("stack"), c)
+    assert c.h_thresh == g["h_thresh"]
+
+
+@pytest.mark.parametrize("n,k,hb,tr,seed", [(512, 11, 500, [0, 20], 7), (384, 31, 1000, [-3, 11], 8),
+                                            (320, 51, 500, [0, 20], 9), (512, 3, 20000, [-3, 25], 10)])
+def test_disk_pipeline_vs_oracle_seeded(n, k, hb, tr, seed):
+    img, r = synth.synthetic_disk(n, seed)
+    d_or = synth.FakeDisk(img.astype(np.float64), r)
+    co.OracleChips(medfilt_kernel=k, h_bins=hb, threshold_range=tr).run(d_or, keep_contours=False)
+    c, d = run_gpu_disk(img, r, medfilt_kernel=k, h_bins=hb, threshold_range=tr)
+    if hasattr(d_or, "solar_ch_regions"):
+        regs = list(d_or.solar_ch_regions.__dict__.values())
+        lims = [x.lim for x in regs]
+        probs = [x.prob for x in regs]
+        raw = [x.raw_map.astype(np.uint8) for x in regs]
+        maps = [x.map.astype(np.uint8) for x in regs]
+        st = None
+        try:
+            st, _ = co.prob_stack([x.map for x in regs], probs)
+        except ValueError:
+            pass
+    else:
+        lims = probs = raw = maps = st = None
+    compare_disk(d, d_or.solar_filter.filt_disk, d_or.histogram.hbase, d_or.histogram.hbins,
+                 d_or.histogram.bound, np.array(d_or.histogram.peaks), lims, probs, raw, maps, st, c)
+
+
+def test_float64_storage_path_not_f32_representable():
+    img, r = synth.synthetic_disk(256, 21)
+    img64 = img.astype(np.float64) * (1.0 + 1e-9) + 1e-7       # needs real float64 storage
+    assert not np.array_equal(img64.astype(np.float32).astype(np.float64), img64)
+    d_or = synth.FakeDisk(img64, r)
+    co.OracleChips(medfilt_kernel=11).run(d_or, keep_contours=False)
+    c, d = run_gpu_disk(img64, r, medfilt_kernel=11)
+    regs = list(d_or.solar_ch_regions.__dict__.values())
+    compare_disk(d, d_or.solar_filter.filt_disk, d_or.histogram.hbase, d_or.histogram.hbins,
+                 d_or.histogram.bound, np.array(d_or.histogram.peaks), [x.lim for x in regs],
+                 [x.prob for x in regs], [x.raw_map.astype(np.uint8) for x in regs],
+                 [x.map.astype(np.uint8) for x in regs])
+
+
+@pytest.mark.parametrize("name", ["syn_180x360_k3", "syn_96x240_k11"])
+def test_synoptic_pipeline_vs_reference_golden(name):
+    from pychips_b200 import SynopticChips
+    g = load_golden(name)
+    img = g["image"]
+    H, W = img.shape
+    s = synth.FakeSynoptic(img.astype(np.float64))
+    sc = SynopticChips(s, base_folder="/tmp/chips_b200_test/", medfilt_kernel=int(g["kw_medfilt_kernel"]),
+                       h_bins=int(g["kw_h_bins"]),
+                       threshold_range=[int(v) for v in g["kw_threshold_range"]])
+    sc.run_CHIPS()
+    assert np.array_equal(s.solar_filter, g["solar_filter"].astype(np.float64))
+    assert np.array_equal(s.histogram.hbase, g["hbase"])
+    assert np.array_equal(s.histogram.bound, g["bound"])
+    assert np.array_equal(np.array(s.histogram.peaks), g["peaks"])
+    keys = list(s.solar_ch_regions.__dict__.keys())
+    assert keys == list(g["keys"])
+    T = len(keys)
+    maps = np.unpackbits(g["maps"])[:T * H * W].reshape(T, H, W)
+    for t, k in enumerate(keys):
+        reg = s.solar_ch_regions.__dict__[k]
+        assert np.array_equal(reg.map.astype(np.uint8), maps[t]), t
+        assert np.array_equal(reg.prob, g["probs"][t], equal_nan=True)
+
+
+# ----------------------------------------------------------------------------- stage level
+@pytest.mark.parametrize("hb", [1, 7, 500, 5000, 20000])
+def test_histogram_stage_vs_numpy(hb):
+    eng = _engine()
+    dev = eng.require_cuda()
+    rng = np.random.default_rng(hb)
+    x = np.concatenate([rng.normal(28, 3, 30000), rng.normal(130, 15, 70000)]).astype(np.float32)
+    img = x.reshape(250, 400)
+    det = eng.Detector(eng.Geometry(250, 400, 0, 0, -1), 1, hb, 0, 4, 4, dev)
+    t = torch.from_numpy(img).to(dev)
+    det.filt.copy_(t)
+    det.histogram(recompute_minmax=True)
+    det.select_threshold(5, None)
+    cn, en = np.histogram(img.astype(np.float64).ravel(), bins=hb)
+    hn, _ = np.histogram(img.astype(np.float64).ravel(), bins=hb, density=True)
+    assert np.array_equal(det.counts.cpu().numpy(), cn)
+    assert np.array_equal(det.edges.cpu().numpy(), en)
+    assert np.array_equal(det.density.cpu().numpy(), hn)
+    res = det.result()
+    pk, _ = signal.find_peaks(hn, height=np.max(hn) / 5)
+    assert res.n_peaks == len(pk)
+    assert np.array_equal(det.peak_index[:res.n_peaks].cpu().numpy(), pk)
+    assert res.h_thresh == np.max(hn) / 5
+    assert res.n_samples == img.size
+
+
+def test_histogram_constant_image_and_sticky_threshold():
+    eng = _engine()
+    dev = eng.require_cuda()
+    img = np.full((64, 64), 3.0, np.float32)
+    det = eng.Detector(eng.Geometry(64, 64, 0, 0, -1), 1, 10, 0, 2, 4, dev)
+    det.filt.copy_(torch.from_numpy(img).to(dev))
+    det.histogram(recompute_minmax=True)
+    det.select_threshold(5, 0.125)
+    cn, en = np.histogram(img.astype(np.float64).ravel(), bins=10)
+    assert np.array_equal(det.counts.cpu().numpy(), cn)
+    assert np.array_equal(det.edges.cpu().numpy(), en)
+    assert det.result().h_thresh == 0.125
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_cleanup_stage_on_random_levels(seed):
+    """Inject a random nested level image and compare W, final maps, labels and 2*areas with
+    the first-principles spec (itself pinned to cv2 in test_first_principles.py)."""
+    eng = _engine()
+    dev = eng.require_cuda()
+    from test_first_principles import _random_nested_levels
+    rng = np.random.default_rng(1000 + seed)
+    n, T = int(rng.integers(40, 300)), int(rng.integers(1, 12))
+    r = int(n * rng.uniform(0.3, 0.6))           # > n/2: the disk is clipped by the image border
+    c = n // 2
+    on = fp.circle_mask(n, n, c, c, r)
+    lev = np.where(on, _random_nested_levels(rng, n, T), T).astype(np.uint8)
+    thr = float(rng.choice([0.0, 1e-3, 5e-3]))
+    det = eng.Detector(eng.Geometry(n, n, c, c, r), 3, 8, 0, T, 4, dev)
+    det.level.copy_(torch.from_numpy(lev).to(dev))
+    det.cleanup(thr)
+    # the spec treats everything outside the image as border; off-disk pixels have level T
+    W, maps, labels, areas = fp.cleanup_levels(lev, T, r, thr)
+    assert np.array_equal(det.fill.cpu().numpy(), W)
+    got = det.expand_maps(0).cpu().numpy()
+    for t in range(T):
+        assert np.array_equal(got[t], maps[t]), (seed, t)
+        lab, a2 = det.labels(t)
+        assert np.array_equal(lab, labels[t]), (seed, t)
+        assert np.array_equal(a2, areas[t][1:]), (seed, t)
+    res = det.result()
+    for t in range(T):
+        assert res.n_comp[t] == len(areas[t]) - 1
+        assert res.n_kept[t] == int(((areas[t][1:] * 0.5) / (np.pi * r ** 2) >= thr).sum())
+
+
+def test_labels_vs_scipy_on_pipeline_output():
+    img, r = synth.synthetic_disk(384, 3)
+    c, d = run_gpu_disk(img, r, medfilt_kernel=11)
+    keys = list(d.solar_ch_regions.__dict__.keys())
+    for t in (0, len(keys) // 2, len(keys) - 1):
+        reg = d.solar_ch_regions.__dict__[keys[t]]
+        lab, a2 = c.labels(d, t)
+        ref, n = ndimage.label(reg.filled_map > 0, structure=np.ones((3, 3)))
+        assert np.array_equal(lab, ref)
+        assert np.array_equal(reg.filled_map > 0, ndimage.binary_fill_holes(reg.raw_map > 0))
+
+
+# ----------------------------------------------------------------------------- full size
+def test_full_size_4096_properties():
+    """BASELINE config 2 (4096^2, k=51, h_bins=500, [0,20]): size-independent properties."""
+    eng = _engine()
+    n = 4096
+    img, r = synth.synthetic_disk(n, 0)
+    c, d = run_gpu_disk(img, r, dtype=np.float32)
+    det = c._detector(d)
+    res = det.result()
+    assert res.median_errors == 0 and res.n_peaks > 0
+    on = fp.circle_mask(n, n, n // 2, n // 2, r)
+    assert res.n_samples == int(on.sum())
+    filt = det.filt.cpu().numpy()
+    # histogram: counts of the GPU == numpy on the GPU-filtered data; first peak -> limit_0
+    cn, en = np.histogram(filt[on].astype(np.float64), bins=500)
+    assert np.array_equal(det.counts.cpu().numpy(), cn)
+    hn, _ = np.histogram(filt[on].astype(np.float64), bins=500, density=True)
+    pk, _ = signal.find_peaks(hn, height=np.max(hn) / 5)
+    assert res.limit_0 == (en[:-1] + np.diff(en))[pk[0]]
+    lims = np.array(res.limits[:det.T])
+    assert np.array_equal(lims, np.round(res.limit_0 + np.arange(0, 20), 4))
+    lev = det.level.cpu().numpy()
+    assert np.array_equal(lev, fp.level_image(filt, on, lims))
+    W = det.fill.cpu().numpy()
+    K = det.keep.cpu().numpy()
+    assert np.all(W <= lev) and np.all(K >= W)
+    assert np.all(K[~on] == det.T)
+    maps = det.expand_maps(0).cpu().numpy()
+    for t in (0, 5, 19):
+        assert np.array_equal(W <= t, ndimage.binary_fill_holes(lev <= t))
+        assert np.array_equal(maps[t], (K <= t).astype(np.uint8))
+        lab, nl = ndimage.label(W <= t, structure=np.ones((3, 3)))
+        a2 = fp.twice_area_quads(W <= t, lab, nl)
+        keep = (a2 * 0.5) / (np.pi * r ** 2) >= 1e-3
+        keep[0] = False
+        assert np.array_equal(maps[t], keep[lab].astype(np.uint8))
+    for t in range(1, det.T):
+        assert np.all(maps[t] >= maps[t - 1])
+    pr = fp.prob_from_counts(fp.prob_counts(filt[on], res.limit_0, lims))
+    assert np.allclose(np.array(res.probs[:det.T]), pr, rtol=REL, atol=0, equal_nan=True)
