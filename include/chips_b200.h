@@ -59,7 +59,7 @@ typedef struct chips_plan {
   size_t off_bounds;     /* 256 bucket boundaries (ordered keys, 8 B each)                */
   size_t off_bucket;     /* u8  [bp_rows][bp_pitch]   padded bucket image                 */
   size_t off_bstar;      /* u8  [H][W]   median bucket per pixel                          */
-  size_t off_rres;       /* u16 [H][W]   residual rank inside that bucket                 */
+  size_t off_rres;       /* u32 [H][W]   residual rank | (bucket population << 16)        */
   size_t off_filt;       /* elem[H][W]   masked median (filt_disk)                        */
   size_t off_minmax;     /* 2 ordered keys (8 B each)                                     */
   size_t off_counts;     /* i64 [h_bins]                                                  */
@@ -75,6 +75,9 @@ typedef struct chips_plan {
   size_t off_parent_b;   /* u32 [roi_h*roi_w + 1]   background union-find                 */
   size_t off_parent_c;   /* u32 [T][roi_h*roi_w]    per-threshold union-find              */
   size_t off_area;       /* u32 [T][roi_h*roi_w]    2*area accumulators at roots          */
+  size_t off_pending;    /* u32 [roi_h*roi_w]  hole-fill work list grouped by level       */
+  size_t off_lvl;        /* u32 [512]          per-level counts / offsets / cursors, tile count */
+  size_t off_tiles;      /* u32 [#32x8 tiles]  list of tiles that hold filled-mask pixels */
   size_t bytes;          /* total workspace size                                          */
 } chips_plan;
 

@@ -37,7 +37,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    cmd += os.environ.get("CHIPS_EXTRA_NVCC_FLAGS", "").split()
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", os.environ.get("CHIPS_LIB_OUT", LIB)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

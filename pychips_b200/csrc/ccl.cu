@@ -61,73 +61,144 @@ struct Roi {
 };
 
 // ------------------------------------------------------------------ phase B
-__global__ void __launch_bounds__(256) k_fill_init(Roi g, uint8_t* __restrict__ Wimg,
-                                                   uint32_t* __restrict__ parent) {
-  int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
-  int y = g.y0 + blockIdx.y;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) parent[0] = kBorder;
-  if (x >= g.x0 + g.w) return;
-  uint32_t n = g.li(x, y) + 1;
-  parent[n] = n;
-  if (on_disk(x, y, g.cx, g.cy, g.r)) Wimg[(size_t)y * g.W + x] = 0;
-}
-
 // Row-run linking for the pixels of one level set (`sel`): every pixel points at the start
 // of its run inside the warp's 32-pixel span, a run that continues across the span boundary
-// points at the last pixel of the previous span (chains hop 32 pixels at a time).
+// points at the last pixel of the previous span (chains hop 32 pixels at a time).  Returns
+// the link target (or `me` when not selected).  Must be called by all 32 lanes; lanes of a
+// warp hold 32 consecutive pixels of one row.
 template <typename Sel>
-__device__ __forceinline__ void link_row_runs(const Roi& g, uint32_t* __restrict__ parent,
-                                              uint32_t node_off, Sel sel) {
-  int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
-  int y = g.y0 + blockIdx.y;
+__device__ __forceinline__ uint32_t row_run_target(const Roi& g, int x, int y, bool valid,
+                                                   uint32_t me, Sel sel) {
   int lane = threadIdx.x & 31;
-  bool act = (x < g.x0 + g.w) && sel(x, y);
+  bool act = valid && sel(x, y);
   unsigned m = __ballot_sync(0xFFFFFFFFu, act);
   bool left_act = false;
   if (lane == 0 && act) left_act = (x - 1 >= g.x0) && sel(x - 1, y);
   left_act = __shfl_sync(0xFFFFFFFFu, left_act, 0);
-  if (!act) return;
+  if (!act) return me;
   unsigned z = ~m & ((1u << lane) - 1u);
   int s = z ? (32 - __clz(z)) : 0;
-  uint32_t me = g.li(x, y) + node_off;
-  uint32_t tgt;
-  if (s == 0 && left_act) tgt = me - (uint32_t)lane - 1u;     // last pixel of previous span
-  else tgt = me - (uint32_t)(lane - s);
-  parent[me] = tgt;
+  if (s == 0 && left_act) return me - (uint32_t)lane - 1u;   // last pixel of previous span
+  return me - (uint32_t)(lane - s);
 }
 
+// B1: parent init for every ROI pixel (run links for the bulk background = pixels in no
+// mask at all, self otherwise) and W = 0 on-disk / T off-disk.
 __global__ void __launch_bounds__(256) k_fill_bulk_link(Roi g, const uint8_t* __restrict__ lev, int T,
+                                                        uint8_t* __restrict__ Wimg,
                                                         uint32_t* __restrict__ parent) {
-  link_row_runs(g, parent, 1u, [&](int x, int y) {
-    return on_disk(x, y, g.cx, g.cy, g.r) && lev[(size_t)y * g.W + x] == T;
+  int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
+  int y = g.y0 + blockIdx.y;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) parent[0] = kBorder;
+  bool valid = x < g.x0 + g.w;
+  uint32_t me = valid ? g.li(x, y) + 1u : 0u;
+  uint32_t tgt = row_run_target(g, x, y, valid, me, [&](int xx, int yy) {
+    return on_disk(xx, yy, g.cx, g.cy, g.r) && lev[(size_t)yy * g.W + xx] == T;
   });
+  if (!valid) return;
+  parent[me] = tgt;
+  Wimg[(size_t)y * g.W + x] = on_disk(x, y, g.cx, g.cy, g.r) ? 0 : (uint8_t)T;
 }
 
-// unions of the pixels that enter the background at round t (level == t+1) with their
-// already-active 4-neighbours (level >= t+1) and with the border node.
-template <bool BULK>
-__global__ void __launch_bounds__(256) k_fill_union(Roi g, const uint8_t* __restrict__ lev, int t,
-                                                    uint32_t* __restrict__ parent) {
+__device__ __forceinline__ int level_at(const Roi& g, const uint8_t* __restrict__ lev, int xx, int yy) {
+  if (!g.inside(xx, yy)) return -1;            // outside the disk / image: the border set
+  return lev[(size_t)yy * g.W + xx];
+}
+
+// B2: vertical + border unions of the bulk background (left edges are the run links).
+__global__ void __launch_bounds__(256) k_fill_bulk_union(Roi g, const uint8_t* __restrict__ lev, int T,
+                                                         uint32_t* __restrict__ parent) {
   int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
   int y = g.y0 + blockIdx.y;
   if (x >= g.x0 + g.w) return;
-  const int lv = t + 1;
-  if (lev[(size_t)y * g.W + x] != lv || !on_disk(x, y, g.cx, g.cy, g.r)) return;
+  if (lev[(size_t)y * g.W + x] != T || !on_disk(x, y, g.cx, g.cy, g.r)) return;
   uint32_t me = g.li(x, y) + 1;
-  auto level_at = [&](int xx, int yy) -> int {   // -1 = outside (border)
-    if (!g.inside(xx, yy)) return -1;
-    return lev[(size_t)yy * g.W + xx];
-  };
-  int l_l = level_at(x - 1, y), l_r = level_at(x + 1, y);
-  int l_u = level_at(x, y - 1), l_d = level_at(x, y + 1);
+  int l_l = level_at(g, lev, x - 1, y), l_r = level_at(g, lev, x + 1, y);
+  int l_u = level_at(g, lev, x, y - 1), l_d = level_at(g, lev, x, y + 1);
   if (l_l < 0 || l_r < 0 || l_u < 0 || l_d < 0) uf_unite(parent, me, kBorder);
-  if (BULK) {
-    // left edge done by the run links; vertical edge unless implied by left & up-left
-    if (l_u == lv) {
-      bool implied = (l_l == lv) && (level_at(x - 1, y - 1) == lv);
-      if (!implied) uf_unite(parent, me, me - (uint32_t)g.w);
+  if (l_u == T) {
+    bool implied = (l_l == T) && (level_at(g, lev, x - 1, y - 1) == T);
+    if (!implied) uf_unite(parent, me, me - (uint32_t)g.w);
+  }
+}
+
+// B3/B5: bulk pixels that reached the border get W = T; everything else on the disk (pixels
+// of some mask, and bulk pixels enclosed by masks) is "pending".  PASS 0 counts pending pixels
+// per level, PASS 1 scatters their ROI-local indices into a list grouped by level.
+template <int PASS>
+__global__ void __launch_bounds__(256) k_fill_pending(Roi g, const uint8_t* __restrict__ lev, int T,
+                                                      uint8_t* __restrict__ Wimg,
+                                                      uint32_t* __restrict__ parent,
+                                                      uint32_t* __restrict__ lvl_count,
+                                                      uint32_t* __restrict__ lvl_cursor,
+                                                      uint32_t* __restrict__ pending) {
+  __shared__ uint32_t scnt[CHIPS_MAX_T + 1];
+  if (PASS == 0) {
+    for (int i = threadIdx.x; i <= T; i += blockDim.x) scnt[i] = 0;
+    __syncthreads();
+  }
+  int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
+  int y = g.y0 + blockIdx.y;
+  int mylev = -1;
+  if (x < g.x0 + g.w && on_disk(x, y, g.cx, g.cy, g.r)) {
+    size_t o = (size_t)y * g.W + x;
+    int l = lev[o];
+    if (PASS == 0) {
+      if (l == T && uf_find(parent, g.li(x, y) + 1) == kBorder) Wimg[o] = (uint8_t)T;
+      else mylev = l;
+    } else {
+      if (!(l == T && Wimg[o] == T)) mylev = l;
     }
-  } else {
+  }
+  unsigned act = __ballot_sync(0xFFFFFFFFu, mylev >= 0);
+  if (mylev >= 0) {
+    unsigned peers = __match_any_sync(act, mylev);
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(peers) - 1;
+    if (PASS == 0) {
+      if (lane == leader) atomicAdd(&scnt[mylev], __popc(peers));
+    } else {
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(&lvl_cursor[mylev], __popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      pending[base + __popc(peers & ((1u << lane) - 1u))] = g.li(x, y);
+    }
+  }
+  if (PASS == 0) {
+    __syncthreads();
+    for (int i = threadIdx.x; i <= T; i += blockDim.x)
+      if (scnt[i]) atomicAdd(&lvl_count[i], scnt[i]);
+  }
+}
+
+// B4: offsets[l] = first list slot of level l (offsets[T+1] = total); cursor = copy.
+__global__ void k_fill_offsets(int T, uint32_t* __restrict__ lvl_count,
+                               uint32_t* __restrict__ lvl_offset, uint32_t* __restrict__ lvl_cursor) {
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int l = 0; l <= T; ++l) {
+      lvl_offset[l] = run;
+      lvl_cursor[l] = run;
+      run += lvl_count[l];
+    }
+    lvl_offset[T + 1] = run;
+  }
+}
+
+// Round t (descending): the pending pixels of level t+1 join the background.
+__global__ void __launch_bounds__(256) k_fill_round_union(Roi g, const uint8_t* __restrict__ lev, int t,
+                                                          const uint32_t* __restrict__ lvl_offset,
+                                                          const uint32_t* __restrict__ pending,
+                                                          uint32_t* __restrict__ parent) {
+  const int lv = t + 1;
+  const uint32_t beg = lvl_offset[lv], end = lvl_offset[lv + 1];
+  for (uint32_t i = beg + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
+    uint32_t li = pending[i];
+    int y = g.y0 + (int)(li / (uint32_t)g.w), x = g.x0 + (int)(li % (uint32_t)g.w);
+    uint32_t me = li + 1;
+    int l_l = level_at(g, lev, x - 1, y), l_r = level_at(g, lev, x + 1, y);
+    int l_u = level_at(g, lev, x, y - 1), l_d = level_at(g, lev, x, y + 1);
+    if (l_l < 0 || l_r < 0 || l_u < 0 || l_d < 0) uf_unite(parent, me, kBorder);
     if (l_l >= lv) uf_unite(parent, me, me - 1u);
     if (l_u >= lv) uf_unite(parent, me, me - (uint32_t)g.w);
     if (l_r > lv) uf_unite(parent, me, me + 1u);
@@ -135,85 +206,146 @@ __global__ void __launch_bounds__(256) k_fill_union(Roi g, const uint8_t* __rest
   }
 }
 
-__global__ void __launch_bounds__(256) k_fill_assign(Roi g, const uint8_t* __restrict__ lev, int t,
-                                                     uint8_t* __restrict__ Wimg,
-                                                     uint32_t* __restrict__ parent) {
-  int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
-  int y = g.y0 + blockIdx.y;
-  if (x >= g.x0 + g.w) return;
-  size_t o = (size_t)y * g.W + x;
-  if (lev[o] <= t || Wimg[o] != 0 || !on_disk(x, y, g.cx, g.cy, g.r)) return;
-  if (uf_find(parent, g.li(x, y) + 1) == kBorder) Wimg[o] = (uint8_t)(t + 1);
+// ... and every active (level > t), still unassigned pending pixel that now reaches the
+// border gets W = t+1.  Active pending pixels are the list suffix starting at level t+1.
+__global__ void __launch_bounds__(256) k_fill_round_assign(Roi g, int t, int T,
+                                                           const uint32_t* __restrict__ lvl_offset,
+                                                           const uint32_t* __restrict__ pending,
+                                                           uint8_t* __restrict__ Wimg,
+                                                           uint32_t* __restrict__ parent) {
+  const uint32_t beg = lvl_offset[t + 1], end = lvl_offset[T + 1];
+  for (uint32_t i = beg + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
+    uint32_t li = pending[i];
+    int y = g.y0 + (int)(li / (uint32_t)g.w), x = g.x0 + (int)(li % (uint32_t)g.w);
+    size_t o = (size_t)y * g.W + x;
+    if (Wimg[o] != 0) continue;
+    if (uf_find(parent, li + 1) == kBorder) Wimg[o] = (uint8_t)(t + 1);
+  }
 }
 
 // ------------------------------------------------------------------ phase C
-__global__ void __launch_bounds__(256) k_ccl_link(Roi g, const uint8_t* __restrict__ Wimg,
-                                                  uint32_t* __restrict__ parent_all,
-                                                  uint32_t* __restrict__ area_all) {
-  const int t = blockIdx.z;
-  const size_t n = (size_t)g.w * g.h;
-  uint32_t* parent = parent_all + (size_t)t * n;
-  uint32_t* area = area_all + (size_t)t * n;
-  int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
-  int y = g.y0 + blockIdx.y;
-  if (x < g.x0 + g.w && Wimg[(size_t)y * g.W + x] <= t) area[g.li(x, y)] = 0;
-  link_row_runs(g, parent, 0u, [&](int xx, int yy) { return Wimg[(size_t)yy * g.W + xx] <= t; });
-}
+// Work is restricted to "active" 32x8 tiles (tiles that hold at least one pixel of some
+// filled mask, W < T); each of the T labellings walks the same tile list (blockIdx.y = t).
+constexpr int kTileW = 32, kTileH = 8;
 
-__global__ void __launch_bounds__(256) k_ccl_union(Roi g, const uint8_t* __restrict__ Wimg,
-                                                   uint32_t* __restrict__ parent_all) {
-  const int t = blockIdx.z;
-  uint32_t* parent = parent_all + (size_t)t * g.w * g.h;
-  int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
-  int y = g.y0 + blockIdx.y;
-  if (x >= g.x0 + g.w || y == g.y0) return;
-  auto fg = [&](int xx, int yy) -> bool {
-    return xx >= g.x0 && xx < g.x0 + g.w && yy >= g.y0 && yy < g.y0 + g.h &&
-           Wimg[(size_t)yy * g.W + xx] <= t;
-  };
-  if (!fg(x, y)) return;
-  uint32_t me = g.li(x, y);
-  bool up = fg(x, y - 1), ul = fg(x - 1, y - 1), ur = fg(x + 1, y - 1);
-  bool lf = fg(x - 1, y), rt = fg(x + 1, y);
-  if (up) {
-    if (!(lf && ul)) uf_unite(parent, me, me - (uint32_t)g.w);
-  } else {
-    if (ul && !lf) uf_unite(parent, me, me - (uint32_t)g.w - 1u);
-    if (ur && !rt) uf_unite(parent, me, me - (uint32_t)g.w + 1u);
-  }
-}
-
-// 2*area = 2*Q4 + Q3 over every 2x2 quad of the zero-padded filled set
-__global__ void __launch_bounds__(256) k_ccl_area(Roi g, const uint8_t* __restrict__ Wimg,
-                                                  uint32_t* __restrict__ parent_all,
-                                                  uint32_t* __restrict__ area_all) {
-  const int t = blockIdx.z;
-  const size_t n = (size_t)g.w * g.h;
-  uint32_t* parent = parent_all + (size_t)t * n;
-  uint32_t* area = area_all + (size_t)t * n;
-  int qx = g.x0 - 1 + blockIdx.x * blockDim.x + threadIdx.x;   // quad = (qx..qx+1, qy..qy+1)
-  int qy = g.y0 - 1 + blockIdx.y;
-  auto fg = [&](int xx, int yy) -> bool {
-    return xx >= g.x0 && xx < g.x0 + g.w && yy >= g.y0 && yy < g.y0 + g.h &&
-           Wimg[(size_t)yy * g.W + xx] <= t;
-  };
-  uint32_t root = 0xFFFFFFFFu, add = 0;
-  if (qx < g.x0 + g.w) {
-    bool a = fg(qx, qy), b = fg(qx + 1, qy), c = fg(qx, qy + 1), d = fg(qx + 1, qy + 1);
-    int s = (int)a + (int)b + (int)c + (int)d;
-    if (s >= 3) {
-      int px = a ? qx : qx + 1, py = qy;   // a, else b: one of the top pair is set when s >= 3
-      root = uf_find(parent, g.li(px, py));
-      add = (s == 4) ? 2u : 1u;
+__global__ void __launch_bounds__(256) k_tile_list(Roi g, const uint8_t* __restrict__ Wimg, int T,
+                                                   int tiles_x, int tiles_y,
+                                                   uint32_t* __restrict__ tile_count,
+                                                   uint32_t* __restrict__ tiles) {
+  // one warp per tile: lane = column, loop over the 8 rows
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= tiles_x * tiles_y) return;
+  int tj = warp % tiles_x, ti = warp / tiles_x;
+  int x = g.x0 + tj * kTileW + lane;
+  bool any = false;
+  if (x < g.x0 + g.w) {
+    for (int dy = 0; dy < kTileH; ++dy) {
+      int y = g.y0 + ti * kTileH + dy;
+      if (y < g.y0 + g.h) any |= Wimg[(size_t)y * g.W + x] < T;
     }
   }
-  // warp-aggregate per root before the global atomic
-  unsigned active = __ballot_sync(0xFFFFFFFFu, add != 0);
-  if (add) {
-    unsigned peers = __match_any_sync(active, root);
-    uint32_t sum = 0;
-    for (unsigned mm = peers; mm; mm &= mm - 1) sum += __shfl_sync(peers, add, __ffs(mm) - 1);
-    if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&area[root], sum);
+  if (__any_sync(0xFFFFFFFFu, any) && lane == 0) tiles[atomicAdd(tile_count, 1u)] = (uint32_t)warp;
+}
+
+struct TileCtx {
+  int x, y;
+  bool valid;
+};
+__device__ __forceinline__ TileCtx tile_pixel(const Roi& g, uint32_t tile, int tiles_x) {
+  int tj = tile % tiles_x, ti = tile / tiles_x;
+  TileCtx c;
+  c.x = g.x0 + tj * kTileW + (threadIdx.x & 31);
+  c.y = g.y0 + ti * kTileH + (threadIdx.x >> 5);
+  c.valid = c.x < g.x0 + g.w && c.y < g.y0 + g.h;
+  return c;
+}
+
+__device__ __forceinline__ bool fg_at(const Roi& g, const uint8_t* __restrict__ Wimg, int t, int xx,
+                                      int yy) {
+  return xx >= g.x0 && xx < g.x0 + g.w && yy >= g.y0 && yy < g.y0 + g.h &&
+         Wimg[(size_t)yy * g.W + xx] <= t;
+}
+
+__global__ void __launch_bounds__(256) k_ccl_link(Roi g, const uint8_t* __restrict__ Wimg, int tiles_x,
+                                                  const uint32_t* __restrict__ tile_count,
+                                                  const uint32_t* __restrict__ tiles,
+                                                  uint32_t* __restrict__ parent_all,
+                                                  uint32_t* __restrict__ area_all) {
+  const int t = blockIdx.y;
+  const size_t n = (size_t)g.w * g.h;
+  uint32_t* parent = parent_all + (size_t)t * n;
+  uint32_t* area = area_all + (size_t)t * n;
+  const uint32_t nt = *tile_count;
+  for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
+    TileCtx c = tile_pixel(g, tiles[i], tiles_x);
+    uint32_t me = c.valid ? g.li(c.x, c.y) : 0u;
+    bool fg = c.valid && Wimg[(size_t)c.y * g.W + c.x] <= t;
+    uint32_t tgt = row_run_target(g, c.x, c.y, c.valid, me,
+                                  [&](int xx, int yy) { return Wimg[(size_t)yy * g.W + xx] <= t; });
+    if (fg) {
+      parent[me] = tgt;
+      area[me] = 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ccl_union(Roi g, const uint8_t* __restrict__ Wimg, int tiles_x,
+                                                   const uint32_t* __restrict__ tile_count,
+                                                   const uint32_t* __restrict__ tiles,
+                                                   uint32_t* __restrict__ parent_all) {
+  const int t = blockIdx.y;
+  uint32_t* parent = parent_all + (size_t)t * g.w * g.h;
+  const uint32_t nt = *tile_count;
+  for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
+    TileCtx c = tile_pixel(g, tiles[i], tiles_x);
+    if (!c.valid || c.y == g.y0 || !fg_at(g, Wimg, t, c.x, c.y)) continue;
+    const int x = c.x, y = c.y;
+    uint32_t me = g.li(x, y);
+    bool up = fg_at(g, Wimg, t, x, y - 1), ul = fg_at(g, Wimg, t, x - 1, y - 1);
+    bool ur = fg_at(g, Wimg, t, x + 1, y - 1);
+    bool lf = fg_at(g, Wimg, t, x - 1, y), rt = fg_at(g, Wimg, t, x + 1, y);
+    if (up) {
+      if (!(lf && ul)) uf_unite(parent, me, me - (uint32_t)g.w);
+    } else {
+      if (ul && !lf) uf_unite(parent, me, me - (uint32_t)g.w - 1u);
+      if (ur && !rt) uf_unite(parent, me, me - (uint32_t)g.w + 1u);
+    }
+  }
+}
+
+// 2*area = 2*Q4 + Q3 over every 2x2 quad of the zero-padded filled set.  Each quad is charged
+// to its first set pixel in raster order, so only two quads per foreground pixel p matter:
+//   A = {p, right, down, down-right}              (p is the top-left pixel)
+//   B = {left, p, down-left, down} with left unset (p is the top-right pixel; s = 3 at most)
+__global__ void __launch_bounds__(256) k_ccl_area(Roi g, const uint8_t* __restrict__ Wimg, int tiles_x,
+                                                  const uint32_t* __restrict__ tile_count,
+                                                  const uint32_t* __restrict__ tiles,
+                                                  uint32_t* __restrict__ parent_all,
+                                                  uint32_t* __restrict__ area_all) {
+  const int t = blockIdx.y;
+  const size_t n = (size_t)g.w * g.h;
+  uint32_t* parent = parent_all + (size_t)t * n;
+  uint32_t* area = area_all + (size_t)t * n;
+  const uint32_t nt = *tile_count;
+  for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
+    TileCtx c = tile_pixel(g, tiles[i], tiles_x);
+    uint32_t root = 0xFFFFFFFFu, add = 0;
+    if (c.valid && fg_at(g, Wimg, t, c.x, c.y)) {
+      const int x = c.x, y = c.y;
+      bool r_ = fg_at(g, Wimg, t, x + 1, y), d_ = fg_at(g, Wimg, t, x, y + 1);
+      bool dr = fg_at(g, Wimg, t, x + 1, y + 1);
+      int sa = 1 + (int)r_ + (int)d_ + (int)dr;
+      add = (sa == 4) ? 2u : (sa == 3 ? 1u : 0u);
+      if (d_ && !fg_at(g, Wimg, t, x - 1, y) && fg_at(g, Wimg, t, x - 1, y + 1)) add += 1u;
+      if (add) root = uf_find(parent, g.li(x, y));
+    }
+    unsigned active = __ballot_sync(0xFFFFFFFFu, add != 0);
+    if (add) {      // warp-aggregate per root before the global atomic
+      unsigned peers = __match_any_sync(active, root);
+      uint32_t sum = 0;
+      for (unsigned mm = peers; mm; mm &= mm - 1) sum += __shfl_sync(peers, add, __ffs(mm) - 1);
+      if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&area[root], sum);
+    }
   }
 }
 
@@ -222,59 +354,73 @@ __device__ __forceinline__ bool area_kept(uint32_t a2, double disk_area, double 
   return __ddiv_rn(__dmul_rn((double)a2, 0.5), disk_area) >= thr;
 }
 
-__global__ void __launch_bounds__(256) k_ccl_stats(Roi g, const uint8_t* __restrict__ Wimg,
+__global__ void __launch_bounds__(256) k_ccl_stats(Roi g, const uint8_t* __restrict__ Wimg, int tiles_x,
+                                                   const uint32_t* __restrict__ tile_count,
+                                                   const uint32_t* __restrict__ tiles,
                                                    const uint32_t* __restrict__ parent_all,
                                                    const uint32_t* __restrict__ area_all,
                                                    double disk_area, double thr,
                                                    chips_result* __restrict__ res) {
-  const int t = blockIdx.z;
+  const int t = blockIdx.y;
   const size_t n = (size_t)g.w * g.h;
-  int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
-  int y = g.y0 + blockIdx.y;
-  bool root = false, kept = false;
-  if (x < g.x0 + g.w && Wimg[(size_t)y * g.W + x] <= t) {
-    uint32_t me = g.li(x, y);
-    if (parent_all[(size_t)t * n + me] == me) {
-      root = true;
-      kept = area_kept(area_all[(size_t)t * n + me], disk_area, thr);
+  const uint32_t nt = *tile_count;
+  int nroot = 0, nkept = 0;
+  for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
+    TileCtx c = tile_pixel(g, tiles[i], tiles_x);
+    if (c.valid && Wimg[(size_t)c.y * g.W + c.x] <= t) {
+      uint32_t me = g.li(c.x, c.y);
+      if (parent_all[(size_t)t * n + me] == me) {
+        ++nroot;
+        nkept += area_kept(area_all[(size_t)t * n + me], disk_area, thr) ? 1 : 0;
+      }
     }
   }
-  unsigned mr = __ballot_sync(0xFFFFFFFFu, root), mk = __ballot_sync(0xFFFFFFFFu, kept);
+  for (int o = 16; o > 0; o >>= 1) {
+    nroot += __shfl_xor_sync(0xFFFFFFFFu, nroot, o);
+    nkept += __shfl_xor_sync(0xFFFFFFFFu, nkept, o);
+  }
   if ((threadIdx.x & 31) == 0) {
-    if (mr) atomicAdd(&res->n_comp[t], __popc(mr));
-    if (mk) atomicAdd(&res->n_kept[t], __popc(mk));
+    if (nroot) atomicAdd(&res->n_comp[t], nroot);
+    if (nkept) atomicAdd(&res->n_kept[t], nkept);
   }
 }
 
 __global__ void __launch_bounds__(256) k_ccl_keep(Roi g, const uint8_t* __restrict__ Wimg, int T,
+                                                  int tiles_x, const uint32_t* __restrict__ tile_count,
+                                                  const uint32_t* __restrict__ tiles,
                                                   uint32_t* __restrict__ parent_all,
                                                   const uint32_t* __restrict__ area_all,
                                                   double disk_area, double thr,
                                                   uint8_t* __restrict__ keep) {
   const size_t n = (size_t)g.w * g.h;
-  int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
-  int y = g.y0 + blockIdx.y;
-  if (x >= g.x0 + g.w) return;
-  size_t o = (size_t)y * g.W + x;
-  int w = Wimg[o];
-  int kk = T;
-  uint32_t me = g.li(x, y);
-  for (int t = w; t < T; ++t) {
-    uint32_t root = uf_find(parent_all + (size_t)t * n, me);
-    if (area_kept(area_all[(size_t)t * n + root], disk_area, thr)) {
-      kk = t;
-      break;
+  const uint32_t nt = *tile_count;
+  for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
+    TileCtx c = tile_pixel(g, tiles[i], tiles_x);
+    if (!c.valid) continue;
+    size_t o = (size_t)c.y * g.W + c.x;
+    int w = Wimg[o];
+    if (w >= T) continue;                      // keep[] is pre-filled with T
+    int kk = T;
+    uint32_t me = g.li(c.x, c.y);
+    for (int t = w; t < T; ++t) {
+      uint32_t root = uf_find(parent_all + (size_t)t * n, me);
+      if (area_kept(area_all[(size_t)t * n + root], disk_area, thr)) {
+        kk = t;
+        break;
+      }
     }
+    keep[o] = (uint8_t)kk;
   }
-  keep[o] = (uint8_t)kk;
 }
 
-__global__ void k_clear_counts(chips_result* res) {
+__global__ void k_cleanup_reset(chips_result* res, uint32_t* lvl_count, uint32_t* tile_count) {
   int t = threadIdx.x;
   if (t < CHIPS_MAX_T) {
     res->n_kept[t] = 0;
     res->n_comp[t] = 0;
   }
+  if (t <= CHIPS_MAX_T + 1) lvl_count[t] = 0;
+  if (t == 0) *tile_count = 0;
 }
 
 // ------------------------------------------------------------------ expansion / debugging
@@ -354,15 +500,16 @@ __global__ void __launch_bounds__(256) k_prob_stack(const uint8_t* __restrict__ 
     poisoned = bad ? 1 : 0;
   }
   __syncthreads();
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int kk = keep[i];
-  double v = poisoned ? NAN : suffix[kk > T ? T : kk];
-  if (accumulate) {
-    // running sum for the batch uncertainty map: NaN (= "no detection") counts as 0
-    out[i] += (O)((poisoned || v == 0.0) ? 0.0 : v);
-  } else {
-    out[i] = (O)((v == 0.0) ? NAN : v);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    int kk = keep[i];
+    double v = poisoned ? NAN : suffix[kk > T ? T : kk];
+    if (accumulate) {
+      // running sum for the batch uncertainty map: "no detection" counts as 0
+      if (!poisoned && v != 0.0) out[i] += (O)v;
+    } else {
+      out[i] = (O)((v == 0.0) ? NAN : v);
+    }
   }
 }
 
@@ -379,7 +526,7 @@ using namespace chips;
 
 extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, double disk_area,
                              double area_threshold, void* ws, void* stream) {
-  if (!plan || !ws) return CHIPS_E_ARG;
+  if (!plan || !ws || !plan->masked) return CHIPS_E_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* w = (unsigned char*)ws;
   const int T = plan->T;
@@ -390,35 +537,47 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
   uint32_t* parent_b = reinterpret_cast<uint32_t*>(w + plan->off_parent_b);
   uint32_t* parent_c = reinterpret_cast<uint32_t*>(w + plan->off_parent_c);
   uint32_t* area = reinterpret_cast<uint32_t*>(w + plan->off_area);
+  uint32_t* pending = reinterpret_cast<uint32_t*>(w + plan->off_pending);
+  uint32_t* lvl = reinterpret_cast<uint32_t*>(w + plan->off_lvl);       // count | offset | cursor
+  uint32_t* lvl_count = lvl, *lvl_offset = lvl + 128, *lvl_cursor = lvl + 256;
+  uint32_t* tile_count = lvl + 384;
+  uint32_t* tiles = reinterpret_cast<uint32_t*>(w + plan->off_tiles);
   chips_result* res = reinterpret_cast<chips_result*>(w + plan->off_result);
   Roi g = make_roi(plan, cx, cy, r);
   dim3 blk(256);
   dim3 grid((g.w + 255) / 256, g.h);
-  dim3 gridq((g.w + 1 + 255) / 256, g.h + 1);
+  const int tiles_x = (g.w + kTileW - 1) / kTileW, tiles_y = (g.h + kTileH - 1) / kTileH;
+  const int ntiles = tiles_x * tiles_y;
 
   CHIPS_CUDA(cudaMemsetAsync(Wimg, T, n_img, st));
   CHIPS_CUDA(cudaMemsetAsync(keep, T, n_img, st));
-  k_clear_counts<<<1, CHIPS_MAX_T, 0, st>>>(res);
-  k_fill_init<<<grid, blk, 0, st>>>(g, Wimg, parent_b);
-  CHIPS_CHECK_LAUNCH();
+  k_cleanup_reset<<<1, 128, 0, st>>>(res, lvl_count, tile_count);
   // round T-1: the bulk background (pixels in no mask at all)
-  k_fill_bulk_link<<<grid, blk, 0, st>>>(g, lev, T, parent_b);
-  k_fill_union<true><<<grid, blk, 0, st>>>(g, lev, T - 1, parent_b);
-  k_fill_assign<<<grid, blk, 0, st>>>(g, lev, T - 1, Wimg, parent_b);
+  k_fill_bulk_link<<<grid, blk, 0, st>>>(g, lev, T, Wimg, parent_b);
+  k_fill_bulk_union<<<grid, blk, 0, st>>>(g, lev, T, parent_b);
+  k_fill_pending<0><<<grid, blk, 0, st>>>(g, lev, T, Wimg, parent_b, lvl_count, lvl_cursor, pending);
+  k_fill_offsets<<<1, 32, 0, st>>>(T, lvl_count, lvl_offset, lvl_cursor);
+  k_fill_pending<1><<<grid, blk, 0, st>>>(g, lev, T, Wimg, parent_b, lvl_count, lvl_cursor, pending);
   CHIPS_CHECK_LAUNCH();
+  // the bulk pixels that did not reach the border in round T-1 stay pending at level T and
+  // are re-examined by every later round (suffix of the list)
+  const int gl = 2 * kNumSM;
   for (int t = T - 2; t >= 0; --t) {
-    k_fill_union<false><<<grid, blk, 0, st>>>(g, lev, t, parent_b);
-    k_fill_assign<<<grid, blk, 0, st>>>(g, lev, t, Wimg, parent_b);
+    k_fill_round_union<<<gl, blk, 0, st>>>(g, lev, t, lvl_offset, pending, parent_b);
+    k_fill_round_assign<<<gl, blk, 0, st>>>(g, t, T, lvl_offset, pending, Wimg, parent_b);
   }
   CHIPS_CHECK_LAUNCH();
-  dim3 gridz(grid.x, grid.y, T), gridqz(gridq.x, gridq.y, T);
-  k_ccl_link<<<gridz, blk, 0, st>>>(g, Wimg, parent_c, area);
-  k_ccl_union<<<gridz, blk, 0, st>>>(g, Wimg, parent_c);
-  k_ccl_area<<<gridqz, blk, 0, st>>>(g, Wimg, parent_c, area);
-  k_ccl_stats<<<gridz, blk, 0, st>>>(g, Wimg, parent_c, area, disk_area, area_threshold, res);
-  k_ccl_keep<<<grid, blk, 0, st>>>(g, Wimg, T, parent_c, area, disk_area, area_threshold, keep);
+  k_tile_list<<<(ntiles * 32 + 255) / 256, blk, 0, st>>>(g, Wimg, T, tiles_x, tiles_y, tile_count, tiles);
+  dim3 gridt(4 * kNumSM, T);
+  k_ccl_link<<<gridt, blk, 0, st>>>(g, Wimg, tiles_x, tile_count, tiles, parent_c, area);
+  k_ccl_union<<<gridt, blk, 0, st>>>(g, Wimg, tiles_x, tile_count, tiles, parent_c);
+  k_ccl_area<<<gridt, blk, 0, st>>>(g, Wimg, tiles_x, tile_count, tiles, parent_c, area);
+  k_ccl_stats<<<gridt, blk, 0, st>>>(g, Wimg, tiles_x, tile_count, tiles, parent_c, area, disk_area,
+                                     area_threshold, res);
+  k_ccl_keep<<<8 * kNumSM, blk, 0, st>>>(g, Wimg, T, tiles_x, tile_count, tiles, parent_c, area,
+                                         disk_area, area_threshold, keep);
   CHIPS_CHECK_LAUNCH();
-  count_launch(10 + 2 * (T - 1));
+  count_launch(6 + 2 * (T - 1) + 6);
   return CHIPS_OK;
 }
 
@@ -473,7 +632,7 @@ extern "C" int chips_prob_stack(const chips_plan* plan, double lower_lim, void* 
   if (!plan || !out || !ws) return CHIPS_E_ARG;
   unsigned char* w = (unsigned char*)ws;
   size_t n = (size_t)plan->H * plan->W;
-  unsigned grid = (unsigned)((n + 255) / 256);
+  unsigned grid = 8 * kNumSM;
   const uint8_t* keep = w + plan->off_keep;
   const chips_result* res = reinterpret_cast<const chips_result*>(w + plan->off_result);
   cudaStream_t st = (cudaStream_t)stream;

@@ -124,36 +124,84 @@ __device__ __forceinline__ int huang_slot(int tid) {
   return lane * 2 + (warp & 1) + (warp >> 1) * 64;
 }
 
-template <int DELTA>
-__device__ __forceinline__ void huang_row(uint16_t* __restrict__ my, const uint8_t* __restrict__ row,
-                                          int k, int med, int& lt) {
-  constexpr int NT = kHuangThreads;
-  uintptr_t a = reinterpret_cast<uintptr_t>(row);
-  const uint32_t* wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-  int sh = (int)(a & 3) * 8;
-  uint32_t w0 = __ldg(wp);
-  int j = 0;
-  for (; j + 4 <= k; j += 4) {
-    uint32_t w1 = __ldg(wp + (j >> 2) + 1);
+// Streams the k bucket bytes that start at `row` (any alignment) through aligned 32-bit
+// loads + funnel shifts.
+struct RowReader {
+  const uint32_t* wp;
+  int sh;
+  uint32_t w0;
+  __device__ __forceinline__ RowReader(const uint8_t* row) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(row);
+    wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    sh = (int)(a & 3) * 8;
+    w0 = __ldg(wp);
+  }
+  __device__ __forceinline__ uint32_t next(int word) {   // bytes [4*word, 4*word+4)
+    uint32_t w1 = __ldg(wp + word + 1);
     uint32_t v = __funnelshift_r(w0, w1, sh);
     w0 = w1;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int b = (v >> (8 * i)) & 255;
-      uint16_t* c = my + b * NT;
-      *c = (uint16_t)(*c + DELTA);
-      lt += (b < med) ? DELTA : 0;
-    }
+    return v;
+  }
+};
+
+// +1 for two entering elements; the two read-modify-writes are issued together (the loads
+// are independent) unless both hit the same bin.
+__device__ __forceinline__ void huang_add2(uint16_t* __restrict__ my, int a, int b, int med, int& lt) {
+  constexpr int NT = kHuangThreads;
+  uint16_t* pa = my + a * NT;
+  uint16_t* pb = my + b * NT;
+  // branch-free: both loads first; if a == b the second store (same address, program order)
+  // wins and carries the +2
+  uint16_t ca = *pa, cb = *pb;
+  *pa = (uint16_t)(ca + 1);
+  *pb = (uint16_t)(cb + 1 + (a == b));
+  lt += (a < med) + (b < med);
+}
+__device__ __forceinline__ void huang_add1(uint16_t* __restrict__ my, int a, int med, int& lt) {
+  uint16_t* pa = my + a * kHuangThreads;
+  *pa = (uint16_t)(*pa + 1);
+  lt += (a < med);
+}
+// +1 for the entering element a, -1 for the leaving element b
+__device__ __forceinline__ void huang_swap(uint16_t* __restrict__ my, int a, int b, int med, int& lt) {
+  constexpr int NT = kHuangThreads;
+  // branch-free: if a == b both stores write the unchanged count back
+  uint16_t* pa = my + a * NT;
+  uint16_t* pb = my + b * NT;
+  uint16_t ca = *pa, cb = *pb;
+  int d = (a != b);
+  *pa = (uint16_t)(ca + d);
+  *pb = (uint16_t)(cb - d);
+  lt += (a < med) - (b < med);
+}
+
+__device__ __forceinline__ void huang_add_row(uint16_t* __restrict__ my, const uint8_t* row, int k,
+                                              int med, int& lt) {
+  RowReader rd(row);
+  int j = 0;
+  for (; j + 4 <= k; j += 4) {
+    uint32_t v = rd.next(j >> 2);
+    huang_add2(my, v & 255, (v >> 8) & 255, med, lt);
+    huang_add2(my, (v >> 16) & 255, v >> 24, med, lt);
   }
   if (j < k) {
-    uint32_t w1 = __ldg(wp + (j >> 2) + 1);
-    uint32_t v = __funnelshift_r(w0, w1, sh);
-    for (int i = 0; i < k - j; ++i) {
-      int b = (v >> (8 * i)) & 255;
-      uint16_t* c = my + b * NT;
-      *c = (uint16_t)(*c + DELTA);
-      lt += (b < med) ? DELTA : 0;
-    }
+    uint32_t v = rd.next(j >> 2);
+    for (int i = 0; i < k - j; ++i) huang_add1(my, (v >> (8 * i)) & 255, med, lt);
+  }
+}
+
+__device__ __forceinline__ void huang_swap_row(uint16_t* __restrict__ my, const uint8_t* add,
+                                               const uint8_t* rem, int k, int med, int& lt) {
+  RowReader ra(add), rb(rem);
+  int j = 0;
+  for (; j + 4 <= k; j += 4) {
+    uint32_t va = ra.next(j >> 2), vb = rb.next(j >> 2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) huang_swap(my, (va >> (8 * i)) & 255, (vb >> (8 * i)) & 255, med, lt);
+  }
+  if (j < k) {
+    uint32_t va = ra.next(j >> 2), vb = rb.next(j >> 2);
+    for (int i = 0; i < k - j; ++i) huang_swap(my, (va >> (8 * i)) & 255, (vb >> (8 * i)) & 255, med, lt);
   }
 }
 
@@ -161,7 +209,7 @@ __global__ void __launch_bounds__(kHuangThreads) k_huang(const uint8_t* __restri
                                                          int half, int k, int W, int rx0, int ry0,
                                                          int rw, int rh, int L, int cx, int cy, int r,
                                                          uint8_t* __restrict__ bstar,
-                                                         uint16_t* __restrict__ rres) {
+                                                         uint32_t* __restrict__ rres) {
   constexpr int NT = kHuangThreads;
   extern __shared__ __align__(16) uint16_t hist[];
   const int tid = threadIdx.x;
@@ -189,135 +237,290 @@ __global__ void __launch_bounds__(kHuangThreads) k_huang(const uint8_t* __restri
   const int R = (k * k - 1) >> 1;
   int med = 0, lt = 0;
   // padded coordinates: image (y, x) lives at Bp[(y+half)*pitch + x+half]; the window of
-  // centre column x starts at padded column x.
+  // centre column x starts at padded column x, the window row of image row yy is padded row
+  // yy + half.
   const uint8_t* col = Bp + x;
-  for (int yy = ya - half; yy < yb + half; ++yy) {
-    huang_row<+1>(my, col + (size_t)(yy + half) * pitch, k, med, lt);
-    int yo = yy - k;
-    if (yo >= ya - half) huang_row<-1>(my, col + (size_t)(yo + half) * pitch, k, med, lt);
-    int y = yy - half;
-    if (y >= ya) {
-      while (lt > R) {
-        --med;
-        lt -= my[med * NT];
-      }
-      while (true) {
-        int c = my[med * NT];
-        if (lt + c > R) break;
-        lt += c;
-        ++med;
-      }
-      size_t o = (size_t)y * W + x;
-      bstar[o] = (uint8_t)med;
-      rres[o] = (uint16_t)(R - lt);
+  auto prow = [&](int yy) { return col + (size_t)(yy + half) * pitch; };
+  for (int yy = ya - half; yy < ya + half; ++yy) huang_add_row(my, prow(yy), k, med, lt);
+  for (int y = ya; y < yb; ++y) {
+    if (y == ya) huang_add_row(my, prow(y + half), k, med, lt);
+    else huang_swap_row(my, prow(y + half), prow(y - half - 1), k, med, lt);
+    while (lt > R) {
+      --med;
+      lt -= my[med * NT];
     }
+    int c;
+    while (true) {
+      c = my[med * NT];
+      if (lt + c > R) break;
+      lt += c;
+      ++med;
+    }
+    size_t o = (size_t)y * W + x;
+    bstar[o] = (uint8_t)med;
+    rres[o] = (uint32_t)(R - lt) | ((uint32_t)c << 16);   // residual rank | bucket population
   }
 }
 
 // ------------------------------------------------------------------ 4. tier 2: tile refine
+// One CTA per 16x16 output tile.
+//   a. bitmap of the buckets the tile's pixels need (tier-1 output);
+//   b. the tile's (16+k-1)^2 input region (bucket bytes + ordered keys) is staged in shared
+//      memory with coalesced, mutually independent loads;
+//   c. a counting sort collects the positions of the region pixels whose bucket is needed,
+//      grouped by (bucket, leading digit of the key inside the bucket's key range);
+//   d. each warp finishes the sort inside the small sub-groups (shuffle rank sort, in place);
+//   e. every thread walks the sorted candidates of ITS bucket from the nearer end, counting
+//      those inside its own k x k window, until it reaches its residual rank.
+// Epilogue: masked store + min/max reduction (histogram range).
+constexpr int kMaxSub = 1024;   // sub-group counters per tile: groups * digits <= kMaxSub
+
+template <typename K>
+__device__ __forceinline__ int bit_length(K v) {
+  return (sizeof(K) == 8) ? 64 - __clzll((long long)v) : 32 - __clz((int)v);
+}
+
+__device__ __forceinline__ bool in_window(unsigned p, unsigned bias, unsigned win) {
+  // p = (ry << 8) | rx, bias = (ty << 8) | tx.  A borrow out of the low byte (rx < tx) leaves a
+  // low byte >= 256 - 15 > win, a negative row difference wraps the whole word: both rejected.
+  unsigned t = p - bias;
+  return ((t >> 8) <= win) & ((t & 255u) <= win);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kTile* kTile) k_refine(
     const T* __restrict__ img, const uint8_t* __restrict__ Bp, int pitch,
-    const uint8_t* __restrict__ bstar, const uint16_t* __restrict__ rres,
+    const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres,
     const typename Key<T>::type* __restrict__ bounds, int H, int W, int half, int rx0, int ry0,
     int rw, int rh, int cx, int cy, int r, int cap, T* __restrict__ out,
-    typename Key<T>::type* __restrict__ minmax, int* __restrict__ err) {
+    typename Key<T>::type* __restrict__ minmax, int* __restrict__ err, uint32_t* __restrict__ dbg) {
   using K = typename Key<T>::type;
+  constexpr int NT = kTile * kTile;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  K* ckey = reinterpret_cast<K*>(smem_raw);
-  uint16_t* cpos = reinterpret_cast<uint16_t*>(smem_raw + (size_t)cap * sizeof(K));
-  __shared__ uint32_t need[8];
-  __shared__ int ccount;
+  K* skey = reinterpret_cast<K*>(smem_raw);                                   // [RS*RS]
+  uint16_t* cpos = reinterpret_cast<uint16_t*>(smem_raw + (size_t)cap * sizeof(K));   // [cap]
+  uint8_t* sbyte = smem_raw + (size_t)cap * (sizeof(K) + sizeof(uint16_t));   // [RS*RS]
+  __shared__ uint32_t need[8], needpfx[9];
+  __shared__ uint16_t glut[kBuckets];          // bucket -> group (0xFFFF: not needed by this tile)
+  __shared__ K gklo[kBuckets];
+  __shared__ uint8_t gshift[kBuckets];
+  __shared__ uint32_t sgstart[kMaxSub], sgcur[kMaxSub];
+  __shared__ uint32_t wsum[NT / 32];
   __shared__ int nactive;
+#ifdef CHIPS_DEBUG_TIMING
+  long long t_0 = clock64(), t_1 = 0, t_2 = 0;
+#endif
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & (kTile - 1), ty = tid >> 4;
   const int X0 = rx0 + blockIdx.x * kTile, Y0 = ry0 + blockIdx.y * kTile;
   const int x = X0 + tx, y = Y0 + ty;
   const bool active = (x < rx0 + rw) && (y < ry0 + rh) && on_disk(x, y, cx, cy, r);
   if (tid < 8) need[tid] = 0;
-  if (tid == 0) {
-    ccount = 0;
-    nactive = 0;
-  }
+  if (tid == 0) nactive = 0;
   __syncthreads();
-  int bs = 0, rr = 0;
+  int bs = 0, rr = 0, mpop = 0;
   if (active) {
     size_t o = (size_t)y * W + x;
     bs = bstar[o];
-    rr = rres[o];
+    uint32_t pk = rres[o];
+    rr = (int)(pk & 0xFFFFu);
+    mpop = (int)(pk >> 16);
     atomicOr(&need[bs >> 5], 1u << (bs & 31));
     nactive = 1;
   }
   __syncthreads();
   if (nactive == 0) return;
 
-  // gather candidates of the needed buckets from the (kTile+2*half)^2 input region
+  // ---- b. stage the region: warp w takes rows w, w+8, ...; lanes take columns (coalesced)
   const int RS = kTile + 2 * half;
-  const int lane = tid & 31;
-  for (int ryb = 0; ryb < RS; ryb += kTile) {      // uniform trip counts: ballots below
-    const int ry = ryb + ty;
-    const uint8_t* brow = Bp + (size_t)(Y0 + min(ry, RS - 1)) * pitch + X0;
-    for (int rxb = 0; rxb < RS; rxb += kTile) {
-      const int rx = rxb + tx;
-      bool hit = false;
-      if (rx < RS && ry < RS) {
-        int b = brow[rx];
-        hit = (need[b >> 5] >> (b & 31)) & 1u;
+  {
+    const bool interior = (X0 - half >= 0) && (Y0 - half >= 0) && (X0 - half + RS <= W) &&
+                          (Y0 - half + RS <= H);
+    for (int ry = warp; ry < RS; ry += NT / 32) {
+      const uint8_t* brow = Bp + (size_t)(Y0 + ry) * pitch + X0;
+      const int iy = Y0 + ry - half;
+      const T* irow = img + ((long long)iy * W + (X0 - half));
+      for (int rx = lane; rx < RS; rx += 32) {
+        T v;
+        if (interior) {
+          v = irow[rx];
+        } else {
+          int ix = X0 + rx - half;
+          v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? irow[rx] : (T)0;
+        }
+        sbyte[ry * RS + rx] = brow[rx];
+        skey[ry * RS + rx] = Key<T>::enc(v);
       }
-      unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-      if (m) {
-        int base = 0;
-        int leader = __ffs(m) - 1;
-        if (lane == leader) base = atomicAdd(&ccount, __popc(m));
-        base = __shfl_sync(0xFFFFFFFFu, base, leader);
-        if (hit) {
-          int slot = base + __popc(m & ((1u << lane) - 1));
-          int iy = Y0 + ry - half, ix = X0 + rx - half;
-          T v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? img[(size_t)iy * W + ix] : (T)0;
-          if (slot < cap) {
-            ckey[slot] = Key<T>::enc(v);
+    }
+  }
+  if (tid < 9) {
+    uint32_t p = 0;
+    for (int i = 0; i < tid; ++i) p += __popc(need[i]);
+    needpfx[tid] = p;
+  }
+  __syncthreads();
+  const int ngroups = (int)needpfx[8];
+  // digits per group: 16 unless the tile needs so many buckets that groups*16 > kMaxSub
+  const int dlog = ngroups <= kMaxSub / 16 ? 4 : (ngroups <= kMaxSub / 8 ? 3 : 2);
+  const int nsg = ngroups << dlog;
+  {   // key range of bucket `tid` -> digit shift of its group; clear the sub-group counters
+    const int b = tid;
+    uint16_t gl = 0xFFFF;
+    if ((need[b >> 5] >> (b & 31)) & 1u) {
+      K klo = (b == 0) ? (K)0 : bounds[b - 1];
+      K span = bounds[b] - klo;               // bucket = [klo, bounds[b]) ; bounds[255] = kMax
+      if (b == kBuckets - 1 && span != Key<T>::kMax) span += 1;   // the last bucket is closed
+      int g = (int)(needpfx[b >> 5] + __popc(need[b >> 5] & ((1u << (b & 31)) - 1u)));
+      gl = (uint16_t)g;
+      gklo[g] = klo;
+      gshift[g] = (uint8_t)max(0, bit_length<K>(span - 1) - dlog);
+    }
+    glut[b] = gl;
+    for (int i = tid; i < nsg; i += NT) sgstart[i] = 0;
+  }
+  __syncthreads();
+
+  // ---- c. count, prefix, scatter (all from shared memory)
+  const int ndm1 = (1 << dlog) - 1;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int ry = ty; ry < RS; ry += kTile) {
+      for (int rx = tx; rx < RS; rx += kTile) {
+        const int ri = ry * RS + rx;
+        const int g = glut[sbyte[ri]];
+        if (g != 0xFFFF) {
+          K dg = (skey[ri] - gklo[g]) >> gshift[g];
+          int sg = (g << dlog) + (int)(dg < (K)ndm1 ? dg : (K)ndm1);
+          if (pass == 0) {
+            atomicAdd(&sgstart[sg], 1u);
+          } else {
+            uint32_t slot = atomicAdd(&sgcur[sg], 1u);
             cpos[slot] = (uint16_t)((ry << 8) | rx);
           }
         }
       }
     }
-  }
-  __syncthreads();
-  const int C = min(ccount, cap);
-  int n2 = 2;
-  while (n2 < C) n2 <<= 1;
-  for (int i = C + tid; i < n2; i += kTile * kTile) {
-    ckey[i] = Key<T>::kMax;
-    cpos[i] = 0xFFFF;
-  }
-  __syncthreads();
-  bitonic_sort<K, true>(ckey, cpos, n2, tid, kTile * kTile);
-
-  K kmin = Key<T>::kMax, kmax = 0;
-  if (active) {
-    K lowkey = (bs == 0) ? (K)0 : bounds[bs - 1];
-    int lo = 0, hi = C;   // first index with ckey >= lowkey
-    while (lo < hi) {
-      int mid = (lo + hi) >> 1;
-      if (ckey[mid] < lowkey) lo = mid + 1; else hi = mid;
+    __syncthreads();
+    if (pass == 0) {    // exclusive scan of the nsg counters (contiguous chunk per thread)
+      const int per = (nsg + NT - 1) / NT;
+      const int lo = tid * per, hi = min(lo + per, nsg);
+      uint32_t s = 0;
+      for (int i = lo; i < hi; ++i) s += sgstart[i];
+      uint32_t inc = s;
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += n;
+      }
+      if (lane == 31) wsum[warp] = inc;
+      __syncthreads();
+      uint32_t base = 0;
+      for (int wv = 0; wv < warp; ++wv) base += wsum[wv];
+      uint32_t run = base + inc - s;
+      for (int i = lo; i < hi; ++i) {
+        uint32_t c = sgstart[i];
+        sgstart[i] = run;
+        sgcur[i] = run;
+        run += c;
+      }
+      __syncthreads();
     }
-    const unsigned span = 2u * (unsigned)half;
-    int cnt = 0, found = -1;
-    for (int i = lo; i < C; ++i) {
-      unsigned p = cpos[i];
-      if ((p >> 8) - (unsigned)ty <= span && (p & 255u) - (unsigned)tx <= span) {
-        if (cnt == rr) {
-          found = i;
-          break;
+  }
+#ifdef CHIPS_DEBUG_TIMING
+  t_1 = clock64();
+#endif
+  auto key_at = [&](unsigned p) -> K { return skey[(p >> 8) * RS + (p & 255u)]; };
+
+  // ---- d. finish the sort inside each sub-group, one warp per sub-group
+  for (int sg = warp; sg < nsg; sg += NT / 32) {
+    const int s0 = (int)sgstart[sg], n = (int)sgcur[sg] - s0;
+    if (n <= 1) continue;
+    if (n <= 32) {
+      uint16_t pos = (lane < n) ? cpos[s0 + lane] : (uint16_t)0;
+      K key = (lane < n) ? key_at(pos) : Key<T>::kMax;
+      int rank = 0;
+      for (int j = 0; j < n; ++j) {
+        K o = __shfl_sync(0xFFFFFFFFu, key, j);
+        rank += (o < key || (o == key && j < lane)) ? 1 : 0;
+      }
+      __syncwarp();
+      if (lane < n) cpos[s0 + rank] = pos;
+    } else {
+      K mn = Key<T>::kMax, mx = 0;
+      for (int i = lane; i < n; i += 32) {
+        K v = key_at(cpos[s0 + i]);
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        K a = __shfl_xor_sync(0xFFFFFFFFu, mn, o), b2 = __shfl_xor_sync(0xFFFFFFFFu, mx, o);
+        mn = a < mn ? a : mn;
+        mx = b2 > mx ? b2 : mx;
+      }
+      if (mn != mx) {   // many distinct keys in one digit of a bucket -> odd-even transposition
+        for (int ph = 0; ph < n; ++ph) {
+          for (int i = (ph & 1) + 2 * lane; i + 1 < n; i += 64) {
+            uint16_t pa = cpos[s0 + i], pb = cpos[s0 + i + 1];
+            if (key_at(pa) > key_at(pb)) {
+              cpos[s0 + i] = pb;
+              cpos[s0 + i + 1] = pa;
+            }
+          }
+          __syncwarp();
         }
-        ++cnt;
       }
     }
-    K res = 0;
+  }
+  __syncthreads();
+#ifdef CHIPS_DEBUG_TIMING
+  t_2 = clock64();
+#endif
+
+  // ---- e. walk the sorted candidates of my bucket from the nearer end
+  K kmin = Key<T>::kMax, kmax = 0;
+  if (active) {
+    const int g = glut[bs];
+    const int beg = (int)sgstart[g << dlog], end = (int)sgcur[(g << dlog) + ndm1];
+    const unsigned win = 2u * (unsigned)half;
+    const unsigned bias = ((unsigned)ty << 8) | (unsigned)tx;
+    const bool fwd = 2 * rr < mpop;
+    const int want = fwd ? rr : mpop - 1 - rr;     // in-window candidates to skip
+    const int step = fwd ? 1 : -1;
+    int i = fwd ? beg : end - 1;
+    int left = end - beg;
+    int cnt = 0, found = -1;
+    for (; left >= 4; left -= 4, i += 4 * step) {
+      unsigned p0 = cpos[i], p1 = cpos[i + step], p2 = cpos[i + 2 * step], p3 = cpos[i + 3 * step];
+      int c0 = in_window(p0, bias, win), c1 = in_window(p1, bias, win);
+      int c2 = in_window(p2, bias, win), c3 = in_window(p3, bias, win);
+      int c = c0 + c1 + c2 + c3;
+      if (cnt + c > want) {                        // the target is one of these four
+        if (c0 && cnt == want) found = i;
+        cnt += c0;
+        if (found < 0 && c1 && cnt == want) found = i + step;
+        cnt += c1;
+        if (found < 0 && c2 && cnt == want) found = i + 2 * step;
+        cnt += c2;
+        if (found < 0) found = i + 3 * step;
+        break;
+      }
+      cnt += c;
+    }
+    if (found < 0) {
+      for (; left > 0; --left, i += step) {
+        if (in_window(cpos[i], bias, win)) {
+          if (cnt == want) {
+            found = i;
+            break;
+          }
+          ++cnt;
+        }
+      }
+    }
+    K res;
     if (found >= 0) {
-      res = ckey[found];
-    } else {
+      res = key_at(cpos[found]);
+    } else {                                   // inconsistent tier-1 data: must never happen
       atomicAdd(err, 1);
       res = Key<T>::enc((T)0);
     }
@@ -337,6 +540,17 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
     atomic_min_key(&minmax[0], kmin);
     atomic_max_key(&minmax[1], kmax);
   }
+#ifdef CHIPS_DEBUG_TIMING
+  __syncthreads();
+  if (tid == 0 && dbg) {
+    uint32_t* d = dbg + 4 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x);
+    long long t_3 = clock64();
+    d[0] = (uint32_t)(t_1 - t_0);
+    d[1] = (uint32_t)(t_2 - t_1);
+    d[2] = (uint32_t)(t_3 - t_2);
+    d[3] = (uint32_t)sgcur[nsg - 1];     // number of candidates
+  }
+#endif
 }
 
 // ------------------------------------------------------------------ brute-force checker
@@ -395,9 +609,7 @@ __global__ void k_copy_masked(const T* __restrict__ in, T* __restrict__ out, int
 // ------------------------------------------------------------------ host-side launchers
 static int refine_cap(int k) {
   int rs = kTile + (k - 1);
-  int n = rs * rs, c = 2;
-  while (c < n) c <<= 1;
-  return c;
+  return (rs * rs + 7) & ~7;
 }
 
 template <typename T>
@@ -409,7 +621,7 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
   K* minmax = reinterpret_cast<K*>(ws + p->off_minmax);
   uint8_t* Bp = ws + p->off_bucket;
   uint8_t* bstar = ws + p->off_bstar;
-  uint16_t* rres = reinterpret_cast<uint16_t*>(ws + p->off_rres);
+  uint32_t* rres = reinterpret_cast<uint32_t*>(ws + p->off_rres);
   int* err = &reinterpret_cast<chips_result*>(ws + p->off_result)->median_errors;
   const int rx0 = p->roi_x0, ry0 = p->roi_y0, rw = p->roi_w, rh = p->roi_h;
 
@@ -445,10 +657,21 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
   if (stages & 4) {  // tier 1
     // run length: aim at >= 4 CTAs per SM worth of work, but keep the (k-1)-row warm-up
     // of every run amortised (L >= 2k).
+    // run length L: every run pays a (k-1)-row warm-up; 3 CTAs (64 KB of histograms each) are
+    // resident per SM.  Minimise waves(L) * (L + k).
     int nbx = (rw + kHuangThreads - 1) / kHuangThreads;
-    int L = 2 * k;
-    while (L < rh && (long long)nbx * ((rh + L - 1) / L) > 8LL * kNumSM) L += k;
-    if (L > rh) L = rh;
+    const long long resident = 3LL * kNumSM;
+    int L = rh;
+    long long best = -1;
+    for (int cand = (k < 8 ? 8 : k); cand <= rh; ++cand) {
+      long long blocks = (long long)nbx * ((rh + cand - 1) / cand);
+      long long waves = (blocks + resident - 1) / resident;
+      long long cost = waves * (cand + k);
+      if (best < 0 || cost < best) {
+        best = cost;
+        L = cand;
+      }
+    }
     dim3 grid(nbx, (rh + L - 1) / L);
     size_t smem = (size_t)kBuckets * kHuangThreads * sizeof(uint16_t);
     CHIPS_CUDA(cudaFuncSetAttribute(k_huang, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -459,12 +682,13 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
   }
   if (stages & 8) {  // tier 2
     int cap = refine_cap(k);
-    size_t smem = (size_t)cap * (sizeof(K) + sizeof(uint16_t));
+    size_t smem = (size_t)cap * (sizeof(K) + sizeof(uint16_t) + 1);
     CHIPS_CUDA(cudaFuncSetAttribute(k_refine<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((rw + kTile - 1) / kTile, (rh + kTile - 1) / kTile);
     k_refine<T><<<grid, kTile * kTile, smem, st>>>(in, Bp, p->bp_pitch, bstar, rres, bounds, H, W,
                                                    half, rx0, ry0, rw, rh, cx, cy, r, cap, out,
-                                                   minmax, err);
+                                                   minmax, err,
+                                                   reinterpret_cast<uint32_t*>(ws + p->off_parent_c));
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }

@@ -33,15 +33,16 @@ extern "C" int chips_plan_init(chips_plan* p, int H, int W, int k, int h_bins, i
     p->roi_x0 = 0; p->roi_y0 = 0; p->roi_w = W; p->roi_h = H;
   }
   const int half = k >> 1;
-  p->bp_pitch = (int)align_up((size_t)W + 2 * half + 16, 16);
-  p->bp_rows = H + 2 * half;
+  // + one 16-pixel tile of slack: the last refine tile of a row/column reads past the ROI
+  p->bp_pitch = (int)align_up((size_t)W + 2 * half + 32, 16);
+  p->bp_rows = H + 2 * half + 16;
   const size_t n = (size_t)H * W, nr = (size_t)p->roi_w * p->roi_h;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   p->off_bounds = take(256 * 8);
   p->off_bucket = take((size_t)p->bp_pitch * p->bp_rows);
   p->off_bstar = take(n);
-  p->off_rres = take(n * 2);
+  p->off_rres = take(n * 4);
   p->off_filt = take(n * elem);
   p->off_minmax = take(16);
   p->off_counts = take((size_t)h_bins * 8);
@@ -58,8 +59,12 @@ extern "C" int chips_plan_init(chips_plan* p, int H, int W, int k, int h_bins, i
     p->off_parent_b = take((nr + 1) * 4);
     p->off_parent_c = take(nr * 4 * T);
     p->off_area = take(nr * 4 * T);
+    p->off_pending = take(nr * 4);
+    p->off_lvl = take(512 * 4);
+    p->off_tiles = take(((size_t)((p->roi_w + 31) / 32) * ((p->roi_h + 7) / 8) + 1) * 4);
   } else {   // the synoptic variant has no contour/cleanup step (syn_chips.py:237-251)
     p->off_parent_b = p->off_parent_c = p->off_area = off;
+    p->off_pending = p->off_lvl = p->off_tiles = off;
   }
   p->bytes = off;
   return CHIPS_OK;
