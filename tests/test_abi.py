@@ -1,0 +1,83 @@
+"""CPU: the C-ABI library loads, exports every symbol `include/chips_b200.h` declares, and the
+ctypes mirrors of its structs match the C layout (checked with gcc).  No compute calls."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+HDR = os.path.join(ROOT, "include", "chips_b200.h")
+
+
+def declared_functions():
+    src = open(HDR).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(?:int|long long)\s+(chips_\w+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from pychips_b200 import _lib, build
+    build.build_library()
+    lib = C.CDLL(build.LIB)
+    names = declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in chips_b200.h but not exported"
+    assert set(_lib.SIGNATURES) == set(names), set(_lib.SIGNATURES) ^ set(names)
+    assert _lib.load().chips_version() == 100
+
+
+def test_struct_layouts_match_c(tmp_path):
+    from pychips_b200 import _lib
+    prog = tmp_path / "sz.c"
+    prog.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "chips_b200.h"\n'
+        'int main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(chips_result), sizeof(chips_plan),'
+        ' offsetof(chips_result, n_samples), offsetof(chips_result, median_errors),'
+        ' offsetof(chips_plan, off_bounds), offsetof(chips_plan, bytes));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    got = [C.sizeof(_lib.Result), C.sizeof(_lib.Plan), _lib.Result.n_samples.offset,
+           _lib.Result.median_errors.offset, _lib.Plan.off_bounds.offset, _lib.Plan.bytes.offset]
+    assert [int(v) for v in out] == got
+
+
+def test_plan_init_geometry_and_argument_errors():
+    from pychips_b200 import _lib
+    lib = _lib.load()
+    p = _lib.Plan()
+    assert lib.chips_plan_init(C.byref(p), 4096, 4096, 51, 500, 20, 4, 2048, 2048, 1577) == 0
+    assert (p.roi_x0, p.roi_y0, p.roi_w, p.roi_h) == (471, 471, 3155, 3155)
+    assert p.masked == 1 and p.bytes > 0 and p.bp_pitch % 16 == 0
+    offs = [getattr(p, f) for f, _ in _lib.Plan._fields_ if f.startswith("off_")]
+    assert all(o % 256 == 0 for o in offs) and offs == sorted(offs)
+    # unmasked (synoptic): whole image, no union-find buffers
+    assert lib.chips_plan_init(C.byref(p), 1440, 3600, 3, 5000, 25, 4, 0, 0, -1) == 0
+    assert (p.roi_w, p.roi_h, p.masked) == (3600, 1440, 0)
+    assert p.off_parent_b == p.off_area == p.bytes
+    # disk clipped by the image border
+    assert lib.chips_plan_init(C.byref(p), 100, 100, 5, 10, 3, 8, 50, 50, 80) == 0
+    assert (p.roi_x0, p.roi_y0, p.roi_w, p.roi_h) == (0, 0, 100, 100)
+    for bad in [(64, 64, 4, 10, 3, 4), (64, 64, 77, 10, 3, 4), (64, 64, 5, 0, 3, 4),
+                (64, 64, 5, 10, 0, 4), (64, 64, 5, 10, 65, 4), (64, 64, 5, 10, 3, 2), (0, 64, 5, 10, 3, 4)]:
+        assert lib.chips_plan_init(C.byref(p), *bad, 32, 32, 20) == -1, bad
+    assert lib.chips_plan_init(None, 64, 64, 5, 10, 3, 4, 32, 32, 20) == -1
+
+
+def test_null_pointers_are_rejected_without_touching_the_gpu():
+    from pychips_b200 import _lib
+    lib = _lib.load()
+    p = _lib.Plan()
+    lib.chips_plan_init(C.byref(p), 64, 64, 5, 10, 3, 4, 32, 32, 20)
+    assert lib.chips_medfilt2d(None, None, C.byref(p), 32, 32, 20, None, None) == -1
+    assert lib.chips_histogram(None, C.byref(p), 32, 32, 20, None, None) == -1
+    assert lib.chips_threshold_prob(None, C.byref(p), 32, 32, 20, 0.8, None, None) == -1
+    assert lib.chips_cleanup(C.byref(p), 32, 32, 20, 1.0, 1e-3, None, None) == -1
+    assert lib.chips_detect(None, C.byref(p), 32, 32, 20, 5.0, float("nan"), 0, 3, 0.8, 1e-3,
+                            None, None, None) == -1
+    assert lib.chips_select_threshold(C.byref(p), 5.0, float("nan"), 0, 7, None, None) == -1
+    assert lib.chips_medfilt2d_bruteforce(None, None, 8, 8, 3, 4, 0, 0, -1, None) == -1
