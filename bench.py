@@ -30,7 +30,7 @@ UNIT = "images/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4, help="images per GPU per step")
@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--t1", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=2)
+    ap.add_argument("--streams", type=int, default=4)
     return ap.parse_args()
 
 
@@ -53,22 +53,56 @@ def workload(a):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region (NVML, ~2 ms period;
+    falls back to polling nvidia-smi)."""
+    R_NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
-        self.index, self.samples, self._stop, self._th = index, [], threading.Event(), None
+        self.index, self.sm, self.mx, self.reasons = index, [], [], set()
+        self._stop, self._th, self._h, self._nv = threading.Event(), None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self._nv = None
+
+    def _sample_nvml(self):
+        nv, h = self._nv, self._h
+        self.sm.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        self.mx.append(int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+        try:
+            bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        for bit, name in self.R_NAMES.items():
+            if bits & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+        v = [x.strip() for x in out.strip().split(",")]
+        if len(v) >= 6 and v[0].isdigit():
+            self.sm.append(int(v[0]))
+            self.mx.append(int(v[1]))
+            for name, flag in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                   "sw_power_cap"], v[2:6]):
+                if flag.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.samples.append([v.strip() for v in out.strip().split(",")])
+                self._sample_nvml() if self._nv else self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.002 if self._nv else 0.2)
 
     def __enter__(self):
         self._th = threading.Thread(target=self._run, daemon=True)
@@ -80,13 +114,10 @@ class ClockSampler:
         self._th.join(timeout=6)
 
     def summary(self):
-        sm = sorted(int(s[0]) for s in self.samples if len(s) >= 6 and s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if len(s) >= 6 and s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples if len(s) >= 6
-                          for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": "nvml" if self._nv else "nvidia-smi"}
 
 
 def measured_peak():
@@ -117,7 +148,7 @@ def run_reference(a):
     pool = mp.get_context("spawn").Pool(procs)
     try:
         outs = None
-        for _ in range(a.warmup):
+        for _ in range(min(a.warmup, 1)):     # one untimed pass warms the worker pool / page cache
             ct.pool_throughput(a.n, a.k, a.h_bins, tr, procs, band_rows=8, thr_sample=1, pool=pool)
         t0 = time.perf_counter()
         vals = []
@@ -140,7 +171,7 @@ def run_reference(a):
         "note": "oracle port of the reference CPU path (numpy/scipy/OpenCV), extrapolated from a "
                 "bounded per-image sample; the reference is single-threaded so cores = processes",
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------- CUDA arm
@@ -323,15 +354,25 @@ def run_b200(a):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        _emit(line)
 
 
 def main():
     a = parse()
+    # exactly ONE line on stdout: route everything else (NCCL banners, warnings from child
+    # libraries) to stderr and keep the real stdout for the JSON line
+    real_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    global _emit
+    _emit = lambda line: (real_out.write(json.dumps(line) + "\n"), real_out.flush())
     if a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)
+
+
+_emit = lambda line: print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

@@ -59,6 +59,23 @@ __device__ __forceinline__ bool on_disk(int x, int y, int cx, int cy, int r) {
   return dx * dx + dy * dy <= (long long)r * (long long)r;
 }
 
+// on-disk columns [xa, xb) of image row y inside the ROI columns [rx0, rx0+rw); false if none
+__device__ __forceinline__ bool row_chord(int y, int cx, int cy, int r, int rx0, int rw, int& xa,
+                                          int& xb) {
+  xa = rx0;
+  xb = rx0 + rw;
+  if (r < 0) return true;
+  long long dy = y - cy;
+  long long rem = (long long)r * r - dy * dy;
+  if (rem < 0) return false;
+  long long dx = (long long)sqrt((double)rem);
+  while ((dx + 1) * (dx + 1) <= rem) ++dx;
+  while (dx * dx > rem) --dx;
+  xa = max(xa, cx - (int)dx);
+  xb = min(xb, cx + (int)dx + 1);
+  return xa < xb;
+}
+
 // np.linspace edge i (fp64, multiply THEN add, never fused), last edge forced to `last`
 __device__ __forceinline__ double linspace_edge(int i, int nbins, double first, double last,
                                                 double step) {

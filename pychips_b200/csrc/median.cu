@@ -296,16 +296,19 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
     typename Key<T>::type* __restrict__ minmax, int* __restrict__ err, uint32_t* __restrict__ dbg) {
   using K = typename Key<T>::type;
   constexpr int NT = kTile * kTile;
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  K* skey = reinterpret_cast<K*>(smem_raw);                                   // [RS*RS]
-  uint16_t* cpos = reinterpret_cast<uint16_t*>(smem_raw + (size_t)cap * sizeof(K));   // [cap]
-  uint8_t* sbyte = smem_raw + (size_t)cap * (sizeof(K) + sizeof(uint16_t));   // [RS*RS]
+  K* skey = reinterpret_cast<K*>(smem_raw);                                     // [RS*RS] keys
+  uint16_t* rsg = reinterpret_cast<uint16_t*>(smem_raw + (size_t)cap * sizeof(K));   // [RS*RS] sub-group of a region pixel
+  uint16_t* cpos = rsg + cap;      // [C] candidate positions grouped by sub-group (unsorted)
+  uint16_t* csg = cpos + cap;      // [C] sub-group of a candidate
+  uint16_t* spos = rsg;            // [C] candidate positions, fully sorted (aliases rsg)
   __shared__ uint32_t need[8], needpfx[9];
   __shared__ uint16_t glut[kBuckets];          // bucket -> group (0xFFFF: not needed by this tile)
   __shared__ K gklo[kBuckets];
   __shared__ uint8_t gshift[kBuckets];
   __shared__ uint32_t sgstart[kMaxSub], sgcur[kMaxSub];
-  __shared__ uint32_t wsum[NT / 32];
+  __shared__ uint32_t wsum[NW];
   __shared__ int nactive;
 #ifdef CHIPS_DEBUG_TIMING
   long long t_0 = clock64(), t_1 = 0, t_2 = 0;
@@ -331,29 +334,6 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
   }
   __syncthreads();
   if (nactive == 0) return;
-
-  // ---- b. stage the region: warp w takes rows w, w+8, ...; lanes take columns (coalesced)
-  const int RS = kTile + 2 * half;
-  {
-    const bool interior = (X0 - half >= 0) && (Y0 - half >= 0) && (X0 - half + RS <= W) &&
-                          (Y0 - half + RS <= H);
-    for (int ry = warp; ry < RS; ry += NT / 32) {
-      const uint8_t* brow = Bp + (size_t)(Y0 + ry) * pitch + X0;
-      const int iy = Y0 + ry - half;
-      const T* irow = img + ((long long)iy * W + (X0 - half));
-      for (int rx = lane; rx < RS; rx += 32) {
-        T v;
-        if (interior) {
-          v = irow[rx];
-        } else {
-          int ix = X0 + rx - half;
-          v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? irow[rx] : (T)0;
-        }
-        sbyte[ry * RS + rx] = brow[rx];
-        skey[ry * RS + rx] = Key<T>::enc(v);
-      }
-    }
-  }
   if (tid < 9) {
     uint32_t p = 0;
     for (int i = 0; i < tid; ++i) p += __popc(need[i]);
@@ -364,6 +344,7 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
   // digits per group: 16 unless the tile needs so many buckets that groups*16 > kMaxSub
   const int dlog = ngroups <= kMaxSub / 16 ? 4 : (ngroups <= kMaxSub / 8 ? 3 : 2);
   const int nsg = ngroups << dlog;
+  const int ndm1 = (1 << dlog) - 1;
   {   // key range of bucket `tid` -> digit shift of its group; clear the sub-group counters
     const int b = tid;
     uint16_t gl = 0xFFFF;
@@ -381,95 +362,113 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
   }
   __syncthreads();
 
-  // ---- c. count, prefix, scatter (all from shared memory)
-  const int ndm1 = (1 << dlog) - 1;
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    for (int ry = ty; ry < RS; ry += kTile) {
-      for (int rx = tx; rx < RS; rx += kTile) {
-        const int ri = ry * RS + rx;
-        const int g = glut[sbyte[ri]];
-        if (g != 0xFFFF) {
-          K dg = (skey[ri] - gklo[g]) >> gshift[g];
-          int sg = (g << dlog) + (int)(dg < (K)ndm1 ? dg : (K)ndm1);
-          if (pass == 0) {
-            atomicAdd(&sgstart[sg], 1u);
+  // ---- b. stage the region (warp w: rows w, w+8, ...; lanes: columns -> coalesced) and
+  //         count the members of every sub-group.  The loads of a row are issued together and
+  //         the next row is prefetched before the current one is consumed.
+  const int RS = kTile + 2 * half;
+  {
+    const bool interior = (X0 - half >= 0) && (Y0 - half >= 0) && (X0 - half + RS <= W) &&
+                          (Y0 - half + RS <= H);
+    constexpr int MAXC = (kTile + CHIPS_MAX_K - 1 + 31) / 32;   // column chunks per row (<= 3)
+    T v[MAXC], vn[MAXC];
+    int bb[MAXC], bn[MAXC];
+    auto load_row = [&](int ry, T* vv, int* bv) {
+      const uint8_t* brow = Bp + (size_t)(Y0 + ry) * pitch + X0;
+      const int iy = Y0 + ry - half;
+      const T* irow = img + ((long long)iy * W + (X0 - half));
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const int rx = lane + 32 * c;
+        if (rx < RS) {
+          if (interior) {
+            vv[c] = irow[rx];
           } else {
-            uint32_t slot = atomicAdd(&sgcur[sg], 1u);
-            cpos[slot] = (uint16_t)((ry << 8) | rx);
+            int ix = X0 + rx - half;
+            vv[c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? irow[rx] : (T)0;
           }
+          bv[c] = brow[rx];
         }
       }
-    }
-    __syncthreads();
-    if (pass == 0) {    // exclusive scan of the nsg counters (contiguous chunk per thread)
-      const int per = (nsg + NT - 1) / NT;
-      const int lo = tid * per, hi = min(lo + per, nsg);
-      uint32_t s = 0;
-      for (int i = lo; i < hi; ++i) s += sgstart[i];
-      uint32_t inc = s;
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc += n;
+    };
+    if (warp < RS) load_row(warp, v, bb);
+    for (int ry = warp; ry < RS; ry += NW) {
+      if (ry + NW < RS) load_row(ry + NW, vn, bn);
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c) {
+        const int rx = lane + 32 * c;
+        if (rx < RS) {
+          const int ri = ry * RS + rx;
+          K key = Key<T>::enc(v[c]);
+          skey[ri] = key;
+          const int g = glut[bb[c]];
+          uint16_t sg = 0xFFFF;
+          if (g != 0xFFFF) {
+            K dg = (key - gklo[g]) >> gshift[g];
+            sg = (uint16_t)((g << dlog) + (int)(dg < (K)ndm1 ? dg : (K)ndm1));
+            atomicAdd(&sgstart[sg], 1u);
+          }
+          rsg[ri] = sg;
+        }
+        v[c] = vn[c];
+        bb[c] = bn[c];
       }
-      if (lane == 31) wsum[warp] = inc;
-      __syncthreads();
-      uint32_t base = 0;
-      for (int wv = 0; wv < warp; ++wv) base += wsum[wv];
-      uint32_t run = base + inc - s;
-      for (int i = lo; i < hi; ++i) {
-        uint32_t c = sgstart[i];
-        sgstart[i] = run;
-        sgcur[i] = run;
-        run += c;
-      }
-      __syncthreads();
     }
   }
+  __syncthreads();
+  {   // exclusive scan of the nsg counters (contiguous chunk per thread)
+    const int per = (nsg + NT - 1) / NT;
+    const int lo = tid * per, hi = min(lo + per, nsg);
+    uint32_t s = 0;
+    for (int i = lo; i < hi; ++i) s += sgstart[i];
+    uint32_t inc = s;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int wv = 0; wv < warp; ++wv) base += wsum[wv];
+    uint32_t run = base + inc - s;
+    for (int i = lo; i < hi; ++i) {
+      uint32_t c = sgstart[i];
+      sgstart[i] = run;
+      sgcur[i] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  // ---- c. scatter candidate positions into their sub-groups
+  for (int ry = ty; ry < RS; ry += kTile) {
+    for (int rx = tx; rx < RS; rx += kTile) {
+      const unsigned sg = rsg[ry * RS + rx];
+      if (sg != 0xFFFFu) {
+        uint32_t slot = atomicAdd(&sgcur[sg], 1u);
+        cpos[slot] = (uint16_t)((ry << 8) | rx);
+        csg[slot] = (uint16_t)sg;
+      }
+    }
+  }
+  __syncthreads();
 #ifdef CHIPS_DEBUG_TIMING
   t_1 = clock64();
 #endif
   auto key_at = [&](unsigned p) -> K { return skey[(p >> 8) * RS + (p & 255u)]; };
+  const int C = (int)sgcur[nsg - 1];
 
-  // ---- d. finish the sort inside each sub-group, one warp per sub-group
-  for (int sg = warp; sg < nsg; sg += NT / 32) {
-    const int s0 = (int)sgstart[sg], n = (int)sgcur[sg] - s0;
-    if (n <= 1) continue;
-    if (n <= 32) {
-      uint16_t pos = (lane < n) ? cpos[s0 + lane] : (uint16_t)0;
-      K key = (lane < n) ? key_at(pos) : Key<T>::kMax;
-      int rank = 0;
-      for (int j = 0; j < n; ++j) {
-        K o = __shfl_sync(0xFFFFFFFFu, key, j);
-        rank += (o < key || (o == key && j < lane)) ? 1 : 0;
-      }
-      __syncwarp();
-      if (lane < n) cpos[s0 + rank] = pos;
-    } else {
-      K mn = Key<T>::kMax, mx = 0;
-      for (int i = lane; i < n; i += 32) {
-        K v = key_at(cpos[s0 + i]);
-        mn = v < mn ? v : mn;
-        mx = v > mx ? v : mx;
-      }
-      for (int o = 16; o > 0; o >>= 1) {
-        K a = __shfl_xor_sync(0xFFFFFFFFu, mn, o), b2 = __shfl_xor_sync(0xFFFFFFFFu, mx, o);
-        mn = a < mn ? a : mn;
-        mx = b2 > mx ? b2 : mx;
-      }
-      if (mn != mx) {   // many distinct keys in one digit of a bucket -> odd-even transposition
-        for (int ph = 0; ph < n; ++ph) {
-          for (int i = (ph & 1) + 2 * lane; i + 1 < n; i += 64) {
-            uint16_t pa = cpos[s0 + i], pb = cpos[s0 + i + 1];
-            if (key_at(pa) > key_at(pb)) {
-              cpos[s0 + i] = pb;
-              cpos[s0 + i + 1] = pa;
-            }
-          }
-          __syncwarp();
-        }
-      }
+  // ---- d. finish the sort: every candidate finds its rank inside its sub-group (rsg is dead
+  //         from here on; spos aliases it)
+  for (int e = tid; e < C; e += NT) {
+    const unsigned sg = csg[e];
+    const int s0 = (int)sgstart[sg], s1 = (int)sgcur[sg];
+    const unsigned p = cpos[e];
+    const K key = key_at(p);
+    int rank = s0;
+    for (int j = s0; j < s1; ++j) {
+      const K o = key_at(cpos[j]);
+      rank += (o < key || (o == key && j < e)) ? 1 : 0;
     }
+    spos[rank] = (uint16_t)p;
   }
   __syncthreads();
 #ifdef CHIPS_DEBUG_TIMING
@@ -490,7 +489,7 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
     int left = end - beg;
     int cnt = 0, found = -1;
     for (; left >= 4; left -= 4, i += 4 * step) {
-      unsigned p0 = cpos[i], p1 = cpos[i + step], p2 = cpos[i + 2 * step], p3 = cpos[i + 3 * step];
+      unsigned p0 = spos[i], p1 = spos[i + step], p2 = spos[i + 2 * step], p3 = spos[i + 3 * step];
       int c0 = in_window(p0, bias, win), c1 = in_window(p1, bias, win);
       int c2 = in_window(p2, bias, win), c3 = in_window(p3, bias, win);
       int c = c0 + c1 + c2 + c3;
@@ -508,7 +507,7 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
     }
     if (found < 0) {
       for (; left > 0; --left, i += step) {
-        if (in_window(cpos[i], bias, win)) {
+        if (in_window(spos[i], bias, win)) {
           if (cnt == want) {
             found = i;
             break;
@@ -519,7 +518,7 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
     }
     K res;
     if (found >= 0) {
-      res = key_at(cpos[found]);
+      res = key_at(spos[found]);
     } else {                                   // inconsistent tier-1 data: must never happen
       atomicAdd(err, 1);
       res = Key<T>::enc((T)0);
@@ -548,7 +547,7 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
     d[0] = (uint32_t)(t_1 - t_0);
     d[1] = (uint32_t)(t_2 - t_1);
     d[2] = (uint32_t)(t_3 - t_2);
-    d[3] = (uint32_t)sgcur[nsg - 1];     // number of candidates
+    d[3] = (uint32_t)C;
   }
 #endif
 }
@@ -682,7 +681,7 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
   }
   if (stages & 8) {  // tier 2
     int cap = refine_cap(k);
-    size_t smem = (size_t)cap * (sizeof(K) + sizeof(uint16_t) + 1);
+    size_t smem = (size_t)cap * (sizeof(K) + 3 * sizeof(uint16_t));
     CHIPS_CUDA(cudaFuncSetAttribute(k_refine<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((rw + kTile - 1) / kTile, (rh + kTile - 1) / kTile);
     k_refine<T><<<grid, kTile * kTile, smem, st>>>(in, Bp, p->bp_pitch, bstar, rres, bounds, H, W,

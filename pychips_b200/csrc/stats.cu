@@ -52,6 +52,19 @@ __global__ void __launch_bounds__(256) k_minmax(const T* __restrict__ filt, int 
 }
 
 // ------------------------------------------------------------------ histogram
+// numpy's bin of v: trunc(((v-first)/denom)*nbins) then at most one step down / up against the
+// linspace edges.  Since that guess is within one bin of the bin whose edges bracket v, the
+// result IS the bracketing bin; we reach the same bin from a cheap fp32 guess and exact fp64
+// edge comparisons (no fp64 divide per pixel).
+__device__ __forceinline__ int hist_bin(double v, int nbins, double first, double last, double step,
+                                        float first_f, float scale_f) {
+  int g = (int)(((float)v - first_f) * scale_f);
+  g = min(max(g, 0), nbins - 1);
+  while (g > 0 && v < linspace_edge(g, nbins, first, last, step)) --g;
+  while (g < nbins - 1 && v >= linspace_edge(g + 1, nbins, first, last, step)) ++g;
+  return g;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_hist(const T* __restrict__ filt, int W, int rx0, int ry0,
                                               int rw, int rh, int cx, int cy, int r,
@@ -83,17 +96,33 @@ __global__ void __launch_bounds__(256) k_hist(const T* __restrict__ filt, int W,
   }
   const double denom = __dsub_rn(last, first);
   const double step = __ddiv_rn(denom, (double)nbins);
+  const float first_f = (float)first, scale_f = (float)((double)nbins / denom);
   uint32_t* mine = sh + ((threadIdx.x >> 5) % copies) * nbins;
   for (int y = ry0 + blockIdx.x; y < ry0 + rh; y += gridDim.x) {
-    for (int x = rx0 + threadIdx.x; x < rx0 + rw; x += blockDim.x) {
-      if (!on_disk(x, y, cx, cy, r)) continue;
-      double v = (double)filt[(size_t)y * W + x];
-      double f = __dmul_rn(__ddiv_rn(__dsub_rn(v, first), denom), (double)nbins);
-      int idx = (int)f;                       // astype(intp): truncation
-      if (idx == nbins) idx -= 1;
-      if (v < linspace_edge(idx, nbins, first, last, step)) idx -= 1;
-      if (idx != nbins - 1 && v >= linspace_edge(idx + 1, nbins, first, last, step)) idx += 1;
-      atomicAdd(&mine[idx], 1u);
+    int xa, xb;
+    if (!row_chord(y, cx, cy, r, rx0, rw, xa, xb)) continue;
+    const T* row = filt + (size_t)y * W;
+    for (int x = (xa & ~3) + 4 * (int)threadIdx.x; x < xb; x += 4 * (int)blockDim.x) {
+      int idx[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int xi = x + i;
+        idx[i] = (xi >= xa && xi < xb)
+                     ? hist_bin((double)row[xi], nbins, first, last, step, first_f, scale_f) : -1;
+      }
+      // neighbouring pixels of the median-filtered image mostly share a bin: merge first
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (idx[i] < 0) continue;
+        unsigned c = 1;
+#pragma unroll
+        for (int j = i + 1; j < 4; ++j)
+          if (idx[j] == idx[i]) {
+            ++c;
+            idx[j] = -1;
+          }
+        atomicAdd(&mine[idx[i]], c);
+      }
     }
   }
   __syncthreads();
@@ -230,31 +259,49 @@ __global__ void __launch_bounds__(256) k_threshold_prob(const T* __restrict__ fi
   __shared__ double slim[CHIPS_MAX_T];
   __shared__ uint32_t tab[(CHIPS_MAX_T + 1) * CHIPS_PROB_BINS];
   const int nT = res->n_thresholds;
-  const bool have = res->n_peaks > 0;
+  const bool have = res->n_peaks > 0 && nT > 0;
   for (int i = threadIdx.x; i < nT; i += blockDim.x) slim[i] = res->limits[i];
   for (int i = threadIdx.x; i < (nT + 1) * CHIPS_PROB_BINS; i += blockDim.x) tab[i] = 0;
   __syncthreads();
+  if (!have) return;                 // lev is pre-filled with T: no regions (chips.py:355)
   int t_inv = 0;                     // limits ascend: the ones < -1 are a prefix
   for (int t = 0; t < nT; ++t) t_inv += (slim[t] < -1.0) ? 1 : 0;
   const double limit_0 = res->limit_0;
-  const double top = have ? slim[nT - 1] : 0.0;
+  const double top = slim[nT - 1];
+  const bool vec = (W & 3) == 0;
   for (int y = ry0 + blockIdx.x; y < ry0 + rh; y += gridDim.x) {
-    for (int x = rx0 + threadIdx.x; x < rx0 + rw; x += blockDim.x) {
-      int level = nT;
-      if (have && on_disk(x, y, cx, cy, r)) {
-        double v = (double)filt[(size_t)y * W + x];
-        if (v <= top) {
-          level = 0;
-          for (int t = 0; t < nT; ++t) level += (slim[t] < v) ? 1 : 0;   // first t with v <= lim_t
-          double d = __dsub_rn(v, limit_0);
-          int bin = 0;
+    int xa, xb;
+    if (!row_chord(y, cx, cy, r, rx0, rw, xa, xb)) continue;
+    const T* row = filt + (size_t)y * W;
+    uint8_t* lrow = lev + (size_t)y * W;
+    for (int x = (xa & ~3) + 4 * (int)threadIdx.x; x < xb; x += 4 * (int)blockDim.x) {
+      uint32_t packed = 0;
 #pragma unroll
-          for (int j = 1; j < CHIPS_PROB_BINS; ++j) bin += (d <= kProbCut[j]) ? 1 : 0;
-          atomicAdd(&tab[level * CHIPS_PROB_BINS + bin], 1u);
-          level = max(level, t_inv);             // chips.py:372-374: lim < -1 wipes the mask
+      for (int i = 0; i < 4; ++i) {
+        int xi = x + i;
+        int level = nT;
+        if (xi >= xa && xi < xb) {
+          double v = (double)row[xi];
+          if (v <= top) {
+            level = 0;
+            for (int t = 0; t < nT; ++t) level += (slim[t] < v) ? 1 : 0;   // first t with v <= lim_t
+            double d = __dsub_rn(v, limit_0);
+            int bin = 0;
+#pragma unroll
+            for (int j = 1; j < CHIPS_PROB_BINS; ++j) bin += (d <= kProbCut[j]) ? 1 : 0;
+            atomicAdd(&tab[level * CHIPS_PROB_BINS + bin], 1u);
+            level = max(level, t_inv);             // chips.py:372-374: lim < -1 wipes the mask
+          }
         }
+        packed |= (uint32_t)level << (8 * i);
       }
-      lev[(size_t)y * W + x] = (uint8_t)level;
+      if (vec) {                      // bytes outside the chord carry T, the pre-filled value
+        *reinterpret_cast<uint32_t*>(lrow + x) = packed;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (x + i >= xa && x + i < xb) lrow[x + i] = (uint8_t)(packed >> (8 * i));
+      }
     }
   }
   __syncthreads();

@@ -2,6 +2,7 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+import pychips_b200.build as _b; _b.LIB = os.environ.get("CHIPS_LIB", _b.LIB)
 from pychips_b200 import engine, synth
 
 n, k = 4096, int(sys.argv[1]) if len(sys.argv) > 1 else 51
