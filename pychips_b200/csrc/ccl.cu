@@ -144,8 +144,17 @@ __global__ void __launch_bounds__(256) k_fill_pending(Roi g, const uint8_t* __re
     size_t o = (size_t)y * g.W + x;
     int l = lev[o];
     if (PASS == 0) {
-      if (l == T && uf_find(parent, g.li(x, y) + 1) == kBorder) Wimg[o] = (uint8_t)T;
-      else mylev = l;
+      if (l == T) {
+        // flatten: every bulk pixel points straight at its root, so the finds of the later
+        // rounds (which mostly hit bulk neighbours) are one hop
+        const uint32_t me = g.li(x, y) + 1;
+        const uint32_t root = uf_find(parent, me);
+        if (root != me) parent[me] = root;
+        if (root == kBorder) Wimg[o] = (uint8_t)T;
+        else mylev = l;
+      } else {
+        mylev = l;
+      }
     } else {
       if (!(l == T && Wimg[o] == T)) mylev = l;
     }
@@ -185,7 +194,9 @@ __global__ void k_fill_offsets(int T, uint32_t* __restrict__ lvl_count,
   }
 }
 
-// Round t (descending): the pending pixels of level t+1 join the background.
+// Round t (descending): the pending pixels of level t+1 join the background.  The roots of
+// the pixel and of its (up to 5) union partners are chased together so the dependent global
+// loads of the finds overlap; the hooks themselves go through uf_unite.
 __global__ void __launch_bounds__(256) k_fill_round_union(Roi g, const uint8_t* __restrict__ lev, int t,
                                                           const uint32_t* __restrict__ lvl_offset,
                                                           const uint32_t* __restrict__ pending,
@@ -198,11 +209,28 @@ __global__ void __launch_bounds__(256) k_fill_round_union(Roi g, const uint8_t* 
     uint32_t me = li + 1;
     int l_l = level_at(g, lev, x - 1, y), l_r = level_at(g, lev, x + 1, y);
     int l_u = level_at(g, lev, x, y - 1), l_d = level_at(g, lev, x, y + 1);
-    if (l_l < 0 || l_r < 0 || l_u < 0 || l_d < 0) uf_unite(parent, me, kBorder);
-    if (l_l >= lv) uf_unite(parent, me, me - 1u);
-    if (l_u >= lv) uf_unite(parent, me, me - (uint32_t)g.w);
-    if (l_r > lv) uf_unite(parent, me, me + 1u);
-    if (l_d > lv) uf_unite(parent, me, me + (uint32_t)g.w);
+    uint32_t node[5];
+    bool use[5];
+    use[0] = (l_l < 0 || l_r < 0 || l_u < 0 || l_d < 0); node[0] = kBorder;
+    use[1] = l_l >= lv;  node[1] = me - 1u;
+    use[2] = l_u >= lv;  node[2] = me - (uint32_t)g.w;
+    use[3] = l_r > lv;   node[3] = me + 1u;
+    use[4] = l_d > lv;   node[4] = me + (uint32_t)g.w;
+    if (!(use[0] | use[1] | use[2] | use[3] | use[4])) continue;
+    uint32_t rm = me;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) if (!use[j]) node[j] = me;
+    for (int hop = 0; hop < 64; ++hop) {        // bounded: uf_unite finishes whatever is left
+      uint32_t pm = parent[rm], p0 = parent[node[0]], p1 = parent[node[1]], p2 = parent[node[2]],
+               p3 = parent[node[3]], p4 = parent[node[4]];
+      bool done = (pm == rm) & (p0 == node[0]) & (p1 == node[1]) & (p2 == node[2]) &
+                  (p3 == node[3]) & (p4 == node[4]);
+      rm = pm; node[0] = p0; node[1] = p1; node[2] = p2; node[3] = p3; node[4] = p4;
+      if (done) break;
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+      if (use[j] && node[j] != rm) uf_unite(parent, rm, node[j]);
   }
 }
 
@@ -337,7 +365,10 @@ __global__ void __launch_bounds__(256) k_ccl_area(Roi g, const uint8_t* __restri
       int sa = 1 + (int)r_ + (int)d_ + (int)dr;
       add = (sa == 4) ? 2u : (sa == 3 ? 1u : 0u);
       if (d_ && !fg_at(g, Wimg, t, x - 1, y) && fg_at(g, Wimg, t, x - 1, y + 1)) add += 1u;
-      if (add) root = uf_find(parent, g.li(x, y));
+      // flatten while we are here: stats / keep / roots then find every root in one hop
+      const uint32_t me = g.li(x, y);
+      root = uf_find(parent, me);
+      if (root != me) parent[me] = root;
     }
     unsigned active = __ballot_sync(0xFFFFFFFFu, add != 0);
     if (add) {      // warp-aggregate per root before the global atomic

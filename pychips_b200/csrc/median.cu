@@ -144,65 +144,79 @@ struct RowReader {
   }
 };
 
+// number of the 4 bytes of w that are < m (m in 0..255), branch-free SWAR: the low 7 bits are
+// compared through a borrow-free subtraction, the top bits by boolean algebra.
+__device__ __forceinline__ int count_bytes_below(uint32_t w, uint32_t m4, uint32_t m4lo) {
+  const uint32_t Hm = 0x80808080u;
+  uint32_t t = ((w & ~Hm) | Hm) - m4lo;           // bit 7 of each byte: (w&0x7f) >= (m&0x7f)
+  uint32_t lt = ((~w & m4) | (~(w ^ m4) & ~t)) & Hm;
+  return __popc(lt);
+}
+
 // +1 for two entering elements; the two read-modify-writes are issued together (the loads
-// are independent) unless both hit the same bin.
-__device__ __forceinline__ void huang_add2(uint16_t* __restrict__ my, int a, int b, int med, int& lt) {
+// are independent); if both hit the same bin the second store (program order) carries the +2.
+__device__ __forceinline__ void huang_add2(uint16_t* __restrict__ my, int a, int b) {
   constexpr int NT = kHuangThreads;
   uint16_t* pa = my + a * NT;
   uint16_t* pb = my + b * NT;
-  // branch-free: both loads first; if a == b the second store (same address, program order)
-  // wins and carries the +2
   uint16_t ca = *pa, cb = *pb;
-  *pa = (uint16_t)(ca + 1);
-  *pb = (uint16_t)(cb + 1 + (a == b));
-  lt += (a < med) + (b < med);
+  uint16_t na = (uint16_t)(ca + 1);
+  *pa = na;
+  *pb = (uint16_t)((a == b ? na : cb) + 1);
 }
-__device__ __forceinline__ void huang_add1(uint16_t* __restrict__ my, int a, int med, int& lt) {
+__device__ __forceinline__ void huang_add1(uint16_t* __restrict__ my, int a) {
   uint16_t* pa = my + a * kHuangThreads;
   *pa = (uint16_t)(*pa + 1);
-  lt += (a < med);
 }
-// +1 for the entering element a, -1 for the leaving element b
-__device__ __forceinline__ void huang_swap(uint16_t* __restrict__ my, int a, int b, int med, int& lt) {
+// +1 for the entering element a, -1 for the leaving element b (a == b: net zero, the second
+// store writes the original count back)
+__device__ __forceinline__ void huang_swap(uint16_t* __restrict__ my, int a, int b) {
   constexpr int NT = kHuangThreads;
-  // branch-free: if a == b both stores write the unchanged count back
   uint16_t* pa = my + a * NT;
   uint16_t* pb = my + b * NT;
   uint16_t ca = *pa, cb = *pb;
-  int d = (a != b);
-  *pa = (uint16_t)(ca + d);
-  *pb = (uint16_t)(cb - d);
-  lt += (a < med) - (b < med);
+  uint16_t na = (uint16_t)(ca + 1);
+  *pa = na;
+  *pb = (uint16_t)((a == b ? na : cb) - 1);
 }
 
 __device__ __forceinline__ void huang_add_row(uint16_t* __restrict__ my, const uint8_t* row, int k,
                                               int med, int& lt) {
   RowReader rd(row);
-  int j = 0;
+  const uint32_t m4 = (uint32_t)med * 0x01010101u, m4lo = m4 & 0x7F7F7F7Fu;
+  int j = 0, acc = 0;
   for (; j + 4 <= k; j += 4) {
     uint32_t v = rd.next(j >> 2);
-    huang_add2(my, v & 255, (v >> 8) & 255, med, lt);
-    huang_add2(my, (v >> 16) & 255, v >> 24, med, lt);
+    acc += count_bytes_below(v, m4, m4lo);
+    huang_add2(my, v & 255, (v >> 8) & 255);
+    huang_add2(my, (v >> 16) & 255, v >> 24);
   }
   if (j < k) {
     uint32_t v = rd.next(j >> 2);
-    for (int i = 0; i < k - j; ++i) huang_add1(my, (v >> (8 * i)) & 255, med, lt);
+    acc += count_bytes_below(v | (0xFFFFFFFFu << (8 * (k - j))), m4, m4lo);
+    for (int i = 0; i < k - j; ++i) huang_add1(my, (v >> (8 * i)) & 255);
   }
+  lt += acc;
 }
 
 __device__ __forceinline__ void huang_swap_row(uint16_t* __restrict__ my, const uint8_t* add,
                                                const uint8_t* rem, int k, int med, int& lt) {
   RowReader ra(add), rb(rem);
-  int j = 0;
+  const uint32_t m4 = (uint32_t)med * 0x01010101u, m4lo = m4 & 0x7F7F7F7Fu;
+  int j = 0, acc = 0;
   for (; j + 4 <= k; j += 4) {
     uint32_t va = ra.next(j >> 2), vb = rb.next(j >> 2);
+    acc += count_bytes_below(va, m4, m4lo) - count_bytes_below(vb, m4, m4lo);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) huang_swap(my, (va >> (8 * i)) & 255, (vb >> (8 * i)) & 255, med, lt);
+    for (int i = 0; i < 4; ++i) huang_swap(my, (va >> (8 * i)) & 255, (vb >> (8 * i)) & 255);
   }
   if (j < k) {
     uint32_t va = ra.next(j >> 2), vb = rb.next(j >> 2);
-    for (int i = 0; i < k - j; ++i) huang_swap(my, (va >> (8 * i)) & 255, (vb >> (8 * i)) & 255, med, lt);
+    const uint32_t inval = 0xFFFFFFFFu << (8 * (k - j));
+    acc += count_bytes_below(va | inval, m4, m4lo) - count_bytes_below(vb | inval, m4, m4lo);
+    for (int i = 0; i < k - j; ++i) huang_swap(my, (va >> (8 * i)) & 255, (vb >> (8 * i)) & 255);
   }
+  lt += acc;
 }
 
 __global__ void __launch_bounds__(kHuangThreads) k_huang(const uint8_t* __restrict__ Bp, int pitch,
