@@ -72,6 +72,8 @@ class ClockSampler:
     def _sample_nvml(self):
         nv, h = self._nv, self._h
         self.sm.append(int(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        if len(self.sm) % 4 != 1:            # reasons / max clock: every 4th sample
+            return
         self.mx.append(int(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
         try:
             bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))

@@ -21,6 +21,7 @@
 //
 // k_median_brute is an independent per-thread radix-select used only as the at-scale
 // checker in the tests.
+#include <cuda_pipeline.h>
 #include <math.h>
 #include "common.cuh"
 
@@ -376,55 +377,47 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
   }
   __syncthreads();
 
-  // ---- b. stage the region (warp w: rows w, w+8, ...; lanes: columns -> coalesced) and
-  //         count the members of every sub-group.  The loads of a row are issued together and
-  //         the next row is prefetched before the current one is consumed.
+  // ---- b. stage the region with asynchronous global->shared copies (LDGSTS: every copy of the
+  //         tile is in flight at once, no registers held), then one shared-memory pass turns
+  //         values into ordered keys, looks up each pixel's sub-group and counts the members.
   const int RS = kTile + 2 * half;
+  const int bpitch = (RS + 6) & ~3;                 // staged bucket rows, word aligned
   {
+    T* sraw = reinterpret_cast<T*>(skey);           // raw values first, keys in place afterwards
+    uint8_t* sbyte = reinterpret_cast<uint8_t*>(csg);   // dead before csg is written
     const bool interior = (X0 - half >= 0) && (Y0 - half >= 0) && (X0 - half + RS <= W) &&
                           (Y0 - half + RS <= H);
-    constexpr int MAXC = (kTile + CHIPS_MAX_K - 1 + 31) / 32;   // column chunks per row (<= 3)
-    T v[MAXC], vn[MAXC];
-    int bb[MAXC], bn[MAXC];
-    auto load_row = [&](int ry, T* vv, int* bv) {
-      const uint8_t* brow = Bp + (size_t)(Y0 + ry) * pitch + X0;
+    const int bmis = X0 & 3;                        // bucket row starts at word (X0 & ~3)
+    const int bwords = (bmis + RS + 3) >> 2;
+    for (int ry = warp; ry < RS; ry += NW) {
       const int iy = Y0 + ry - half;
       const T* irow = img + ((long long)iy * W + (X0 - half));
-#pragma unroll
-      for (int c = 0; c < MAXC; ++c) {
-        const int rx = lane + 32 * c;
-        if (rx < RS) {
-          if (interior) {
-            vv[c] = irow[rx];
-          } else {
-            int ix = X0 + rx - half;
-            vv[c] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? irow[rx] : (T)0;
-          }
-          bv[c] = brow[rx];
-        }
+      for (int rx = lane; rx < RS; rx += 32) {
+        int ix = X0 + rx - half;
+        if (interior || (iy >= 0 && iy < H && ix >= 0 && ix < W))
+          __pipeline_memcpy_async(&sraw[ry * RS + rx], &irow[rx], sizeof(T));
+        else
+          sraw[ry * RS + rx] = (T)0;                // zero padding of medfilt2d
       }
-    };
-    if (warp < RS) load_row(warp, v, bb);
-    for (int ry = warp; ry < RS; ry += NW) {
-      if (ry + NW < RS) load_row(ry + NW, vn, bn);
-#pragma unroll
-      for (int c = 0; c < MAXC; ++c) {
-        const int rx = lane + 32 * c;
-        if (rx < RS) {
-          const int ri = ry * RS + rx;
-          K key = Key<T>::enc(v[c]);
-          skey[ri] = key;
-          const int g = glut[bb[c]];
-          uint16_t sg = 0xFFFF;
-          if (g != 0xFFFF) {
-            K dg = (key - gklo[g]) >> gshift[g];
-            sg = (uint16_t)((g << dlog) + (int)(dg < (K)ndm1 ? dg : (K)ndm1));
-            atomicAdd(&sgstart[sg], 1u);
-          }
-          rsg[ri] = sg;
+      const uint32_t* bw = reinterpret_cast<const uint32_t*>(Bp + (size_t)(Y0 + ry) * pitch + (X0 & ~3));
+      if (lane < bwords) __pipeline_memcpy_async(sbyte + ry * bpitch + 4 * lane, bw + lane, 4);
+    }
+    __pipeline_commit();
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    for (int ry = ty; ry < RS; ry += kTile) {
+      for (int rx = tx; rx < RS; rx += kTile) {
+        const int ri = ry * RS + rx;
+        K key = Key<T>::enc(sraw[ri]);
+        skey[ri] = key;
+        const int g = glut[sbyte[ry * bpitch + bmis + rx]];
+        uint16_t sg = 0xFFFF;
+        if (g != 0xFFFF) {
+          K dg = (key - gklo[g]) >> gshift[g];
+          sg = (uint16_t)((g << dlog) + (int)(dg < (K)ndm1 ? dg : (K)ndm1));
+          atomicAdd(&sgstart[sg], 1u);
         }
-        v[c] = vn[c];
-        bb[c] = bn[c];
+        rsg[ri] = sg;
       }
     }
   }
