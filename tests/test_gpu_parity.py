@@ -359,3 +359,97 @@ def test_full_size_4096_properties():
         assert np.all(maps[t] >= maps[t - 1])
     pr = fp.prob_from_counts(fp.prob_counts(filt[on], res.limit_0, lims))
     assert np.allclose(np.array(res.probs[:det.T]), pr, rtol=REL, atol=0, equal_nan=True)
+
+
+# ----------------------------------------------------------------------------- BASELINE configs
+def test_config4_synoptic_full_size_vs_oracle():
+    """BASELINE config 4: 3600x1440 Carrington map, defaults k=3, h_bins=5000, [-5,20]."""
+    from pychips_b200 import SynopticChips
+    img = synth.synthetic_synoptic(1440, 3600, 0)
+    s_or = synth.FakeSynoptic(img.astype(np.float64))
+    co.OracleSynopticChips().run(s_or)
+    s = synth.FakeSynoptic(img.astype(np.float64))
+    sc = SynopticChips(s, base_folder="/tmp/chips_b200_test/")
+    sc.run_CHIPS()
+    assert np.array_equal(s.solar_filter, s_or.solar_filter)
+    assert np.array_equal(s.histogram.hbase, s_or.histogram.hbase)
+    assert np.array_equal(np.array(s.histogram.peaks), np.array(s_or.histogram.peaks))
+    assert list(s.solar_ch_regions.__dict__) == list(s_or.solar_ch_regions.__dict__)
+    assert len(s.solar_ch_regions.__dict__) == 25
+    for k, ref in s_or.solar_ch_regions.__dict__.items():
+        got = s.solar_ch_regions.__dict__[k]
+        assert np.array_equal(got.map, ref.map), k
+        assert np.array_equal(got.prob, ref.prob, equal_nan=True), k
+    # the dark region crossing the 0/360 degree seam is detected on both edges
+    top = list(s.solar_ch_regions.__dict__.values())[-1].map
+    assert top[:, 0].sum() > 0 and top[:, -1].sum() > 0
+
+
+@pytest.mark.parametrize("k", [11, 31, 51, 71])
+def test_config5_sweep_kernel_sizes_16_thresholds(k):
+    """BASELINE config 5 (test_ROI_plots.py:72-76 kernels) x 16 thresholds [-3,13]."""
+    n = 320
+    img, r = synth.synthetic_disk(n, 50 + k)
+    d_or = synth.FakeDisk(img.astype(np.float64), r)
+    co.OracleChips(medfilt_kernel=k, h_bins=5000, threshold_range=[-3, 13]).run(d_or, keep_contours=False)
+    c, d = run_gpu_disk(img, r, medfilt_kernel=k, h_bins=5000, threshold_range=[-3, 13])
+    regs = list(d_or.solar_ch_regions.__dict__.values())
+    assert len(regs) == 16
+    compare_disk(d, d_or.solar_filter.filt_disk, d_or.histogram.hbase, d_or.histogram.hbins,
+                 d_or.histogram.bound, np.array(d_or.histogram.peaks), [x.lim for x in regs],
+                 [x.prob for x in regs], [x.raw_map.astype(np.uint8) for x in regs],
+                 [x.map.astype(np.uint8) for x in regs])
+
+
+def test_config3_time_series_runner_matches_single_image_path():
+    """BASELINE config 3 in miniature: drifting series with jittered radius through
+    SeriesRunner (2 streams, H2D per image) == the per-image Chips path; summed probability
+    map == sum of the per-image stacks."""
+    from pychips_b200 import series
+    n, k = 256, 11
+    imgs, radii = [], []
+    for i in range(5):
+        r = int(synth.pixel_radius_for(n) * (1.0 + 0.01 * ((i % 3) - 1)))
+        im, _ = synth.synthetic_disk(n, seed=i, radius=r, drift=0.5 * i)
+        imgs.append(im)
+        radii.append(r)
+    runner = series.SeriesRunner(n, n, k, 500, (0, 20), n_streams=2, want_maps=False)
+    res = runner.run([torch.from_numpy(im).pin_memory() for im in imgs], radii)
+    total = np.zeros((n, n))
+    for i, (im, r) in enumerate(zip(imgs, radii)):
+        c, d = run_gpu_disk(im, r, dtype=np.float32, medfilt_kernel=k)
+        regs = list(d.solar_ch_regions.__dict__.values())
+        assert np.array_equal(res.limits[i], [x.lim for x in regs])
+        assert np.array_equal(res.probs[i], [x.prob for x in regs], equal_nan=True)
+        K = np.full((n, n), len(regs), dtype=np.uint8)
+        for t in range(len(regs) - 1, -1, -1):
+            K[regs[t].map > 0] = t
+        assert np.array_equal(res.keep[i], K)
+        st = c.probability_map(d)
+        total += np.nan_to_num(st, nan=0.0)
+    assert np.allclose(res.prob_map_sum.cpu().numpy(), total, rtol=1e-5, atol=1e-6)
+
+
+def test_h_thresh_is_sticky_across_wavelengths():
+    """chips.py:240-241: the first disk's h_thresh is reused for later disks of the same Chips."""
+    from pychips_b200 import Chips
+    a, r = synth.synthetic_disk(256, 1)
+    b, _ = synth.synthetic_disk(256, 2)
+    d1 = synth.FakeDisk(a.astype(np.float64), r, wavelength=193)
+    d2 = synth.FakeDisk((b * 1.3).astype(np.float32).astype(np.float64), r, wavelength=211)
+    c = Chips(synth.FakeAIA([d1, d2]), base_folder="/tmp/chips_b200_test/", medfilt_kernel=11)
+    c.run_CHIPS()
+    o = co.OracleChips(medfilt_kernel=11)
+    e1 = synth.FakeDisk(a.astype(np.float64), r)
+    e2 = synth.FakeDisk((b * 1.3).astype(np.float32).astype(np.float64), r)
+    o.run(e1, keep_contours=False)
+    o.run(e2, keep_contours=False)
+    assert d1.histogram.h_thresh == e1.histogram.h_thresh == d2.histogram.h_thresh == e2.histogram.h_thresh
+    assert np.array_equal(np.array(d2.histogram.peaks), np.array(e2.histogram.peaks))
+    # memoisation: a second run is a no-op unless clear_prev_runs
+    before = d1.solar_ch_regions
+    c.run_CHIPS(193, 256)
+    assert d1.solar_ch_regions is before
+    c.run_CHIPS(193, 256, clear_prev_runs=True)
+    assert d1.solar_ch_regions is not before
+    assert list(d1.solar_ch_regions.__dict__) == list(before.__dict__)
