@@ -106,11 +106,8 @@ __device__ __forceinline__ int level_at(const Roi& g, const uint8_t* __restrict_
 }
 
 // B2: vertical + border unions of the bulk background (left edges are the run links).
-__global__ void __launch_bounds__(256) k_fill_bulk_union(Roi g, const uint8_t* __restrict__ lev, int T,
-                                                         uint32_t* __restrict__ parent) {
-  int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
-  int y = g.y0 + blockIdx.y;
-  if (x >= g.x0 + g.w) return;
+__device__ __forceinline__ void bulk_union_pixel(const Roi& g, const uint8_t* __restrict__ lev, int T,
+                                                 uint32_t* __restrict__ parent, int x, int y) {
   if (lev[(size_t)y * g.W + x] != T || !on_disk(x, y, g.cx, g.cy, g.r)) return;
   uint32_t me = g.li(x, y) + 1;
   int l_l = level_at(g, lev, x - 1, y), l_r = level_at(g, lev, x + 1, y);
@@ -119,6 +116,33 @@ __global__ void __launch_bounds__(256) k_fill_bulk_union(Roi g, const uint8_t* _
   if (l_u == T) {
     bool implied = (l_l == T) && (level_at(g, lev, x - 1, y - 1) == T);
     if (!implied) uf_unite(parent, me, me - (uint32_t)g.w);
+  }
+}
+
+// 4 pixels per thread.  Deep inside the quiet Sun nothing has to be done: if the 6x3 pixel
+// neighbourhood of the group is entirely bulk and entirely on the disk, every vertical edge
+// is implied by the row-run links and no pixel touches the border.
+__global__ void __launch_bounds__(256) k_fill_bulk_union(Roi g, const uint8_t* __restrict__ lev, int T,
+                                                         uint32_t* __restrict__ parent) {
+  const int x4 = (g.x0 & ~3) + 4 * (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int y = g.y0 + blockIdx.y;
+  if (x4 >= g.x0 + g.w) return;
+  if ((g.W & 3) == 0 && x4 >= g.x0 + 1 && x4 + 5 <= g.x0 + g.w && y > g.y0 && y + 1 < g.y0 + g.h) {
+    // the disk is convex: its 4 corners on-disk => the whole 6x3 box is
+    if (on_disk(x4 - 1, y - 1, g.cx, g.cy, g.r) && on_disk(x4 + 4, y - 1, g.cx, g.cy, g.r) &&
+        on_disk(x4 - 1, y + 1, g.cx, g.cy, g.r) && on_disk(x4 + 4, y + 1, g.cx, g.cy, g.r)) {
+      const uint32_t T4 = (uint32_t)T * 0x01010101u;
+      const uint8_t* c = lev + (size_t)y * g.W + x4;
+      const uint32_t cur = *reinterpret_cast<const uint32_t*>(c);
+      const uint32_t up = *reinterpret_cast<const uint32_t*>(c - g.W);
+      const uint32_t dn = *reinterpret_cast<const uint32_t*>(c + g.W);
+      if (cur == T4 && up == T4 && dn == T4 && c[-1] == T && c[4] == T && c[-g.W - 1] == T) return;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = x4 + i;
+    if (x >= g.x0 && x < g.x0 + g.w) bulk_union_pixel(g, lev, T, parent, x, y);
   }
 }
 
@@ -140,23 +164,32 @@ __global__ void __launch_bounds__(256) k_fill_pending(Roi g, const uint8_t* __re
   int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
   int y = g.y0 + blockIdx.y;
   int mylev = -1;
+  bool bulk = false;
   if (x < g.x0 + g.w && on_disk(x, y, g.cx, g.cy, g.r)) {
     size_t o = (size_t)y * g.W + x;
     int l = lev[o];
     if (PASS == 0) {
-      if (l == T) {
-        // flatten: every bulk pixel points straight at its root, so the finds of the later
-        // rounds (which mostly hit bulk neighbours) are one hop
-        const uint32_t me = g.li(x, y) + 1;
-        const uint32_t root = uf_find(parent, me);
-        if (root != me) parent[me] = root;
-        if (root == kBorder) Wimg[o] = (uint8_t)T;
-        else mylev = l;
-      } else {
-        mylev = l;
-      }
+      if (l == T) bulk = true;
+      else mylev = l;
     } else {
       if (!(l == T && Wimg[o] == T)) mylev = l;
+    }
+  }
+  if (PASS == 0) {
+    // bulk pixels of one row run share their root: the first lane of each run inside the warp's
+    // span finds it, the others copy it.  Everybody is flattened (later finds are one hop).
+    const int lane = threadIdx.x & 31;
+    const unsigned mb = __ballot_sync(0xFFFFFFFFu, bulk);
+    const unsigned z = ~mb & ((1u << lane) - 1u);
+    const int s = bulk ? (z ? (32 - __clz(z)) : 0) : lane;
+    uint32_t root = 0;
+    const uint32_t me = bulk ? g.li(x, y) + 1 : 0u;
+    if (bulk && s == lane) root = uf_find(parent, me);
+    root = __shfl_sync(0xFFFFFFFFu, root, s);
+    if (bulk) {
+      if (root != me) parent[me] = root;
+      if (root == kBorder) Wimg[(size_t)y * g.W + x] = (uint8_t)T;
+      else mylev = T;
     }
   }
   unsigned act = __ballot_sync(0xFFFFFFFFu, mylev >= 0);
@@ -294,49 +327,75 @@ __device__ __forceinline__ bool fg_at(const Roi& g, const uint8_t* __restrict__ 
          Wimg[(size_t)yy * g.W + xx] <= t;
 }
 
-__global__ void __launch_bounds__(256) k_ccl_link(Roi g, const uint8_t* __restrict__ Wimg, int tiles_x,
-                                                  const uint32_t* __restrict__ tile_count,
+// W of a pixel as an int, 255 (= never foreground) outside the ROI
+__device__ __forceinline__ int w_at(const Roi& g, const uint8_t* __restrict__ Wimg, int xx, int yy) {
+  return (xx >= g.x0 && xx < g.x0 + g.w && yy >= g.y0 && yy < g.y0 + g.h)
+             ? (int)Wimg[(size_t)yy * g.W + xx] : 255;
+}
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  return v;
+}
+
+// All T labellings in one sweep over the active tiles: every thread loads the W values it needs
+// ONCE and loops over the thresholds t >= W (a pixel is foreground from its W upwards).  The
+// loop variable is warp-uniform (starts at the smallest W of the warp's 32-pixel row span) so
+// the ballots / match_any inside see consistent participants.
+__global__ void __launch_bounds__(256) k_ccl_link(Roi g, const uint8_t* __restrict__ Wimg, int T,
+                                                  int tiles_x, const uint32_t* __restrict__ tile_count,
                                                   const uint32_t* __restrict__ tiles,
                                                   uint32_t* __restrict__ parent_all,
                                                   uint32_t* __restrict__ area_all) {
-  const int t = blockIdx.y;
   const size_t n = (size_t)g.w * g.h;
-  uint32_t* parent = parent_all + (size_t)t * n;
-  uint32_t* area = area_all + (size_t)t * n;
   const uint32_t nt = *tile_count;
+  const int lane = threadIdx.x & 31;
   for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
     TileCtx c = tile_pixel(g, tiles[i], tiles_x);
-    uint32_t me = c.valid ? g.li(c.x, c.y) : 0u;
-    bool fg = c.valid && Wimg[(size_t)c.y * g.W + c.x] <= t;
-    uint32_t tgt = row_run_target(g, c.x, c.y, c.valid, me,
-                                  [&](int xx, int yy) { return Wimg[(size_t)yy * g.W + xx] <= t; });
-    if (fg) {
-      parent[me] = tgt;
-      area[me] = 0;
+    const int w = c.valid ? (int)Wimg[(size_t)c.y * g.W + c.x] : 255;
+    int wl = 255;                                  // pixel left of the span (lane 0 only)
+    if (lane == 0) wl = w_at(g, Wimg, c.x - 1, c.y);
+    wl = __shfl_sync(0xFFFFFFFFu, wl, 0);
+    const uint32_t me = c.valid ? g.li(c.x, c.y) : 0u;
+    for (int t = warp_min(w); t < T; ++t) {
+      const bool act = w <= t;
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, act);
+      if (!act) continue;
+      const unsigned z = ~m & ((1u << lane) - 1u);
+      const int s = z ? (32 - __clz(z)) : 0;
+      uint32_t tgt = (s == 0 && wl <= t) ? me - (uint32_t)lane - 1u : me - (uint32_t)(lane - s);
+      parent_all[(size_t)t * n + me] = tgt;
+      area_all[(size_t)t * n + me] = 0;
     }
   }
 }
 
-__global__ void __launch_bounds__(256) k_ccl_union(Roi g, const uint8_t* __restrict__ Wimg, int tiles_x,
-                                                   const uint32_t* __restrict__ tile_count,
+__global__ void __launch_bounds__(256) k_ccl_union(Roi g, const uint8_t* __restrict__ Wimg, int T,
+                                                   int tiles_x, const uint32_t* __restrict__ tile_count,
                                                    const uint32_t* __restrict__ tiles,
                                                    uint32_t* __restrict__ parent_all) {
-  const int t = blockIdx.y;
-  uint32_t* parent = parent_all + (size_t)t * g.w * g.h;
+  const size_t n = (size_t)g.w * g.h;
   const uint32_t nt = *tile_count;
   for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
     TileCtx c = tile_pixel(g, tiles[i], tiles_x);
-    if (!c.valid || c.y == g.y0 || !fg_at(g, Wimg, t, c.x, c.y)) continue;
+    if (!c.valid || c.y == g.y0) continue;
     const int x = c.x, y = c.y;
-    uint32_t me = g.li(x, y);
-    bool up = fg_at(g, Wimg, t, x, y - 1), ul = fg_at(g, Wimg, t, x - 1, y - 1);
-    bool ur = fg_at(g, Wimg, t, x + 1, y - 1);
-    bool lf = fg_at(g, Wimg, t, x - 1, y), rt = fg_at(g, Wimg, t, x + 1, y);
-    if (up) {
-      if (!(lf && ul)) uf_unite(parent, me, me - (uint32_t)g.w);
-    } else {
-      if (ul && !lf) uf_unite(parent, me, me - (uint32_t)g.w - 1u);
-      if (ur && !rt) uf_unite(parent, me, me - (uint32_t)g.w + 1u);
+    const int w = Wimg[(size_t)y * g.W + x];
+    if (w >= T) continue;
+    const int wu = w_at(g, Wimg, x, y - 1), wul = w_at(g, Wimg, x - 1, y - 1);
+    const int wur = w_at(g, Wimg, x + 1, y - 1), wlf = w_at(g, Wimg, x - 1, y);
+    const int wrt = w_at(g, Wimg, x + 1, y);
+    if (min(wu, min(wul, wur)) >= T) continue;     // nothing above in any mask
+    const uint32_t me = g.li(x, y);
+    for (int t = w; t < T; ++t) {
+      uint32_t* parent = parent_all + (size_t)t * n;
+      const bool up = wu <= t, ul = wul <= t, ur = wur <= t, lf = wlf <= t, rt = wrt <= t;
+      if (up) {
+        if (!(lf && ul)) uf_unite(parent, me, me - (uint32_t)g.w);
+      } else {
+        if (ul && !lf) uf_unite(parent, me, me - (uint32_t)g.w - 1u);
+        if (ur && !rt) uf_unite(parent, me, me - (uint32_t)g.w + 1u);
+      }
     }
   }
 }
@@ -345,37 +404,44 @@ __global__ void __launch_bounds__(256) k_ccl_union(Roi g, const uint8_t* __restr
 // to its first set pixel in raster order, so only two quads per foreground pixel p matter:
 //   A = {p, right, down, down-right}              (p is the top-left pixel)
 //   B = {left, p, down-left, down} with left unset (p is the top-right pixel; s = 3 at most)
-__global__ void __launch_bounds__(256) k_ccl_area(Roi g, const uint8_t* __restrict__ Wimg, int tiles_x,
-                                                  const uint32_t* __restrict__ tile_count,
+__global__ void __launch_bounds__(256) k_ccl_area(Roi g, const uint8_t* __restrict__ Wimg, int T,
+                                                  int tiles_x, const uint32_t* __restrict__ tile_count,
                                                   const uint32_t* __restrict__ tiles,
                                                   uint32_t* __restrict__ parent_all,
                                                   uint32_t* __restrict__ area_all) {
-  const int t = blockIdx.y;
   const size_t n = (size_t)g.w * g.h;
-  uint32_t* parent = parent_all + (size_t)t * n;
-  uint32_t* area = area_all + (size_t)t * n;
   const uint32_t nt = *tile_count;
+  const int lane = threadIdx.x & 31;
   for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
     TileCtx c = tile_pixel(g, tiles[i], tiles_x);
-    uint32_t root = 0xFFFFFFFFu, add = 0;
-    if (c.valid && fg_at(g, Wimg, t, c.x, c.y)) {
-      const int x = c.x, y = c.y;
-      bool r_ = fg_at(g, Wimg, t, x + 1, y), d_ = fg_at(g, Wimg, t, x, y + 1);
-      bool dr = fg_at(g, Wimg, t, x + 1, y + 1);
-      int sa = 1 + (int)r_ + (int)d_ + (int)dr;
-      add = (sa == 4) ? 2u : (sa == 3 ? 1u : 0u);
-      if (d_ && !fg_at(g, Wimg, t, x - 1, y) && fg_at(g, Wimg, t, x - 1, y + 1)) add += 1u;
-      // flatten while we are here: stats / keep / roots then find every root in one hop
-      const uint32_t me = g.li(x, y);
-      root = uf_find(parent, me);
-      if (root != me) parent[me] = root;
+    const int x = c.x, y = c.y;
+    const int w = c.valid ? (int)Wimg[(size_t)y * g.W + x] : 255;
+    int wr = 255, wd = 255, wdr = 255, wl = 255, wdl = 255;
+    if (w < T) {
+      wr = w_at(g, Wimg, x + 1, y);
+      wd = w_at(g, Wimg, x, y + 1);
+      wdr = w_at(g, Wimg, x + 1, y + 1);
+      wl = w_at(g, Wimg, x - 1, y);
+      wdl = w_at(g, Wimg, x - 1, y + 1);
     }
-    unsigned active = __ballot_sync(0xFFFFFFFFu, add != 0);
-    if (add) {      // warp-aggregate per root before the global atomic
-      unsigned peers = __match_any_sync(active, root);
-      uint32_t sum = 0;
-      for (unsigned mm = peers; mm; mm &= mm - 1) sum += __shfl_sync(peers, add, __ffs(mm) - 1);
-      if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&area[root], sum);
+    const uint32_t me = c.valid ? g.li(x, y) : 0u;
+    for (int t = warp_min(w); t < T; ++t) {
+      uint32_t root = 0xFFFFFFFFu, add = 0;
+      if (w <= t) {
+        const int sa = 1 + (int)(wr <= t) + (int)(wd <= t) + (int)(wdr <= t);
+        add = (sa == 4) ? 2u : (sa == 3 ? 1u : 0u);
+        if (wd <= t && wl > t && wdl <= t) add += 1u;
+        // flatten while we are here: stats / keep / roots then find every root in one hop
+        uint32_t* parent = parent_all + (size_t)t * n;
+        root = uf_find(parent, me);
+        if (root != me) parent[me] = root;
+      }
+      const unsigned active = __ballot_sync(0xFFFFFFFFu, add != 0);
+      if (add) {      // warp-aggregate per root before the global atomic
+        const unsigned peers = __match_any_sync(active, root);
+        const uint32_t sum = __reduce_add_sync(peers, add);
+        if (lane == __ffs(peers) - 1) atomicAdd(&area_all[(size_t)t * n + root], sum);
+      }
     }
   }
 }
@@ -385,34 +451,43 @@ __device__ __forceinline__ bool area_kept(uint32_t a2, double disk_area, double 
   return __ddiv_rn(__dmul_rn((double)a2, 0.5), disk_area) >= thr;
 }
 
-__global__ void __launch_bounds__(256) k_ccl_stats(Roi g, const uint8_t* __restrict__ Wimg, int tiles_x,
-                                                   const uint32_t* __restrict__ tile_count,
+__global__ void __launch_bounds__(256) k_ccl_stats(Roi g, const uint8_t* __restrict__ Wimg, int T,
+                                                   int tiles_x, const uint32_t* __restrict__ tile_count,
                                                    const uint32_t* __restrict__ tiles,
                                                    const uint32_t* __restrict__ parent_all,
                                                    const uint32_t* __restrict__ area_all,
                                                    double disk_area, double thr,
                                                    chips_result* __restrict__ res) {
-  const int t = blockIdx.y;
+  __shared__ int s_root[CHIPS_MAX_T], s_kept[CHIPS_MAX_T];
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    s_root[t] = 0;
+    s_kept[t] = 0;
+  }
+  __syncthreads();
   const size_t n = (size_t)g.w * g.h;
   const uint32_t nt = *tile_count;
-  int nroot = 0, nkept = 0;
+  const int lane = threadIdx.x & 31;
   for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
     TileCtx c = tile_pixel(g, tiles[i], tiles_x);
-    if (c.valid && Wimg[(size_t)c.y * g.W + c.x] <= t) {
-      uint32_t me = g.li(c.x, c.y);
-      if (parent_all[(size_t)t * n + me] == me) {
-        ++nroot;
-        nkept += area_kept(area_all[(size_t)t * n + me], disk_area, thr) ? 1 : 0;
+    const int w = c.valid ? (int)Wimg[(size_t)c.y * g.W + c.x] : 255;
+    const uint32_t me = c.valid ? g.li(c.x, c.y) : 0u;
+    for (int t = warp_min(w); t < T; ++t) {
+      bool root = false, kept = false;
+      if (w <= t && parent_all[(size_t)t * n + me] == me) {
+        root = true;
+        kept = area_kept(area_all[(size_t)t * n + me], disk_area, thr);
+      }
+      const unsigned mr = __ballot_sync(0xFFFFFFFFu, root), mk = __ballot_sync(0xFFFFFFFFu, kept);
+      if (lane == 0) {
+        if (mr) atomicAdd(&s_root[t], __popc(mr));
+        if (mk) atomicAdd(&s_kept[t], __popc(mk));
       }
     }
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    nroot += __shfl_xor_sync(0xFFFFFFFFu, nroot, o);
-    nkept += __shfl_xor_sync(0xFFFFFFFFu, nkept, o);
-  }
-  if ((threadIdx.x & 31) == 0) {
-    if (nroot) atomicAdd(&res->n_comp[t], nroot);
-    if (nkept) atomicAdd(&res->n_kept[t], nkept);
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    if (s_root[t]) atomicAdd(&res->n_comp[t], s_root[t]);
+    if (s_kept[t]) atomicAdd(&res->n_kept[t], s_kept[t]);
   }
 }
 
@@ -585,7 +660,8 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
   k_cleanup_reset<<<1, 128, 0, st>>>(res, lvl_count, tile_count);
   // round T-1: the bulk background (pixels in no mask at all)
   k_fill_bulk_link<<<grid, blk, 0, st>>>(g, lev, T, Wimg, parent_b);
-  k_fill_bulk_union<<<grid, blk, 0, st>>>(g, lev, T, parent_b);
+  dim3 grid4((g.w / 4 + 2 + 255) / 256, g.h);
+  k_fill_bulk_union<<<grid4, blk, 0, st>>>(g, lev, T, parent_b);
   k_fill_pending<0><<<grid, blk, 0, st>>>(g, lev, T, Wimg, parent_b, lvl_count, lvl_cursor, pending);
   k_fill_offsets<<<1, 32, 0, st>>>(T, lvl_count, lvl_offset, lvl_cursor);
   k_fill_pending<1><<<grid, blk, 0, st>>>(g, lev, T, Wimg, parent_b, lvl_count, lvl_cursor, pending);
@@ -599,12 +675,12 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
   }
   CHIPS_CHECK_LAUNCH();
   k_tile_list<<<(ntiles * 32 + 255) / 256, blk, 0, st>>>(g, Wimg, T, tiles_x, tiles_y, tile_count, tiles);
-  dim3 gridt(4 * kNumSM, T);
-  k_ccl_link<<<gridt, blk, 0, st>>>(g, Wimg, tiles_x, tile_count, tiles, parent_c, area);
-  k_ccl_union<<<gridt, blk, 0, st>>>(g, Wimg, tiles_x, tile_count, tiles, parent_c);
-  k_ccl_area<<<gridt, blk, 0, st>>>(g, Wimg, tiles_x, tile_count, tiles, parent_c, area);
-  k_ccl_stats<<<gridt, blk, 0, st>>>(g, Wimg, tiles_x, tile_count, tiles, parent_c, area, disk_area,
-                                     area_threshold, res);
+  const int gridt = 8 * kNumSM;
+  k_ccl_link<<<gridt, blk, 0, st>>>(g, Wimg, T, tiles_x, tile_count, tiles, parent_c, area);
+  k_ccl_union<<<gridt, blk, 0, st>>>(g, Wimg, T, tiles_x, tile_count, tiles, parent_c);
+  k_ccl_area<<<gridt, blk, 0, st>>>(g, Wimg, T, tiles_x, tile_count, tiles, parent_c, area);
+  k_ccl_stats<<<gridt, blk, 0, st>>>(g, Wimg, T, tiles_x, tile_count, tiles, parent_c, area,
+                                     disk_area, area_threshold, res);
   k_ccl_keep<<<8 * kNumSM, blk, 0, st>>>(g, Wimg, T, tiles_x, tile_count, tiles, parent_c, area,
                                          disk_area, area_threshold, keep);
   CHIPS_CHECK_LAUNCH();
