@@ -21,8 +21,11 @@
 //
 // k_median_brute is an independent per-thread radix-select used only as the at-scale
 // checker in the tests.
+#include <cuda.h>
 #include <cuda_pipeline.h>
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace chips {
@@ -308,13 +311,15 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
     const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres,
     const typename Key<T>::type* __restrict__ bounds, int H, int W, int half, int rx0, int ry0,
     int rw, int rh, int cx, int cy, int r, int cap, T* __restrict__ out,
-    typename Key<T>::type* __restrict__ minmax, int* __restrict__ err, uint32_t* __restrict__ dbg) {
+    typename Key<T>::type* __restrict__ minmax, int* __restrict__ err, uint32_t* __restrict__ dbg,
+    int use_tma, const __grid_constant__ CUtensorMap tm_img, const __grid_constant__ CUtensorMap tm_bkt) {
   using K = typename Key<T>::type;
   constexpr int NT = kTile * kTile;
   constexpr int NW = NT / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  K* skey = reinterpret_cast<K*>(smem_raw);                                     // [RS*RS] keys
-  uint16_t* rsg = reinterpret_cast<uint16_t*>(smem_raw + (size_t)cap * sizeof(K));   // [RS*RS] sub-group of a region pixel
+  extern __shared__ __align__(128) unsigned char smem_tile[];
+  __shared__ __align__(8) uint64_t tma_bar;
+  K* skey = reinterpret_cast<K*>(smem_tile);                                    // [RS*vpitch] keys
+  uint16_t* rsg = reinterpret_cast<uint16_t*>(smem_tile + (size_t)cap * sizeof(K));   // [RS*RS] sub-group of a region pixel
   uint16_t* cpos = rsg + cap;      // [C] candidate positions grouped by sub-group (unsorted)
   uint16_t* csg = cpos + cap;      // [C] sub-group of a candidate
   uint16_t* spos = rsg;            // [C] candidate positions, fully sorted (aliases rsg)
@@ -377,37 +382,76 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
   }
   __syncthreads();
 
-  // ---- b. stage the region with asynchronous global->shared copies (LDGSTS: every copy of the
-  //         tile is in flight at once, no registers held), then one shared-memory pass turns
-  //         values into ordered keys, looks up each pixel's sub-group and counts the members.
+  // ---- b. stage the region asynchronously, then one shared-memory pass turns values into
+  //         ordered keys, looks up each pixel's sub-group and counts the members.
+  //         TMA path: two 2-D tensor-tile loads (cp.async.bulk.tensor) issued by one thread and
+  //         tracked by an mbarrier; out-of-image coordinates are zero-filled by the TMA unit,
+  //         which IS medfilt2d's zero padding.  Fallback: per-lane LDGSTS copies.
   const int RS = kTile + 2 * half;
-  const int bpitch = (RS + 6) & ~3;                 // staged bucket rows, word aligned
+  constexpr int EPA = 16 / (int)sizeof(T);          // elements per 16 bytes
+  // TMA needs the first byte of a box row 16-byte aligned: start the boxes at the aligned
+  // column at or left of the region (vmis / bmis = how far the region sits inside the box)
+  const int vpitch = (RS + 2 * EPA - 2) & ~(EPA - 1);
+  const int vx0 = use_tma ? ((X0 - half) & ~(EPA - 1)) : (X0 - half);   // & on negatives rounds down
+  const int vmis = (X0 - half) - vx0;
+  const int bpitch = use_tma ? ((RS + 30) & ~15) : ((RS + 6) & ~3);
+  const int bmis = use_tma ? (X0 & 15) : (X0 & 3);  // LDGSTS rows start at word (X0 & ~3)
   {
     T* sraw = reinterpret_cast<T*>(skey);           // raw values first, keys in place afterwards
     uint8_t* sbyte = reinterpret_cast<uint8_t*>(csg);   // dead before csg is written
-    const bool interior = (X0 - half >= 0) && (Y0 - half >= 0) && (X0 - half + RS <= W) &&
-                          (Y0 - half + RS <= H);
-    const int bmis = X0 & 3;                        // bucket row starts at word (X0 & ~3)
-    const int bwords = (bmis + RS + 3) >> 2;
-    for (int ry = warp; ry < RS; ry += NW) {
-      const int iy = Y0 + ry - half;
-      const T* irow = img + ((long long)iy * W + (X0 - half));
-      for (int rx = lane; rx < RS; rx += 32) {
-        int ix = X0 + rx - half;
-        if (interior || (iy >= 0 && iy < H && ix >= 0 && ix < W))
-          __pipeline_memcpy_async(&sraw[ry * RS + rx], &irow[rx], sizeof(T));
-        else
-          sraw[ry * RS + rx] = (T)0;                // zero padding of medfilt2d
+    if (use_tma) {
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+      if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       }
-      const uint32_t* bw = reinterpret_cast<const uint32_t*>(Bp + (size_t)(Y0 + ry) * pitch + (X0 & ~3));
-      if (lane < bwords) __pipeline_memcpy_async(sbyte + ry * bpitch + 4 * lane, bw + lane, 4);
+      __syncthreads();
+      if (tid == 0) {
+        const uint32_t bytes = (uint32_t)(RS * vpitch * (int)sizeof(T) + RS * bpitch);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+            "[%0], [%1, {%2, %3}], [%4];" ::"r"((uint32_t)__cvta_generic_to_shared(sraw)),
+            "l"(reinterpret_cast<uint64_t>(&tm_img)), "r"(vx0), "r"(Y0 - half), "r"(bar)
+            : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+            "[%0], [%1, {%2, %3}], [%4];" ::"r"((uint32_t)__cvta_generic_to_shared(sbyte)),
+            "l"(reinterpret_cast<uint64_t>(&tm_bkt)), "r"(X0 & ~15), "r"(Y0), "r"(bar)
+            : "memory");
+      }
+      uint32_t ok = 0;
+      for (int spin = 0; !ok && spin < (1 << 22); ++spin) {   // bounded: a bad descriptor must not hang
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok) : "r"(bar) : "memory");
+      }
+      if (!ok && tid == 0) atomicAdd(err, 1 << 20);
+    } else {
+      const bool interior = (X0 - half >= 0) && (Y0 - half >= 0) && (X0 - half + RS <= W) &&
+                            (Y0 - half + RS <= H);
+      const int bwords = (bmis + RS + 3) >> 2;
+      for (int ry = warp; ry < RS; ry += NW) {
+        const int iy = Y0 + ry - half;
+        const T* irow = img + ((long long)iy * W + (X0 - half));
+        for (int rx = lane; rx < RS; rx += 32) {
+          int ix = X0 + rx - half;
+          if (interior || (iy >= 0 && iy < H && ix >= 0 && ix < W))
+            __pipeline_memcpy_async(&sraw[ry * vpitch + rx], &irow[rx], sizeof(T));   // vmis == 0 here
+          else
+            sraw[ry * vpitch + rx] = (T)0;          // zero padding of medfilt2d
+        }
+        const uint32_t* bw = reinterpret_cast<const uint32_t*>(Bp + (size_t)(Y0 + ry) * pitch + (X0 & ~3));
+        if (lane < bwords) __pipeline_memcpy_async(sbyte + ry * bpitch + 4 * lane, bw + lane, 4);
+      }
+      __pipeline_commit();
+      __pipeline_wait_prior(0);
+      __syncthreads();
     }
-    __pipeline_commit();
-    __pipeline_wait_prior(0);
-    __syncthreads();
     for (int ry = ty; ry < RS; ry += kTile) {
       for (int rx = tx; rx < RS; rx += kTile) {
-        const int ri = ry * RS + rx;
+        const int ri = ry * vpitch + vmis + rx;
         K key = Key<T>::enc(sraw[ri]);
         skey[ri] = key;
         const int g = glut[sbyte[ry * bpitch + bmis + rx]];
@@ -448,7 +492,7 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
   // ---- c. scatter candidate positions into their sub-groups
   for (int ry = ty; ry < RS; ry += kTile) {
     for (int rx = tx; rx < RS; rx += kTile) {
-      const unsigned sg = rsg[ry * RS + rx];
+      const unsigned sg = rsg[ry * vpitch + vmis + rx];
       if (sg != 0xFFFFu) {
         uint32_t slot = atomicAdd(&sgcur[sg], 1u);
         cpos[slot] = (uint16_t)((ry << 8) | rx);
@@ -460,7 +504,7 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
 #ifdef CHIPS_DEBUG_TIMING
   t_1 = clock64();
 #endif
-  auto key_at = [&](unsigned p) -> K { return skey[(p >> 8) * RS + (p & 255u)]; };
+  auto key_at = [&](unsigned p) -> K { return skey[(p >> 8) * vpitch + vmis + (p & 255u)]; };
   const int C = (int)sgcur[nsg - 1];
 
   // ---- d. finish the sort: every candidate finds its rank inside its sub-group (rsg is dead
@@ -613,9 +657,51 @@ __global__ void k_copy_masked(const T* __restrict__ in, T* __restrict__ out, int
 }
 
 // ------------------------------------------------------------------ host-side launchers
-static int refine_cap(int k) {
+static int refine_vpitch(int k, int elem) {
+  int rs = kTile + (k - 1), epa = 16 / elem;
+  return (rs + 2 * epa - 2) & ~(epa - 1);
+}
+static int refine_cap(int k, int elem) {
   int rs = kTile + (k - 1);
-  return (rs * rs + 7) & ~7;
+  return (rs * refine_vpitch(k, elem) + 31) & ~31;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major tensor [rows][cols] of `elem`-byte words, box [box_rows][box_cols], OOB -> 0
+static bool make_tile_map(CUtensorMap* tm, const void* base, int elem, long long cols, long long rows,
+                          long long row_bytes, int box_cols, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || getenv("CHIPS_NO_TMA")) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_bytes & 15) || ((box_cols * elem) & 15) ||
+      box_cols > 256 || box_rows > 256 || box_cols > cols || box_rows > rows)
+    return false;     // (a box larger than the tensor faults on sm_100a: tiny images use LDGSTS)
+  CUtensorMapDataType dt = elem == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                         : elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <typename T>
@@ -687,14 +773,24 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
     count_launch();
   }
   if (stages & 8) {  // tier 2
-    int cap = refine_cap(k);
+    int cap = refine_cap(k, (int)sizeof(T));
     size_t smem = (size_t)cap * (sizeof(K) + 3 * sizeof(uint16_t));
+    const int rs = kTile + 2 * half;
+    const int vp = refine_vpitch(k, (int)sizeof(T));
+    CUtensorMap tm_img, tm_bkt;
+    memset(&tm_img, 0, sizeof(tm_img));
+    memset(&tm_bkt, 0, sizeof(tm_bkt));
+    // rs >= 24: the staged bucket tile (rs x ((rs+30)&~15) bytes) must fit the area it aliases
+    int use_tma = rs >= 24 &&
+                  make_tile_map(&tm_img, in, (int)sizeof(T), W, H, (long long)W * sizeof(T), vp, rs) &&
+                  make_tile_map(&tm_bkt, Bp, 1, p->bp_pitch, p->bp_rows, p->bp_pitch, (rs + 30) & ~15, rs);
     CHIPS_CUDA(cudaFuncSetAttribute(k_refine<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((rw + kTile - 1) / kTile, (rh + kTile - 1) / kTile);
     k_refine<T><<<grid, kTile * kTile, smem, st>>>(in, Bp, p->bp_pitch, bstar, rres, bounds, H, W,
                                                    half, rx0, ry0, rw, rh, cx, cy, r, cap, out,
                                                    minmax, err,
-                                                   reinterpret_cast<uint32_t*>(ws + p->off_parent_c));
+                                                   reinterpret_cast<uint32_t*>(ws + p->off_parent_c),
+                                                   use_tma, tm_img, tm_bkt);
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }
