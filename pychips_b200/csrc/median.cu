@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kHuangThreads) k_huang(const uint8_t* __restri
 //   e. every thread walks the sorted candidates of ITS bucket from the nearer end, counting
 //      those inside its own k x k window, until it reaches its residual rank.
 // Epilogue: masked store + min/max reduction (histogram range).
-constexpr int kMaxSub = 1024;   // sub-group counters per tile: groups * digits <= kMaxSub
+constexpr int kMaxSub = 2048;   // sub-group counters per tile: groups * digits <= kMaxSub
 
 template <typename K>
 __device__ __forceinline__ int bit_length(K v) {
@@ -361,8 +361,10 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
   }
   __syncthreads();
   const int ngroups = (int)needpfx[8];
-  // digits per group: 16 unless the tile needs so many buckets that groups*16 > kMaxSub
-  const int dlog = ngroups <= kMaxSub / 16 ? 4 : (ngroups <= kMaxSub / 8 ? 3 : 2);
+  // digits per group: as many as the counter budget allows (64 for <= 32 buckets, the common
+  // case): finer sub-groups make the rank sort below cheaper
+  const int dlog = ngroups <= kMaxSub / 64 ? 6 : ngroups <= kMaxSub / 32 ? 5
+                 : ngroups <= kMaxSub / 16 ? 4 : 3;
   const int nsg = ngroups << dlog;
   const int ndm1 = (1 << dlog) - 1;
   {   // key range of bucket `tid` -> digit shift of its group; clear the sub-group counters
