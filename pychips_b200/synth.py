@@ -34,6 +34,18 @@ def _ellipse(xx, yy, x0, y0, a, b, th):
     return (u / a) ** 2 + (v / b) ** 2
 
 
+def _ellipse_mask(xx, yy, x0, y0, a, b, th):
+    """`_ellipse(...) <= 1` evaluated only inside the ellipse's bounding box (same values)."""
+    n0, n1 = xx.shape
+    rad = max(a, b) + 2
+    i0, i1 = max(0, int(np.floor(y0 - rad))), min(n0, int(np.ceil(y0 + rad)) + 1)
+    j0, j1 = max(0, int(np.floor(x0 - rad))), min(n1, int(np.ceil(x0 + rad)) + 1)
+    m = np.zeros(xx.shape, dtype=bool)
+    if i0 < i1 and j0 < j1:
+        m[i0:i1, j0:j1] = _ellipse(xx[i0:i1, j0:j1], yy[i0:i1, j0:j1], x0, y0, a, b, th) <= 1.0
+    return m
+
+
 def synthetic_disk(n: int = 1024, seed: int = 0, radius: int | None = None,
                    drift: float = 0.0) -> tuple[np.ndarray, int]:
     """Return (image float32 [n, n], pixel_radius).
@@ -64,12 +76,11 @@ def synthetic_disk(n: int = 1024, seed: int = 0, radius: int | None = None,
         a = grng.uniform(0.10, 0.30) * r
         b = grng.uniform(0.07, 0.20) * r
         th = grng.uniform(0, np.pi) + 0.01 * drift
-        e = _ellipse(xx, yy, x0, y0, a, b, th)
-        reg = e <= 1.0
+        reg = _ellipse_mask(xx, yy, x0, y0, a, b, th)
         if i == 0:                      # bright island inside the first region
-            reg &= ~(_ellipse(xx, yy, x0, y0, 0.35 * a, 0.35 * b, th) <= 1.0)
+            reg &= ~_ellipse_mask(xx, yy, x0, y0, 0.35 * a, 0.35 * b, th)
             # and a dark core inside the island (nested hole/island path)
-            reg |= _ellipse(xx, yy, x0, y0, 0.12 * a, 0.12 * b, th) <= 1.0
+            reg |= _ellipse_mask(xx, yy, x0, y0, 0.12 * a, 0.12 * b, th)
         dark |= reg
     img = np.where(dark & on, np.float32(25.0), img).astype(np.float32)
     img += rng.gamma(2.0, 2.0, size=(n, n)).astype(np.float32)
