@@ -78,6 +78,7 @@ typedef struct chips_plan {
   size_t off_pending;    /* u32 [roi_h*roi_w]  hole-fill work list grouped by level       */
   size_t off_lvl;        /* u32 [512]          per-level counts / offsets / cursors, tile count */
   size_t off_tiles;      /* u32 [#32x8 tiles]  list of tiles that hold filled-mask pixels */
+  size_t off_ovf;        /* u32 [1 + #16x16 tiles]  median tier 2: count + list of slow-path tiles */
   size_t bytes;          /* total workspace size                                          */
 } chips_plan;
 

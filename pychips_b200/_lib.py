@@ -34,7 +34,7 @@ class Plan(C.Structure):
                  "off_counts", "off_density", "off_edges", "off_bound", "off_peaks",
                  "off_result", "off_level", "off_fill", "off_keep", "off_probtab",
                  "off_parent_b", "off_parent_c", "off_area", "off_pending", "off_lvl",
-                 "off_tiles", "bytes")]
+                 "off_tiles", "off_ovf", "bytes")]
 
 
 _vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t

@@ -306,18 +306,18 @@ __device__ __forceinline__ bool in_window(unsigned p, unsigned bias, unsigned wi
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kTile* kTile) k_refine(
+__device__ __forceinline__ void refine_tile_staged(
+    const int tile_x, const int tile_y, uint32_t& tma_phase, const uint32_t bar,
     const T* __restrict__ img, const uint8_t* __restrict__ Bp, int pitch,
     const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres,
     const typename Key<T>::type* __restrict__ bounds, int H, int W, int half, int rx0, int ry0,
     int rw, int rh, int cx, int cy, int r, int cap, T* __restrict__ out,
-    typename Key<T>::type* __restrict__ minmax, int* __restrict__ err, uint32_t* __restrict__ dbg,
-    int use_tma, const __grid_constant__ CUtensorMap tm_img, const __grid_constant__ CUtensorMap tm_bkt) {
+    typename Key<T>::type* __restrict__ minmax, int* __restrict__ err,
+    int use_tma, const CUtensorMap* tm_img, const CUtensorMap* tm_bkt) {
   using K = typename Key<T>::type;
   constexpr int NT = kTile * kTile;
   constexpr int NW = NT / 32;
   extern __shared__ __align__(128) unsigned char smem_tile[];
-  __shared__ __align__(8) uint64_t tma_bar;
   K* skey = reinterpret_cast<K*>(smem_tile);                                    // [RS*vpitch] keys
   uint16_t* rsg = reinterpret_cast<uint16_t*>(smem_tile + (size_t)cap * sizeof(K));   // [RS*RS] sub-group of a region pixel
   uint16_t* cpos = rsg + cap;      // [C] candidate positions grouped by sub-group (unsorted)
@@ -330,13 +330,10 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
   __shared__ uint32_t sgstart[kMaxSub], sgcur[kMaxSub];
   __shared__ uint32_t wsum[NW];
   __shared__ int nactive;
-#ifdef CHIPS_DEBUG_TIMING
-  long long t_0 = clock64(), t_1 = 0, t_2 = 0;
-#endif
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & (kTile - 1), ty = tid >> 4;
-  const int X0 = rx0 + blockIdx.x * kTile, Y0 = ry0 + blockIdx.y * kTile;
+  const int X0 = rx0 + tile_x * kTile, Y0 = ry0 + tile_y * kTile;
   const int x = X0 + tx, y = Y0 + ty;
   const bool active = (x < rx0 + rw) && (y < ry0 + rh) && on_disk(x, y, cx, cy, r);
   if (tid < 8) need[tid] = 0;
@@ -402,33 +399,30 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
     T* sraw = reinterpret_cast<T*>(skey);           // raw values first, keys in place afterwards
     uint8_t* sbyte = reinterpret_cast<uint8_t*>(csg);   // dead before csg is written
     if (use_tma) {
-      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
       if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      }
-      __syncthreads();
-      if (tid == 0) {
+        // earlier tiles of this CTA touched the buffers through the generic proxy
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         const uint32_t bytes = (uint32_t)(RS * vpitch * (int)sizeof(T) + RS * bpitch);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                      : "memory");
         asm volatile(
             "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
             "[%0], [%1, {%2, %3}], [%4];" ::"r"((uint32_t)__cvta_generic_to_shared(sraw)),
-            "l"(reinterpret_cast<uint64_t>(&tm_img)), "r"(vx0), "r"(Y0 - half), "r"(bar)
+            "l"(reinterpret_cast<uint64_t>(tm_img)), "r"(vx0), "r"(Y0 - half), "r"(bar)
             : "memory");
         asm volatile(
             "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
             "[%0], [%1, {%2, %3}], [%4];" ::"r"((uint32_t)__cvta_generic_to_shared(sbyte)),
-            "l"(reinterpret_cast<uint64_t>(&tm_bkt)), "r"(X0 & ~15), "r"(Y0), "r"(bar)
+            "l"(reinterpret_cast<uint64_t>(tm_bkt)), "r"(X0 & ~15), "r"(Y0), "r"(bar)
             : "memory");
       }
       uint32_t ok = 0;
       for (int spin = 0; !ok && spin < (1 << 22); ++spin) {   // bounded: a bad descriptor must not hang
         asm volatile(
-            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-            : "=r"(ok) : "r"(bar) : "memory");
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok) : "r"(bar), "r"(tma_phase) : "memory");
       }
+      tma_phase ^= 1u;
       if (!ok && tid == 0) atomicAdd(err, 1 << 20);
     } else {
       const bool interior = (X0 - half >= 0) && (Y0 - half >= 0) && (X0 - half + RS <= W) &&
@@ -503,9 +497,6 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
     }
   }
   __syncthreads();
-#ifdef CHIPS_DEBUG_TIMING
-  t_1 = clock64();
-#endif
   auto key_at = [&](unsigned p) -> K { return skey[(p >> 8) * vpitch + vmis + (p & 255u)]; };
   const int C = (int)sgcur[nsg - 1];
 
@@ -524,9 +515,6 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
     spos[rank] = (uint16_t)p;
   }
   __syncthreads();
-#ifdef CHIPS_DEBUG_TIMING
-  t_2 = clock64();
-#endif
 
   // ---- e. walk the sorted candidates of my bucket from the nearer end
   K kmin = Key<T>::kMax, kmax = 0;
@@ -572,6 +560,369 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine(
     K res;
     if (found >= 0) {
       res = key_at(spos[found]);
+    } else {                                   // inconsistent tier-1 data: must never happen
+      atomicAdd(err, 1);
+      res = Key<T>::enc((T)0);
+    }
+    out[(size_t)y * W + x] = Key<T>::dec(res);
+    kmin = res;
+    kmax = res;
+  }
+  // min/max of the masked output for the histogram range (np.histogram's a.min()/a.max())
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    K a = __shfl_xor_sync(0xFFFFFFFFu, kmin, o);
+    K b = __shfl_xor_sync(0xFFFFFFFFu, kmax, o);
+    kmin = a < kmin ? a : kmin;
+    kmax = b > kmax ? b : kmax;
+  }
+  if (lane == 0 && kmin <= kmax) {
+    atomic_min_key(&minmax[0], kmin);
+    atomic_max_key(&minmax[1], kmax);
+  }
+}
+
+// Slow path of tier 2: tiles whose candidate set does not fit the fast path's fixed buffers
+// (large flat areas: every region pixel shares the median's bucket) are refined with the whole
+// region staged in shared memory.  A fixed grid walks the overflow list left by k_refine_fast.
+template <typename T>
+__global__ void __launch_bounds__(kTile* kTile) k_refine_list(
+    const uint32_t* __restrict__ ovf, int gx, const T* __restrict__ img,
+    const uint8_t* __restrict__ Bp, int pitch, const uint8_t* __restrict__ bstar,
+    const uint32_t* __restrict__ rres, const typename Key<T>::type* __restrict__ bounds, int H, int W,
+    int half, int rx0, int ry0, int rw, int rh, int cx, int cy, int r, int cap, T* __restrict__ out,
+    typename Key<T>::type* __restrict__ minmax, int* __restrict__ err, int use_tma,
+    const __grid_constant__ CUtensorMap tm_img, const __grid_constant__ CUtensorMap tm_bkt) {
+  __shared__ __align__(8) uint64_t tma_bar;
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+  const uint32_t n = ovf[0];
+  if (blockIdx.x >= n) return;
+  if (use_tma) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  uint32_t phase = 0;
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint32_t t = ovf[1 + i];
+    refine_tile_staged<T>((int)(t % (uint32_t)gx), (int)(t / (uint32_t)gx), phase, bar, img, Bp, pitch,
+                          bstar, rres, bounds, H, W, half, rx0, ry0, rw, rh, cx, cy, r, cap, out,
+                          minmax, err, use_tma, &tm_img, &tm_bkt);
+    __syncthreads();      // the next tile reuses every shared buffer
+  }
+}
+
+// Fast path of tier 2.  One CTA per 16x16 output tile:
+//   a. bitmap + range [bmin, bmax] of the buckets the tile's pixels need (tier-1 output);
+//   b. the bucket bytes of the tile's (16+k-1)^2 region are streamed from the padded bucket
+//      image with aligned 128-bit loads; bytes in a needed bucket become candidates
+//      (position + group), typically ~5 % of the region;
+//   c. only the candidates' values are fetched (zero padding outside the image), keyed and
+//      counting-sorted by (bucket, leading key digits); a rank sort finishes each sub-group;
+//   d. every thread walks the sorted candidates of ITS bucket from the nearer end, counting
+//      those inside its own k x k window, until it reaches its residual rank.
+// Tiles with more than kFastCap candidates go to the overflow list (k_refine_list).
+constexpr int kFastCap = 2048;   // candidates per tile on the fast path
+constexpr int kFastSub = 1024;   // (bucket, digit) sub-groups per tile
+
+__device__ __forceinline__ uint32_t sum_u16x8(const uint4 c) {
+  return (c.x & 0xFFFFu) + (c.x >> 16) + (c.y & 0xFFFFu) + (c.y >> 16) + (c.z & 0xFFFFu) + (c.z >> 16) +
+         (c.w & 0xFFFFu) + (c.w >> 16);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTile* kTile, 4) k_refine_fast(
+    const T* __restrict__ img, const uint8_t* __restrict__ Bp, int pitch,
+    const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres,
+    const typename Key<T>::type* __restrict__ bounds, int H, int W, int half, int rx0, int ry0,
+    int rw, int rh, int cx, int cy, int r, T* __restrict__ out,
+    typename Key<T>::type* __restrict__ minmax, int* __restrict__ err, uint32_t* __restrict__ ovf,
+    int force_overflow, uint32_t* __restrict__ dbg) {
+  using K = typename Key<T>::type;
+  constexpr int NT = kTile * kTile;
+  constexpr int NW = NT / 32;
+  static_assert(NW == 8, "one uint4 of u16 counters per sub-group");
+  extern __shared__ __align__(128) unsigned char smem_tile[];
+  K* tkey = reinterpret_cast<K*>(smem_tile);
+  K* ckey = tkey + kFastCap;
+  uint16_t* tpos = reinterpret_cast<uint16_t*>(ckey + kFastCap);
+  uint16_t* cpos = tpos + kFastCap;
+  uint16_t* tsg = cpos + kFastCap;
+  uint16_t* csg = tsg + kFastCap;
+  K* skey = tkey;               // sorted keys / positions reuse the unsorted first-pass arrays
+  uint16_t* spos = tpos;
+  uint8_t* tg = reinterpret_cast<uint8_t*>(csg);   // group of a first-pass candidate (dead before csg)
+  __shared__ uint32_t need[8], needpfx[9];
+  __shared__ uint16_t glut[kBuckets];          // bucket -> group (0xFFFF: not needed by this tile)
+  __shared__ K gklo[kBuckets];
+  __shared__ uint8_t gshift[kBuckets];
+  // warp-private sub-group counters [sub-group][warp] (shared-memory atomics cost 2 cycles per
+  // lane on the one LSU of the SM; a warp resolves its own collisions with match.any instead)
+  uint16_t* wcnt = csg + kFastCap;                 // [kFastSub][NW], 16-byte aligned
+  __shared__ uint16_t sgoff[kFastSub + 1];
+  __shared__ uint32_t wsum[NW];
+  __shared__ int nactive;
+  __shared__ uint32_t ncand;
+#ifdef CHIPS_DEBUG_TIMING
+  long long t_0 = clock64(), t_1 = 0, t_2 = 0;
+#endif
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const int tx = tid & (kTile - 1), ty = tid >> 4;
+  const int X0 = rx0 + blockIdx.x * kTile, Y0 = ry0 + blockIdx.y * kTile;
+  const int x = X0 + tx, y = Y0 + ty;
+  const bool active = (x < rx0 + rw) && (y < ry0 + rh) && on_disk(x, y, cx, cy, r);
+  if (tid < 8) need[tid] = 0;
+  if (tid == 0) {
+    nactive = 0;
+    ncand = 0;
+  }
+  __syncthreads();
+  int bs = 0, rr = 0, mpop = 0;
+  if (active) {
+    size_t o = (size_t)y * W + x;
+    bs = bstar[o];
+    uint32_t pk = rres[o];
+    rr = (int)(pk & 0xFFFFu);
+    mpop = (int)(pk >> 16);
+    atomicOr(&need[bs >> 5], 1u << (bs & 31));
+    nactive = 1;
+  }
+  __syncthreads();
+  if (nactive == 0) return;
+  if (tid < 9) {
+    uint32_t p = 0;
+    for (int i = 0; i < tid; ++i) p += __popc(need[i]);
+    needpfx[tid] = p;
+  }
+  __syncthreads();
+  const int ngroups = (int)needpfx[8];
+  {   // key range of bucket `tid` -> group tables (gshift holds the span's bit length for now)
+    const int b = tid;
+    uint16_t gl = 0xFFFF;
+    if ((need[b >> 5] >> (b & 31)) & 1u) {
+      K klo = (b == 0) ? (K)0 : bounds[b - 1];
+      K span = bounds[b] - klo;               // bucket = [klo, bounds[b]) ; bounds[255] = kMax
+      if (b == kBuckets - 1 && span != Key<T>::kMax) span += 1;   // the last bucket is closed
+      int g = (int)(needpfx[b >> 5] + __popc(need[b >> 5] & ((1u << (b & 31)) - 1u)));
+      gl = (uint16_t)g;
+      gklo[g] = klo;
+      gshift[g] = (uint8_t)bit_length<K>(span - 1);
+    }
+    glut[b] = gl;
+  }
+  __syncthreads();
+
+  // ---- b. stream the region's bucket bytes; collect (position, group) of the candidates
+  const int RS = kTile + 2 * half;
+  {
+    const int xoff = X0 & 15;
+    const int nseg = (xoff + RS + 15) >> 4;
+    const int ntask = RS * nseg;
+    const uint8_t* base = Bp + (size_t)Y0 * pitch + (X0 & ~15);
+    for (int t0 = 0; t0 < ntask; t0 += NT) {
+      const int task = t0 + tid;
+      uint32_t m = 0;
+      uint64_t wlo = 0, whi = 0;
+      int ry = 0, rxb = 0;
+      if (task < ntask) {
+        ry = task / nseg;
+        const int seg = task - ry * nseg;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)ry * pitch + 16 * seg));
+        wlo = ((uint64_t)v.y << 32) | v.x;
+        whi = ((uint64_t)v.w << 32) | v.z;
+        rxb = 16 * seg - xoff;                               // region column of byte 0
+        const int lo = max(0, -rxb), hi = min(16, RS - rxb);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const unsigned b = (unsigned)((i < 8 ? wlo : whi) >> (8 * (i & 7))) & 255u;
+          m |= ((need[b >> 5] >> (b & 31)) & 1u) << i;       // 8 words, 8 banks: conflict-free
+        }
+        m &= (0xFFFFu >> (16 - hi)) & (0xFFFFu << lo);
+      }
+      // one shared-memory atomic per warp: exclusive scan of the hit counts
+      const uint32_t n = (uint32_t)__popc(m);
+      uint32_t inc = n;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      uint32_t wbase = 0;
+      if (lane == 31 && inc) wbase = atomicAdd(&ncand, inc);
+      wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
+      uint32_t slot = wbase + inc - n;
+      while (m) {
+        const int i = __ffs(m) - 1;
+        m &= m - 1;
+        if (slot < (uint32_t)kFastCap) {
+          const unsigned b = (unsigned)((i < 8 ? wlo : whi) >> (8 * (i & 7))) & 255u;
+          tpos[slot] = (uint16_t)((ry << 8) | (rxb + i));
+          tg[slot] = (uint8_t)glut[b];
+        }
+        ++slot;
+      }
+    }
+  }
+  __syncthreads();
+  const int C = (int)ncand;
+  if (C > kFastCap || force_overflow) {
+    if (tid == 0) {
+      uint32_t i = atomicAdd(&ovf[0], 1u);
+      ovf[1 + i] = blockIdx.y * gridDim.x + blockIdx.x;
+    }
+    return;
+  }
+  // digits per group: enough sub-groups that the rank sort below sees ~1 candidate each
+  int dlog = 0;
+  while (dlog < 6 && (ngroups << (dlog + 1)) <= kFastSub && (ngroups << dlog) < C) ++dlog;
+  const int nsg = ngroups << dlog;
+  const int ndm1 = (1 << dlog) - 1;
+  if (tid < ngroups) gshift[tid] = (uint8_t)max(0, (int)gshift[tid] - dlog);
+  uint4* wcnt4 = reinterpret_cast<uint4*>(wcnt);
+  for (int i = tid; i < nsg; i += NT) wcnt4[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+
+  // ---- c. fetch + key the candidates, count the sub-groups (warp-private counters)
+  for (int e0 = warp * 32; e0 < C; e0 += NT) {
+    const int e = e0 + lane;
+    unsigned sg = 0xFFFFu;
+    if (e < C) {
+      const unsigned p = tpos[e];
+      const int iy = Y0 + (int)(p >> 8) - half, ix = X0 + (int)(p & 255u) - half;
+      const T v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(&img[(size_t)iy * W + ix]) : (T)0;
+      const K key = Key<T>::enc(v);
+      const int g = tg[e];
+      const K dg = (key - gklo[g]) >> gshift[g];
+      sg = (unsigned)((g << dlog) + (int)(dg < (K)ndm1 ? dg : (K)ndm1));
+      tkey[e] = key;
+      tsg[e] = (uint16_t)sg;
+    }
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, sg);
+    if (e < C && (peers & lt_mask) == 0) {
+      uint16_t* c = &wcnt[sg * NW + warp];
+      *c = (uint16_t)(*c + __popc(peers));
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  {   // exclusive scan over (sub-group, warp): contiguous sub-groups per thread
+    const int per = (nsg + NT - 1) / NT;
+    const int lo = tid * per, hi = min(lo + per, nsg);
+    uint32_t s = 0;
+    for (int i = lo; i < hi; ++i) s += sum_u16x8(wcnt4[i]);
+    uint32_t inc = s;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int wv = 0; wv < warp; ++wv) base += wsum[wv];
+    uint32_t run = base + inc - s;
+    for (int i = lo; i < hi; ++i) {
+      const uint4 c = wcnt4[i];
+      sgoff[i] = (uint16_t)run;
+      uint4 o;
+      uint32_t a0 = run, a1 = a0 + (c.x & 0xFFFFu), a2 = a1 + (c.x >> 16), a3 = a2 + (c.y & 0xFFFFu);
+      uint32_t a4 = a3 + (c.y >> 16), a5 = a4 + (c.z & 0xFFFFu), a6 = a5 + (c.z >> 16);
+      uint32_t a7 = a6 + (c.w & 0xFFFFu);
+      run = a7 + (c.w >> 16);
+      o.x = a0 | (a1 << 16);
+      o.y = a2 | (a3 << 16);
+      o.z = a4 | (a5 << 16);
+      o.w = a6 | (a7 << 16);
+      wcnt4[i] = o;
+    }
+    if (tid == 0) sgoff[nsg] = (uint16_t)C;
+  }
+  __syncthreads();
+  for (int e0 = warp * 32; e0 < C; e0 += NT) {     // scatter into the sub-groups
+    const int e = e0 + lane;
+    const unsigned sg = e < C ? (unsigned)tsg[e] : 0xFFFFu;
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, sg);
+    uint32_t slot = 0;
+    if (e < C) slot = wcnt[sg * NW + warp];
+    __syncwarp();
+    if (e < C) {
+      if ((peers & lt_mask) == 0) wcnt[sg * NW + warp] = (uint16_t)(slot + __popc(peers));
+      slot += __popc(peers & lt_mask);
+      cpos[slot] = tpos[e];
+      ckey[slot] = tkey[e];
+      csg[slot] = (uint16_t)sg;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+#ifdef CHIPS_DEBUG_TIMING
+  t_1 = clock64();
+#endif
+  // rank sort inside each sub-group -> fully sorted (skey, spos)
+  for (int e = tid; e < C; e += NT) {
+    const unsigned sg = csg[e];
+    const int s0 = (int)sgoff[sg], s1 = (int)sgoff[sg + 1];
+    const K key = ckey[e];
+    int rank = s0;
+    for (int j = s0; j < s1; ++j) {
+      const K o = ckey[j];
+      rank += (o < key || (o == key && j < e)) ? 1 : 0;
+    }
+    spos[rank] = cpos[e];
+    skey[rank] = key;
+  }
+  __syncthreads();
+#ifdef CHIPS_DEBUG_TIMING
+  t_2 = clock64();
+#endif
+
+  // ---- d. walk the sorted candidates of my bucket from the nearer end
+  K kmin = Key<T>::kMax, kmax = 0;
+  if (active) {
+    const int g = glut[bs];
+    const int beg = (int)sgoff[g << dlog], end = (int)sgoff[(g + 1) << dlog];
+    const unsigned win = 2u * (unsigned)half;
+    const unsigned bias = ((unsigned)ty << 8) | (unsigned)tx;
+    const bool fwd = 2 * rr < mpop;
+    const int want = fwd ? rr : mpop - 1 - rr;     // in-window candidates to skip
+    const int step = fwd ? 1 : -1;
+    int i = fwd ? beg : end - 1;
+    int left = end - beg;
+    int cnt = 0, found = -1;
+    for (; left >= 4; left -= 4, i += 4 * step) {
+      unsigned p0 = spos[i], p1 = spos[i + step], p2 = spos[i + 2 * step], p3 = spos[i + 3 * step];
+      int c0 = in_window(p0, bias, win), c1 = in_window(p1, bias, win);
+      int c2 = in_window(p2, bias, win), c3 = in_window(p3, bias, win);
+      int c = c0 + c1 + c2 + c3;
+      if (cnt + c > want) {                        // the target is one of these four
+        if (c0 && cnt == want) found = i;
+        cnt += c0;
+        if (found < 0 && c1 && cnt == want) found = i + step;
+        cnt += c1;
+        if (found < 0 && c2 && cnt == want) found = i + 2 * step;
+        cnt += c2;
+        if (found < 0) found = i + 3 * step;
+        break;
+      }
+      cnt += c;
+    }
+    if (found < 0) {
+      for (; left > 0; --left, i += step) {
+        if (in_window(spos[i], bias, win)) {
+          if (cnt == want) {
+            found = i;
+            break;
+          }
+          ++cnt;
+        }
+      }
+    }
+    K res;
+    if (found >= 0) {
+      res = skey[found];
     } else {                                   // inconsistent tier-1 data: must never happen
       atomicAdd(err, 1);
       res = Key<T>::enc((T)0);
@@ -774,7 +1125,20 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }
-  if (stages & 8) {  // tier 2
+  if (stages & 8) {  // tier 2: fast path over every tile, then the overflow list
+    uint32_t* ovf = reinterpret_cast<uint32_t*>(ws + p->off_ovf);
+    const int gx = (rw + kTile - 1) / kTile, gy = (rh + kTile - 1) / kTile;
+    static const int force_ovf = getenv("CHIPS_REFINE_STAGED") ? 1 : 0;   // tests: slow path only
+    CHIPS_CUDA(cudaMemsetAsync(ovf, 0, sizeof(uint32_t), st));
+    const size_t smem_fast = (size_t)kFastCap * (2 * sizeof(K) + 4 * sizeof(uint16_t)) +
+                             (size_t)kFastSub * (kTile * kTile / 32) * sizeof(uint16_t);
+    CHIPS_CUDA(cudaFuncSetAttribute(k_refine_fast<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)smem_fast));
+    k_refine_fast<T><<<dim3(gx, gy), kTile * kTile, smem_fast, st>>>(
+        in, Bp, p->bp_pitch, bstar, rres, bounds, H, W, half, rx0, ry0, rw, rh, cx, cy, r, out, minmax,
+        err, ovf, force_ovf, reinterpret_cast<uint32_t*>(ws + p->off_parent_c));
+    CHIPS_CHECK_LAUNCH();
+    count_launch();
     int cap = refine_cap(k, (int)sizeof(T));
     size_t smem = (size_t)cap * (sizeof(K) + 3 * sizeof(uint16_t));
     const int rs = kTile + 2 * half;
@@ -786,13 +1150,12 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
     int use_tma = rs >= 24 &&
                   make_tile_map(&tm_img, in, (int)sizeof(T), W, H, (long long)W * sizeof(T), vp, rs) &&
                   make_tile_map(&tm_bkt, Bp, 1, p->bp_pitch, p->bp_rows, p->bp_pitch, (rs + 30) & ~15, rs);
-    CHIPS_CUDA(cudaFuncSetAttribute(k_refine<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((rw + kTile - 1) / kTile, (rh + kTile - 1) / kTile);
-    k_refine<T><<<grid, kTile * kTile, smem, st>>>(in, Bp, p->bp_pitch, bstar, rres, bounds, H, W,
-                                                   half, rx0, ry0, rw, rh, cx, cy, r, cap, out,
-                                                   minmax, err,
-                                                   reinterpret_cast<uint32_t*>(ws + p->off_parent_c),
-                                                   use_tma, tm_img, tm_bkt);
+    CHIPS_CUDA(cudaFuncSetAttribute(k_refine_list<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long ntiles = (long long)gx * gy;
+    const int nlist = (int)(ntiles < 3LL * kNumSM ? ntiles : 3LL * kNumSM);
+    k_refine_list<T><<<nlist, kTile * kTile, smem, st>>>(ovf, gx, in, Bp, p->bp_pitch, bstar, rres, bounds,
+                                                         H, W, half, rx0, ry0, rw, rh, cx, cy, r, cap, out,
+                                                         minmax, err, use_tma, tm_img, tm_bkt);
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }
