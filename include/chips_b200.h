@@ -55,9 +55,13 @@ typedef struct chips_result {
 typedef struct chips_plan {
   int32_t H, W, k, h_bins, T, elem, masked, pad_;
   int32_t roi_x0, roi_y0, roi_w, roi_h;   /* bounding box of the disk (whole image if unmasked) */
-  int32_t bp_pitch, bp_rows;              /* padded bucket image geometry                 */
-  size_t off_bounds;     /* 256 bucket boundaries (ordered keys, 8 B each)                */
-  size_t off_bucket;     /* u8  [bp_rows][bp_pitch]   padded bucket image                 */
+  /* median blocks: the ROI is cut into blk_nbx x blk_nby blocks of 128 columns x blk_rows rows
+   * (blk_rows a multiple of 16); each block has its own 256 quantile boundaries and a bucket
+   * image of its halo-extended region, bp_rows x bp_pitch bytes                            */
+  int32_t bp_pitch, bp_rows;
+  int32_t blk_rows, blk_nbx, blk_nby, pad2_;
+  size_t off_bounds;     /* [blocks][256] bucket boundaries (ordered keys, 8 B each)      */
+  size_t off_bucket;     /* u8  [blocks][bp_rows][bp_pitch]   block-local bucket images   */
   size_t off_bstar;      /* u8  [H][W]   median bucket per pixel                          */
   size_t off_rres;       /* u32 [H][W]   residual rank | (bucket population << 16)        */
   size_t off_filt;       /* elem[H][W]   masked median (filt_disk)                        */

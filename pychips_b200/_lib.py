@@ -28,7 +28,8 @@ class Plan(C.Structure):
     """Mirror of `chips_plan`."""
     _fields_ = [(n, C.c_int32) for n in
                 ("H", "W", "k", "h_bins", "T", "elem", "masked", "pad_",
-                 "roi_x0", "roi_y0", "roi_w", "roi_h", "bp_pitch", "bp_rows")] + \
+                 "roi_x0", "roi_y0", "roi_w", "roi_h", "bp_pitch", "bp_rows",
+                 "blk_rows", "blk_nbx", "blk_nby", "pad2_")] + \
                [(n, C.c_size_t) for n in
                 ("off_bounds", "off_bucket", "off_bstar", "off_rres", "off_filt", "off_minmax",
                  "off_counts", "off_density", "off_edges", "off_bound", "off_peaks",

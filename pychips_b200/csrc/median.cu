@@ -4,9 +4,14 @@
 // /root/reference/chips/syn_chips.py:106.  A median is a pure order statistic, so any
 // exact selection reproduces scipy to the bit.  The B200 design is a two-tier selection:
 //
-//   1. k_bounds      one CTA: 4096 samples of the ROI, bitonic sort in shared memory,
-//                    255 quantile boundaries  ->  256 value buckets.
-//   2. k_bucketize   image -> padded uint8 bucket image (zero padding = bucket of 0.0).
+//   0. the ROI is cut into blocks of 128 columns x L rows (L a multiple of the 16-pixel
+//      refine tile, chosen by chips_plan_init so that one wave of tier-1 CTAs covers the ROI).
+//   1. k_bounds      one CTA per block: 1024 samples of the block's halo-extended region,
+//                    bitonic sort in shared memory, 255 LOCAL quantile boundaries -> 256 value
+//                    buckets of equal local mass (a window's median bucket then holds ~1 % of
+//                    the window instead of ~6 % with image-wide quantiles: tier 2 shrinks).
+//   2. k_bucketize   per block: uint8 bucket image of the extended region (zero padding
+//                    outside the image = bucket of 0.0).
 //   3. k_huang       tier 1: every thread slides its own k x k window down one image
 //                    column (Huang's O(k) update: +k / -k bucket counts per step) with a
 //                    thread-private 256-bin histogram kept in shared memory in a
@@ -21,7 +26,6 @@
 //
 // k_median_brute is an independent per-thread radix-select used only as the at-scale
 // checker in the tests.
-#include <cuda.h>
 #include <cuda_pipeline.h>
 #include <math.h>
 #include <stdlib.h>
@@ -31,7 +35,7 @@
 namespace chips {
 
 constexpr int kBuckets = 256;
-constexpr int kSamples = 4096;
+constexpr int kSamples = 1024;   // per block
 constexpr int kHuangThreads = 128;
 constexpr int kTile = 16;
 
@@ -60,29 +64,48 @@ __device__ __forceinline__ void bitonic_sort(K* key, uint16_t* pos, int n, int t
   }
 }
 
+// ------------------------------------------------------------------ 0. block geometry
+// Block b = (bx, by) covers image columns [rx0 + 128 bx, +128) and rows [ry0 + L by, +L); its
+// bucket image holds the block extended by `half` on every side: image (x, y) lives at local
+// (x - X0b + half, y - Y0b + half), pitch LP (multiple of 16), LR rows.
+struct BlockGeom {
+  int rx0, ry0, L, nbx, LP, LR, half;
+};
+
+// does the rectangle [x0, x0+w) x [y0, y0+h) hold an on-disk pixel?
+__device__ __forceinline__ bool rect_on_disk(int x0, int y0, int w, int h, int cx, int cy, int r) {
+  if (r < 0) return true;
+  int nx = min(max(cx, x0), x0 + w - 1), ny = min(max(cy, y0), y0 + h - 1);
+  return on_disk(nx, ny, cx, cy, r);
+}
+
 // ------------------------------------------------------------------ 1. boundaries
 template <typename T>
-__global__ void __launch_bounds__(1024) k_bounds(const T* __restrict__ img, int W, int rx0, int ry0,
-                                                 int rw, int rh,
-                                                 typename Key<T>::type* __restrict__ bounds,
-                                                 typename Key<T>::type* __restrict__ minmax) {
+__global__ void __launch_bounds__(256) k_bounds(const T* __restrict__ img, int H, int W, BlockGeom g,
+                                                int cx, int cy, int r,
+                                                typename Key<T>::type* __restrict__ bounds,
+                                                typename Key<T>::type* __restrict__ minmax) {
   using K = typename Key<T>::type;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  K* s = reinterpret_cast<K*>(smem_raw);
+  __shared__ K s[kSamples];
+  const int blk = blockIdx.x, bx = blk % g.nbx, by = blk / g.nbx;
+  if (blk == 0 && threadIdx.x == 0) {
+    minmax[0] = Key<T>::kMax;   // running min
+    minmax[1] = 0;              // running max
+  }
+  const int X = g.rx0 + kHuangThreads * bx, Y = g.ry0 + g.L * by;
+  if (!rect_on_disk(X, Y, kHuangThreads, g.L, cx, cy, r)) return;
+  const int ew = kHuangThreads + 2 * g.half, eh = g.L + 2 * g.half;
   for (int i = threadIdx.x; i < kSamples; i += blockDim.x) {
-    int sy = i >> 6, sx = i & 63;
-    int y = ry0 + (int)(((long long)(2 * sy + 1) * rh) >> 7);
-    int x = rx0 + (int)(((long long)(2 * sx + 1) * rw) >> 7);
-    s[i] = Key<T>::enc(img[(size_t)y * W + x]);
+    int sy = i >> 5, sx = i & 31;
+    int y = Y - g.half + (((2 * sy + 1) * eh) >> 6);
+    int x = X - g.half + (((2 * sx + 1) * ew) >> 6);
+    T v = (y >= 0 && y < H && x >= 0 && x < W) ? img[(size_t)y * W + x] : (T)0;
+    s[i] = Key<T>::enc(v);
   }
   __syncthreads();
   bitonic_sort<K, false>(s, nullptr, kSamples, threadIdx.x, blockDim.x);
   for (int i = threadIdx.x; i < kBuckets; i += blockDim.x)
-    bounds[i] = (i < kBuckets - 1) ? s[(i + 1) * (kSamples / kBuckets)] : Key<T>::kMax;
-  if (threadIdx.x == 0) {
-    minmax[0] = Key<T>::kMax;   // running min
-    minmax[1] = 0;              // running max
-  }
+    bounds[(size_t)blk * kBuckets + i] = (i < kBuckets - 1) ? s[(i + 1) * (kSamples / kBuckets)] : Key<T>::kMax;
 }
 
 template <typename K>
@@ -96,28 +119,30 @@ __device__ __forceinline__ int bucket_of(const K* __restrict__ bnd, K key) {
 }
 
 // ------------------------------------------------------------------ 2. bucket image
+// grid (ceil(LR / 4), blocks), 64 x 4 threads: one thread = 4 bytes of one local row
 template <typename T>
-__global__ void __launch_bounds__(256) k_bucketize(const T* __restrict__ img, int H, int W, int half,
-                                                   int pitch, int prow0, int pcol0_w, int ncol_w,
+__global__ void __launch_bounds__(256) k_bucketize(const T* __restrict__ img, int H, int W, BlockGeom g,
+                                                   int cx, int cy, int r,
                                                    const typename Key<T>::type* __restrict__ bounds,
                                                    uint8_t* __restrict__ Bp) {
   using K = typename Key<T>::type;
   __shared__ K sb[kBuckets];
-  for (int i = threadIdx.x; i < kBuckets; i += blockDim.x) sb[i] = bounds[i];
+  const int blk = blockIdx.y, bx = blk % g.nbx, by = blk / g.nbx;
+  const int X = g.rx0 + kHuangThreads * bx, Y = g.ry0 + g.L * by;
+  if (!rect_on_disk(X, Y, kHuangThreads, g.L, cx, cy, r)) return;
+  sb[threadIdx.x] = bounds[(size_t)blk * kBuckets + threadIdx.x];
   __syncthreads();
-  int cw = blockIdx.x * blockDim.x + threadIdx.x;   // word column inside the span
-  if (cw >= ncol_w) return;
-  int py = prow0 + blockIdx.y;
-  int px = (pcol0_w + cw) * 4;
-  int y = py - half;
-  uint32_t word = 0;
+  const int word = threadIdx.x & 63, row = blockIdx.x * 4 + (threadIdx.x >> 6);
+  if (word * 4 >= g.LP || row >= g.LR) return;
+  const int y = Y - g.half + row;
+  uint32_t out = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    int x = px + i - half;
+    int x = X - g.half + word * 4 + i;
     T v = (y >= 0 && y < H && x >= 0 && x < W) ? img[(size_t)y * W + x] : (T)0;
-    word |= (uint32_t)bucket_of<K>(sb, Key<T>::enc(v)) << (8 * i);
+    out |= (uint32_t)bucket_of<K>(sb, Key<T>::enc(v)) << (8 * i);
   }
-  *reinterpret_cast<uint32_t*>(Bp + (size_t)py * pitch + px) = word;
+  *reinterpret_cast<uint32_t*>(Bp + ((size_t)blk * g.LR + row) * g.LP + word * 4) = out;
 }
 
 // ------------------------------------------------------------------ 3. tier 1: Huang
@@ -223,17 +248,18 @@ __device__ __forceinline__ void huang_swap_row(uint16_t* __restrict__ my, const 
   lt += acc;
 }
 
-__global__ void __launch_bounds__(kHuangThreads) k_huang(const uint8_t* __restrict__ Bp, int pitch,
-                                                         int half, int k, int W, int rx0, int ry0,
-                                                         int rw, int rh, int L, int cx, int cy, int r,
-                                                         uint8_t* __restrict__ bstar,
+__global__ void __launch_bounds__(kHuangThreads) k_huang(const uint8_t* __restrict__ Bp, BlockGeom g,
+                                                         int k, int W, int rw, int rh, int cx, int cy,
+                                                         int r, uint8_t* __restrict__ bstar,
                                                          uint32_t* __restrict__ rres) {
   constexpr int NT = kHuangThreads;
   extern __shared__ __align__(16) uint16_t hist[];
   const int tid = threadIdx.x;
+  const int half = g.half, pitch = g.LP, rx0 = g.rx0, ry0 = g.ry0;
   const int x = rx0 + blockIdx.x * NT + tid;
-  int ya = ry0 + blockIdx.y * L;
-  int yb = min(ya + L, ry0 + rh);
+  const int Yb = ry0 + blockIdx.y * g.L;
+  int ya = Yb;
+  int yb = min(ya + g.L, ry0 + rh);
   bool valid = x < rx0 + rw;
   if (valid && r >= 0) {
     long long dx = x - cx;
@@ -254,11 +280,10 @@ __global__ void __launch_bounds__(kHuangThreads) k_huang(const uint8_t* __restri
   for (int b = 0; b < kBuckets; ++b) my[b * NT] = 0;
   const int R = (k * k - 1) >> 1;
   int med = 0, lt = 0;
-  // padded coordinates: image (y, x) lives at Bp[(y+half)*pitch + x+half]; the window of
-  // centre column x starts at padded column x, the window row of image row yy is padded row
-  // yy + half.
-  const uint8_t* col = Bp + x;
-  auto prow = [&](int yy) { return col + (size_t)(yy + half) * pitch; };
+  // block-local coordinates: the window of the block's column `tid` starts at local column tid,
+  // the window row of image row yy is local row yy - Yb + half.
+  const uint8_t* col = Bp + (size_t)(blockIdx.y * g.nbx + blockIdx.x) * g.LR * pitch + tid;
+  auto prow = [&](int yy) { return col + (size_t)(yy - Yb + half) * pitch; };
   for (int yy = ya - half; yy < ya + half; ++yy) huang_add_row(my, prow(yy), k, med, lt);
   for (int y = ya; y < yb; ++y) {
     if (y == ya) huang_add_row(my, prow(y + half), k, med, lt);
@@ -307,13 +332,11 @@ __device__ __forceinline__ bool in_window(unsigned p, unsigned bias, unsigned wi
 
 template <typename T>
 __device__ __forceinline__ void refine_tile_staged(
-    const int tile_x, const int tile_y, uint32_t& tma_phase, const uint32_t bar,
-    const T* __restrict__ img, const uint8_t* __restrict__ Bp, int pitch,
-    const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres,
-    const typename Key<T>::type* __restrict__ bounds, int H, int W, int half, int rx0, int ry0,
-    int rw, int rh, int cx, int cy, int r, int cap, T* __restrict__ out,
-    typename Key<T>::type* __restrict__ minmax, int* __restrict__ err,
-    int use_tma, const CUtensorMap* tm_img, const CUtensorMap* tm_bkt) {
+    const int tile_x, const int tile_y, const T* __restrict__ img, const uint8_t* __restrict__ Bp_all,
+    const BlockGeom g, const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres,
+    const typename Key<T>::type* __restrict__ bounds_all, int H, int W, int rw, int rh, int cx, int cy,
+    int r, int cap, T* __restrict__ out, typename Key<T>::type* __restrict__ minmax,
+    int* __restrict__ err) {
   using K = typename Key<T>::type;
   constexpr int NT = kTile * kTile;
   constexpr int NW = NT / 32;
@@ -333,6 +356,12 @@ __device__ __forceinline__ void refine_tile_staged(
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid & (kTile - 1), ty = tid >> 4;
+  const int half = g.half, pitch = g.LP, rx0 = g.rx0, ry0 = g.ry0;
+  const int by = (tile_y * kTile) / g.L, blk = by * g.nbx + (tile_x >> 3);
+  const typename Key<T>::type* __restrict__ bounds = bounds_all + (size_t)blk * kBuckets;
+  // block-local origin of the tile's region (the +half of the local frame cancels the -half)
+  const uint8_t* __restrict__ Bp = Bp_all + ((size_t)blk * g.LR + (tile_y * kTile - by * g.L)) * pitch +
+                                   (tile_x & 7) * kTile;
   const int X0 = rx0 + tile_x * kTile, Y0 = ry0 + tile_y * kTile;
   const int x = X0 + tx, y = Y0 + ty;
   const bool active = (x < rx0 + rw) && (y < ry0 + rh) && on_disk(x, y, cx, cy, r);
@@ -381,64 +410,32 @@ __device__ __forceinline__ void refine_tile_staged(
   }
   __syncthreads();
 
-  // ---- b. stage the region asynchronously, then one shared-memory pass turns values into
-  //         ordered keys, looks up each pixel's sub-group and counts the members.
-  //         TMA path: two 2-D tensor-tile loads (cp.async.bulk.tensor) issued by one thread and
-  //         tracked by an mbarrier; out-of-image coordinates are zero-filled by the TMA unit,
-  //         which IS medfilt2d's zero padding.  Fallback: per-lane LDGSTS copies.
+  // ---- b. stage the region (values + bucket bytes) with per-lane LDGSTS copies, then one
+  //         shared-memory pass turns values into ordered keys, looks up each pixel's sub-group
+  //         and counts the members.
   const int RS = kTile + 2 * half;
   constexpr int EPA = 16 / (int)sizeof(T);          // elements per 16 bytes
-  // TMA needs the first byte of a box row 16-byte aligned: start the boxes at the aligned
-  // column at or left of the region (vmis / bmis = how far the region sits inside the box)
   const int vpitch = (RS + 2 * EPA - 2) & ~(EPA - 1);
-  const int vx0 = use_tma ? ((X0 - half) & ~(EPA - 1)) : (X0 - half);   // & on negatives rounds down
-  const int vmis = (X0 - half) - vx0;
-  const int bpitch = use_tma ? ((RS + 30) & ~15) : ((RS + 6) & ~3);
-  const int bmis = use_tma ? (X0 & 15) : (X0 & 3);  // LDGSTS rows start at word (X0 & ~3)
+  constexpr int vmis = 0, bmis = 0;
+  const int bpitch = (RS + 6) & ~3;
   {
     T* sraw = reinterpret_cast<T*>(skey);           // raw values first, keys in place afterwards
     uint8_t* sbyte = reinterpret_cast<uint8_t*>(csg);   // dead before csg is written
-    if (use_tma) {
-      if (tid == 0) {
-        // earlier tiles of this CTA touched the buffers through the generic proxy
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const uint32_t bytes = (uint32_t)(RS * vpitch * (int)sizeof(T) + RS * bpitch);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-                     : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
-            "[%0], [%1, {%2, %3}], [%4];" ::"r"((uint32_t)__cvta_generic_to_shared(sraw)),
-            "l"(reinterpret_cast<uint64_t>(tm_img)), "r"(vx0), "r"(Y0 - half), "r"(bar)
-            : "memory");
-        asm volatile(
-            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
-            "[%0], [%1, {%2, %3}], [%4];" ::"r"((uint32_t)__cvta_generic_to_shared(sbyte)),
-            "l"(reinterpret_cast<uint64_t>(tm_bkt)), "r"(X0 & ~15), "r"(Y0), "r"(bar)
-            : "memory");
-      }
-      uint32_t ok = 0;
-      for (int spin = 0; !ok && spin < (1 << 22); ++spin) {   // bounded: a bad descriptor must not hang
-        asm volatile(
-            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-            : "=r"(ok) : "r"(bar), "r"(tma_phase) : "memory");
-      }
-      tma_phase ^= 1u;
-      if (!ok && tid == 0) atomicAdd(err, 1 << 20);
-    } else {
+    {
       const bool interior = (X0 - half >= 0) && (Y0 - half >= 0) && (X0 - half + RS <= W) &&
                             (Y0 - half + RS <= H);
-      const int bwords = (bmis + RS + 3) >> 2;
+      const int bwords = (RS + 3) >> 2;
       for (int ry = warp; ry < RS; ry += NW) {
         const int iy = Y0 + ry - half;
         const T* irow = img + ((long long)iy * W + (X0 - half));
         for (int rx = lane; rx < RS; rx += 32) {
           int ix = X0 + rx - half;
           if (interior || (iy >= 0 && iy < H && ix >= 0 && ix < W))
-            __pipeline_memcpy_async(&sraw[ry * vpitch + rx], &irow[rx], sizeof(T));   // vmis == 0 here
+            __pipeline_memcpy_async(&sraw[ry * vpitch + rx], &irow[rx], sizeof(T));
           else
             sraw[ry * vpitch + rx] = (T)0;          // zero padding of medfilt2d
         }
-        const uint32_t* bw = reinterpret_cast<const uint32_t*>(Bp + (size_t)(Y0 + ry) * pitch + (X0 & ~3));
+        const uint32_t* bw = reinterpret_cast<const uint32_t*>(Bp + (size_t)ry * pitch);
         if (lane < bwords) __pipeline_memcpy_async(sbyte + ry * bpitch + 4 * lane, bw + lane, 4);
       }
       __pipeline_commit();
@@ -588,28 +585,15 @@ __device__ __forceinline__ void refine_tile_staged(
 template <typename T>
 __global__ void __launch_bounds__(kTile* kTile) k_refine_list(
     const uint32_t* __restrict__ ovf, int gx, const T* __restrict__ img,
-    const uint8_t* __restrict__ Bp, int pitch, const uint8_t* __restrict__ bstar,
+    const uint8_t* __restrict__ Bp, BlockGeom g, const uint8_t* __restrict__ bstar,
     const uint32_t* __restrict__ rres, const typename Key<T>::type* __restrict__ bounds, int H, int W,
-    int half, int rx0, int ry0, int rw, int rh, int cx, int cy, int r, int cap, T* __restrict__ out,
-    typename Key<T>::type* __restrict__ minmax, int* __restrict__ err, int use_tma,
-    const __grid_constant__ CUtensorMap tm_img, const __grid_constant__ CUtensorMap tm_bkt) {
-  __shared__ __align__(8) uint64_t tma_bar;
-  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+    int rw, int rh, int cx, int cy, int r, int cap, T* __restrict__ out,
+    typename Key<T>::type* __restrict__ minmax, int* __restrict__ err) {
   const uint32_t n = ovf[0];
-  if (blockIdx.x >= n) return;
-  if (use_tma) {
-    if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-  }
-  uint32_t phase = 0;
   for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
     const uint32_t t = ovf[1 + i];
-    refine_tile_staged<T>((int)(t % (uint32_t)gx), (int)(t / (uint32_t)gx), phase, bar, img, Bp, pitch,
-                          bstar, rres, bounds, H, W, half, rx0, ry0, rw, rh, cx, cy, r, cap, out,
-                          minmax, err, use_tma, &tm_img, &tm_bkt);
+    refine_tile_staged<T>((int)(t % (uint32_t)gx), (int)(t / (uint32_t)gx), img, Bp, g, bstar, rres,
+                          bounds, H, W, rw, rh, cx, cy, r, cap, out, minmax, err);
     __syncthreads();      // the next tile reuses every shared buffer
   }
 }
@@ -634,10 +618,10 @@ __device__ __forceinline__ uint32_t sum_u16x8(const uint4 c) {
 
 template <typename T>
 __global__ void __launch_bounds__(kTile* kTile, 4) k_refine_fast(
-    const T* __restrict__ img, const uint8_t* __restrict__ Bp, int pitch,
+    const T* __restrict__ img, const uint8_t* __restrict__ Bp_all, const BlockGeom g,
     const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres,
-    const typename Key<T>::type* __restrict__ bounds, int H, int W, int half, int rx0, int ry0,
-    int rw, int rh, int cx, int cy, int r, T* __restrict__ out,
+    const typename Key<T>::type* __restrict__ bounds_all, int H, int W, int rw, int rh, int cx, int cy,
+    int r, T* __restrict__ out,
     typename Key<T>::type* __restrict__ minmax, int* __restrict__ err, uint32_t* __restrict__ ovf,
     int force_overflow, uint32_t* __restrict__ dbg) {
   using K = typename Key<T>::type;
@@ -672,6 +656,13 @@ __global__ void __launch_bounds__(kTile* kTile, 4) k_refine_fast(
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const int tx = tid & (kTile - 1), ty = tid >> 4;
+  const int half = g.half, pitch = g.LP, rx0 = g.rx0, ry0 = g.ry0;
+  const int by = ((int)blockIdx.y * kTile) / g.L, blk = by * g.nbx + ((int)blockIdx.x >> 3);
+  const K* __restrict__ bounds = bounds_all + (size_t)blk * kBuckets;
+  // block-local origin of the tile's region (the +half of the local frame cancels the -half);
+  // 16-byte aligned: LP and the tile's column offset are multiples of 16
+  const uint8_t* __restrict__ Bp = Bp_all + ((size_t)blk * g.LR + ((int)blockIdx.y * kTile - by * g.L)) * pitch +
+                                   ((int)blockIdx.x & 7) * kTile;
   const int X0 = rx0 + blockIdx.x * kTile, Y0 = ry0 + blockIdx.y * kTile;
   const int x = X0 + tx, y = Y0 + ty;
   const bool active = (x < rx0 + rw) && (y < ry0 + rh) && on_disk(x, y, cx, cy, r);
@@ -719,10 +710,9 @@ __global__ void __launch_bounds__(kTile* kTile, 4) k_refine_fast(
   // ---- b. stream the region's bucket bytes; collect (position, group) of the candidates
   const int RS = kTile + 2 * half;
   {
-    const int xoff = X0 & 15;
-    const int nseg = (xoff + RS + 15) >> 4;
+    const int nseg = (RS + 15) >> 4;
     const int ntask = RS * nseg;
-    const uint8_t* base = Bp + (size_t)Y0 * pitch + (X0 & ~15);
+    const uint8_t* base = Bp;
     for (int t0 = 0; t0 < ntask; t0 += NT) {
       const int task = t0 + tid;
       uint32_t m = 0;
@@ -734,14 +724,14 @@ __global__ void __launch_bounds__(kTile* kTile, 4) k_refine_fast(
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)ry * pitch + 16 * seg));
         wlo = ((uint64_t)v.y << 32) | v.x;
         whi = ((uint64_t)v.w << 32) | v.z;
-        rxb = 16 * seg - xoff;                               // region column of byte 0
-        const int lo = max(0, -rxb), hi = min(16, RS - rxb);
+        rxb = 16 * seg;                                      // region column of byte 0
+        const int hi = min(16, RS - rxb);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const unsigned b = (unsigned)((i < 8 ? wlo : whi) >> (8 * (i & 7))) & 255u;
           m |= ((need[b >> 5] >> (b & 31)) & 1u) << i;       // 8 words, 8 banks: conflict-free
         }
-        m &= (0xFFFFu >> (16 - hi)) & (0xFFFFu << lo);
+        m &= 0xFFFFu >> (16 - hi);
       }
       // one shared-memory atomic per warp: exclusive scan of the hit counts
       const uint32_t n = (uint32_t)__popc(m);
@@ -1019,44 +1009,6 @@ static int refine_cap(int k, int elem) {
   return (rs * refine_vpitch(k, elem) + 31) & ~31;
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// 2-D row-major tensor [rows][cols] of `elem`-byte words, box [box_rows][box_cols], OOB -> 0
-static bool make_tile_map(CUtensorMap* tm, const void* base, int elem, long long cols, long long rows,
-                          long long row_bytes, int box_cols, int box_rows) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  if (!fn || getenv("CHIPS_NO_TMA")) return false;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_bytes & 15) || ((box_cols * elem) & 15) ||
-      box_cols > 256 || box_rows > 256 || box_cols > cols || box_rows > rows)
-    return false;     // (a box larger than the tensor faults on sm_100a: tiny images use LDGSTS)
-  CUtensorMapDataType dt = elem == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
-                         : elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64;
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  return fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <typename T>
 static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy, int r,
                         unsigned char* ws, cudaStream_t st, int stages) {
@@ -1069,15 +1021,12 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
   uint32_t* rres = reinterpret_cast<uint32_t*>(ws + p->off_rres);
   int* err = &reinterpret_cast<chips_result*>(ws + p->off_result)->median_errors;
   const int rx0 = p->roi_x0, ry0 = p->roi_y0, rw = p->roi_w, rh = p->roi_h;
+  const BlockGeom g = {rx0, ry0, p->blk_rows, p->blk_nbx, p->bp_pitch, p->bp_rows, half};
+  const int nblocks = p->blk_nbx * p->blk_nby;
 
   if (stages & 1) {
     CHIPS_CUDA(cudaMemsetAsync(out, 0, (size_t)H * W * sizeof(T), st));
     CHIPS_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
-    CHIPS_CUDA(cudaFuncSetAttribute(k_bounds<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(kSamples * sizeof(K))));
-    k_bounds<T><<<1, 1024, kSamples * sizeof(K), st>>>(in, W, rx0, ry0, rw, rh, bounds, minmax);
-    CHIPS_CHECK_LAUNCH();
-    count_launch();
   }
   if (k == 1) {
     // medfilt2d with a 1x1 kernel is the identity (then masked); min/max via k_minmax later
@@ -1087,41 +1036,22 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
     count_launch();
     return CHIPS_OK;
   }
-  if (stages & 2) {  // bucket image over the ROI expanded by the halo (padded coordinates)
-    int prow0 = ry0, prow1 = ry0 + rh + 2 * half;            // padded rows [ry0, ry0+rh+2h)
-    int pcol0_w = rx0 / 4;
-    int pcol1_w = (rx0 + rw + 2 * half + 8 + 3) / 4;         // + slack for the funnel loads
-    if (pcol1_w * 4 > p->bp_pitch) pcol1_w = p->bp_pitch / 4;
-    int ncol_w = pcol1_w - pcol0_w;
-    dim3 grid((ncol_w + 255) / 256, prow1 - prow0);
-    k_bucketize<T><<<grid, 256, 0, st>>>(in, H, W, half, p->bp_pitch, prow0, pcol0_w, ncol_w,
-                                         bounds, Bp);
+  if (stages & 1) {  // local quantile boundaries of every block
+    k_bounds<T><<<nblocks, 256, 0, st>>>(in, H, W, g, cx, cy, r, bounds, minmax);
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }
-  if (stages & 4) {  // tier 1
-    // run length: aim at >= 4 CTAs per SM worth of work, but keep the (k-1)-row warm-up
-    // of every run amortised (L >= 2k).
-    // run length L: every run pays a (k-1)-row warm-up; 3 CTAs (64 KB of histograms each) are
-    // resident per SM.  Minimise waves(L) * (L + k).
-    int nbx = (rw + kHuangThreads - 1) / kHuangThreads;
-    const long long resident = 3LL * kNumSM;
-    int L = rh;
-    long long best = -1;
-    for (int cand = (k < 8 ? 8 : k); cand <= rh; ++cand) {
-      long long blocks = (long long)nbx * ((rh + cand - 1) / cand);
-      long long waves = (blocks + resident - 1) / resident;
-      long long cost = waves * (cand + k);
-      if (best < 0 || cost < best) {
-        best = cost;
-        L = cand;
-      }
-    }
-    dim3 grid(nbx, (rh + L - 1) / L);
+  if (stages & 2) {  // bucket image of every block's halo-extended region
+    dim3 grid((p->bp_rows + 3) / 4, nblocks);
+    k_bucketize<T><<<grid, 256, 0, st>>>(in, H, W, g, cx, cy, r, bounds, Bp);
+    CHIPS_CHECK_LAUNCH();
+    count_launch();
+  }
+  if (stages & 4) {  // tier 1: one CTA per block
+    dim3 grid(p->blk_nbx, p->blk_nby);
     size_t smem = (size_t)kBuckets * kHuangThreads * sizeof(uint16_t);
     CHIPS_CUDA(cudaFuncSetAttribute(k_huang, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_huang<<<grid, kHuangThreads, smem, st>>>(Bp, p->bp_pitch, half, k, W, rx0, ry0, rw, rh, L, cx,
-                                               cy, r, bstar, rres);
+    k_huang<<<grid, kHuangThreads, smem, st>>>(Bp, g, k, W, rw, rh, cx, cy, r, bstar, rres);
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }
@@ -1135,27 +1065,17 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
     CHIPS_CUDA(cudaFuncSetAttribute(k_refine_fast<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)smem_fast));
     k_refine_fast<T><<<dim3(gx, gy), kTile * kTile, smem_fast, st>>>(
-        in, Bp, p->bp_pitch, bstar, rres, bounds, H, W, half, rx0, ry0, rw, rh, cx, cy, r, out, minmax,
-        err, ovf, force_ovf, reinterpret_cast<uint32_t*>(ws + p->off_parent_c));
+        in, Bp, g, bstar, rres, bounds, H, W, rw, rh, cx, cy, r, out, minmax, err, ovf, force_ovf,
+        reinterpret_cast<uint32_t*>(ws + p->off_parent_c));
     CHIPS_CHECK_LAUNCH();
     count_launch();
     int cap = refine_cap(k, (int)sizeof(T));
     size_t smem = (size_t)cap * (sizeof(K) + 3 * sizeof(uint16_t));
-    const int rs = kTile + 2 * half;
-    const int vp = refine_vpitch(k, (int)sizeof(T));
-    CUtensorMap tm_img, tm_bkt;
-    memset(&tm_img, 0, sizeof(tm_img));
-    memset(&tm_bkt, 0, sizeof(tm_bkt));
-    // rs >= 24: the staged bucket tile (rs x ((rs+30)&~15) bytes) must fit the area it aliases
-    int use_tma = rs >= 24 &&
-                  make_tile_map(&tm_img, in, (int)sizeof(T), W, H, (long long)W * sizeof(T), vp, rs) &&
-                  make_tile_map(&tm_bkt, Bp, 1, p->bp_pitch, p->bp_rows, p->bp_pitch, (rs + 30) & ~15, rs);
     CHIPS_CUDA(cudaFuncSetAttribute(k_refine_list<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long ntiles = (long long)gx * gy;
     const int nlist = (int)(ntiles < 3LL * kNumSM ? ntiles : 3LL * kNumSM);
-    k_refine_list<T><<<nlist, kTile * kTile, smem, st>>>(ovf, gx, in, Bp, p->bp_pitch, bstar, rres, bounds,
-                                                         H, W, half, rx0, ry0, rw, rh, cx, cy, r, cap, out,
-                                                         minmax, err, use_tma, tm_img, tm_bkt);
+    k_refine_list<T><<<nlist, kTile * kTile, smem, st>>>(ovf, gx, in, Bp, g, bstar, rres, bounds, H, W, rw,
+                                                         rh, cx, cy, r, cap, out, minmax, err);
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }

@@ -33,14 +33,37 @@ extern "C" int chips_plan_init(chips_plan* p, int H, int W, int k, int h_bins, i
     p->roi_x0 = 0; p->roi_y0 = 0; p->roi_w = W; p->roi_h = H;
   }
   const int half = k >> 1;
-  // + one 16-pixel tile of slack: the last refine tile of a row/column reads past the ROI
-  p->bp_pitch = (int)align_up((size_t)W + 2 * half + 32, 16);
-  p->bp_rows = H + 2 * half + 16;
+  {  // median blocks (median.cu): 128 columns x L rows, L a multiple of the 16-pixel refine tile.
+     // Every tier-1 run pays a (k-1)-row warm-up and 3 CTAs (64 KB of histograms each) are
+     // resident per SM: minimise waves(L) * (L + k).
+    const int nbx = (p->roi_w + 127) / 128;
+    const long long resident = 3LL * kNumSM;
+    const int lmax = (int)align_up((size_t)p->roi_h, 16);
+    int L = lmax;
+    long long best = -1;
+    for (int cand = (int)align_up((size_t)(k < 16 ? 16 : k), 16); cand <= lmax; cand += 16) {
+      long long blocks = (long long)nbx * ((p->roi_h + cand - 1) / cand);
+      long long waves = (blocks + resident - 1) / resident;
+      long long cost = waves * (cand + k);
+      if (best < 0 || cost < best) {
+        best = cost;
+        L = cand;
+      }
+    }
+    p->blk_rows = L;
+    p->blk_nbx = nbx;
+    p->blk_nby = (p->roi_h + L - 1) / L;
+    p->pad2_ = 0;
+    // + 16 bytes of slack: 128-bit row reads of the last refine tile / funnel loads of tier 1
+    p->bp_pitch = (int)align_up((size_t)128 + 2 * half + 16, 16);
+    p->bp_rows = L + 2 * half;
+  }
+  const size_t nblk = (size_t)p->blk_nbx * p->blk_nby;
   const size_t n = (size_t)H * W, nr = (size_t)p->roi_w * p->roi_h;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  p->off_bounds = take(256 * 8);
-  p->off_bucket = take((size_t)p->bp_pitch * p->bp_rows);
+  p->off_bounds = take(nblk * 256 * 8);
+  p->off_bucket = take(nblk * p->bp_pitch * p->bp_rows);
   p->off_bstar = take(n);
   p->off_rres = take(n * 4);
   p->off_filt = take(n * elem);

@@ -58,7 +58,8 @@ def test_plan_init_geometry_and_argument_errors():
     # unmasked (synoptic): whole image, no union-find buffers
     assert lib.chips_plan_init(C.byref(p), 1440, 3600, 3, 5000, 25, 4, 0, 0, -1) == 0
     assert (p.roi_w, p.roi_h, p.masked) == (3600, 1440, 0)
-    assert p.off_parent_b == p.off_area == p.bytes
+    assert p.off_parent_b == p.off_area == p.off_ovf < p.bytes
+    assert p.blk_rows % 16 == 0 and p.blk_nbx == 29 and p.blk_nby * p.blk_rows >= 1440
     # disk clipped by the image border
     assert lib.chips_plan_init(C.byref(p), 100, 100, 5, 10, 3, 8, 50, 50, 80) == 0
     assert (p.roi_x0, p.roi_y0, p.roi_w, p.roi_h) == (0, 0, 100, 100)
