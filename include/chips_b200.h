@@ -157,6 +157,37 @@ int chips_detect(const void* image, const chips_plan* plan, int cx, int cy, int 
                  double porb_threshold, double area_threshold, uint8_t* maps_or_null,
                  void* ws, void* stream);
 
+/* ---- SURVEY.md §8(f) row 1  replaces: CleanFl.create_coronal_hole_candidates,
+ *      cleanup.py:69-200 (three co-registered wavelengths of the same size; the reference's
+ *      skimage resize is the identity then), and the mask hook chips.py:376-377. ---------- */
+typedef struct chips_fl_params {   /* cleanup.py:52-60 */
+  double clip_negative;
+  double clip_211_log[2], clip_193_log[2], clip_171_log[2];
+  double bmmix_value, bmhot_value, bmcool_value;
+} chips_fl_params;
+
+typedef struct chips_fl_stats {    /* written by the device */
+  double mean171, mean193, mean211;       /* np.mean of the clipped images, cleanup.py:158-178 */
+  double thr_mix, thr_hot, thr_cool;      /* right-hand sides of the three comparisons          */
+  int64_t n_mix, n_hot, n_cool, n_cand;   /* on-disk pixels set in each stored bitmap           */
+  int64_t n_near;                         /* pixels within one float32 ulp of a threshold       */
+} chips_fl_stats;
+
+#define CHIPS_FL_MIX 1    /* bmmix  (before the disk mask)          */
+#define CHIPS_FL_HOT 2    /* bmhot                                   */
+#define CHIPS_FL_COOL 4   /* bmcool                                  */
+#define CHIPS_FL_CAND 8   /* bmcool * bmmix * bmhot                  */
+#define CHIPS_FL_DISK 16  /* filled cv2.circle disk mask             */
+
+size_t chips_fl_workspace_bytes(int H, int W);
+/* bits[H][W]: OR of CHIPS_FL_* per pixel; stats, ws: device memory */
+int chips_fl_candidates(const void* d171, const void* d193, const void* d211, int H, int W,
+                        int elem, int cx, int cy, int r, const chips_fl_params* h_params,
+                        uint8_t* bits, chips_fl_stats* stats, void* ws, void* stream);
+/* level[i] = T (in no mask) wherever bits[i] lacks CHIPS_FL_CAND; call between
+ * chips_threshold_prob and chips_cleanup */
+int chips_apply_candidates(const chips_plan* plan, const uint8_t* bits, void* ws, void* stream);
+
 /* helper: f64 -> f32 demotion with an exactness flag (1 = every value representable) */
 int chips_demote_f64(const double* in, float* out, size_t n, int32_t* all_exact, void* stream);
 

@@ -105,7 +105,8 @@ def clean_small_scale_structures(contours, hierarchy, data, disk_area, area_thre
 
 # --------------------------------------------------------------------------- rows F, I
 def extract_CHs_CHBs(filt_disk, n_mask, resolution, pixel_radius, peaks, threshold_range,
-                     porb_threshold=0.8, area_threshold=1e-3, keep_contours=True):
+                     porb_threshold=0.8, area_threshold=1e-3, keep_contours=True,
+                     candidate_bitmap=None):
     """chips.py:341-403.  Returns an ordered dict str(lim) -> Namespace, or None when the
     histogram had no peak (chips.py:355: `solar_ch_regions` is then never set)."""
     tr = np.arange(threshold_range[0], threshold_range[1])
@@ -127,6 +128,8 @@ def extract_CHs_CHBs(filt_disk, n_mask, resolution, pixel_radius, peaks, thresho
             tmp_data[tmp_data > lim] = 0
             tmp_data[tmp_data == -1] = 1
         tmp_data[np.isnan(tmp_data)] = 0
+        if candidate_bitmap is not None:                       # chips.py:376-377 (run_fl_cleanup)
+            tmp_data = tmp_data * candidate_bitmap
         p = calculate_prob(np.copy(data).ravel(), [lim, limit_0], porb_threshold)
         contours, hierarchy = cv2.findContours(tmp_data.astype(np.uint8), cv2.RETR_TREE,
                                                cv2.CHAIN_APPROX_SIMPLE)
@@ -178,7 +181,9 @@ class OracleChips:
     reference's sticky `h_thresh` (chips.py:240-241) and `hasattr` memoisation."""
 
     def __init__(self, medfilt_kernel=51, h_bins=500, h_thresh=None, ht_peak_ratio=5,
-                 threshold_range=(0, 20), porb_threshold=0.8, area_threshold=1e-3):
+                 threshold_range=(0, 20), porb_threshold=0.8, area_threshold=1e-3,
+                 candidate_bitmap=None):
+        self.candidate_bitmap = candidate_bitmap     # CleanFl output when run_fl_cleanup=True
         self.medfilt_kernel = medfilt_kernel
         self.h_bins = h_bins
         self.h_thresh = h_thresh
@@ -198,7 +203,7 @@ class OracleChips:
         disk.set_value("histogram", Namespace(**hd))
         regs = extract_CHs_CHBs(filt_disk, n_mask, disk.resolution, disk.pixel_radius,
                                 hd["peaks"], self.threshold_range, self.porb_threshold,
-                                self.area_threshold, keep_contours)
+                                self.area_threshold, keep_contours, self.candidate_bitmap)
         if regs is not None:
             disk.set_value("solar_ch_regions", Namespace(**regs))
         return disk

@@ -38,6 +38,21 @@ class Plan(C.Structure):
                  "off_tiles", "off_ovf", "bytes")]
 
 
+class FlParams(C.Structure):
+    """Mirror of `chips_fl_params` (defaults: /root/reference/chips/cleanup.py:52-60)."""
+    _fields_ = [("clip_negative", C.c_double), ("clip_211_log", C.c_double * 2),
+                ("clip_193_log", C.c_double * 2), ("clip_171_log", C.c_double * 2),
+                ("bmmix_value", C.c_double), ("bmhot_value", C.c_double), ("bmcool_value", C.c_double)]
+
+
+class FlStats(C.Structure):
+    """Mirror of `chips_fl_stats`."""
+    _fields_ = [(n, C.c_double) for n in ("mean171", "mean193", "mean211", "thr_mix", "thr_hot", "thr_cool")] + \
+               [(n, C.c_int64) for n in ("n_mix", "n_hot", "n_cool", "n_cand", "n_near")]
+
+
+FL_MIX, FL_HOT, FL_COOL, FL_CAND, FL_DISK = 1, 2, 4, 8, 16
+
 _vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
 _PP = C.POINTER(Plan)
 
@@ -60,6 +75,10 @@ SIGNATURES = {
     "chips_prob_stack": ([_PP, _d, _vp, _i, _i, _vp, _vp], C.c_int),
     "chips_detect": ([_vp, _PP, _i, _i, _i, _d, _d, _i, _i, _d, _d, _vp, _vp, _vp], C.c_int),
     "chips_demote_f64": ([_vp, _vp, _sz, _vp, _vp], C.c_int),
+    "chips_fl_workspace_bytes": ([_i, _i], C.c_size_t),
+    "chips_fl_candidates": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, C.POINTER(FlParams), _vp, _vp, _vp, _vp],
+                            C.c_int),
+    "chips_apply_candidates": ([_PP, _vp, _vp, _vp], C.c_int),
 }
 
 _lib = None

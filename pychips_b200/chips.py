@@ -9,7 +9,7 @@ kernels behind `libchips_b200.so`; result arrays are materialised from device me
 on first attribute access.  There is no CPU fallback.
 
 Out of scope: plotting (`plot_diagonestics`), `to_netcdf`, filament cleanup
-(`run_fl_cleanup=True` raises), `compute_similarity_measures`.
+plots, `compute_similarity_measures`.  `run_fl_cleanup=True` uses `cleanup.CleanFl` (csrc/fl.cu).
 """
 from __future__ import annotations
 
@@ -82,10 +82,6 @@ class Chips(object):
         self.porb_threshold = porb_threshold
         self.area_threshold = area_threshold
         self.run_fl_cleanup = run_fl_cleanup
-        if run_fl_cleanup:
-            raise NotImplementedError(
-                "run_fl_cleanup=True (chips/cleanup.py CHIMERA candidates) is outside the "
-                "accelerated path; see DESIGN.md 'out of scope'.")
         self.device = engine.require_cuda(device)
         self._det = {}                   # id(disk) -> Detector
         self._img = {}                   # id(disk) -> device image
@@ -108,6 +104,8 @@ class Chips(object):
     # ---- chips.py:110-150
     def run_CHIPS(self, wavelength: int = None, resolution: int = None,
                   clear_prev_runs: bool = False) -> None:
+        if self.run_fl_cleanup:
+            self.run_filament_cleanup()
         resolution = self.aia.resolution if resolution is None else resolution
         if (wavelength is not None) and (resolution is not None):
             if (wavelength in self.aia.wavelengths) and (resolution == self.aia.resolution):
@@ -124,6 +122,22 @@ class Chips(object):
                     self.process_CHIPS(disk, clear_prev_runs)
                 else:
                     logger.error(f"No entry for {wavelength} and {resolution}!!!")
+        return
+
+    # ---- chips.py:619-672.  The reference re-registers level-1 FITS files for 171/193/211 A
+    # (chips/fetch.py, outside the accelerated path); here the three wavelengths must already be
+    # in `self.aia.datasets`.  The summary plot (:663-670) is presentation.
+    def run_filament_cleanup(self, params: dict = None, **_plot_kwargs) -> None:
+        from .cleanup import DEFAULT_PARAMS, CleanFl
+        logger.info("Into the filament Cleanups!")
+        missing = [w for w in (171, 193, 211) if w not in self.aia.datasets]
+        if missing:
+            raise ValueError(
+                f"run_fl_cleanup needs the 171/193/211 A disks in aia.datasets (missing {missing}); "
+                "fetching / registering them is outside the accelerated path")
+        self.cf = CleanFl(self.aia, resolution=self.aia.resolution,
+                          params=DEFAULT_PARAMS if params is None else params, device=self.device)
+        self.cf.create_coronal_hole_candidates()
         return
 
     # ---- chips.py:152-171 (the plotter call at :170 is presentation, not detection)
@@ -266,6 +280,10 @@ class Chips(object):
                         det.select_threshold(self.ht_peak_ratio, disk.histogram.h_thresh)
                         det.state.add("hist")
                     det.threshold_prob(self.porb_threshold)
+                    if self.run_fl_cleanup:          # chips.py:376-377
+                        engine._lib.check(det.lib.chips_apply_candidates(
+                            det._pp, engine._ptr(self.cf.bits), engine._ptr(det.ws),
+                            engine._stream_ptr()), "chips_apply_candidates")
                     det.cleanup(self.area_threshold)
                     res = det.result()
                 if res.median_errors:

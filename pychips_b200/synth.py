@@ -167,3 +167,41 @@ class FakeSynoptic:
 def make_aia(n=1024, seed=0, dtype=np.float64, wavelength=193):
     img, r = synthetic_disk(n, seed)
     return FakeAIA(FakeDisk(img.astype(dtype), r, wavelength))
+
+
+def synthetic_triplet(n: int = 1024, seed: int = 0):
+    """Three co-registered AIA-like images (171, 193, 211 A) of the same synthetic Sun, float32,
+    for the filament-cleanup path (`/root/reference/chips/cleanup.py:69-200`): coronal holes are
+    dark in all three bands, "filaments" are dark in 193 but keep a cool (171-bright) signature,
+    so the CHIMERA ratios separate them.  Returns ({171: img, 193: img, 211: img}, pixel_radius)."""
+    i193, r = synthetic_disk(n, seed)
+    rng = np.random.default_rng(seed + 424242)
+    cx = cy = n // 2
+    yy, xx = np.mgrid[0:n, 0:n].astype(np.float32)
+    on = (xx - cx) ** 2 + (yy - cy) ** 2 <= np.float32(r) ** 2
+    base = np.maximum(i193 - rng.gamma(2.0, 2.0, size=(n, n)).astype(np.float32) * 0.5, 0.5)
+    # filament-like strips: dark in 193/211, nearly unchanged in 171
+    fil = np.zeros((n, n), dtype=bool)
+    frng = np.random.default_rng(seed + 99)
+    for _ in range(int(frng.integers(2, 5))):
+        ang = frng.uniform(0, 2 * np.pi)
+        rad = frng.uniform(0.1, 0.8) * r
+        fil |= _ellipse_mask(xx, yy, cx + rad * np.cos(ang), cy + rad * np.sin(ang),
+                             frng.uniform(0.08, 0.2) * r, frng.uniform(0.01, 0.03) * r,
+                             frng.uniform(0, np.pi))
+    fil &= on
+    i193 = np.where(fil, np.float32(30.0) + i193 * np.float32(0.05), i193).astype(np.float32)
+    i171 = (1.9 * base ** 0.92 + rng.gamma(2.0, 3.0, size=(n, n))).astype(np.float32)
+    i211 = (0.02 * base ** 1.7 + rng.gamma(2.0, 0.8, size=(n, n))).astype(np.float32)
+    i211 = np.where(fil, i211 * np.float32(0.35), i211).astype(np.float32)
+    # a few non-positive pixels exercise clip_negative / log10(0) = -inf (cleanup.py:131-139)
+    bad = rng.random((n, n)) < 2e-4
+    i171 = np.where(bad, np.float32(-1.0), i171).astype(np.float32)
+    i211 = np.where(np.roll(bad, 3, axis=1), np.float32(0.0), i211).astype(np.float32)
+    return {171: np.ascontiguousarray(i171), 193: np.ascontiguousarray(i193),
+            211: np.ascontiguousarray(i211)}, r
+
+
+def make_triplet_aia(n=1024, seed=0, dtype=np.float64):
+    imgs, r = synthetic_triplet(n, seed)
+    return FakeAIA([FakeDisk(imgs[w].astype(dtype), r, w) for w in (171, 193, 211)])

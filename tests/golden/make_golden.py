@@ -113,9 +113,75 @@ def make_syn(name, h, w, seed, kw):
     print(name, "peaks", len(s_ref.histogram.peaks), "T", len(keys))
 
 
+FL_CASES = {
+    # name: (N, seed, kwargs of the 193 A detection that consumes the candidate bitmap)
+    "fl_n256_k11": (256, 5, dict(medfilt_kernel=11, h_bins=500, threshold_range=[0, 12])),
+}
+
+
+def make_fl(name, n, seed, kw):
+    """UNMODIFIED `chips.cleanup.CleanFl` (with skimage's resize stubbed by the identity, see
+    oracle/cleanfl_oracle.py) and the UNMODIFIED Chips stage methods with `run_fl_cleanup`."""
+    import types
+    from argparse import Namespace
+    from oracle import cleanfl_oracle as fo
+    rh.load_reference()
+    sk = types.ModuleType("skimage.transform")
+    sk.resize = fo.identity_resize
+    sys.modules["skimage.transform"] = sk
+    sys.modules.pop("chips.cleanup", None)
+    from chips.cleanup import CleanFl
+    aia = synth.make_triplet_aia(n, seed)
+    aia.save_dir = "/tmp/"
+    imgs = {w: aia.datasets[w][n].normalized.data for w in (171, 193, 211)}
+    r = aia.datasets[193][n].pixel_radius
+    cf = CleanFl(aia, resolution=n)
+    ret = cf.create_coronal_hole_candidates()
+    o = fo.create_coronal_hole_candidates(imgs[171], imgs[193], imgs[211], r, n)
+    for a, b in zip(ret, (o.candidate, o.bmmix, o.bmhot, o.bmcool, o.disk_mask)):
+        assert _same(a, b)
+    for a, b in ((cf.candidate_bitmap, o.candidate_bitmap), (cf.bmmix, o.bmmix_m),
+                 (cf.bmhot, o.bmhot_m), (cf.bmcool, o.bmcool_m)):
+        assert _same(a, b)
+    # detection on the 193 A disk with the hook chips.py:376-377
+    Chips, _ = rh.load_reference()
+    d_ref = aia.datasets[193][n]
+    c = Chips(aia, base_folder="/tmp/chips_ref/", run_fl_cleanup=True, **kw)
+    c.cf = cf
+    c.extract_solar_masks(d_ref); c.run_filters(d_ref); c.extract_histogram(d_ref); c.extract_CHs_CHBs(d_ref)
+    d_or = synth.FakeDisk(imgs[193].copy(), r)
+    co.OracleChips(candidate_bitmap=o.candidate_bitmap, **kw).run(d_or)
+    keys = list(d_ref.solar_ch_regions.__dict__.keys())
+    assert keys == list(d_or.solar_ch_regions.__dict__.keys())
+    maps, raw, probs, lims = [], [], [], []
+    for k in keys:
+        a, b = d_ref.solar_ch_regions.__dict__[k], d_or.solar_ch_regions.__dict__[k]
+        assert _same(a.map, b.map) and _same(a.prob, b.prob), k
+        maps.append(a.map.astype(np.uint8)); raw.append(b.raw_map.astype(np.uint8))
+        probs.append(a.prob); lims.append(a.lim)
+    np.savez_compressed(
+        os.path.join(HERE, name + ".npz"), seed=seed, n=n, pixel_radius=r,
+        img171=imgs[171].astype(np.float32), img193=imgs[193].astype(np.float32),
+        img211=imgs[211].astype(np.float32),
+        planes=np.packbits(np.array([ret[0], ret[1], ret[2], ret[3], cf.candidate_bitmap]).astype(np.uint8)),
+        thresholds=np.array(o.thresholds), means=np.array(o.means),
+        keys=np.array(keys), limits=np.array(lims), probs=np.array(probs),
+        maps=np.packbits(np.array(maps)), raw_maps=np.packbits(np.array(raw)),
+        kw_medfilt_kernel=kw["medfilt_kernel"], kw_h_bins=kw["h_bins"],
+        kw_threshold_range=np.array(kw["threshold_range"]))
+    on = o.disk_mask > 0
+    print(name, "candidate fill on disk", float(o.candidate[on].mean()), "T", len(keys))
+
+
 if __name__ == "__main__":
     assert rh.available(), "reference tree missing"
+    if len(sys.argv) > 1 and sys.argv[1] == "fl":
+        for name, (n, seed, kw) in FL_CASES.items():
+            make_fl(name, n, seed, kw)
+        sys.exit(0)
     for name, (n, seed, scale, kw) in DISK_CASES.items():
         make_disk(name, n, seed, scale, kw)
     for name, (h, w, seed, kw) in SYN_CASES.items():
         make_syn(name, h, w, seed, kw)
+    for name, (n, seed, kw) in FL_CASES.items():
+        make_fl(name, n, seed, kw)

@@ -15,7 +15,7 @@ HDR = os.path.join(ROOT, "include", "chips_b200.h")
 def declared_functions():
     src = open(HDR).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(?:int|long long)\s+(chips_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(?:int|long long|size_t)\s+(chips_\w+)\s*\(", src)))
 
 
 def test_library_builds_and_exports_every_declared_symbol():

@@ -453,3 +453,82 @@ def test_h_thresh_is_sticky_across_wavelengths():
     c.run_CHIPS(193, 256, clear_prev_runs=True)
     assert d1.solar_ch_regions is not before
     assert list(d1.solar_ch_regions.__dict__) == list(before.__dict__)
+
+
+# ----------------------------------------------------------------------------- filament cleanup
+def _fl_planes(cf, ret):
+    return [np.asarray(a) for a in (ret[0], ret[1], ret[2], ret[3], cf.candidate_bitmap, cf.bmmix,
+                                    cf.bmhot, cf.bmcool)]
+
+
+@pytest.mark.parametrize("n,seed,dtype", [(512, 3, np.float64), (1024, 1, np.float32),
+                                          (300, 2, np.float64), (77, 4, np.float64)])
+def test_fl_candidates_vs_oracle(n, seed, dtype):
+    """CleanFl.create_coronal_hole_candidates (cleanup.py:69-200)."""
+    from oracle import cleanfl_oracle as fo
+    from pychips_b200.cleanup import CleanFl
+    aia = synth.make_triplet_aia(n, seed, dtype=dtype)
+    r = aia.datasets[193][n].pixel_radius
+    imgs = [np.asarray(aia.datasets[w][n].normalized.data) for w in (171, 193, 211)]
+    o = fo.create_coronal_hole_candidates(imgs[0], imgs[1], imgs[2], r, n)
+    cf = CleanFl(aia, resolution=n)
+    ret = cf.create_coronal_hole_candidates()
+    st = cf.stats
+    got_thr = np.array([st.thr_mix, st.thr_hot, st.thr_cool])
+    got_mean = np.array([st.mean171, st.mean193, st.mean211])
+    pow2 = (n * n) % 128 == 0 and ((n * n) // 128) & ((n * n) // 128 - 1) == 0
+    if pow2:            # numpy's pairwise summation order reproduced exactly
+        assert np.array_equal(got_mean, np.array(o.means)) and np.array_equal(got_thr, np.array(o.thresholds))
+    assert np.allclose(got_thr, np.array(o.thresholds), rtol=1e-12, atol=0)
+    ref = [o.candidate, o.bmmix, o.bmhot, o.bmcool, o.candidate_bitmap, o.bmmix_m, o.bmhot_m, o.bmcool_m]
+    diff = sum(int((a != b).sum()) for a, b in zip(_fl_planes(cf, ret), ref))
+    # bit-exact except pixels within one float32 ulp of a threshold (counted by the kernel)
+    assert diff <= (0 if pow2 else 8 * st.n_near), (diff, st.n_near)
+    assert ret[0].dtype == np.float32 and cf.candidate_bitmap.dtype == np.float64
+    assert np.array_equal(ret[4], o.disk_mask)
+    on = o.disk_mask > 0
+    assert st.n_cand == int(o.candidate[on].sum()) or not pow2
+    assert 0.02 < o.candidate[on].mean() < 0.5      # the synthetic case is not degenerate
+
+
+def test_fl_pipeline_vs_reference_golden():
+    """Chips(run_fl_cleanup=True) on the 193 A disk against the unmodified reference."""
+    from pychips_b200 import Chips
+    g = load_golden("fl_n256_k11")
+    n, r = int(g["n"]), int(g["pixel_radius"])
+    disks = [synth.FakeDisk(g[k].astype(np.float64), r, w)
+             for k, w in (("img171", 171), ("img193", 193), ("img211", 211))]
+    aia = synth.FakeAIA(disks)
+    c = Chips(aia, base_folder="/tmp/chips_b200_test/", run_fl_cleanup=True,
+              medfilt_kernel=int(g["kw_medfilt_kernel"]), h_bins=int(g["kw_h_bins"]),
+              threshold_range=[int(v) for v in g["kw_threshold_range"]])
+    c.run_CHIPS(wavelength=193, resolution=n)
+    planes = np.unpackbits(g["planes"])[:5 * n * n].reshape(5, n, n)
+    assert np.array_equal(c.cf.candidate_bitmap.astype(np.uint8), planes[4])
+    assert np.array_equal(np.array([c.cf.stats.thr_mix, c.cf.stats.thr_hot, c.cf.stats.thr_cool]),
+                          g["thresholds"])
+    d = disks[1]
+    keys = list(d.solar_ch_regions.__dict__.keys())
+    assert keys == list(g["keys"])
+    T = len(keys)
+    maps = np.unpackbits(g["maps"])[:T * n * n].reshape(T, n, n)
+    raw = np.unpackbits(g["raw_maps"])[:T * n * n].reshape(T, n, n)
+    for t, k in enumerate(keys):
+        reg = d.solar_ch_regions.__dict__[k]
+        assert np.array_equal(reg.raw_map.astype(np.uint8), raw[t]), ("raw", t)
+        assert np.array_equal(reg.map.astype(np.uint8), maps[t]), ("map", t)
+        gp = g["probs"][t]
+        assert (np.isnan(gp) and np.isnan(reg.prob)) or abs(reg.prob - gp) <= REL * abs(gp)
+    assert maps.sum() > 0 and (maps != raw).any()
+
+
+def test_fl_requires_three_wavelengths_and_same_size():
+    from pychips_b200 import Chips
+    from pychips_b200.cleanup import CleanFl
+    aia = synth.make_aia(128, 0)
+    with pytest.raises(ValueError):
+        Chips(aia, base_folder="/tmp/chips_b200_test/", run_fl_cleanup=True).run_CHIPS()
+    a3 = synth.make_triplet_aia(128, 0)
+    small = synth._Map(np.ones((64, 64)))
+    with pytest.raises(NotImplementedError):      # resampling (skimage resize) is out of scope
+        CleanFl(a3, resolution=128).create_coronal_hole_candidates(smap171=small)

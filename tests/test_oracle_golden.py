@@ -86,3 +86,31 @@ def test_reference_still_agrees_when_present():
         a, b = d1.solar_ch_regions.__dict__[k], d2.solar_ch_regions.__dict__[k]
         assert np.array_equal(a.map, b.map)
         assert np.array_equal(a.prob, b.prob, equal_nan=True)
+
+
+def test_cleanfl_oracle_matches_reference_golden():
+    """oracle/cleanfl_oracle.py + the candidate hook of chips_oracle against the outputs of the
+    unmodified `chips.cleanup.CleanFl` / `Chips(run_fl_cleanup=True)` stage methods."""
+    from oracle import cleanfl_oracle as fo
+    g = load_golden("fl_n256_k11")
+    n, r = int(g["n"]), int(g["pixel_radius"])
+    imgs = [g[k].astype(np.float64) for k in ("img171", "img193", "img211")]
+    o = fo.create_coronal_hole_candidates(imgs[0], imgs[1], imgs[2], r, n)
+    planes = np.unpackbits(g["planes"])[:5 * n * n].reshape(5, n, n)
+    for i, a in enumerate((o.candidate, o.bmmix, o.bmhot, o.bmcool, o.candidate_bitmap)):
+        assert np.array_equal(planes[i], a.astype(np.uint8)), i
+    assert np.array_equal(g["thresholds"], np.array(o.thresholds))
+    assert np.array_equal(g["means"], np.array(o.means))
+    d = synth.FakeDisk(imgs[1], r)
+    co.OracleChips(medfilt_kernel=int(g["kw_medfilt_kernel"]), h_bins=int(g["kw_h_bins"]),
+                   threshold_range=list(g["kw_threshold_range"]),
+                   candidate_bitmap=o.candidate_bitmap).run(d)
+    keys = list(d.solar_ch_regions.__dict__.keys())
+    assert keys == list(g["keys"])
+    T = len(keys)
+    maps, raw = unpack(g["maps"], T, n, n), unpack(g["raw_maps"], T, n, n)
+    for t, k in enumerate(keys):
+        reg = d.solar_ch_regions.__dict__[k]
+        assert np.array_equal(maps[t], reg.map.astype(np.uint8))
+        assert np.array_equal(raw[t], reg.raw_map.astype(np.uint8))
+        assert np.array_equal(g["probs"][t], reg.prob, equal_nan=True)
