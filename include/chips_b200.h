@@ -188,6 +188,17 @@ int chips_fl_candidates(const void* d171, const void* d193, const void* d211, in
  * chips_threshold_prob and chips_cleanup */
 int chips_apply_candidates(const chips_plan* plan, const uint8_t* bits, void* ws, void* stream);
 
+/* ---- SURVEY.md §8(f) row 2  replaces: the `data[:, :, i] = region.map` cube of Chips.to_netcdf,
+ *      chips.py:570-586.  cube is float32 [H][W][T] (T innermost), 1.0 / 0.0; `which` as in
+ *      chips_expand_maps. ------------------------------------------------------------------ */
+int chips_pack_cube(const chips_plan* plan, int which, float* cube, void* ws, void* stream);
+
+/* ---- SURVEY.md §8(f) row 4  replaces: Chips.compute_similarity_measures, chips.py:592-617.
+ *      map, map0: [H][W] of `elem` bytes; out: double[H + 2] = per-row cosine similarity (NaN for
+ *      rows with sum(map[i]) <= 0), then np.nanmean of them and the number of rows used. ---- */
+int chips_row_cosine(const void* map, const void* map0, int H, int W, int elem, double* out,
+                     void* stream);
+
 /* helper: f64 -> f32 demotion with an exactness flag (1 = every value representable) */
 int chips_demote_f64(const double* in, float* out, size_t n, int32_t* all_exact, void* stream);
 

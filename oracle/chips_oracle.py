@@ -234,3 +234,33 @@ class OracleSynopticChips:
         if regs is not None:
             syn.set_value("solar_ch_regions", Namespace(**regs))
         return syn
+
+
+# --------------------------------------------------------------------------- SURVEY §8(f) rows 2, 4
+def netcdf_arrays(disk):
+    """The arrays `Chips.to_netcdf` stores in the `ch_regions` group (chips.py:570-586):
+    `data[:, :, i] = region.map` as float32 ("f4" variable) and the list of probabilities."""
+    keys = list(disk.solar_ch_regions.__dict__.keys())
+    res = disk.resolution
+    data, probs = np.zeros((res, res, len(keys))), []
+    for i, k in enumerate(keys):
+        region = getattr(disk.solar_ch_regions, str(k))
+        data[:, :, i] = region.map
+        probs.append(region.prob)
+    return data.astype(np.float32), probs
+
+
+def compute_similarity_measures(map, map0):
+    """chips.py:592-617 (row-wise cosine similarity through scikit-learn, then np.nanmean)."""
+    from sklearn.metrics.pairwise import cosine_similarity
+    measures = {"cosine_sim": np.nan}
+    cosine_sim = []
+    for i in range(map.shape[0]):
+        if np.sum(map[i, :]) > 0:
+            a, b = (np.array([list(map[i, :])]), np.array([list(map0[i, :])]))
+            cosine_sim.append(cosine_similarity(a, b)[0, 0])
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", RuntimeWarning)
+        measures["cosine_sim"] = np.nanmean(cosine_sim)
+    return measures

@@ -79,6 +79,8 @@ SIGNATURES = {
     "chips_fl_candidates": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, C.POINTER(FlParams), _vp, _vp, _vp, _vp],
                             C.c_int),
     "chips_apply_candidates": ([_PP, _vp, _vp, _vp], C.c_int),
+    "chips_pack_cube": ([_PP, _i, _vp, _vp, _vp], C.c_int),
+    "chips_row_cosine": ([_vp, _vp, _i, _i, _i, _vp, _vp], C.c_int),
 }
 
 _lib = None

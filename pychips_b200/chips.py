@@ -8,8 +8,7 @@ memoisation and the sticky `h_thresh` of the reference.  All arithmetic runs in 
 kernels behind `libchips_b200.so`; result arrays are materialised from device memory lazily
 on first attribute access.  There is no CPU fallback.
 
-Out of scope: plotting (`plot_diagonestics`), `to_netcdf`, filament cleanup
-plots, `compute_similarity_measures`.  `run_fl_cleanup=True` uses `cleanup.CleanFl` (csrc/fl.cu).
+Out of scope: plotting (`plot_diagonestics`, the filament summary plot).  `run_fl_cleanup=True` uses `cleanup.CleanFl` (csrc/fl.cu).
 """
 from __future__ import annotations
 
@@ -318,6 +317,65 @@ class Chips(object):
         """Canonical component labels (raster order of first pixel) of the hole-filled mask
         at threshold `lim_index`, and 2*contourArea per label."""
         return self._detector(disk).labels(lim_index)
+
+    # ---- chips.py:512-590.  The region cube is packed on the device (chips_pack_cube); the file
+    # is written with netCDF4 in the reference's group layout when that package is importable,
+    # otherwise as NetCDF-3 (ncio.py; the classic format has no groups: variables are named
+    # "<group>_<variable>").
+    def to_netcdf(self, wavelength: int, resolution: int, file_name: str = None) -> str:
+        disk = self.aia.datasets[wavelength][resolution]
+        file_name = (file_name if file_name
+                     else f"{disk.date.strftime('%Y-%m-%d-%H-%M')}_{wavelength}A_{resolution}.nc")
+        file = self.folder + f"/{file_name}"
+        logger.info(f"Save to file: {file}")
+        groups = {"fits": dict(fitdata=(("xarcs", "yarcs"), np.asarray(disk.normalized.data)))}
+        if hasattr(disk, "solar_filter"):
+            groups["filter"] = dict(
+                solar_disk=(("xarcs", "yarcs"), disk.solar_filter.solar_disk),
+                filt_disk=(("xarcs", "yarcs"), disk.solar_filter.filt_disk))
+        L = 0
+        if hasattr(disk, "solar_ch_regions"):
+            cube, probs = self.region_cube(disk)
+            L = len(probs)
+            groups["ch_regions"] = dict(ch_regions=(("xarcs", "yarcs", "probs"), cube),
+                                        probs=(("probs",), np.asarray(probs)))
+        dims = dict(xarcs=resolution, yarcs=resolution, probs=L)
+        try:
+            from netCDF4 import Dataset
+        except ImportError:
+            Dataset = None
+        if Dataset is not None:
+            nc = Dataset(file, "w", format="NETCDF4")
+            for gname, variables in groups.items():
+                grp = nc.createGroup(gname)
+                used = sorted({d for dd, _ in variables.values() for d in dd}, key=list(dims).index)
+                for d in used:
+                    grp.createDimension(d, dims[d])
+                for vname, (dd, value) in variables.items():
+                    grp.createVariable(vname, "f4", dd)[:] = value
+            nc.close()
+        else:
+            from . import ncio
+            flat = {f"{g}_{v}": spec for g, variables in groups.items() for v, spec in variables.items()}
+            ncio.write_float32(file, {d: s for d, s in dims.items() if s}, flat)
+        return file
+
+    def region_cube(self, disk):
+        """(float32 [res, res, L] cube with cube[:, :, i] = map of the i-th threshold, probs) —
+        the arrays `to_netcdf` stores (chips.py:570-586)."""
+        det = self._detector(disk)
+        with torch.cuda.device(self.device):
+            cube = det.pack_cube(0).cpu().numpy()
+        probs = [r.prob for r in disk.solar_ch_regions.__dict__.values()]
+        return cube, probs
+
+    # ---- chips.py:592-617
+    def compute_similarity_measures(self, map: np.ndarray, map0: np.ndarray, measure: str = "Hu") -> dict:
+        import warnings
+        _, mean, used = engine.row_cosine(map, map0, self.device)
+        if used == 0:
+            warnings.warn("Mean of empty slice", RuntimeWarning)      # np.nanmean([]) in the reference
+        return {"cosine_sim": np.float64(mean)}
 
     def plot_diagonestics(self, *a, **k) -> None:
         raise NotImplementedError("plotting is outside the accelerated path (SURVEY.md §2 row 6)")

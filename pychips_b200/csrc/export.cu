@@ -1,0 +1,162 @@
+// export.cu — output-side helpers of the detection path.
+//
+//   k_pack_cube      the `[res, res, L]` float32 region cube that Chips.to_netcdf stores
+//                    (/root/reference/chips/chips.py:570-586: data[:, :, i] = region.map), written
+//                    straight from the level-encoded result image: HBM-write bound, one warp
+//                    = 32 pixels = 32*T consecutive floats stored as aligned 128-bit words.
+//   k_row_cosine     Chips.compute_similarity_measures (chips.py:592-617): for every row i with
+//                    sum(map[i]) > 0 the cosine similarity of map[i] and map0[i] as
+//                    sklearn.metrics.pairwise.cosine_similarity computes it (rows L2-normalised,
+//                    zero norms replaced by 1, then the dot product); k_cosine_mean = np.nanmean.
+#include <math.h>
+#include "common.cuh"
+
+namespace chips {
+
+__global__ void __launch_bounds__(256) k_pack_cube(const uint8_t* __restrict__ src, size_t npix, int T,
+                                                   float* __restrict__ cube) {
+  const int lane = threadIdx.x & 31;
+  const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t p0 = warp * 32;
+  if (p0 >= npix) return;
+  const size_t p = p0 + lane;
+  const int mine = p < npix ? (int)src[p] : 255;          // first threshold whose map holds the pixel
+  const int nvalid = (int)(npix - p0 < 32 ? npix - p0 : 32);
+  const int nquad = nvalid * T / 4;                        // whole float4 words of this warp's run
+  float* base = cube + p0 * (size_t)T;                     // 32*T floats per warp: 128-byte aligned
+  for (int q0 = 0; q0 < 8 * T; q0 += 32) {                // uniform trip count: shuffles below
+    const int q = q0 + lane;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int e = 4 * q + j, px = e / T, t = e - px * T;
+      const int first = __shfl_sync(0xFFFFFFFFu, mine, px & 31);
+      v[j] = first <= t ? 1.0f : 0.0f;
+    }
+    if (q < nquad) {
+      *reinterpret_cast<float4*>(base + 4 * q) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if (q < 8 * T) {                                // ragged tail of the last warp
+      for (int j = 0; j < 4; ++j)
+        if (4 * q + j < nvalid * T) base[4 * q + j] = v[j];
+    }
+  }
+}
+
+// one CTA per row: out[row] = cosine similarity, NaN for rows the reference skips
+template <typename T>
+__global__ void __launch_bounds__(256) k_row_cosine(const T* __restrict__ a, const T* __restrict__ b, int W,
+                                                    double* __restrict__ out) {
+  __shared__ double red[3][8];
+  __shared__ double na_s, nb_s;
+  const T* ra = a + (size_t)blockIdx.x * W;
+  const T* rb = b + (size_t)blockIdx.x * W;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto block_sum3 = [&](double& x, double& y, double& z) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      x += __shfl_xor_sync(0xFFFFFFFFu, x, o);
+      y += __shfl_xor_sync(0xFFFFFFFFu, y, o);
+      z += __shfl_xor_sync(0xFFFFFFFFu, z, o);
+    }
+    __syncthreads();
+    if (lane == 0) {
+      red[0][warp] = x;
+      red[1][warp] = y;
+      red[2][warp] = z;
+    }
+    __syncthreads();
+    x = y = z = 0.0;
+    for (int i = 0; i < 8; ++i) {
+      x += red[0][i];
+      y += red[1][i];
+      z += red[2][i];
+    }
+  };
+  double s = 0.0, aa = 0.0, bb = 0.0;
+  for (int i = threadIdx.x; i < W; i += blockDim.x) {
+    const double x = (double)ra[i], y = (double)rb[i];
+    s += x;
+    aa += x * x;
+    bb += y * y;
+  }
+  block_sum3(s, aa, bb);
+  if (threadIdx.x == 0) {
+    double na = sqrt(aa), nb = sqrt(bb);
+    na_s = na == 0.0 ? 1.0 : na;         // sklearn.preprocessing.normalize: zero norms -> 1
+    nb_s = nb == 0.0 ? 1.0 : nb;
+  }
+  __syncthreads();
+  const double na = na_s, nb = nb_s;
+  double dot = 0.0, z1 = 0.0, z2 = 0.0;
+  for (int i = threadIdx.x; i < W; i += blockDim.x) dot += ((double)ra[i] / na) * ((double)rb[i] / nb);
+  block_sum3(dot, z1, z2);
+  if (threadIdx.x == 0) out[blockIdx.x] = (s > 0.0) ? dot : nan("");   // `if np.sum(map[i, :]) > 0`
+}
+
+// np.nanmean of the appended similarities: out[H] = mean, out[H+1] = number of rows used
+__global__ void __launch_bounds__(1024) k_cosine_mean(double* __restrict__ out, int H) {
+  __shared__ double sred[32];
+  __shared__ int cred[32];
+  double s = 0.0;
+  int c = 0;
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    const double v = out[i];
+    if (v == v) {
+      s += v;
+      ++c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sred[threadIdx.x >> 5] = s;
+    cred[threadIdx.x >> 5] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = 0.0;
+    c = 0;
+    for (int i = 0; i < 32; ++i) {
+      s += sred[i];
+      c += cred[i];
+    }
+    out[H] = c ? s / (double)c : nan("");
+    out[H + 1] = (double)c;
+  }
+}
+
+}  // namespace chips
+
+using namespace chips;
+
+extern "C" int chips_pack_cube(const chips_plan* plan, int which, float* cube, void* ws, void* stream) {
+  if (!plan || !cube || !ws || which < 0 || which > 2) return CHIPS_E_ARG;
+  const size_t n = (size_t)plan->H * plan->W;
+  const unsigned char* w = (const unsigned char*)ws;
+  const uint8_t* src = w + (which == 1 ? plan->off_level : (which == 2 ? plan->off_fill : plan->off_keep));
+  const size_t warps = (n + 31) / 32;
+  k_pack_cube<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(src, n, plan->T, cube);
+  CHIPS_CHECK_LAUNCH();
+  count_launch();
+  return CHIPS_OK;
+}
+
+extern "C" int chips_row_cosine(const void* map, const void* map0, int H, int W, int elem, double* out,
+                                void* stream) {
+  if (!map || !map0 || !out || H < 1 || W < 1) return CHIPS_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (elem == 4)
+    k_row_cosine<float><<<H, 256, 0, st>>>((const float*)map, (const float*)map0, W, out);
+  else if (elem == 8)
+    k_row_cosine<double><<<H, 256, 0, st>>>((const double*)map, (const double*)map0, W, out);
+  else
+    return CHIPS_E_ARG;
+  CHIPS_CHECK_LAUNCH();
+  k_cosine_mean<<<1, 1024, 0, st>>>(out, H);
+  CHIPS_CHECK_LAUNCH();
+  count_launch(2);
+  return CHIPS_OK;
+}

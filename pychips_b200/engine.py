@@ -190,6 +190,14 @@ class Detector:
                                              _ptr(self.ws), _stream_ptr()), "chips_expand_map")
         return out
 
+    def pack_cube(self, which: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+        """float32 [H,W,T] region cube of `Chips.to_netcdf` (chips.py:570-586)."""
+        if out is None:
+            out = torch.empty((self.geom.H, self.geom.W, self.T), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.chips_pack_cube(self._pp, which, _ptr(out), _ptr(self.ws), _stream_ptr()),
+                   "chips_pack_cube")
+        return out
+
     def roots(self, t: int):
         roots = torch.empty((self.geom.H, self.geom.W), dtype=torch.int32, device=self.device)
         area2 = torch.empty((self.geom.H, self.geom.W), dtype=torch.int32, device=self.device)
@@ -238,6 +246,26 @@ def to_device_image(data: np.ndarray, device, allow_demote: bool = True):
     if int(flag.item()) == 1:
         return t32, 4
     return t64, 8
+
+
+def row_cosine(map_: np.ndarray, map0: np.ndarray, device=None):
+    """Per-row cosine similarities and their nanmean (`chips_row_cosine`).  Returns
+    (rows [H] float64 with NaN for skipped rows, mean, rows_used)."""
+    device = require_cuda(device)
+    a = np.ascontiguousarray(map_)
+    b = np.ascontiguousarray(map0)
+    if a.ndim != 2 or a.shape != b.shape:
+        raise ValueError("map and map0 must be 2-D arrays of the same shape")
+    dt = np.float32 if (a.dtype == np.float32 and b.dtype == np.float32) else np.float64
+    with torch.cuda.device(device):
+        ta = torch.from_numpy(a.astype(dt, copy=False)).to(device)
+        tb = torch.from_numpy(b.astype(dt, copy=False)).to(device)
+        out = torch.empty(a.shape[0] + 2, dtype=torch.float64, device=device)
+        _lib.check(_lib.load().chips_row_cosine(_ptr(ta), _ptr(tb), a.shape[0], a.shape[1],
+                                                ta.element_size(), _ptr(out), _stream_ptr()),
+                   "chips_row_cosine")
+        h = out.cpu().numpy()
+    return h[:-2], h[-2], int(h[-1])
 
 
 def medfilt2d(data: np.ndarray, k: int, device=None) -> np.ndarray:

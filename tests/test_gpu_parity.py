@@ -532,3 +532,72 @@ def test_fl_requires_three_wavelengths_and_same_size():
     small = synth._Map(np.ones((64, 64)))
     with pytest.raises(NotImplementedError):      # resampling (skimage resize) is out of scope
         CleanFl(a3, resolution=128).create_coronal_hole_candidates(smap171=small)
+
+
+# ----------------------------------------------------------------------------- outputs (§8(f) rows 2, 4)
+def test_region_cube_and_netcdf_file(tmp_path):
+    """Chips.to_netcdf (chips.py:512-590): the [res, res, L] f4 cube packed on the device equals
+    the reference's `data[:, :, i] = region.map`; the written file round-trips."""
+    n = 320
+    img, r = synth.synthetic_disk(n, 9)
+    d_or = synth.FakeDisk(img.astype(np.float64), r)
+    co.OracleChips(medfilt_kernel=11).run(d_or, keep_contours=False)
+    want, probs = co.netcdf_arrays(d_or)
+    from pychips_b200 import Chips
+    d = synth.FakeDisk(img.astype(np.float64), r)
+    c = Chips(synth.FakeAIA(d), base_folder=str(tmp_path) + "/", medfilt_kernel=11)
+    c.run_CHIPS()
+    cube, got_probs = c.region_cube(d)
+    assert cube.dtype == np.float32 and cube.shape == want.shape
+    assert np.array_equal(cube, want)
+    assert np.allclose(got_probs, probs, rtol=REL, atol=0, equal_nan=True)
+    path = c.to_netcdf(193, n)
+    try:
+        from netCDF4 import Dataset
+        nc = Dataset(path)
+        got = nc["ch_regions"]["ch_regions"][:]
+        filt = nc["filter"]["filt_disk"][:]
+    except ImportError:
+        from scipy.io import netcdf_file
+        nc = netcdf_file(path, "r", mmap=False)
+        got = nc.variables["ch_regions_ch_regions"][:]
+        filt = nc.variables["filter_filt_disk"][:]
+        assert nc.variables["fits_fitdata"].shape == (n, n)
+        assert np.allclose(nc.variables["ch_regions_probs"][:], np.asarray(probs, dtype=np.float32),
+                           equal_nan=True)
+    assert np.array_equal(np.asarray(got), want)
+    assert np.array_equal(np.asarray(filt), d_or.solar_filter.filt_disk.astype(np.float32))
+
+
+@pytest.mark.parametrize("T", [1, 3, 20, 25])
+def test_pack_cube_ragged_sizes(T):
+    eng = _engine()
+    dev = eng.require_cuda()
+    H, W = 37, 53
+    det = eng.Detector(eng.Geometry(H, W, W // 2, H // 2, 15), 3, 8, 0, T, 4, dev)
+    rng = np.random.default_rng(T)
+    keep = rng.integers(0, T + 1, size=(H, W)).astype(np.uint8)
+    det.keep.copy_(torch.from_numpy(keep).to(dev))
+    cube = det.pack_cube(0).cpu().numpy()
+    want = (keep[:, :, None] <= np.arange(T)[None, None, :]).astype(np.float32)
+    assert np.array_equal(cube, want)
+
+
+def test_similarity_measures_vs_sklearn():
+    """Chips.compute_similarity_measures (chips.py:592-617)."""
+    from pychips_b200 import Chips
+    rng = np.random.default_rng(3)
+    a = (rng.random((200, 333)) < 0.2).astype(np.float64)
+    b = (rng.random((200, 333)) < 0.25).astype(np.float64)
+    a[5] = 0          # skipped row (sum == 0)
+    b[9] = 0          # zero-norm partner -> similarity 0
+    a[11] = rng.normal(size=333) + 2.0       # general real-valued rows
+    b[11] = rng.normal(size=333) + 2.0
+    want = co.compute_similarity_measures(a, b)["cosine_sim"]
+    c = Chips(synth.make_aia(64, 0), base_folder="/tmp/chips_b200_test/")
+    got = c.compute_similarity_measures(a, b)["cosine_sim"]
+    assert abs(got - want) <= 1e-12 * abs(want)
+    rows, _, used = _engine().row_cosine(a, b)
+    assert used == 199 and np.isnan(rows[5]) and rows[9] == 0.0
+    with pytest.warns(RuntimeWarning):
+        assert np.isnan(c.compute_similarity_measures(np.zeros((4, 8)), np.ones((4, 8)))["cosine_sim"])

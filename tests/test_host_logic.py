@@ -148,3 +148,25 @@ def test_series_exchange_gloo_world2():
         assert np.array_equal(allstats[:, 1], 20.0 + np.arange(n_total))
         assert np.array_equal(allstats[:, 3:3 + T], np.arange(n_total)[:, None] + np.arange(T)[None])
         assert np.all(psum == 3.0)                                          # 1 + 2 summed over ranks
+
+
+def test_netcdf3_writer_round_trip(tmp_path):
+    """pychips_b200/ncio.py (used by Chips.to_netcdf when netCDF4 is absent) against scipy's reader."""
+    from scipy.io import netcdf_file
+    from pychips_b200 import ncio
+    rng = np.random.default_rng(0)
+    a = rng.random((5, 7)).astype(np.float32)
+    c = rng.random((5, 7, 3))
+    p = np.array([0.1, np.nan, 0.3])
+    path = str(tmp_path / "t.nc")
+    ncio.write_float32(path, dict(xarcs=5, yarcs=7, probs=3),
+                       {"fits_fitdata": (("xarcs", "yarcs"), a),
+                        "ch_regions_ch_regions": (("xarcs", "yarcs", "probs"), c),
+                        "ch_regions_probs": (("probs",), p)})
+    nc = netcdf_file(path, "r", mmap=False)
+    assert nc.dimensions == {"xarcs": 5, "yarcs": 7, "probs": 3}
+    assert np.array_equal(nc.variables["fits_fitdata"][:], a)
+    assert np.array_equal(nc.variables["ch_regions_ch_regions"][:], c.astype(np.float32))
+    assert np.array_equal(nc.variables["ch_regions_probs"][:], p.astype(np.float32), equal_nan=True)
+    with pytest.raises(ValueError):
+        ncio.write_float32(path, dict(x=2), {"v": (("x",), np.zeros(3))})
