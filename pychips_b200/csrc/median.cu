@@ -34,7 +34,7 @@
 
 namespace chips {
 
-constexpr int kBuckets = 256;
+constexpr int kBuckets = 128;   // 8 resident tier-1 warps per SM (24 KB of counters each)
 constexpr int kSamples = 1024;   // per block
 constexpr int kHuangThreads = 128;
 constexpr int kTile = 16;
@@ -113,7 +113,7 @@ __device__ __forceinline__ int bucket_of(const K* __restrict__ bnd, K key) {
   // number of boundaries bnd[0..254] that are <= key  (bnd sorted ascending)
   int b = 0;
 #pragma unroll
-  for (int step = 128; step > 0; step >>= 1)
+  for (int step = kBuckets / 2; step > 0; step >>= 1)
     if (bnd[b + step - 1] <= key) b += step;
   return b;
 }
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(256) k_bucketize(const T* __restrict__ img, in
   const int blk = blockIdx.y, bx = blk % g.nbx, by = blk / g.nbx;
   const int X = g.rx0 + kHuangThreads * bx, Y = g.ry0 + g.L * by;
   if (!rect_on_disk(X, Y, kHuangThreads, g.L, cx, cy, r)) return;
-  sb[threadIdx.x] = bounds[(size_t)blk * kBuckets + threadIdx.x];
+  if (threadIdx.x < kBuckets) sb[threadIdx.x] = bounds[(size_t)blk * kBuckets + threadIdx.x];
   __syncthreads();
   const int word = threadIdx.x & 63, row = blockIdx.x * 4 + (threadIdx.x >> 6);
   if (word * 4 >= g.LP || row >= g.LR) return;
@@ -153,26 +153,6 @@ __device__ __forceinline__ int huang_slot(int tid) {
   return lane * 2 + (warp & 1) + (warp >> 1) * 64;
 }
 
-// Streams the k bucket bytes that start at `row` (any alignment) through aligned 32-bit
-// loads + funnel shifts.
-struct RowReader {
-  const uint32_t* wp;
-  int sh;
-  uint32_t w0;
-  __device__ __forceinline__ RowReader(const uint8_t* row) {
-    uintptr_t a = reinterpret_cast<uintptr_t>(row);
-    wp = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-    sh = (int)(a & 3) * 8;
-    w0 = __ldg(wp);
-  }
-  __device__ __forceinline__ uint32_t next(int word) {   // bytes [4*word, 4*word+4)
-    uint32_t w1 = __ldg(wp + word + 1);
-    uint32_t v = __funnelshift_r(w0, w1, sh);
-    w0 = w1;
-    return v;
-  }
-};
-
 // number of the 4 bytes of w that are < m (m in 0..255), branch-free SWAR: the low 7 bits are
 // compared through a borrow-free subtraction, the top bits by boolean algebra.
 __device__ __forceinline__ int count_bytes_below(uint32_t w, uint32_t m4, uint32_t m4lo) {
@@ -182,127 +162,227 @@ __device__ __forceinline__ int count_bytes_below(uint32_t w, uint32_t m4, uint32
   return __popc(lt);
 }
 
-// +1 for two entering elements; the two read-modify-writes are issued together (the loads
-// are independent); if both hit the same bin the second store (program order) carries the +2.
-__device__ __forceinline__ void huang_add2(uint16_t* __restrict__ my, int a, int b) {
-  constexpr int NT = kHuangThreads;
-  uint16_t* pa = my + a * NT;
-  uint16_t* pb = my + b * NT;
-  uint16_t ca = *pa, cb = *pb;
-  uint16_t na = (uint16_t)(ca + 1);
-  *pa = na;
-  *pb = (uint16_t)((a == b ? na : cb) + 1);
-}
-__device__ __forceinline__ void huang_add1(uint16_t* __restrict__ my, int a) {
-  uint16_t* pa = my + a * kHuangThreads;
-  *pa = (uint16_t)(*pa + 1);
-}
-// +1 for the entering element a, -1 for the leaving element b (a == b: net zero, the second
-// store writes the original count back)
-__device__ __forceinline__ void huang_swap(uint16_t* __restrict__ my, int a, int b) {
-  constexpr int NT = kHuangThreads;
-  uint16_t* pa = my + a * NT;
-  uint16_t* pb = my + b * NT;
-  uint16_t ca = *pa, cb = *pb;
-  uint16_t na = (uint16_t)(ca + 1);
-  *pa = na;
-  *pb = (uint16_t)((a == b ? na : cb) - 1);
-}
+// ------------------------------------------------------------------ 3. tier 1: Huang, 4 columns per thread
+// Adjacent columns share 50 of the 51 window columns, so a thread that owns FOUR adjacent
+// output columns x0..x0+3 keeps
+//   core   u16[kBuckets]  histogram of the 48 window columns common to all four windows, and
+//   fringe u32[kBuckets]  four u8 histograms packed in one word: byte j counts the (at most 3 x k)
+//                    pixels that only column j's window adds to the core
+// and pays 48 + 6 counter updates per row for four outputs instead of 4 x 51.  With r[i] the
+// k+3 bucket bytes of one row of the union window (r[0] = column x0 - half), column j's window
+// is r[j .. j+k-1]: r[3 .. k-1] is the core, r[i<3] enters the fringes of columns 0..i (one
+// packed add), r[k+i] the fringes of columns i+1..3.
+// The rank bookkeeping is relative to one pivot bucket P per thread: ltc / ltf count the core /
+// fringe pixels below P (SWAR byte compares while streaming the row); after each row P is
+// walked through the four medians in turn.
+// One warp = one 128-column block; a CTA holds two warps (two horizontally adjacent blocks) so
+// that the u16 core counters of lane l of both warps share bank l (conflict-free).
+constexpr int kH4Warps = 2;
+constexpr int kH4Stride = 32 * kH4Warps;   // counters of one bucket, all threads of the CTA
 
-__device__ __forceinline__ void huang_add_row(uint16_t* __restrict__ my, const uint8_t* row, int k,
-                                              int med, int& lt) {
-  RowReader rd(row);
-  const uint32_t m4 = (uint32_t)med * 0x01010101u, m4lo = m4 & 0x7F7F7F7Fu;
-  int j = 0, acc = 0;
-  for (; j + 4 <= k; j += 4) {
-    uint32_t v = rd.next(j >> 2);
-    acc += count_bytes_below(v, m4, m4lo);
-    huang_add2(my, v & 255, (v >> 8) & 255);
-    huang_add2(my, (v >> 16) & 255, v >> 24);
-  }
-  if (j < k) {
-    uint32_t v = rd.next(j >> 2);
-    acc += count_bytes_below(v | (0xFFFFFFFFu << (8 * (k - j))), m4, m4lo);
-    for (int i = 0; i < k - j; ++i) huang_add1(my, (v >> (8 * i)) & 255);
-  }
-  lt += acc;
-}
-
-__device__ __forceinline__ void huang_swap_row(uint16_t* __restrict__ my, const uint8_t* add,
-                                               const uint8_t* rem, int k, int med, int& lt) {
-  RowReader ra(add), rb(rem);
-  const uint32_t m4 = (uint32_t)med * 0x01010101u, m4lo = m4 & 0x7F7F7F7Fu;
-  int j = 0, acc = 0;
-  for (; j + 4 <= k; j += 4) {
-    uint32_t va = ra.next(j >> 2), vb = rb.next(j >> 2);
-    acc += count_bytes_below(va, m4, m4lo) - count_bytes_below(vb, m4, m4lo);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) huang_swap(my, (va >> (8 * i)) & 255, (vb >> (8 * i)) & 255);
-  }
-  if (j < k) {
-    uint32_t va = ra.next(j >> 2), vb = rb.next(j >> 2);
-    const uint32_t inval = 0xFFFFFFFFu << (8 * (k - j));
-    acc += count_bytes_below(va | inval, m4, m4lo) - count_bytes_below(vb | inval, m4, m4lo);
-    for (int i = 0; i < k - j; ++i) huang_swap(my, (va >> (8 * i)) & 255, (vb >> (8 * i)) & 255);
-  }
-  lt += acc;
-}
-
-__global__ void __launch_bounds__(kHuangThreads) k_huang(const uint8_t* __restrict__ Bp, BlockGeom g,
-                                                         int k, int W, int rw, int rh, int cx, int cy,
-                                                         int r, uint8_t* __restrict__ bstar,
-                                                         uint32_t* __restrict__ rres) {
-  constexpr int NT = kHuangThreads;
-  extern __shared__ __align__(16) uint16_t hist[];
-  const int tid = threadIdx.x;
+__global__ void __launch_bounds__(32 * kH4Warps) k_huang4(const uint8_t* __restrict__ Bp, BlockGeom g,
+                                                          int k, int W, int rw, int rh, int cx, int cy,
+                                                          int r, uint8_t* __restrict__ bstar,
+                                                          uint32_t* __restrict__ rres, uint32_t* __restrict__ dbg) {
+  extern __shared__ __align__(16) uint32_t h4_smem[];
+#ifdef CHIPS_DEBUG_TIMING
+  const long long t_begin = clock64();
+  unsigned smid;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+#endif
+  uint16_t* core_all = reinterpret_cast<uint16_t*>(h4_smem);          // [kBuckets][kH4Stride] u16
+  uint32_t* fr_all = h4_smem + kBuckets * kH4Stride / 2;               // [kBuckets][kH4Stride] u32
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int bx = blockIdx.x * kH4Warps + warp;
+  if (bx >= g.nbx) return;                                             // no CTA-wide barrier below
   const int half = g.half, pitch = g.LP, rx0 = g.rx0, ry0 = g.ry0;
-  const int x = rx0 + blockIdx.x * NT + tid;
+  uint16_t* myc = core_all + lane * kH4Warps + warp;                   // bank = lane
+  uint32_t* myf = fr_all + warp * 32 + lane;
+  const int x0 = rx0 + bx * kHuangThreads + 4 * lane;
   const int Yb = ry0 + blockIdx.y * g.L;
-  int ya = Yb;
-  int yb = min(ya + g.L, ry0 + rh);
-  bool valid = x < rx0 + rw;
-  if (valid && r >= 0) {
-    long long dx = x - cx;
-    long long rem = (long long)r * r - dx * dx;
-    if (rem < 0) {
-      valid = false;
-    } else {
-      long long dy = (long long)sqrt((double)rem);
-      while ((dy + 1) * (dy + 1) <= rem) ++dy;
-      while (dy * dy > rem) --dy;
-      ya = max(ya, cy - (int)dy);
-      yb = min(yb, cy + (int)dy + 1);
+  int ya[4], yb[4], ya_min = 0x7FFFFFFF, yb_max = -0x7FFFFFFF;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int x = x0 + j;
+    int a = Yb, b = min(Yb + g.L, ry0 + rh);
+    if (x >= rx0 + rw) {
+      b = a;
+    } else if (r >= 0) {
+      long long dx = x - cx;
+      long long rem = (long long)r * r - dx * dx;
+      if (rem < 0) {
+        b = a;
+      } else {
+        long long dy = (long long)sqrt((double)rem);
+        while ((dy + 1) * (dy + 1) <= rem) ++dy;
+        while (dy * dy > rem) --dy;
+        a = max(a, cy - (int)dy);
+        b = min(b, cy + (int)dy + 1);
+      }
+    }
+    ya[j] = a;
+    yb[j] = b;
+    if (a < b) {
+      ya_min = min(ya_min, a);
+      yb_max = max(yb_max, b);
     }
   }
-  if (!valid || ya >= yb) return;
-  uint16_t* my = hist + huang_slot(tid);
+  if (ya_min >= yb_max) return;
 #pragma unroll 8
-  for (int b = 0; b < kBuckets; ++b) my[b * NT] = 0;
-  const int R = (k * k - 1) >> 1;
-  int med = 0, lt = 0;
-  // block-local coordinates: the window of the block's column `tid` starts at local column tid,
-  // the window row of image row yy is local row yy - Yb + half.
-  const uint8_t* col = Bp + (size_t)(blockIdx.y * g.nbx + blockIdx.x) * g.LR * pitch + tid;
-  auto prow = [&](int yy) { return col + (size_t)(yy - Yb + half) * pitch; };
-  for (int yy = ya - half; yy < ya + half; ++yy) huang_add_row(my, prow(yy), k, med, lt);
-  for (int y = ya; y < yb; ++y) {
-    if (y == ya) huang_add_row(my, prow(y + half), k, med, lt);
-    else huang_swap_row(my, prow(y + half), prow(y - half - 1), k, med, lt);
-    while (lt > R) {
-      --med;
-      lt -= my[med * NT];
-    }
-    int c;
-    while (true) {
-      c = my[med * NT];
-      if (lt + c > R) break;
-      lt += c;
-      ++med;
-    }
-    size_t o = (size_t)y * W + x;
-    bstar[o] = (uint8_t)med;
-    rres[o] = (uint32_t)(R - lt) | ((uint32_t)c << 16);   // residual rank | bucket population
+  for (int b = 0; b < kBuckets; ++b) {
+    myc[b * kH4Stride] = 0;
+    myf[b * kH4Stride] = 0;
   }
+  const int R = (k * k - 1) >> 1;
+  const int nw = (k + 3 + 3) >> 2;            // 32-bit words covering r[0 .. k+2]
+  int P = 0, ltc = 0;                         // pivot bucket, core pixels below it
+  uint32_t ltf = 0;                           // fringe pixels below it, one byte per column
+  // block-local coordinates: r[0] of this thread is local column 4*lane (4-byte aligned), the
+  // window row of image row yy is local row yy - Yb + half
+  const uint8_t* col = Bp + (size_t)(blockIdx.y * g.nbx + bx) * g.LR * pitch + 4 * lane;
+  auto prow = [&](int yy) {
+    return reinterpret_cast<const uint32_t*>(col + (size_t)(yy - Yb + half) * pitch);
+  };
+  // one bucket byte `e` at union-window position i entering (sign = +1) or leaving (-1)
+  auto edge_byte = [&](int i, unsigned e, int sign) {
+    if (i >= k + 3) return;
+    if (i >= 3 && i < k) {
+      uint16_t* c = myc + e * kH4Stride;
+      *c = (uint16_t)(*c + sign);
+      ltc += ((int)e < P) ? sign : 0;
+    } else {
+      const uint32_t pat = i < 3 ? (0x01010101u >> (8 * (3 - i))) : (0x01010101u << (8 * (i - k + 1)));
+      uint32_t* f = myf + e * kH4Stride;
+      *f = sign > 0 ? *f + pat : *f - pat;
+      if ((int)e < P) ltf = sign > 0 ? ltf + pat : ltf - pat;
+    }
+  };
+  // A row is k+3 <= 78 bytes: all its words are fetched into registers by independent loads (the
+  // row of the NEXT step while the current one is being counted), so no load latency is exposed
+  // even with only four resident warps per SM.
+  constexpr int kMaxW = (CHIPS_MAX_K + 6) / 4;
+  auto load_row = [&](const uint32_t* row, uint32_t (&v)[kMaxW]) {
+#pragma unroll
+    for (int w = 0; w < kMaxW; ++w)
+      if (w < nw) v[w] = __ldg(row + w);
+  };
+  auto add_row = [&](const uint32_t (&va)[kMaxW]) {
+    const uint32_t m4 = (uint32_t)P * 0x01010101u, m4lo = m4 & 0x7F7F7F7Fu;
+    int acc = 0;
+#pragma unroll
+    for (int w = 0; w < kMaxW; ++w) {
+      if (w >= nw) break;
+      const uint32_t v = va[w];
+      if (w >= 1 && 4 * w + 3 < k) {          // four core pixels
+        acc += count_bytes_below(v, m4, m4lo);
+        const unsigned a0 = v & 255u, a1 = (v >> 8) & 255u, a2 = (v >> 16) & 255u, a3 = v >> 24;
+        uint16_t *p0 = myc + a0 * kH4Stride, *p1 = myc + a1 * kH4Stride;
+        uint16_t c0 = *p0, c1 = *p1;
+        uint16_t n0 = (uint16_t)(c0 + 1);
+        *p0 = n0;
+        *p1 = (uint16_t)((a0 == a1 ? n0 : c1) + 1);
+        uint16_t *p2 = myc + a2 * kH4Stride, *p3 = myc + a3 * kH4Stride;
+        uint16_t c2 = *p2, c3 = *p3;
+        uint16_t n2 = (uint16_t)(c2 + 1);
+        *p2 = n2;
+        *p3 = (uint16_t)((a2 == a3 ? n2 : c3) + 1);
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) edge_byte(4 * w + b, (v >> (8 * b)) & 255u, +1);
+      }
+    }
+    ltc += acc;
+  };
+  auto swap_row = [&](const uint32_t (&xa)[kMaxW], const uint32_t (&xb)[kMaxW]) {
+    const uint32_t m4 = (uint32_t)P * 0x01010101u, m4lo = m4 & 0x7F7F7F7Fu;
+    int acc = 0;
+#pragma unroll
+    for (int w = 0; w < kMaxW; ++w) {
+      if (w >= nw) break;
+      const uint32_t va = xa[w], vb = xb[w];
+      if (w >= 1 && 4 * w + 3 < k) {
+        acc += count_bytes_below(va, m4, m4lo) - count_bytes_below(vb, m4, m4lo);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {         // +1 entering, -1 leaving (same bucket: net zero)
+          const unsigned ea = (va >> (8 * b)) & 255u, eb = (vb >> (8 * b)) & 255u;
+          uint16_t *pa = myc + ea * kH4Stride, *pb = myc + eb * kH4Stride;
+          uint16_t ca = *pa, cb = *pb;
+          uint16_t na = (uint16_t)(ca + 1);
+          *pa = na;
+          *pb = (uint16_t)((ea == eb ? na : cb) - 1);
+        }
+      } else {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          edge_byte(4 * w + b, (va >> (8 * b)) & 255u, +1);
+          edge_byte(4 * w + b, (vb >> (8 * b)) & 255u, -1);
+        }
+      }
+    }
+    ltc += acc;
+  };
+
+  uint32_t ra[kMaxW], rb[kMaxW];
+  load_row(prow(ya_min - half), ra);
+  for (int yy = ya_min - half; yy < ya_min + half; ++yy) {
+    uint32_t nx[kMaxW];
+    load_row(prow(yy + 1), nx);               // rows up to ya_min + half exist in the block image
+    add_row(ra);
+#pragma unroll
+    for (int w = 0; w < kMaxW; ++w) ra[w] = nx[w];
+  }
+  // ra = row ya_min + half (entering at the first output row)
+  for (int y = ya_min; y < yb_max; ++y) {
+    uint32_t na[kMaxW], nb[kMaxW];
+    if (y + 1 < yb_max) {                     // operands of the next step
+      load_row(prow(y + 1 + half), na);
+      load_row(prow(y - half), nb);
+    }
+    if (y == ya_min) add_row(ra);
+    else swap_row(ra, rb);
+#pragma unroll
+    for (int w = 0; w < kMaxW; ++w) {
+      ra[w] = na[w];
+      rb[w] = nb[w];
+    }
+    // Walk the pivot through the four columns' medians, keeping the exact counts below it for
+    // all four (packed) on the way; odd rows visit the columns right to left, so a thread whose
+    // columns straddle a jump of the median (limb, hole boundary) crosses it once per row.
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = ((y - ya_min) & 1) ? 3 - jj : jj;
+      if (y < ya[j] || y >= yb[j]) continue;
+      const int sh = 8 * j;
+      while (ltc + (int)((ltf >> sh) & 255u) > R) {
+        --P;
+        ltc -= myc[P * kH4Stride];
+        ltf -= myf[P * kH4Stride];
+      }
+      int c, lt;
+      while (true) {
+        const int cc = myc[P * kH4Stride];
+        const uint32_t ff = myf[P * kH4Stride];
+        lt = ltc + (int)((ltf >> sh) & 255u);
+        c = cc + (int)((ff >> sh) & 255u);
+        if (lt + c > R) break;
+        ltc += cc;
+        ltf += ff;
+        ++P;
+      }
+      const size_t o = (size_t)y * W + (x0 + j);
+      bstar[o] = (uint8_t)P;
+      rres[o] = (uint32_t)(R - lt) | ((uint32_t)c << 16);   // residual rank | bucket population
+    }
+  }
+#ifdef CHIPS_DEBUG_TIMING
+  if (lane == 0 && dbg) {
+    uint32_t* d = dbg + 4 * (size_t)(blockIdx.y * g.nbx + bx);
+    d[0] = (uint32_t)(clock64() - t_begin);
+    d[1] = smid;
+    d[2] = (uint32_t)(yb_max - ya_min);
+    d[3] = (uint32_t)(t_begin & 0xFFFFFFFFu);
+  }
+#endif
 }
 
 // ------------------------------------------------------------------ 4. tier 2: tile refine
@@ -396,16 +476,16 @@ __device__ __forceinline__ void refine_tile_staged(
   {   // key range of bucket `tid` -> digit shift of its group; clear the sub-group counters
     const int b = tid;
     uint16_t gl = 0xFFFF;
-    if ((need[b >> 5] >> (b & 31)) & 1u) {
+    if (b < kBuckets && ((need[b >> 5] >> (b & 31)) & 1u)) {
       K klo = (b == 0) ? (K)0 : bounds[b - 1];
-      K span = bounds[b] - klo;               // bucket = [klo, bounds[b]) ; bounds[255] = kMax
+      K span = bounds[b] - klo;               // bucket = [klo, bounds[b]) ; the last bound is kMax
       if (b == kBuckets - 1 && span != Key<T>::kMax) span += 1;   // the last bucket is closed
       int g = (int)(needpfx[b >> 5] + __popc(need[b >> 5] & ((1u << (b & 31)) - 1u)));
       gl = (uint16_t)g;
       gklo[g] = klo;
       gshift[g] = (uint8_t)max(0, bit_length<K>(span - 1) - dlog);
     }
-    glut[b] = gl;
+    if (b < kBuckets) glut[b] = gl;
     for (int i = tid; i < nsg; i += NT) sgstart[i] = 0;
   }
   __syncthreads();
@@ -694,16 +774,16 @@ __global__ void __launch_bounds__(kTile* kTile, 4) k_refine_fast(
   {   // key range of bucket `tid` -> group tables (gshift holds the span's bit length for now)
     const int b = tid;
     uint16_t gl = 0xFFFF;
-    if ((need[b >> 5] >> (b & 31)) & 1u) {
+    if (b < kBuckets && ((need[b >> 5] >> (b & 31)) & 1u)) {
       K klo = (b == 0) ? (K)0 : bounds[b - 1];
-      K span = bounds[b] - klo;               // bucket = [klo, bounds[b]) ; bounds[255] = kMax
+      K span = bounds[b] - klo;               // bucket = [klo, bounds[b]) ; the last bound is kMax
       if (b == kBuckets - 1 && span != Key<T>::kMax) span += 1;   // the last bucket is closed
       int g = (int)(needpfx[b >> 5] + __popc(need[b >> 5] & ((1u << (b & 31)) - 1u)));
       gl = (uint16_t)g;
       gklo[g] = klo;
       gshift[g] = (uint8_t)bit_length<K>(span - 1);
     }
-    glut[b] = gl;
+    if (b < kBuckets) glut[b] = gl;
   }
   __syncthreads();
 
@@ -1047,11 +1127,12 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }
-  if (stages & 4) {  // tier 1: one CTA per block
-    dim3 grid(p->blk_nbx, p->blk_nby);
-    size_t smem = (size_t)kBuckets * kHuangThreads * sizeof(uint16_t);
-    CHIPS_CUDA(cudaFuncSetAttribute(k_huang, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_huang<<<grid, kHuangThreads, smem, st>>>(Bp, g, k, W, rw, rh, cx, cy, r, bstar, rres);
+  if (stages & 4) {  // tier 1: one warp per block, two blocks per CTA
+    dim3 grid((p->blk_nbx + kH4Warps - 1) / kH4Warps, p->blk_nby);
+    size_t smem = (size_t)kBuckets * kH4Stride * (sizeof(uint16_t) + sizeof(uint32_t));
+    CHIPS_CUDA(cudaFuncSetAttribute(k_huang4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_huang4<<<grid, 32 * kH4Warps, smem, st>>>(Bp, g, k, W, rw, rh, cx, cy, r, bstar, rres,
+                                                reinterpret_cast<uint32_t*>(ws + p->off_parent_c));
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }

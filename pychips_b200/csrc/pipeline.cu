@@ -34,10 +34,10 @@ extern "C" int chips_plan_init(chips_plan* p, int H, int W, int k, int h_bins, i
   }
   const int half = k >> 1;
   {  // median blocks (median.cu): 128 columns x L rows, L a multiple of the 16-pixel refine tile.
-     // Every tier-1 run pays a (k-1)-row warm-up and 3 CTAs (64 KB of histograms each) are
-     // resident per SM: minimise waves(L) * (L + k).
+     // Every tier-1 run pays a (k-1)-row warm-up; one warp owns one block and 8 warps (24 KB of
+     // histograms each) are resident per SM: minimise waves(L) * (L + k).
     const int nbx = (p->roi_w + 127) / 128;
-    const long long resident = 3LL * kNumSM;
+    const long long resident = 8LL * kNumSM;
     const int lmax = (int)align_up((size_t)p->roi_h, 16);
     int L = lmax;
     long long best = -1;
