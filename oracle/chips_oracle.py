@@ -264,3 +264,32 @@ def compute_similarity_measures(map, map0):
         warnings.simplefilter("ignore", RuntimeWarning)
         measures["cosine_sim"] = np.nanmean(cosine_sim)
     return measures
+
+
+# --------------------------------------------------------------------------- SURVEY §8(f) row 3
+def extract_histograms(filt_disk, n_mask, resolution, hist_xsplit, hist_ysplit, h_bins, h_thresh,
+                       ht_peak_ratio):
+    """Regional histograms, chips.py:260-319.  PARITY UNPINNED: the reference method is dead code
+    (commented out at chips.py:167) and raises NameError when called — `r_peaks`, `regions` and
+    `d` are never defined (its first line binds `histograms, peaks, k`).  This restatement makes
+    the three evident repairs (regions = {}, r_peaks = [], data = the region's masked pixels) and
+    keeps everything else as written, including the column slice `y*yunit : (y+1)*xunit` and
+    `fpeak` collecting peak indices.  Returns (regions dict, fpeak list, sticky h_thresh)."""
+    regions, r_peaks, k = {}, [], 0
+    xunit, yunit = int(resolution / hist_xsplit), int(resolution / hist_ysplit)
+    for x in range(hist_xsplit):
+        for y in range(hist_ysplit):
+            r_disk_data = (filt_disk[x * xunit:(x + 1) * xunit, y * yunit:(y + 1) * xunit] *
+                           n_mask[x * xunit:(x + 1) * xunit, y * yunit:(y + 1) * xunit]).ravel()
+            with np.errstate(invalid="ignore", divide="ignore"):
+                h, be = np.histogram(r_disk_data[~np.isnan(r_disk_data.ravel())], bins=h_bins, density=True)
+            if h_thresh is None:
+                h_thresh = np.max(h) / ht_peak_ratio
+            peaks, _ = signal.find_peaks(h, height=h_thresh)
+            bc = be[:-1] + np.diff(be)
+            if len(peaks) > 1:
+                r_peaks.extend(peaks[:2])
+            regions[k] = Namespace(peaks=peaks, hbase=h, bound=bc, data=r_disk_data, h_thresh=h_thresh,
+                                   h_bins=h_bins)
+            k += 1
+    return regions, r_peaks, h_thresh

@@ -265,6 +265,53 @@ class Chips(object):
                 peak_indexs=pidx))
         return
 
+    # ---- chips.py:260-319.  The reference method is dead code: it is commented out of
+    # process_CHIPS (:167) and raises NameError when called (`r_peaks`, `regions`, `d` are never
+    # defined; its first line binds `histograms, peaks, k` instead).  This is the evident intent —
+    # regions = {}, r_peaks = [], data = the region's masked pixels — with everything else as
+    # written, including the column slice `y*yunit : (y+1)*xunit` and `fpeak` collecting peak
+    # INDICES.  Parity unpinned (no reference output exists); pinned to oracle/chips_oracle.py.
+    def extract_histograms(self, disk) -> None:
+        logger.info(f"Extract solar histograms for different regions {disk.wavelength}/{disk.resolution}")
+        if (not hasattr(disk, "histograms") and (self.hist_xsplit is not None)
+                and (self.hist_ysplit is not None)):
+            det = self._detector(disk)
+            regions, r_peaks, k = {}, [], 0
+            xunit, yunit = (int(disk.resolution / self.hist_xsplit), int(disk.resolution / self.hist_ysplit))
+            H, W = det.geom.H, det.geom.W
+            for x in range(self.hist_xsplit):
+                for y in range(self.hist_ysplit):
+                    y0, y1 = min(x * xunit, H), min((x + 1) * xunit, H)         # first index = rows
+                    x0, x1 = min(y * yunit, W), min((y + 1) * xunit, W)
+                    with torch.cuda.device(self.device):
+                        self._ensure_filt(disk, det)
+                        out = det.region_histogram(y0, y1, x0, max(x0, x1), self.ht_peak_ratio, self.h_thresh)
+                    if out is None:        # no on-disk pixel: numpy's histogram of an empty array
+                        be = np.linspace(0, 1, self.h_bins + 1)
+                        h, bc, peaks, hthr = (np.full(self.h_bins, np.nan), be[:-1] + np.diff(be),
+                                              np.zeros(0, dtype=np.int64), np.float64(np.nan))
+                    else:
+                        h, bc, peaks, hthr = out
+                    if self.h_thresh is None:
+                        self.h_thresh = hthr
+                    if len(peaks) > 1:
+                        r_peaks.extend(peaks[:2])
+
+                    def data(y0=y0, y1=y1, x0=x0, x1=x1):
+                        return (disk.solar_filter.filt_disk[y0:y1, x0:x1] *
+                                disk.solar_mask.n_mask[y0:y1, x0:x1]).ravel()
+
+                    regions[k] = LazyNamespace(_lazy=dict(data=data), peaks=peaks, hbase=h, bound=bc,
+                                               h_thresh=self.h_thresh, h_bins=self.h_bins)
+                    k += 1
+            disk.set_value("histograms", Namespace(**dict(reg=regions, fpeak=r_peaks, keys=range(k))))
+        return
+
+    # ---- chips.py:321-339: an empty stub in the reference (`pass`)
+    def extract_sliding_histograms(self, disk) -> None:
+        logger.info(f"Extract solar histograms for different regions {disk.wavelength}/{disk.resolution}")
+        return
+
     # ---- chips.py:341-403
     def extract_CHs_CHBs(self, disk) -> None:
         logger.info(f"Extract CHs and CHBs for different regions {disk.wavelength}/{disk.resolution}")

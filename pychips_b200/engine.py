@@ -66,8 +66,17 @@ class Detector:
         self.plan = Plan()
         _lib.check(self.lib.chips_plan_init(C.byref(self.plan), geom.H, geom.W, self.k, self.h_bins,
                                             self.T, elem, geom.cx, geom.cy, geom.r), "chips_plan_init")
+        # scratch tail behind the plan's workspace: outputs of the regional histograms
+        # (`region_histogram`), so that they never overwrite the detection's own record
+        self._tail = {}
+        off = (int(self.plan.bytes) + 255) // 256 * 256
+        for name, nbytes in (("minmax", 16), ("counts", self.h_bins * 8), ("density", self.h_bins * 8),
+                             ("edges", (self.h_bins + 1) * 8), ("bound", self.h_bins * 8),
+                             ("peaks", self.h_bins * 4), ("result", C.sizeof(Result))):
+            self._tail[name] = off
+            off = (off + nbytes + 255) // 256 * 256
         with torch.cuda.device(self.device):
-            self.ws = torch.empty(int(self.plan.bytes), dtype=torch.uint8, device=self.device)
+            self.ws = torch.empty(off, dtype=torch.uint8, device=self.device)
         self._pp = C.byref(self.plan)
         self.dtype = torch.float32 if elem == 4 else torch.float64
 
@@ -146,6 +155,43 @@ class Detector:
                                              _stream_ptr()), "chips_minmax")
         _lib.check(self.lib.chips_histogram(_ptr(filt), self._pp, *self._g(), _ptr(self.ws),
                                             _stream_ptr()), "chips_histogram")
+
+    def region_histogram(self, y0: int, y1: int, x0: int, x1: int, ht_peak_ratio: float, h_thresh):
+        """`np.histogram(bins=h_bins, density=True)` + `find_peaks(height=h_thresh)` of the on-disk
+        pixels of `filt[y0:y1, x0:x1]` (the body of the region loop of `Chips.extract_histograms`,
+        chips.py:282-300): the same three kernels as the full-disk histogram, run on a plan whose
+        ROI is the region and whose outputs live in the scratch tail.  Returns
+        (density, bound, peak_indices, h_thresh) as host arrays, or None for an empty region."""
+        p = self.plan
+        rx0, ry0 = max(int(p.roi_x0), x0), max(int(p.roi_y0), y0)
+        rx1, ry1 = min(int(p.roi_x0 + p.roi_w), x1), min(int(p.roi_y0 + p.roi_h), y1)
+        if rx1 <= rx0 or ry1 <= ry0:
+            return None
+        q = Plan.from_buffer_copy(bytes(p))
+        q.roi_x0, q.roi_y0, q.roi_w, q.roi_h = rx0, ry0, rx1 - rx0, ry1 - ry0
+        for name, off in self._tail.items():
+            setattr(q, "off_" + name, off)
+        qp = C.byref(q)
+        h_in = float("nan") if h_thresh is None else float(h_thresh)
+        for fn, args in ((self.lib.chips_minmax, (_ptr(self.filt), qp, *self._g())),
+                         (self.lib.chips_histogram, (_ptr(self.filt), qp, *self._g()))):
+            _lib.check(fn(*args, _ptr(self.ws), _stream_ptr()), fn.__name__)
+        _lib.check(self.lib.chips_select_threshold(qp, float(ht_peak_ratio), h_in, self.t0, self.t1,
+                                                   _ptr(self.ws), _stream_ptr()), "chips_select_threshold")
+
+        def tail(name, dtype, count):
+            o = self._tail[name]
+            nb = count * torch.empty((), dtype=dtype).element_size()
+            return self.ws[o:o + nb].view(dtype)
+
+        res = Result.from_buffer_copy(tail("result", torch.uint8, C.sizeof(Result)).cpu().numpy().tobytes())
+        if res.n_samples == 0:
+            return None
+        npk = int(res.n_peaks)
+        return (tail("density", torch.float64, self.h_bins).cpu().numpy(),
+                tail("bound", torch.float64, self.h_bins).cpu().numpy(),
+                tail("peaks", torch.int32, self.h_bins)[:npk].cpu().numpy().astype(np.int64),
+                np.float64(res.h_thresh))
 
     def select_threshold(self, ht_peak_ratio: float, h_thresh):
         h_in = float("nan") if h_thresh is None else float(h_thresh)

@@ -601,3 +601,38 @@ def test_similarity_measures_vs_sklearn():
     assert used == 199 and np.isnan(rows[5]) and rows[9] == 0.0
     with pytest.warns(RuntimeWarning):
         assert np.isnan(c.compute_similarity_measures(np.zeros((4, 8)), np.ones((4, 8)))["cosine_sim"])
+
+
+# ----------------------------------------------------------------------------- regional histograms (§8(f) row 3)
+@pytest.mark.parametrize("n,xs,ys,hb", [(512, 2, 2, 500), (384, 3, 3, 200), (320, 4, 2, 1000)])
+def test_regional_histograms_vs_oracle(n, xs, ys, hb):
+    """Chips.extract_histograms (chips.py:260-319, repaired dead code — parity unpinned by the
+    reference, pinned to the oracle restatement)."""
+    from pychips_b200 import Chips
+    img, r = synth.synthetic_disk(n, 12)
+    d_or = synth.FakeDisk(img.astype(np.float64), r)
+    o = co.OracleChips(medfilt_kernel=11, h_bins=hb)
+    o.run(d_or, keep_contours=False)
+    regs, fpeak, hthr = co.extract_histograms(d_or.solar_filter.filt_disk, d_or.solar_mask.n_mask, n, xs, ys,
+                                              hb, o.h_thresh, 5)
+    d = synth.FakeDisk(img.astype(np.float64), r)
+    c = Chips(synth.FakeAIA(d), base_folder="/tmp/chips_b200_test/", medfilt_kernel=11, h_bins=hb,
+              hist_xsplit=xs, hist_ysplit=ys)
+    c.run_CHIPS()
+    c.extract_histograms(d)
+    assert list(d.histograms.keys) == list(range(xs * ys)) and len(d.histograms.reg) == len(regs)
+    assert [int(v) for v in d.histograms.fpeak] == [int(v) for v in fpeak]
+    for k, ref in regs.items():
+        got = d.histograms.reg[k]
+        assert np.array_equal(got.hbase, ref.hbase, equal_nan=True), k
+        assert np.array_equal(got.bound, ref.bound), k
+        assert np.array_equal(np.asarray(got.peaks), np.asarray(ref.peaks)), k
+        assert np.array_equal(got.data, ref.data, equal_nan=True), k
+        assert got.h_thresh == ref.h_thresh and got.h_bins == hb
+    # the regional pass must not disturb the detection's own record
+    d2 = synth.FakeDisk(img.astype(np.float64), r)
+    c2 = Chips(synth.FakeAIA(d2), base_folder="/tmp/chips_b200_test/", medfilt_kernel=11, h_bins=hb)
+    c2.extract_solar_masks(d2); c2.run_filters(d2); c2.extract_histogram(d2); c2.extract_histograms(d2)
+    c2.extract_CHs_CHBs(d2)
+    for key, reg in d_or.solar_ch_regions.__dict__.items():
+        assert np.array_equal(d2.solar_ch_regions.__dict__[key].map, reg.map)
