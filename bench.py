@@ -288,8 +288,8 @@ def run_b200(a):
         stages = [
             ("median.k_bounds", k_stage(1), 0),
             ("median.k_bucketize", k_stage(2), 5 * n * n),
-            ("median.k_huang", k_stage(4), 8 * n * n),
-            ("median.k_refine", k_stage(8), 8 * n * n),
+            ("median.k_huang4", k_stage(4), 8 * n * n),
+            ("median.k_refine_fast", k_stage(8), 8 * n * n),
             ("k_hist", lambda: det.histogram(), 4 * n * n),
             ("k_select", lambda: det.select_threshold(5, None), 0),
             ("k_threshold_prob", lambda: det.threshold_prob(0.8), 5 * n * n),
