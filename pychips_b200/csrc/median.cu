@@ -688,8 +688,8 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine_list(
 //   d. every thread walks the sorted candidates of ITS bucket from the nearer end, counting
 //      those inside its own k x k window, until it reaches its residual rank.
 // Tiles with more than kFastCap candidates go to the overflow list (k_refine_list).
-constexpr int kFastCap = 2048;   // candidates per tile on the fast path
-constexpr int kFastSub = 1024;   // (bucket, digit) sub-groups per tile
+constexpr int kFastCap = 1280;   // candidates per tile on the fast path
+constexpr int kFastSub = 512;    // (bucket, digit) sub-groups per tile
 
 __device__ __forceinline__ uint32_t sum_u16x8(const uint4 c) {
   return (c.x & 0xFFFFu) + (c.x >> 16) + (c.y & 0xFFFFu) + (c.y >> 16) + (c.z & 0xFFFFu) + (c.z >> 16) +
@@ -697,7 +697,7 @@ __device__ __forceinline__ uint32_t sum_u16x8(const uint4 c) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kTile* kTile, 4) k_refine_fast(
+__global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
     const T* __restrict__ img, const uint8_t* __restrict__ Bp_all, const BlockGeom g,
     const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres,
     const typename Key<T>::type* __restrict__ bounds_all, int H, int W, int rw, int rh, int cx, int cy,

@@ -1,0 +1,16 @@
+"""One warmed-up 4096^2 detection (+ expand, + filament candidates): the target of ncu captures."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from pychips_b200 import _lib, engine, synth
+n, k = int(os.environ.get("N", 4096)), int(os.environ.get("K", 51))
+img, r = synth.synthetic_disk(n, 0)
+dev = engine.require_cuda()
+t = torch.from_numpy(img).to(dev)
+c = n // 2
+det = engine.Detector(engine.Geometry(n, n, c, c, r), k, 500, 0, 20, 4, dev)
+maps = torch.empty((20, n, n), dtype=torch.uint8, device=dev)
+for _ in range(int(os.environ.get("REPS", 1))):
+    det.detect(t, maps=maps)
+torch.cuda.synchronize()
+print("n_peaks", det.result().n_peaks, "median_errors", det.result().median_errors)
