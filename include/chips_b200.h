@@ -77,11 +77,11 @@ typedef struct chips_plan {
   size_t off_keep;       /* u8  [H][W]   first threshold at which the pixel is in the final map */
   size_t off_probtab;    /* u32 [T+1][20]                                                 */
   size_t off_parent_b;   /* u32 [roi_h*roi_w + 1]   background union-find                 */
-  size_t off_parent_c;   /* u32 [T][roi_h*roi_w]    per-threshold union-find              */
-  size_t off_area;       /* u32 [T][roi_h*roi_w]    2*area accumulators at roots          */
+  size_t off_parent_c;   /* u32 [2][roi_h*roi_w]    component tree: union-find, merge parents */
+  size_t off_area;       /* u32 [roi] 2*area at roots; u8 [3][roi] hook level, kept level, W  */
   size_t off_pending;    /* u32 [roi_h*roi_w]  hole-fill work list grouped by level       */
-  size_t off_lvl;        /* u32 [512]          per-level counts / offsets / cursors, tile count */
-  size_t off_tiles;      /* u32 [#32x8 tiles]  list of tiles that hold filled-mask pixels */
+  size_t off_lvl;        /* u32 [512]          per-level counts / offsets / cursors, phase-C counters */
+  size_t off_tiles;      /* (reserved)                                                    */
   size_t off_ovf;        /* u32 [1 + #16x16 tiles]  median tier 2: count + list of slow-path tiles */
   size_t bytes;          /* total workspace size                                          */
 } chips_plan;

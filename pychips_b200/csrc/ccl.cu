@@ -284,249 +284,275 @@ __global__ void __launch_bounds__(256) k_fill_round_assign(Roi g, int t, int T,
   }
 }
 
-// ------------------------------------------------------------------ phase C
-// Work is restricted to "active" 32x8 tiles (tiles that hold at least one pixel of some
-// filled mask, W < T); each of the T labellings walks the same tile list (blockIdx.y = t).
-constexpr int kTileW = 32, kTileH = 8;
-
-__global__ void __launch_bounds__(256) k_tile_list(Roi g, const uint8_t* __restrict__ Wimg, int T,
-                                                   int tiles_x, int tiles_y,
-                                                   uint32_t* __restrict__ tile_count,
-                                                   uint32_t* __restrict__ tiles) {
-  // one warp per tile: lane = column, loop over the 8 rows
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= tiles_x * tiles_y) return;
-  int tj = warp % tiles_x, ti = warp / tiles_x;
-  int x = g.x0 + tj * kTileW + lane;
-  bool any = false;
-  if (x < g.x0 + g.w) {
-    for (int dy = 0; dy < kTileH; ++dy) {
-      int y = g.y0 + ti * kTileH + dy;
-      if (y < g.y0 + g.h) any |= Wimg[(size_t)y * g.W + x] < T;
-    }
-  }
-  if (__any_sync(0xFFFFFFFFu, any) && lane == 0) tiles[atomicAdd(tile_count, 1u)] = (uint32_t)warp;
-}
-
-struct TileCtx {
-  int x, y;
-  bool valid;
+// ------------------------------------------------------------------ phase C: component tree
+// The T filled masks {W <= t} are nested, so their 8-connected components form a tree: ONE
+// union-find is grown through the levels t = 0 .. T-1 instead of T independent labellings
+// (T x less union-find work and one parent array instead of T).  Two small launches per level
+// (the launch boundary is the grid barrier; other streams fill the GPU meanwhile):
+//   k_tree_union(t)   the pixels with W == t (a list grouped by W) are united with their
+//                     8-neighbours that are already foreground; every OLD root that gets hooked
+//                     is appended to `hooked` (a new pixel that joins a component is not).
+//   k_tree_merge(t)   each node hooked in this level hands its accumulated 2*area to the root
+//                     of the merged component and records (mparent, mlevel) — the merge tree,
+//                     whose chains have strictly increasing levels, i.e. at most T links; each
+//                     new pixel records its root of this level and adds its bit-quad events (a
+//                     2x2 quad adds 1 to 2*contourArea when its third pixel appears and 1 more
+//                     with the fourth: 2*Q4 + Q3).  The atomicAdd that lifts a root over the
+//                     area threshold records klevel[root] = t; component counts are running sums.
+//   k_tree_keep       keep(p) = first level at which p's component is kept: walk p's merge
+//                     chain to the first node with a finite klevel.
+struct Tree {
+  uint32_t* parent;    // [nr] union-find (path-halved)
+  uint32_t* mparent;   // [nr] root of the merged component at the end of the level of the hook
+  uint32_t* area;      // [nr] 2*area accumulated while the node was a root
+  uint8_t* mlevel;     // [nr] level in which the node stopped being a root (255: still a root)
+  uint8_t* klevel;     // [nr] level at which the node, as a root, reached the threshold (255: never)
+  uint8_t* wl;         // [nr] ROI-local copy of W (255 outside every mask)
+  uint32_t* plist;     // foreground pixels (ROI-local index) grouped by W, ascending
+  uint32_t* hooked;    // hooked old roots in hook order
+  uint32_t* offset;    // [T+2] list offsets by W (lvl_offset)
+  uint32_t* ctr;       // [1] hook cursor, [2] kept components, [3] components, [8+t] hook cursor after level t
 };
-__device__ __forceinline__ TileCtx tile_pixel(const Roi& g, uint32_t tile, int tiles_x) {
-  int tj = tile % tiles_x, ti = tile / tiles_x;
-  TileCtx c;
-  c.x = g.x0 + tj * kTileW + (threadIdx.x & 31);
-  c.y = g.y0 + ti * kTileH + (threadIdx.x >> 5);
-  c.valid = c.x < g.x0 + g.w && c.y < g.y0 + g.h;
-  return c;
+
+__device__ __forceinline__ int wl_at(const Roi& g, const uint8_t* __restrict__ wl, int lx, int ly) {
+  return (lx >= 0 && lx < g.w && ly >= 0 && ly < g.h) ? (int)wl[(size_t)ly * g.w + lx] : 255;
 }
 
-__device__ __forceinline__ bool fg_at(const Roi& g, const uint8_t* __restrict__ Wimg, int t, int xx,
-                                      int yy) {
-  return xx >= g.x0 && xx < g.x0 + g.w && yy >= g.y0 && yy < g.y0 + g.h &&
-         Wimg[(size_t)yy * g.W + xx] <= t;
-}
-
-// W of a pixel as an int, 255 (= never foreground) outside the ROI
-__device__ __forceinline__ int w_at(const Roi& g, const uint8_t* __restrict__ Wimg, int xx, int yy) {
-  return (xx >= g.x0 && xx < g.x0 + g.w && yy >= g.y0 && yy < g.y0 + g.h)
-             ? (int)Wimg[(size_t)yy * g.W + xx] : 255;
-}
-__device__ __forceinline__ int warp_min(int v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
-  return v;
-}
-
-// All T labellings in one sweep over the active tiles: every thread loads the W values it needs
-// ONCE and loops over the thresholds t >= W (a pixel is foreground from its W upwards).  The
-// loop variable is warp-uniform (starts at the smallest W of the warp's 32-pixel row span) so
-// the ballots / match_any inside see consistent participants.
-__global__ void __launch_bounds__(256) k_ccl_link(Roi g, const uint8_t* __restrict__ Wimg, int T,
-                                                  int tiles_x, const uint32_t* __restrict__ tile_count,
-                                                  const uint32_t* __restrict__ tiles,
-                                                  uint32_t* __restrict__ parent_all,
-                                                  uint32_t* __restrict__ area_all) {
-  const size_t n = (size_t)g.w * g.h;
-  const uint32_t nt = *tile_count;
-  const int lane = threadIdx.x & 31;
-  for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
-    TileCtx c = tile_pixel(g, tiles[i], tiles_x);
-    const int w = c.valid ? (int)Wimg[(size_t)c.y * g.W + c.x] : 255;
-    int wl = 255;                                  // pixel left of the span (lane 0 only)
-    if (lane == 0) wl = w_at(g, Wimg, c.x - 1, c.y);
-    wl = __shfl_sync(0xFFFFFFFFu, wl, 0);
-    const uint32_t me = c.valid ? g.li(c.x, c.y) : 0u;
-    for (int t = warp_min(w); t < T; ++t) {
-      const bool act = w <= t;
-      const unsigned m = __ballot_sync(0xFFFFFFFFu, act);
-      if (!act) continue;
-      const unsigned z = ~m & ((1u << lane) - 1u);
-      const int s = z ? (32 - __clz(z)) : 0;
-      uint32_t tgt = (s == 0 && wl <= t) ? me - (uint32_t)lane - 1u : me - (uint32_t)(lane - s);
-      parent_all[(size_t)t * n + me] = tgt;
-      area_all[(size_t)t * n + me] = 0;
+__device__ __forceinline__ void uf_unite_rec(const Tree& tr, int t, uint32_t a, uint32_t b) {
+  uint32_t* __restrict__ parent = tr.parent;
+  a = uf_find(parent, a);
+  b = uf_find(parent, b);
+  while (a != b) {
+    if (a < b) {
+      uint32_t x = a;
+      a = b;
+      b = x;
+    }                            // a > b : hook a under b
+    uint32_t old = atomicMin(&parent[a], b);
+    if (old == a) {              // a was a root until now: it is hooked exactly once
+      if (tr.wl[a] != t) tr.hooked[atomicAdd(&tr.ctr[1], 1u)] = a;   // an older component merges
+      a = b;
+    } else {
+      a = old;                   // hooked by somebody else in this level: go on with its parent
     }
   }
 }
 
-__global__ void __launch_bounds__(256) k_ccl_union(Roi g, const uint8_t* __restrict__ Wimg, int T,
-                                                   int tiles_x, const uint32_t* __restrict__ tile_count,
-                                                   const uint32_t* __restrict__ tiles,
-                                                   uint32_t* __restrict__ parent_all) {
-  const size_t n = (size_t)g.w * g.h;
-  const uint32_t nt = *tile_count;
-  for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
-    TileCtx c = tile_pixel(g, tiles[i], tiles_x);
-    if (!c.valid || c.y == g.y0) continue;
-    const int x = c.x, y = c.y;
-    const int w = Wimg[(size_t)y * g.W + x];
-    if (w >= T) continue;
-    const int wu = w_at(g, Wimg, x, y - 1), wul = w_at(g, Wimg, x - 1, y - 1);
-    const int wur = w_at(g, Wimg, x + 1, y - 1), wlf = w_at(g, Wimg, x - 1, y);
-    const int wrt = w_at(g, Wimg, x + 1, y);
-    if (min(wu, min(wul, wur)) >= T) continue;     // nothing above in any mask
+// C1: ROI-local W, per-level counts of the foreground pixels and singleton initialisation
+// (PASS 0); the list grouped by W (PASS 1).
+template <int PASS>
+__global__ void __launch_bounds__(256) k_tree_list(Roi g, const uint8_t* __restrict__ Wimg, int T, Tree tr,
+                                                   uint32_t thr2, uint32_t* __restrict__ lvl_count,
+                                                   uint32_t* __restrict__ lvl_cursor) {
+  __shared__ uint32_t scnt[CHIPS_MAX_T + 1];
+  if (PASS == 0) {
+    for (int i = threadIdx.x; i <= T; i += blockDim.x) scnt[i] = 0;
+    __syncthreads();
+  }
+  const int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x, y = g.y0 + blockIdx.y;
+  int w = -1;
+  if (x < g.x0 + g.w) {
+    const int v = Wimg[(size_t)y * g.W + x];
+    if (v < T) w = v;
+    if (PASS == 0) tr.wl[g.li(x, y)] = (uint8_t)(v < T ? v : 255);
+  }
+  const unsigned act = __ballot_sync(0xFFFFFFFFu, w >= 0);
+  if (w >= 0) {
     const uint32_t me = g.li(x, y);
-    for (int t = w; t < T; ++t) {
-      uint32_t* parent = parent_all + (size_t)t * n;
-      const bool up = wu <= t, ul = wul <= t, ur = wur <= t, lf = wlf <= t, rt = wrt <= t;
-      if (up) {
-        if (!(lf && ul)) uf_unite(parent, me, me - (uint32_t)g.w);
-      } else {
-        if (ul && !lf) uf_unite(parent, me, me - (uint32_t)g.w - 1u);
-        if (ur && !rt) uf_unite(parent, me, me - (uint32_t)g.w + 1u);
-      }
+    const unsigned peers = __match_any_sync(act, w);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    const int lane_x0 = x - lane;                  // image column of lane 0 of this warp
+    if (PASS == 0) {
+      // pixels of one row run that appear at the same level belong to one component from that
+      // level on: link each to the start of its run inside the warp's 32-pixel span (a run that
+      // continues across the span boundary points at the last pixel of the previous span)
+      const unsigned z = ~peers & ((1u << lane) - 1u);
+      const int s = z ? (32 - __clz(z)) : 0;
+      uint32_t tgt = me - (uint32_t)(lane - s);
+      if (s == 0 && lane_x0 > g.x0 && Wimg[(size_t)y * g.W + lane_x0 - 1] == w) tgt = me - (uint32_t)lane - 1u;
+      tr.parent[me] = tgt;
+      tr.area[me] = 0;
+      tr.mlevel[me] = 255;
+      tr.klevel[me] = thr2 == 0 ? (uint8_t)w : 255;   // threshold <= 0: kept from birth
+      if (lane == leader) atomicAdd(&scnt[w], __popc(peers));
+    } else {
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(&lvl_cursor[w], __popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      tr.plist[base + __popc(peers & ((1u << lane) - 1u))] = me;
+    }
+  }
+  if (PASS == 0) {
+    __syncthreads();
+    for (int i = threadIdx.x; i <= T; i += blockDim.x)
+      if (scnt[i]) atomicAdd(&lvl_count[i], scnt[i]);
+  }
+}
+
+__device__ __forceinline__ void tree_stats(const Tree& tr, int t, uint32_t thr2, chips_result* res) {
+  const int ncomp = (int)tr.ctr[3];
+  res->n_comp[t] = ncomp;
+  res->n_kept[t] = thr2 == 0 ? ncomp : (int32_t)tr.ctr[2];
+}
+
+// C2a: unions of the pixels that appear at level t
+__global__ void __launch_bounds__(256) k_tree_union(Roi g, int t, Tree tr, uint32_t thr2,
+                                                    chips_result* __restrict__ res) {
+  const uint32_t nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gtid == 0 && t > 0) tree_stats(tr, t - 1, thr2, res);      // counters of the finished level
+  const uint32_t beg = tr.offset[t], end = tr.offset[t + 1];
+  const uint8_t* __restrict__ wl = tr.wl;
+  for (uint32_t i = beg + gtid; i < end; i += nthreads) {
+    const uint32_t me = tr.plist[i];
+    const int ly = (int)(me / (uint32_t)g.w), lx = (int)(me - (uint32_t)ly * (uint32_t)g.w);
+    const int w_l = wl_at(g, wl, lx - 1, ly), w_r = wl_at(g, wl, lx + 1, ly);
+    const int w_u = wl_at(g, wl, lx, ly - 1), w_d = wl_at(g, wl, lx, ly + 1);
+    const int w_ul = wl_at(g, wl, lx - 1, ly - 1), w_ur = wl_at(g, wl, lx + 1, ly - 1);
+    const int w_dl = wl_at(g, wl, lx - 1, ly + 1), w_dr = wl_at(g, wl, lx + 1, ly + 1);
+    // Smaller raster index: any foreground neighbour; larger index: strictly older ones only (a
+    // same-level neighbour with a larger index unites with us from its side).  A same-level left
+    // neighbour is already linked (row runs); a vertical edge is implied when the horizontal
+    // neighbour and the diagonal next to it are both foreground (they are connected to each
+    // other and to us); a diagonal is implied by the vertical neighbour between.
+    if (w_l < t) uf_unite_rec(tr, t, me, me - 1u);
+    if (w_u <= t) {
+      if (!(w_l <= t && w_ul <= t)) uf_unite_rec(tr, t, me, me - (uint32_t)g.w);
+    } else {
+      if (w_ul <= t && !(w_l <= t)) uf_unite_rec(tr, t, me, me - (uint32_t)g.w - 1u);
+      if (w_ur <= t && !(w_r < t)) uf_unite_rec(tr, t, me, me - (uint32_t)g.w + 1u);
+    }
+    if (w_r < t) uf_unite_rec(tr, t, me, me + 1u);
+    if (w_d < t) {
+      if (!(w_r < t && w_dr < t)) uf_unite_rec(tr, t, me, me + (uint32_t)g.w);
+    } else {
+      if (w_dl < t && !(w_l < t)) uf_unite_rec(tr, t, me, me + (uint32_t)g.w - 1u);
+      if (w_dr < t && !(w_r < t)) uf_unite_rec(tr, t, me, me + (uint32_t)g.w + 1u);
     }
   }
 }
 
-// 2*area = 2*Q4 + Q3 over every 2x2 quad of the zero-padded filled set.  Each quad is charged
-// to its first set pixel in raster order, so only two quads per foreground pixel p matter:
-//   A = {p, right, down, down-right}              (p is the top-left pixel)
-//   B = {left, p, down-left, down} with left unset (p is the top-right pixel; s = 3 at most)
-__global__ void __launch_bounds__(256) k_ccl_area(Roi g, const uint8_t* __restrict__ Wimg, int T,
-                                                  int tiles_x, const uint32_t* __restrict__ tile_count,
-                                                  const uint32_t* __restrict__ tiles,
-                                                  uint32_t* __restrict__ parent_all,
-                                                  uint32_t* __restrict__ area_all) {
-  const size_t n = (size_t)g.w * g.h;
-  const uint32_t nt = *tile_count;
-  const int lane = threadIdx.x & 31;
-  for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
-    TileCtx c = tile_pixel(g, tiles[i], tiles_x);
-    const int x = c.x, y = c.y;
-    const int w = c.valid ? (int)Wimg[(size_t)y * g.W + x] : 255;
-    int wr = 255, wd = 255, wdr = 255, wl = 255, wdl = 255;
-    if (w < T) {
-      wr = w_at(g, Wimg, x + 1, y);
-      wd = w_at(g, Wimg, x, y + 1);
-      wdr = w_at(g, Wimg, x + 1, y + 1);
-      wl = w_at(g, Wimg, x - 1, y);
-      wdl = w_at(g, Wimg, x - 1, y + 1);
-    }
-    const uint32_t me = c.valid ? g.li(x, y) : 0u;
-    for (int t = warp_min(w); t < T; ++t) {
-      uint32_t root = 0xFFFFFFFFu, add = 0;
-      if (w <= t) {
-        const int sa = 1 + (int)(wr <= t) + (int)(wd <= t) + (int)(wdr <= t);
-        add = (sa == 4) ? 2u : (sa == 3 ? 1u : 0u);
-        if (wd <= t && wl > t && wdl <= t) add += 1u;
-        // flatten while we are here: stats / keep / roots then find every root in one hop
-        uint32_t* parent = parent_all + (size_t)t * n;
-        root = uf_find(parent, me);
-        if (root != me) parent[me] = root;
-      }
-      const unsigned active = __ballot_sync(0xFFFFFFFFu, add != 0);
-      if (add) {      // warp-aggregate per root before the global atomic
-        const unsigned peers = __match_any_sync(active, root);
-        const uint32_t sum = __reduce_add_sync(peers, add);
-        if (lane == __ffs(peers) - 1) atomicAdd(&area_all[(size_t)t * n + root], sum);
+// C2b: area hand-over of the hooked roots, merge-tree edges, bit-quad events of the new pixels
+__global__ void __launch_bounds__(256) k_tree_merge(Roi g, int t, Tree tr, uint32_t thr2) {
+  const uint32_t nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t hook_begin = t > 0 ? tr.ctr[8 + t - 1] : 0u, hook_end = tr.ctr[1];
+  if (gtid == 0) tr.ctr[8 + t] = hook_end;
+  int dk = 0, dc = 0;                             // change of the kept / total component counts
+  for (uint32_t i = hook_begin + gtid; i < hook_end; i += nthreads) {
+    const uint32_t a = tr.hooked[i];
+    const uint32_t r = uf_find(tr.parent, a);
+    tr.mparent[a] = r;
+    tr.mlevel[a] = (uint8_t)t;
+    --dc;
+    const uint32_t aa = tr.area[a];
+    if (aa >= thr2) --dk;                         // a kept component stops being a component
+    if (aa) {
+      const uint32_t old = atomicAdd(&tr.area[r], aa);
+      if (old < thr2 && old + aa >= thr2) {
+        tr.klevel[r] = (uint8_t)t;
+        ++dk;
       }
     }
   }
-}
-
-__device__ __forceinline__ bool area_kept(uint32_t a2, double disk_area, double thr) {
-  // chips.py:424-426: cv2.contourArea(cnt) / self.disk_area >= self.area_threshold
-  return __ddiv_rn(__dmul_rn((double)a2, 0.5), disk_area) >= thr;
-}
-
-__global__ void __launch_bounds__(256) k_ccl_stats(Roi g, const uint8_t* __restrict__ Wimg, int T,
-                                                   int tiles_x, const uint32_t* __restrict__ tile_count,
-                                                   const uint32_t* __restrict__ tiles,
-                                                   const uint32_t* __restrict__ parent_all,
-                                                   const uint32_t* __restrict__ area_all,
-                                                   double disk_area, double thr,
-                                                   chips_result* __restrict__ res) {
-  __shared__ int s_root[CHIPS_MAX_T], s_kept[CHIPS_MAX_T];
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    s_root[t] = 0;
-    s_kept[t] = 0;
-  }
-  __syncthreads();
-  const size_t n = (size_t)g.w * g.h;
-  const uint32_t nt = *tile_count;
-  const int lane = threadIdx.x & 31;
-  for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
-    TileCtx c = tile_pixel(g, tiles[i], tiles_x);
-    const int w = c.valid ? (int)Wimg[(size_t)c.y * g.W + c.x] : 255;
-    const uint32_t me = c.valid ? g.li(c.x, c.y) : 0u;
-    for (int t = warp_min(w); t < T; ++t) {
-      bool root = false, kept = false;
-      if (w <= t && parent_all[(size_t)t * n + me] == me) {
-        root = true;
-        kept = area_kept(area_all[(size_t)t * n + me], disk_area, thr);
+  const uint32_t beg = tr.offset[t], end = tr.offset[t + 1];
+  const uint8_t* __restrict__ wl = tr.wl;
+  for (uint32_t i = beg + gtid; i < end; i += nthreads) {
+    const uint32_t me = tr.plist[i];
+    const int ly = (int)(me / (uint32_t)g.w), lx = (int)(me - (uint32_t)ly * (uint32_t)g.w);
+    int wn[3][3];
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) wn[dy + 1][dx + 1] = (dx | dy) ? wl_at(g, wl, lx + dx, ly + dy) : t;
+    uint32_t add = 0;
+    // the four quads that contain p; inside a quad positions are ordered TL, TR, BL, BR
+#pragma unroll
+    for (int qy = 0; qy < 2; ++qy)
+#pragma unroll
+      for (int qx = 0; qx < 2; ++qx) {
+        const int pme = (1 - qy) * 2 + (1 - qx);           // p's position inside this quad
+        int rank = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j == pme) continue;
+          const int wq = wn[qy + (j >> 1)][qx + (j & 1)];
+          rank += (wq < t || (wq == t && j < pme)) ? 1 : 0;
+        }
+        add += (rank >= 2) ? 1u : 0u;
       }
-      const unsigned mr = __ballot_sync(0xFFFFFFFFu, root), mk = __ballot_sync(0xFFFFFFFFu, kept);
-      if (lane == 0) {
-        if (mr) atomicAdd(&s_root[t], __popc(mr));
-        if (mk) atomicAdd(&s_kept[t], __popc(mk));
+    const uint32_t r = uf_find(tr.parent, me);
+    if (r != me) {                                         // joined a component in this level
+      tr.parent[me] = r;                                   // flat: the next level's finds start here
+      tr.mparent[me] = r;
+      tr.mlevel[me] = (uint8_t)t;
+    } else {
+      ++dc;                                                // a new component
+    }
+    // one atomic per root and warp (the pixels of a large component all add to one address)
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, add ? r : 0xFFFFFFFFu);
+    if (add) {
+      const uint32_t sum = __reduce_add_sync(peers, add);
+      if ((threadIdx.x & 31) == __ffs(peers) - 1) {
+        const uint32_t old = atomicAdd(&tr.area[r], sum);
+        if (old < thr2 && old + sum >= thr2) {
+          tr.klevel[r] = (uint8_t)t;
+          ++dk;
+        }
       }
     }
   }
-  __syncthreads();
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    if (s_root[t]) atomicAdd(&res->n_comp[t], s_root[t]);
-    if (s_kept[t]) atomicAdd(&res->n_kept[t], s_kept[t]);
+  dk = __reduce_add_sync(0xFFFFFFFFu, dk);
+  dc = __reduce_add_sync(0xFFFFFFFFu, dc);
+  if ((threadIdx.x & 31) == 0) {
+    if (dk) atomicAdd(&tr.ctr[2], (uint32_t)dk);
+    if (dc) atomicAdd(&tr.ctr[3], (uint32_t)dc);
   }
 }
 
-__global__ void __launch_bounds__(256) k_ccl_keep(Roi g, const uint8_t* __restrict__ Wimg, int T,
-                                                  int tiles_x, const uint32_t* __restrict__ tile_count,
-                                                  const uint32_t* __restrict__ tiles,
-                                                  uint32_t* __restrict__ parent_all,
-                                                  const uint32_t* __restrict__ area_all,
-                                                  double disk_area, double thr,
-                                                  uint8_t* __restrict__ keep) {
-  const size_t n = (size_t)g.w * g.h;
-  const uint32_t nt = *tile_count;
-  for (uint32_t i = blockIdx.x; i < nt; i += gridDim.x) {
-    TileCtx c = tile_pixel(g, tiles[i], tiles_x);
-    if (!c.valid) continue;
-    size_t o = (size_t)c.y * g.W + c.x;
-    int w = Wimg[o];
-    if (w >= T) continue;                      // keep[] is pre-filled with T
-    int kk = T;
-    uint32_t me = g.li(c.x, c.y);
-    for (int t = w; t < T; ++t) {
-      uint32_t root = uf_find(parent_all + (size_t)t * n, me);
-      if (area_kept(area_all[(size_t)t * n + root], disk_area, thr)) {
-        kk = t;
+// C3: keep(p) = first level at which p's component is kept
+__global__ void __launch_bounds__(256) k_tree_keep(Roi g, int T, Tree tr, uint32_t thr2,
+                                                   chips_result* __restrict__ res,
+                                                   uint8_t* __restrict__ keep) {
+  const uint32_t nthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gtid == 0) tree_stats(tr, T - 1, thr2, res);
+  const uint32_t total = tr.offset[T];
+  for (uint32_t i = gtid; i < total; i += nthreads) {
+    const uint32_t me = tr.plist[i];
+    const int ly = (int)(me / (uint32_t)g.w), lx = (int)(me - (uint32_t)ly * (uint32_t)g.w);
+    int tjoin = tr.wl[me], kk = T;
+    uint32_t n = me;
+    for (int hop = 0; hop <= T; ++hop) {
+      const int kl = tr.klevel[n];
+      if (kl != 255) {
+        kk = max(kl, tjoin);
         break;
       }
+      const int ml = tr.mlevel[n];
+      if (ml == 255) break;                       // a final root that never reached the threshold
+      tjoin = ml;
+      n = tr.mparent[n];
     }
-    keep[o] = (uint8_t)kk;
+    keep[(size_t)(g.y0 + ly) * g.W + (g.x0 + lx)] = (uint8_t)kk;
   }
 }
 
-__global__ void k_cleanup_reset(chips_result* res, uint32_t* lvl_count, uint32_t* tile_count) {
+// chips.py:424-426: cv2.contourArea(cnt) / self.disk_area >= self.area_threshold
+static inline bool area_kept(uint32_t a2, double disk_area, double thr) {
+  return ((double)a2 * 0.5) / disk_area >= thr;
+}
+
+__global__ void k_cleanup_reset(chips_result* res, uint32_t* lvl_count, uint32_t* ctr) {
   int t = threadIdx.x;
   if (t < CHIPS_MAX_T) {
     res->n_kept[t] = 0;
     res->n_comp[t] = 0;
   }
   if (t <= CHIPS_MAX_T + 1) lvl_count[t] = 0;
-  if (t == 0) *tile_count = 0;
+  if (t < 8 + CHIPS_MAX_T) ctr[t] = 0;
+}
+
+__global__ void k_zero_counts(uint32_t* lvl_count) {
+  if (threadIdx.x <= CHIPS_MAX_T + 1) lvl_count[threadIdx.x] = 0;
 }
 
 // ------------------------------------------------------------------ expansion / debugging
@@ -556,25 +582,38 @@ __global__ void __launch_bounds__(256) k_expand_one(const uint8_t* __restrict__ 
   if (i < n) out[i] = (src[i] <= t) ? (O)1 : (O)0;
 }
 
-__global__ void __launch_bounds__(256) k_roots(Roi g, const uint8_t* __restrict__ Wimg, int t,
-                                               uint32_t* __restrict__ parent_all,
-                                               const uint32_t* __restrict__ area_all,
-                                               int32_t* __restrict__ roots,
-                                               uint32_t* __restrict__ area_out) {
-  const size_t n = (size_t)g.w * g.h;
+// Root image of level t from the merge tree (chains have increasing levels: stop at the first
+// node that was still a root at level t) and the component's 2*area at that level, re-counted
+// from the bit quads into `acc` (the dead union-find array, zeroed by the caller); each quad is
+// charged to its first set pixel in raster order.
+__global__ void __launch_bounds__(256) k_roots(Roi g, int t, Tree tr, uint32_t* __restrict__ acc,
+                                               int32_t* __restrict__ roots) {
   int x = blockIdx.x * blockDim.x + threadIdx.x;
   int y = blockIdx.y;
   if (x >= g.W) return;
   size_t o = (size_t)y * g.W + x;
   int32_t rr = -1;
-  uint32_t aa = 0;
-  if (x >= g.x0 && x < g.x0 + g.w && y >= g.y0 && y < g.y0 + g.h && Wimg[o] <= t) {
-    uint32_t root = uf_find(parent_all + (size_t)t * n, g.li(x, y));
-    rr = (int32_t)root;
-    aa = area_all[(size_t)t * n + root];
+  const int lx = x - g.x0, ly = y - g.y0;
+  if (wl_at(g, tr.wl, lx, ly) <= t) {
+    uint32_t n = (uint32_t)ly * (uint32_t)g.w + (uint32_t)lx;
+    while (tr.mlevel[n] <= t) n = tr.mparent[n];
+    rr = (int32_t)n;
+    const int wr = wl_at(g, tr.wl, lx + 1, ly), wd = wl_at(g, tr.wl, lx, ly + 1);
+    const int wdr = wl_at(g, tr.wl, lx + 1, ly + 1), wl_ = wl_at(g, tr.wl, lx - 1, ly);
+    const int wdl = wl_at(g, tr.wl, lx - 1, ly + 1);
+    const int sa = 1 + (int)(wr <= t) + (int)(wd <= t) + (int)(wdr <= t);
+    uint32_t add = (sa == 4) ? 2u : (sa == 3 ? 1u : 0u);
+    if (wd <= t && wl_ > t && wdl <= t) add += 1u;
+    if (add) atomicAdd(&acc[n], add);
   }
   roots[o] = rr;
-  if (area_out) area_out[o] = aa;
+}
+
+__global__ void __launch_bounds__(256) k_roots_area(const int32_t* __restrict__ roots,
+                                                    const uint32_t* __restrict__ acc, size_t n,
+                                                    uint32_t* __restrict__ area_out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) area_out[i] = roots[i] >= 0 ? acc[roots[i]] : 0u;
 }
 
 template <typename O>
@@ -626,6 +665,23 @@ static Roi make_roi(const chips_plan* p, int cx, int cy, int r) {
   return g;
 }
 
+static Tree make_tree(const chips_plan* p, unsigned char* w) {
+  const size_t nr = (size_t)p->roi_w * p->roi_h;
+  Tree t;
+  t.parent = reinterpret_cast<uint32_t*>(w + p->off_parent_c);
+  t.mparent = t.parent + nr;
+  t.area = reinterpret_cast<uint32_t*>(w + p->off_area);
+  t.mlevel = reinterpret_cast<uint8_t*>(t.area + nr);
+  t.klevel = t.mlevel + nr;
+  t.wl = t.klevel + nr;
+  t.plist = reinterpret_cast<uint32_t*>(w + p->off_pending);
+  t.hooked = reinterpret_cast<uint32_t*>(w + p->off_parent_b);
+  uint32_t* lvl = reinterpret_cast<uint32_t*>(w + p->off_lvl);
+  t.offset = lvl + 128;
+  t.ctr = lvl + 384;
+  return t;
+}
+
 }  // namespace chips
 
 using namespace chips;
@@ -641,23 +697,18 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
   uint8_t* Wimg = w + plan->off_fill;
   uint8_t* keep = w + plan->off_keep;
   uint32_t* parent_b = reinterpret_cast<uint32_t*>(w + plan->off_parent_b);
-  uint32_t* parent_c = reinterpret_cast<uint32_t*>(w + plan->off_parent_c);
-  uint32_t* area = reinterpret_cast<uint32_t*>(w + plan->off_area);
   uint32_t* pending = reinterpret_cast<uint32_t*>(w + plan->off_pending);
   uint32_t* lvl = reinterpret_cast<uint32_t*>(w + plan->off_lvl);       // count | offset | cursor
   uint32_t* lvl_count = lvl, *lvl_offset = lvl + 128, *lvl_cursor = lvl + 256;
-  uint32_t* tile_count = lvl + 384;
-  uint32_t* tiles = reinterpret_cast<uint32_t*>(w + plan->off_tiles);
+  uint32_t* ctr = lvl + 384;                   // phase C counters
   chips_result* res = reinterpret_cast<chips_result*>(w + plan->off_result);
   Roi g = make_roi(plan, cx, cy, r);
   dim3 blk(256);
   dim3 grid((g.w + 255) / 256, g.h);
-  const int tiles_x = (g.w + kTileW - 1) / kTileW, tiles_y = (g.h + kTileH - 1) / kTileH;
-  const int ntiles = tiles_x * tiles_y;
 
   CHIPS_CUDA(cudaMemsetAsync(Wimg, T, n_img, st));
   CHIPS_CUDA(cudaMemsetAsync(keep, T, n_img, st));
-  k_cleanup_reset<<<1, 128, 0, st>>>(res, lvl_count, tile_count);
+  k_cleanup_reset<<<1, 128, 0, st>>>(res, lvl_count, ctr);
   // round T-1: the bulk background (pixels in no mask at all)
   k_fill_bulk_link<<<grid, blk, 0, st>>>(g, lev, T, Wimg, parent_b);
   dim3 grid4((g.w / 4 + 2 + 255) / 256, g.h);
@@ -674,17 +725,32 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
     k_fill_round_assign<<<gl, blk, 0, st>>>(g, t, T, lvl_offset, pending, Wimg, parent_b);
   }
   CHIPS_CHECK_LAUNCH();
-  k_tile_list<<<(ntiles * 32 + 255) / 256, blk, 0, st>>>(g, Wimg, T, tiles_x, tiles_y, tile_count, tiles);
-  const int gridt = 8 * kNumSM;
-  k_ccl_link<<<gridt, blk, 0, st>>>(g, Wimg, T, tiles_x, tile_count, tiles, parent_c, area);
-  k_ccl_union<<<gridt, blk, 0, st>>>(g, Wimg, T, tiles_x, tile_count, tiles, parent_c);
-  k_ccl_area<<<gridt, blk, 0, st>>>(g, Wimg, T, tiles_x, tile_count, tiles, parent_c, area);
-  k_ccl_stats<<<gridt, blk, 0, st>>>(g, Wimg, T, tiles_x, tile_count, tiles, parent_c, area,
-                                     disk_area, area_threshold, res);
-  k_ccl_keep<<<8 * kNumSM, blk, 0, st>>>(g, Wimg, T, tiles_x, tile_count, tiles, parent_c, area,
-                                         disk_area, area_threshold, keep);
+  // ---- phase C: one union-find grown through the levels (component tree)
+  Tree tr = make_tree(plan, w);
+  uint32_t thr2 = 0xFFFFFFFFu;                 // smallest 2*area that passes chips.py:424-426
+  {
+    const double guess = 2.0 * area_threshold * disk_area;
+    if (guess <= 0.0) {
+      if (area_kept(0u, disk_area, area_threshold)) thr2 = 0;
+    } else if (guess < 4.0e9) {
+      long long a2 = (long long)guess;
+      while (a2 > 0 && area_kept((uint32_t)(a2 - 1), disk_area, area_threshold)) --a2;
+      for (int i = 0; i < 8 && !area_kept((uint32_t)a2, disk_area, area_threshold); ++i) ++a2;
+      if (area_kept((uint32_t)a2, disk_area, area_threshold)) thr2 = (uint32_t)a2;
+    }                                          // NaN / huge threshold: nothing is ever kept
+  }
+  k_zero_counts<<<1, 128, 0, st>>>(lvl_count);
+  k_tree_list<0><<<grid, blk, 0, st>>>(g, Wimg, T, tr, thr2, lvl_count, lvl_cursor);
+  k_fill_offsets<<<1, 32, 0, st>>>(T, lvl_count, lvl_offset, lvl_cursor);
+  k_tree_list<1><<<grid, blk, 0, st>>>(g, Wimg, T, tr, thr2, lvl_count, lvl_cursor);
   CHIPS_CHECK_LAUNCH();
-  count_launch(6 + 2 * (T - 1) + 6);
+  for (int t = 0; t < T; ++t) {
+    k_tree_union<<<gl, blk, 0, st>>>(g, t, tr, thr2, res);
+    k_tree_merge<<<gl, blk, 0, st>>>(g, t, tr, thr2);
+  }
+  k_tree_keep<<<4 * kNumSM, blk, 0, st>>>(g, T, tr, thr2, res, keep);
+  CHIPS_CHECK_LAUNCH();
+  count_launch(6 + 2 * (T - 1) + 5 + 2 * T);
   return CHIPS_OK;
 }
 
@@ -725,10 +791,14 @@ extern "C" int chips_roots(const chips_plan* plan, int cx, int cy, int r, int t,
   if (!plan || !roots || !ws || t < 0 || t >= plan->T) return CHIPS_E_ARG;
   unsigned char* w = (unsigned char*)ws;
   Roi g = make_roi(plan, cx, cy, r);
+  Tree tr = make_tree(plan, w);
+  const size_t nr = (size_t)plan->roi_w * plan->roi_h, npix = (size_t)plan->H * plan->W;
+  cudaStream_t st = (cudaStream_t)stream;
+  CHIPS_CUDA(cudaMemsetAsync(tr.parent, 0, nr * sizeof(uint32_t), st));   // dead after chips_cleanup
   dim3 grid((plan->W + 255) / 256, plan->H);
-  k_roots<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      g, w + plan->off_fill, t, reinterpret_cast<uint32_t*>(w + plan->off_parent_c),
-      reinterpret_cast<const uint32_t*>(w + plan->off_area), roots, twice_area);
+  k_roots<<<grid, 256, 0, st>>>(g, t, tr, tr.parent, roots);
+  if (twice_area)
+    k_roots_area<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(roots, tr.parent, npix, twice_area);
   CHIPS_CHECK_LAUNCH();
   count_launch();
   return CHIPS_OK;

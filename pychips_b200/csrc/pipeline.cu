@@ -80,11 +80,11 @@ extern "C" int chips_plan_init(chips_plan* p, int H, int W, int k, int h_bins, i
   p->off_probtab = take((size_t)(T + 1) * CHIPS_PROB_BINS * 4);
   if (p->masked) {
     p->off_parent_b = take((nr + 1) * 4);
-    p->off_parent_c = take(nr * 4 * T);
-    p->off_area = take(nr * 4 * T);
+    p->off_parent_c = take(nr * 4 * 2);       // union-find + merge-tree parents
+    p->off_area = take(nr * 4 + nr * 3);      // 2*area accumulators; hook level, kept level, local W
     p->off_pending = take(nr * 4);
     p->off_lvl = take(512 * 4);
-    p->off_tiles = take(((size_t)((p->roi_w + 31) / 32) * ((p->roi_h + 7) / 8) + 1) * 4);
+    p->off_tiles = take(256);                  // (reserved)
   } else {   // the synoptic variant has no contour/cleanup step (syn_chips.py:237-251)
     p->off_parent_b = p->off_parent_c = p->off_area = off;
     p->off_pending = p->off_lvl = p->off_tiles = off;
