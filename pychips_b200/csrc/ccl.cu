@@ -14,7 +14,8 @@
 //
 // Phase B (W): ONE union-find over the disk, thresholds visited in DEscending order so the
 // outer background only ever grows; a pixel's W is the round in which it first joins the
-// border set.  Phase C: the T foreground labellings are independent -> gridDim.z = T.
+// border set.  Phase C: the filled masks are nested too, so ONE union-find grown through the
+// ASCENDING levels gives all T labellings as a component tree (see "phase C" below).
 // Union-find = min-index roots, atomicMin hooking (Komura/Playne), path halving in find.
 #include "common.cuh"
 
