@@ -275,7 +275,7 @@ def test_histogram_constant_image_and_sticky_threshold():
     assert det.result().h_thresh == 0.125
 
 
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", list(range(8)) + [100, 101, 102, 103])
 def test_cleanup_stage_on_random_levels(seed):
     """Inject a random nested level image and compare W, final maps, labels and 2*areas with
     the first-principles spec (itself pinned to cv2 in test_first_principles.py)."""
@@ -289,6 +289,10 @@ def test_cleanup_stage_on_random_levels(seed):
     on = fp.circle_mask(n, n, c, c, r)
     lev = np.where(on, _random_nested_levels(rng, n, T), T).astype(np.uint8)
     thr = float(rng.choice([0.0, 1e-3, 5e-3]))
+    if seed >= 100:          # deep trees, "nothing is ever kept" and "everything is kept"
+        T = int(rng.integers(20, 40))
+        lev = np.where(on, _random_nested_levels(rng, n, T), T).astype(np.uint8)
+        thr = [10.0, 0.0, 2e-4, -1.0][seed - 100]
     det = eng.Detector(eng.Geometry(n, n, c, c, r), 3, 8, 0, T, 4, dev)
     det.level.copy_(torch.from_numpy(lev).to(dev))
     det.cleanup(thr)
