@@ -717,7 +717,6 @@ __global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
   uint16_t* csg = tsg + kFastCap;
   K* skey = tkey;               // sorted keys / positions reuse the unsorted first-pass arrays
   uint16_t* spos = tpos;
-  uint8_t* tg = reinterpret_cast<uint8_t*>(csg);   // group of a first-pass candidate (dead before csg)
   __shared__ uint32_t need[8], needpfx[9];
   __shared__ uint16_t glut[kBuckets];          // bucket -> group (0xFFFF: not needed by this tile)
   __shared__ K gklo[kBuckets];
@@ -828,11 +827,7 @@ __global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
       while (m) {
         const int i = __ffs(m) - 1;
         m &= m - 1;
-        if (slot < (uint32_t)kFastCap) {
-          const unsigned b = (unsigned)((i < 8 ? wlo : whi) >> (8 * (i & 7))) & 255u;
-          tpos[slot] = (uint16_t)((ry << 8) | (rxb + i));
-          tg[slot] = (uint8_t)glut[b];
-        }
+        if (slot < (uint32_t)kFastCap) tpos[slot] = (uint16_t)((ry << 8) | (rxb + i));
         ++slot;
       }
     }
@@ -865,7 +860,7 @@ __global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
       const int iy = Y0 + (int)(p >> 8) - half, ix = X0 + (int)(p & 255u) - half;
       const T v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(&img[(size_t)iy * W + ix]) : (T)0;
       const K key = Key<T>::enc(v);
-      const int g = tg[e];
+      const int g = glut[__ldg(Bp + (size_t)(p >> 8) * pitch + (p & 255u))];   // bucket byte: L1 hit
       const K dg = (key - gklo[g]) >> gshift[g];
       sg = (unsigned)((g << dlog) + (int)(dg < (K)ndm1 ? dg : (K)ndm1));
       tkey[e] = key;
