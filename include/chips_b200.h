@@ -82,7 +82,7 @@ typedef struct chips_plan {
   size_t off_pending;    /* u32 [roi_h*roi_w]  hole-fill work list grouped by level       */
   size_t off_lvl;        /* u32 [512]          per-level counts / offsets / cursors, phase-C counters */
   size_t off_tiles;      /* (reserved)                                                    */
-  size_t off_ovf;        /* u32 [1 + #16x16 tiles]  median tier 2: count + list of slow-path tiles */
+  size_t off_ovf;        /* u32 [2][1 + #16x16 tiles]  median tier 2: count + list of overflow tiles, two levels */
   size_t bytes;          /* total workspace size                                          */
 } chips_plan;
 

@@ -687,8 +687,10 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine_list(
 //      counting-sorted by (bucket, leading key digits); a rank sort finishes each sub-group;
 //   d. every thread walks the sorted candidates of ITS bucket from the nearer end, counting
 //      those inside its own k x k window, until it reaches its residual rank.
-// Tiles with more than kFastCap candidates go to the overflow list (k_refine_list).
-constexpr int kFastCap = 1280;   // candidates per tile on the fast path
+// Tiles with more than kFastCap candidates are retried with kFastCap2 (k_refine_fast_list); what
+// still overflows (flat areas) goes to the staged slow path (k_refine_list).
+constexpr int kFastCap = 1280;   // candidates per tile, first pass (6 CTAs per SM)
+constexpr int kFastCap2 = 4096;  // second pass over the overflow list
 constexpr int kFastSub = 512;    // (bucket, digit) sub-groups per tile
 
 __device__ __forceinline__ uint32_t sum_u16x8(const uint4 c) {
@@ -697,7 +699,8 @@ __device__ __forceinline__ uint32_t sum_u16x8(const uint4 c) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
+__device__ __forceinline__ void refine_tile_fast(
+    const int tile_x, const int tile_y, const int gx, const int cap,
     const T* __restrict__ img, const uint8_t* __restrict__ Bp_all, const BlockGeom g,
     const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres,
     const typename Key<T>::type* __restrict__ bounds_all, int H, int W, int rw, int rh, int cx, int cy,
@@ -710,11 +713,11 @@ __global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
   static_assert(NW == 8, "one uint4 of u16 counters per sub-group");
   extern __shared__ __align__(128) unsigned char smem_tile[];
   K* tkey = reinterpret_cast<K*>(smem_tile);
-  K* ckey = tkey + kFastCap;
-  uint16_t* tpos = reinterpret_cast<uint16_t*>(ckey + kFastCap);
-  uint16_t* cpos = tpos + kFastCap;
-  uint16_t* tsg = cpos + kFastCap;
-  uint16_t* csg = tsg + kFastCap;
+  K* ckey = tkey + cap;
+  uint16_t* tpos = reinterpret_cast<uint16_t*>(ckey + cap);
+  uint16_t* cpos = tpos + cap;
+  uint16_t* tsg = cpos + cap;
+  uint16_t* csg = tsg + cap;
   K* skey = tkey;               // sorted keys / positions reuse the unsorted first-pass arrays
   uint16_t* spos = tpos;
   __shared__ uint32_t need[8], needpfx[9];
@@ -723,7 +726,7 @@ __global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
   __shared__ uint8_t gshift[kBuckets];
   // warp-private sub-group counters [sub-group][warp] (shared-memory atomics cost 2 cycles per
   // lane on the one LSU of the SM; a warp resolves its own collisions with match.any instead)
-  uint16_t* wcnt = csg + kFastCap;                 // [kFastSub][NW], 16-byte aligned
+  uint16_t* wcnt = csg + cap;                 // [kFastSub][NW], 16-byte aligned
   __shared__ uint16_t sgoff[kFastSub + 1];
   __shared__ uint32_t wsum[NW];
   __shared__ int nactive;
@@ -736,13 +739,13 @@ __global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
   const uint32_t lt_mask = (1u << lane) - 1u;
   const int tx = tid & (kTile - 1), ty = tid >> 4;
   const int half = g.half, pitch = g.LP, rx0 = g.rx0, ry0 = g.ry0;
-  const int by = ((int)blockIdx.y * kTile) / g.L, blk = by * g.nbx + ((int)blockIdx.x >> 3);
+  const int by = (tile_y * kTile) / g.L, blk = by * g.nbx + (tile_x >> 3);
   const K* __restrict__ bounds = bounds_all + (size_t)blk * kBuckets;
   // block-local origin of the tile's region (the +half of the local frame cancels the -half);
   // 16-byte aligned: LP and the tile's column offset are multiples of 16
-  const uint8_t* __restrict__ Bp = Bp_all + ((size_t)blk * g.LR + ((int)blockIdx.y * kTile - by * g.L)) * pitch +
-                                   ((int)blockIdx.x & 7) * kTile;
-  const int X0 = rx0 + blockIdx.x * kTile, Y0 = ry0 + blockIdx.y * kTile;
+  const uint8_t* __restrict__ Bp = Bp_all + ((size_t)blk * g.LR + (tile_y * kTile - by * g.L)) * pitch +
+                                   (tile_x & 7) * kTile;
+  const int X0 = rx0 + tile_x * kTile, Y0 = ry0 + tile_y * kTile;
   const int x = X0 + tx, y = Y0 + ty;
   const bool active = (x < rx0 + rw) && (y < ry0 + rh) && on_disk(x, y, cx, cy, r);
   if (tid < 8) need[tid] = 0;
@@ -827,17 +830,17 @@ __global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
       while (m) {
         const int i = __ffs(m) - 1;
         m &= m - 1;
-        if (slot < (uint32_t)kFastCap) tpos[slot] = (uint16_t)((ry << 8) | (rxb + i));
+        if (slot < (uint32_t)cap) tpos[slot] = (uint16_t)((ry << 8) | (rxb + i));
         ++slot;
       }
     }
   }
   __syncthreads();
   const int C = (int)ncand;
-  if (C > kFastCap || force_overflow) {
+  if (C > cap || force_overflow) {
     if (tid == 0) {
       uint32_t i = atomicAdd(&ovf[0], 1u);
-      ovf[1 + i] = blockIdx.y * gridDim.x + blockIdx.x;
+      ovf[1 + i] = (uint32_t)(tile_y * gx + tile_x);
     }
     return;
   }
@@ -1011,7 +1014,7 @@ __global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
 #ifdef CHIPS_DEBUG_TIMING
   __syncthreads();
   if (tid == 0 && dbg) {
-    uint32_t* d = dbg + 4 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x);
+    uint32_t* d = dbg + 4 * (size_t)(tile_y * gx + tile_x);
     long long t_3 = clock64();
     d[0] = (uint32_t)(t_1 - t_0);
     d[1] = (uint32_t)(t_2 - t_1);
@@ -1019,6 +1022,37 @@ __global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
     d[3] = (uint32_t)C;
   }
 #endif
+}
+
+// first pass: one CTA per tile, `cap` candidates (6 CTAs per SM)
+template <typename T>
+__global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
+    const int cap, const T* __restrict__ img, const uint8_t* __restrict__ Bp_all, const BlockGeom g,
+    const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres,
+    const typename Key<T>::type* __restrict__ bounds_all, int H, int W, int rw, int rh, int cx, int cy,
+    int r, T* __restrict__ out, typename Key<T>::type* __restrict__ minmax, int* __restrict__ err,
+    uint32_t* __restrict__ ovf, int force_overflow, uint32_t* __restrict__ dbg) {
+  refine_tile_fast<T>((int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x, cap, img, Bp_all, g, bstar, rres,
+                      bounds_all, H, W, rw, rh, cx, cy, r, out, minmax, err, ovf, force_overflow, dbg);
+}
+
+// second pass: the tiles that overflowed the first one, with larger buffers (a fixed grid walks
+// the list `ovf_in`); what still does not fit goes to `ovf_out` and the staged slow path
+template <typename T>
+__global__ void __launch_bounds__(kTile* kTile) k_refine_fast_list(
+    const uint32_t* __restrict__ ovf_in, const int gx, const int cap, const T* __restrict__ img,
+    const uint8_t* __restrict__ Bp_all, const BlockGeom g, const uint8_t* __restrict__ bstar,
+    const uint32_t* __restrict__ rres, const typename Key<T>::type* __restrict__ bounds_all, int H, int W,
+    int rw, int rh, int cx, int cy, int r, T* __restrict__ out, typename Key<T>::type* __restrict__ minmax,
+    int* __restrict__ err, uint32_t* __restrict__ ovf_out, int force_overflow) {
+  const uint32_t n = ovf_in[0];
+  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const uint32_t t = ovf_in[1 + i];
+    refine_tile_fast<T>((int)(t % (uint32_t)gx), (int)(t / (uint32_t)gx), gx, cap, img, Bp_all, g, bstar,
+                        rres, bounds_all, H, W, rw, rh, cx, cy, r, out, minmax, err, ovf_out, force_overflow,
+                        nullptr);
+    __syncthreads();      // the next tile reuses every shared buffer
+  }
 }
 
 // ------------------------------------------------------------------ brute-force checker
@@ -1136,21 +1170,31 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
     const int gx = (rw + kTile - 1) / kTile, gy = (rh + kTile - 1) / kTile;
     static const int force_ovf = getenv("CHIPS_REFINE_STAGED") ? 1 : 0;   // tests: slow path only
     CHIPS_CUDA(cudaMemsetAsync(ovf, 0, sizeof(uint32_t), st));
-    const size_t smem_fast = (size_t)kFastCap * (2 * sizeof(K) + 4 * sizeof(uint16_t)) +
-                             (size_t)kFastSub * (kTile * kTile / 32) * sizeof(uint16_t);
+    auto fast_smem = [](int c) {
+      return (size_t)c * (2 * sizeof(K) + 4 * sizeof(uint16_t)) +
+             (size_t)kFastSub * (kTile * kTile / 32) * sizeof(uint16_t);
+    };
+    uint32_t* ovf2 = ovf + (size_t)gx * gy + 1;          // second-level overflow list
+    CHIPS_CUDA(cudaMemsetAsync(ovf2, 0, sizeof(uint32_t), st));
     CHIPS_CUDA(cudaFuncSetAttribute(k_refine_fast<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)smem_fast));
-    k_refine_fast<T><<<dim3(gx, gy), kTile * kTile, smem_fast, st>>>(
-        in, Bp, g, bstar, rres, bounds, H, W, rw, rh, cx, cy, r, out, minmax, err, ovf, force_ovf,
+                                    (int)fast_smem(kFastCap)));
+    k_refine_fast<T><<<dim3(gx, gy), kTile * kTile, fast_smem(kFastCap), st>>>(
+        kFastCap, in, Bp, g, bstar, rres, bounds, H, W, rw, rh, cx, cy, r, out, minmax, err, ovf, force_ovf,
         reinterpret_cast<uint32_t*>(ws + p->off_parent_c));
     CHIPS_CHECK_LAUNCH();
-    count_launch();
+    const long long ntiles = (long long)gx * gy;
+    const int nlist = (int)(ntiles < 3LL * kNumSM ? ntiles : 3LL * kNumSM);
+    CHIPS_CUDA(cudaFuncSetAttribute(k_refine_fast_list<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)fast_smem(kFastCap2)));
+    k_refine_fast_list<T><<<nlist, kTile * kTile, fast_smem(kFastCap2), st>>>(
+        ovf, gx, kFastCap2, in, Bp, g, bstar, rres, bounds, H, W, rw, rh, cx, cy, r, out, minmax, err, ovf2,
+        force_ovf);
+    CHIPS_CHECK_LAUNCH();
+    count_launch(2);
     int cap = refine_cap(k, (int)sizeof(T));
     size_t smem = (size_t)cap * (sizeof(K) + 3 * sizeof(uint16_t));
     CHIPS_CUDA(cudaFuncSetAttribute(k_refine_list<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long ntiles = (long long)gx * gy;
-    const int nlist = (int)(ntiles < 3LL * kNumSM ? ntiles : 3LL * kNumSM);
-    k_refine_list<T><<<nlist, kTile * kTile, smem, st>>>(ovf, gx, in, Bp, g, bstar, rres, bounds, H, W, rw,
+    k_refine_list<T><<<nlist, kTile * kTile, smem, st>>>(ovf2, gx, in, Bp, g, bstar, rres, bounds, H, W, rw,
                                                          rh, cx, cy, r, cap, out, minmax, err);
     CHIPS_CHECK_LAUNCH();
     count_launch();

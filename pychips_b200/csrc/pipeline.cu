@@ -89,7 +89,7 @@ extern "C" int chips_plan_init(chips_plan* p, int H, int W, int k, int h_bins, i
     p->off_parent_b = p->off_parent_c = p->off_area = off;
     p->off_pending = p->off_lvl = p->off_tiles = off;
   }
-  p->off_ovf = take(((size_t)((p->roi_w + 15) / 16) * ((p->roi_h + 15) / 16) + 1) * 4);
+  p->off_ovf = take(2 * ((size_t)((p->roi_w + 15) / 16) * ((p->roi_h + 15) / 16) + 1) * 4);
   p->bytes = off;
   return CHIPS_OK;
 }
