@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(kTile* kTile) k_refine_list(
 // Tiles with more than kFastCap candidates are retried with kFastCap2 (k_refine_fast_list); what
 // still overflows (flat areas) goes to the staged slow path (k_refine_list).
 constexpr int kFastCap = 1280;   // candidates per tile, first pass (6 CTAs per SM)
-constexpr int kFastCap2 = 4096;  // second pass over the overflow list
+constexpr int kFastCap2 = 2560;  // second pass over the overflow list (4 CTAs per SM)
 constexpr int kFastSub = 512;    // (bucket, digit) sub-groups per tile
 
 __device__ __forceinline__ uint32_t sum_u16x8(const uint4 c) {
@@ -1039,7 +1039,7 @@ __global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
 // second pass: the tiles that overflowed the first one, with larger buffers (a fixed grid walks
 // the list `ovf_in`); what still does not fit goes to `ovf_out` and the staged slow path
 template <typename T>
-__global__ void __launch_bounds__(kTile* kTile) k_refine_fast_list(
+__global__ void __launch_bounds__(kTile* kTile, 4) k_refine_fast_list(
     const uint32_t* __restrict__ ovf_in, const int gx, const int cap, const T* __restrict__ img,
     const uint8_t* __restrict__ Bp_all, const BlockGeom g, const uint8_t* __restrict__ bstar,
     const uint32_t* __restrict__ rres, const typename Key<T>::type* __restrict__ bounds_all, int H, int W,
@@ -1183,7 +1183,7 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
         reinterpret_cast<uint32_t*>(ws + p->off_parent_c));
     CHIPS_CHECK_LAUNCH();
     const long long ntiles = (long long)gx * gy;
-    const int nlist = (int)(ntiles < 3LL * kNumSM ? ntiles : 3LL * kNumSM);
+    const int nlist = (int)(ntiles < 4LL * kNumSM ? ntiles : 4LL * kNumSM);
     CHIPS_CUDA(cudaFuncSetAttribute(k_refine_fast_list<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)fast_smem(kFastCap2)));
     k_refine_fast_list<T><<<nlist, kTile * kTile, fast_smem(kFastCap2), st>>>(
