@@ -329,7 +329,20 @@ __device__ double pairwise_sum20(const double* a, int n) {
 
 __global__ void k_prob_epilogue(const uint32_t* __restrict__ probtab, double porb_threshold,
                                 chips_result* __restrict__ res) {
+  // the (T+1) x 20 table is read once, coalesced, into shared memory and prefix-summed over
+  // the thresholds there (per-thread strided global reads made this tiny kernel take 14 us)
+  __shared__ uint32_t stab[(CHIPS_MAX_T + 1) * CHIPS_PROB_BINS];
   const int T = res->n_thresholds;
+  for (int i = threadIdx.x; i < (T + 1) * CHIPS_PROB_BINS; i += blockDim.x) stab[i] = probtab[i];
+  __syncthreads();
+  if (threadIdx.x < CHIPS_PROB_BINS) {
+    uint32_t run = 0;
+    for (int l = 0; l <= T; ++l) {
+      run += stab[l * CHIPS_PROB_BINS + threadIdx.x];
+      stab[l * CHIPS_PROB_BINS + threadIdx.x] = run;
+    }
+  }
+  __syncthreads();
   const int t = threadIdx.x;
   if (t >= T) return;
   if (res->n_peaks <= 0) {
@@ -342,8 +355,7 @@ __global__ void k_prob_epilogue(const uint32_t* __restrict__ probtab, double por
   double all[CHIPS_PROB_BINS], sel[CHIPS_PROB_BINS];
   int nsel = 0;
   for (int j = 0; j < CHIPS_PROB_BINS; ++j) {
-    long long h = 0;
-    for (int l = 0; l <= t; ++l) h += probtab[l * CHIPS_PROB_BINS + j];
+    const long long h = stab[t * CHIPS_PROB_BINS + j];      // counts of levels 0..t
     double e = (j == 20) ? 1.0 : __dadd_rn(__dmul_rn((double)j, stepe), 0.0);
     double b = __dadd_rn(e, halfw);
     double bh = __dmul_rn(b, (double)h);
