@@ -7,22 +7,27 @@
 //   0. the ROI is cut into blocks of 128 columns x L rows (L a multiple of the 16-pixel
 //      refine tile, chosen by chips_plan_init so that one wave of tier-1 CTAs covers the ROI).
 //   1. k_bounds      one CTA per block: 1024 samples of the block's halo-extended region,
-//                    bitonic sort in shared memory, 255 LOCAL quantile boundaries -> 256 value
-//                    buckets of equal local mass (a window's median bucket then holds ~1 % of
+//                    bitonic sort in shared memory, 127 LOCAL quantile boundaries -> 128 value
+//                    buckets of equal local mass (a window's median bucket then holds ~1-2 % of
 //                    the window instead of ~6 % with image-wide quantiles: tier 2 shrinks).
 //   2. k_bucketize   per block: uint8 bucket image of the extended region (zero padding
 //                    outside the image = bucket of 0.0).
-//   3. k_huang       tier 1: every thread slides its own k x k window down one image
-//                    column (Huang's O(k) update: +k / -k bucket counts per step) with a
-//                    thread-private 256-bin histogram kept in shared memory in a
-//                    bank-conflict-free interleaved layout.  Output per pixel: the bucket
-//                    that holds the median and the residual rank inside that bucket.
-//   4. k_refine      tier 2: one CTA per 16x16 output tile gathers, from the tile's
-//                    (16+k-1)^2 input region, only the pixels that fall in a bucket some
-//                    pixel of the tile needs, sorts them by value in shared memory
-//                    (bitonic), and every thread walks its bucket's sorted segment counting
-//                    in-window candidates until it reaches its residual rank.  The fused
-//                    epilogue applies the disk mask and reduces min/max for the histogram.
+//   3. k_huang4      tier 1: one warp per block, every thread slides FOUR adjacent columns
+//                    down the block (Huang's O(k) update) with a shared core histogram of the
+//                    common window columns plus packed per-column fringe counters, private to
+//                    the thread, in shared memory (bank-conflict-free interleaved layout).
+//                    Output per pixel: the bucket that holds the median, the residual rank
+//                    inside that bucket and the bucket's population.
+//   4. k_refine_fast tier 2: one CTA per 16x16 output tile streams the bucket bytes of the
+//                    tile's (16+k-1)^2 region, keeps the pixels that fall in a bucket some
+//                    pixel of the tile needs, fetches only those values, counting-sorts them
+//                    by (bucket, key digits) and rank-sorts inside the sub-groups; every
+//                    thread walks its bucket's sorted candidates counting in-window ones
+//                    until it reaches its residual rank.  The fused epilogue applies the disk
+//                    mask and reduces min/max for the histogram.  Tiles with too many
+//                    candidates are retried with larger buffers (k_refine_fast_list) and, if
+//                    they still overflow (flat areas), refined with the whole region staged
+//                    in shared memory (k_refine_list).
 //
 // k_median_brute is an independent per-thread radix-select used only as the at-scale
 // checker in the tests.
@@ -386,7 +391,7 @@ __global__ void __launch_bounds__(32 * kH4Warps) k_huang4(const uint8_t* __restr
 }
 
 // ------------------------------------------------------------------ 4. tier 2: tile refine
-// One CTA per 16x16 output tile.
+// Staged slow path (k_refine_list).  One CTA per 16x16 output tile.
 //   a. bitmap of the buckets the tile's pixels need (tier-1 output);
 //   b. the tile's (16+k-1)^2 input region (bucket bytes + ordered keys) is staged in shared
 //      memory with coalesced, mutually independent loads;
