@@ -55,6 +55,9 @@ template <> struct Key<double> {
 // filled cv2.circle == integer test
 __device__ __forceinline__ bool on_disk(int x, int y, int cx, int cy, int r) {
   if (r < 0) return true;
+  const unsigned ax = (unsigned)abs(x - cx), ay = (unsigned)abs(y - cy);
+  // exact in 32 bits for every image up to 32768 pixels on a side (2 * 32767^2 < 2^32)
+  if ((ax | ay) < 32768u && (unsigned)r < 46341u) return ax * ax + ay * ay <= (unsigned)r * (unsigned)r;
   long long dx = x - cx, dy = y - cy;
   return dx * dx + dy * dy <= (long long)r * (long long)r;
 }
