@@ -65,16 +65,30 @@ __device__ __forceinline__ int hist_bin(double v, int nbins, double first, doubl
   return g;
 }
 
+// the same with the edges read from a shared-memory table E[0..nbins] (two loads and two fp64
+// compares in the common case instead of two edge evaluations)
+__device__ __forceinline__ int hist_bin_tab(double v, int nbins, const double* __restrict__ E, float first_f,
+                                            float scale_f) {
+  int g = (int)(((float)v - first_f) * scale_f);
+  g = min(max(g, 0), nbins - 1);
+  const double e0 = E[g], e1 = E[g + 1];
+  if (v < e0) {
+    do --g; while (g > 0 && v < E[g]);
+  } else if (v >= e1 && g < nbins - 1) {
+    do ++g; while (g < nbins - 1 && v >= E[g + 1]);
+  }
+  return g;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) k_hist(const T* __restrict__ filt, int W, int rx0, int ry0,
                                               int rw, int rh, int cx, int cy, int r,
                                               const typename Key<T>::type* __restrict__ minmax,
-                                              int nbins, int copies,
+                                              int nbins, int copies, int use_table,
                                               unsigned long long* __restrict__ counts,
                                               chips_result* __restrict__ res) {
   extern __shared__ __align__(16) uint32_t sh[];
   for (int i = threadIdx.x; i < copies * nbins; i += blockDim.x) sh[i] = 0;
-  __syncthreads();
   double first, last;
   {
     typename Key<T>::type k0 = minmax[0], k1 = minmax[1];
@@ -97,6 +111,11 @@ __global__ void __launch_bounds__(256) k_hist(const T* __restrict__ filt, int W,
   const double denom = __dsub_rn(last, first);
   const double step = __ddiv_rn(denom, (double)nbins);
   const float first_f = (float)first, scale_f = (float)((double)nbins / denom);
+  // edge table behind the sub-histograms (8-byte aligned: copies * nbins is rounded up to even)
+  double* E = reinterpret_cast<double*>(sh + ((copies * nbins + 1) & ~1));
+  if (use_table)
+    for (int i = threadIdx.x; i <= nbins; i += blockDim.x) E[i] = linspace_edge(i, nbins, first, last, step);
+  __syncthreads();
   uint32_t* mine = sh + ((threadIdx.x >> 5) % copies) * nbins;
   for (int y = ry0 + blockIdx.x; y < ry0 + rh; y += gridDim.x) {
     int xa, xb;
@@ -107,8 +126,10 @@ __global__ void __launch_bounds__(256) k_hist(const T* __restrict__ filt, int W,
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         int xi = x + i;
-        idx[i] = (xi >= xa && xi < xb)
-                     ? hist_bin((double)row[xi], nbins, first, last, step, first_f, scale_f) : -1;
+        idx[i] = -1;
+        if (xi >= xa && xi < xb)
+          idx[i] = use_table ? hist_bin_tab((double)row[xi], nbins, E, first_f, scale_f)
+                             : hist_bin((double)row[xi], nbins, first, last, step, first_f, scale_f);
       }
       // neighbouring pixels of the median-filtered image mostly share a bin: merge first
 #pragma unroll
@@ -420,7 +441,9 @@ static int hist_impl(const T* filt, const chips_plan* p, int cx, int cy, int r, 
   using K = typename Key<T>::type;
   const int nbins = p->h_bins;
   int copies = hist_copies(nbins);
-  size_t smem = (size_t)copies * nbins * sizeof(uint32_t);
+  const int use_table = nbins <= 4096;          // edges in shared memory (32 KB at most)
+  size_t smem = (size_t)((copies * nbins + 1) & ~1) * sizeof(uint32_t) +
+                (use_table ? (size_t)(nbins + 1) * sizeof(double) : 0);
   if (smem > 200 * 1024) return CHIPS_E_ARG;
   unsigned long long* counts = reinterpret_cast<unsigned long long*>(ws + p->off_counts);
   CHIPS_CUDA(cudaMemsetAsync(counts, 0, (size_t)nbins * sizeof(long long), st));
@@ -428,7 +451,7 @@ static int hist_impl(const T* filt, const chips_plan* p, int cx, int cy, int r, 
   int per_sm = smem > 100 * 1024 ? 1 : (smem > 56 * 1024 ? 2 : 4);
   int grid = min(p->roi_h, per_sm * kNumSM);
   k_hist<T><<<grid, 256, smem, st>>>(filt, p->W, p->roi_x0, p->roi_y0, p->roi_w, p->roi_h, cx, cy, r,
-                                     reinterpret_cast<const K*>(ws + p->off_minmax), nbins, copies,
+                                     reinterpret_cast<const K*>(ws + p->off_minmax), nbins, copies, use_table,
                                      counts, reinterpret_cast<chips_result*>(ws + p->off_result));
   CHIPS_CHECK_LAUNCH();
   count_launch();
