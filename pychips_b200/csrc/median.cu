@@ -109,8 +109,21 @@ __global__ void __launch_bounds__(256) k_bounds(const T* __restrict__ img, int H
   }
   __syncthreads();
   bitonic_sort<K, false>(s, nullptr, kSamples, threadIdx.x, blockDim.x);
-  for (int i = threadIdx.x; i < kBuckets; i += blockDim.x)
-    bounds[(size_t)blk * kBuckets + i] = (i < kBuckets - 1) ? s[(i + 1) * (kSamples / kBuckets)] : Key<T>::kMax;
+  // Quantised intensities (instrument counts, exposure-normalised data) repeat: a value that
+  // fills more than one quantile step yields a run of equal boundaries, i.e. empty buckets.  The
+  // last boundary of such a run is raised by one key so that the bucket below it becomes a POINT
+  // bucket [v, v+1): a median that falls into it is v, known after tier 1 (no candidates, no walk).
+  constexpr int kStep = kSamples / kBuckets;
+  for (int i = threadIdx.x; i < kBuckets; i += blockDim.x) {
+    K b = Key<T>::kMax;
+    if (i < kBuckets - 1) {
+      b = s[(i + 1) * kStep];
+      const bool dup_prev = i > 0 && s[i * kStep] == b;
+      const bool last_of_run = i == kBuckets - 2 || s[(i + 2) * kStep] != b;
+      if (dup_prev && last_of_run && b != Key<T>::kMax) b += 1;
+    }
+    bounds[(size_t)blk * kBuckets + i] = b;
+  }
 }
 
 template <typename K>
@@ -454,17 +467,47 @@ __device__ __forceinline__ void refine_tile_staged(
   if (tid == 0) nactive = 0;
   __syncthreads();
   int bs = 0, rr = 0, mpop = 0;
+  bool walk = false;                  // this pixel needs the candidates of its bucket
+  K point = 0;                        // ... or its median is the only key of a point bucket
   if (active) {
     size_t o = (size_t)y * W + x;
     bs = bstar[o];
     uint32_t pk = rres[o];
     rr = (int)(pk & 0xFFFFu);
     mpop = (int)(pk >> 16);
-    atomicOr(&need[bs >> 5], 1u << (bs & 31));
-    nactive = 1;
+    const K klo = bs ? bounds[bs - 1] : (K)0;
+    if (bs > 0 && bounds[bs] - klo == 1) {
+      point = klo;
+    } else {
+      walk = true;
+      atomicOr(&need[bs >> 5], 1u << (bs & 31));
+      nactive = 1;
+    }
   }
   __syncthreads();
-  if (nactive == 0) return;
+  // min/max of the masked output for the histogram range (np.histogram's a.min()/a.max())
+  auto reduce_minmax = [&](K kmin, K kmax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      K a = __shfl_xor_sync(0xFFFFFFFFu, kmin, o);
+      K b = __shfl_xor_sync(0xFFFFFFFFu, kmax, o);
+      kmin = a < kmin ? a : kmin;
+      kmax = b > kmax ? b : kmax;
+    }
+    if (lane == 0 && kmin <= kmax) {
+      atomic_min_key(&minmax[0], kmin);
+      atomic_max_key(&minmax[1], kmax);
+    }
+  };
+  if (nactive == 0) {                 // nothing to select: point buckets (or an empty tile) only
+    K kmin = Key<T>::kMax, kmax = 0;
+    if (active) {
+      out[(size_t)y * W + x] = Key<T>::dec(point);
+      kmin = kmax = point;
+    }
+    reduce_minmax(kmin, kmax);
+    return;
+  }
   if (tid < 9) {
     uint32_t p = 0;
     for (int i = 0; i < tid; ++i) p += __popc(need[i]);
@@ -600,7 +643,11 @@ __device__ __forceinline__ void refine_tile_staged(
 
   // ---- e. walk the sorted candidates of my bucket from the nearer end
   K kmin = Key<T>::kMax, kmax = 0;
-  if (active) {
+  if (active && !walk) {
+    out[(size_t)y * W + x] = Key<T>::dec(point);
+    kmin = kmax = point;
+  }
+  if (walk) {
     const int g = glut[bs];
     const int beg = (int)sgstart[g << dlog], end = (int)sgcur[(g << dlog) + ndm1];
     const unsigned win = 2u * (unsigned)half;
@@ -650,18 +697,7 @@ __device__ __forceinline__ void refine_tile_staged(
     kmin = res;
     kmax = res;
   }
-  // min/max of the masked output for the histogram range (np.histogram's a.min()/a.max())
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    K a = __shfl_xor_sync(0xFFFFFFFFu, kmin, o);
-    K b = __shfl_xor_sync(0xFFFFFFFFu, kmax, o);
-    kmin = a < kmin ? a : kmin;
-    kmax = b > kmax ? b : kmax;
-  }
-  if (lane == 0 && kmin <= kmax) {
-    atomic_min_key(&minmax[0], kmin);
-    atomic_max_key(&minmax[1], kmax);
-  }
+  reduce_minmax(kmin, kmax);
 }
 
 // Slow path of tier 2: tiles whose candidate set does not fit the fast path's fixed buffers
@@ -760,17 +796,47 @@ __device__ __forceinline__ void refine_tile_fast(
   }
   __syncthreads();
   int bs = 0, rr = 0, mpop = 0;
+  bool walk = false;                  // this pixel needs the candidates of its bucket
+  K point = 0;                        // ... or its median is the only key of a point bucket
   if (active) {
     size_t o = (size_t)y * W + x;
     bs = bstar[o];
     uint32_t pk = rres[o];
     rr = (int)(pk & 0xFFFFu);
     mpop = (int)(pk >> 16);
-    atomicOr(&need[bs >> 5], 1u << (bs & 31));
-    nactive = 1;
+    const K klo = bs ? bounds[bs - 1] : (K)0;
+    if (bs > 0 && bounds[bs] - klo == 1) {
+      point = klo;
+    } else {
+      walk = true;
+      atomicOr(&need[bs >> 5], 1u << (bs & 31));
+      nactive = 1;
+    }
   }
   __syncthreads();
-  if (nactive == 0) return;
+  // min/max of the masked output for the histogram range (np.histogram's a.min()/a.max())
+  auto reduce_minmax = [&](K kmin, K kmax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      K a = __shfl_xor_sync(0xFFFFFFFFu, kmin, o);
+      K b = __shfl_xor_sync(0xFFFFFFFFu, kmax, o);
+      kmin = a < kmin ? a : kmin;
+      kmax = b > kmax ? b : kmax;
+    }
+    if (lane == 0 && kmin <= kmax) {
+      atomic_min_key(&minmax[0], kmin);
+      atomic_max_key(&minmax[1], kmax);
+    }
+  };
+  if (nactive == 0) {                 // nothing to select: point buckets (or an empty tile) only
+    K kmin = Key<T>::kMax, kmax = 0;
+    if (active) {
+      out[(size_t)y * W + x] = Key<T>::dec(point);
+      kmin = kmax = point;
+    }
+    reduce_minmax(kmin, kmax);
+    return;
+  }
   if (tid < 9) {
     uint32_t p = 0;
     for (int i = 0; i < tid; ++i) p += __popc(need[i]);
@@ -954,7 +1020,11 @@ __device__ __forceinline__ void refine_tile_fast(
 
   // ---- d. walk the sorted candidates of my bucket from the nearer end
   K kmin = Key<T>::kMax, kmax = 0;
-  if (active) {
+  if (active && !walk) {
+    out[(size_t)y * W + x] = Key<T>::dec(point);
+    kmin = kmax = point;
+  }
+  if (walk) {
     const int g = glut[bs];
     const int beg = (int)sgoff[g << dlog], end = (int)sgoff[(g + 1) << dlog];
     const unsigned win = 2u * (unsigned)half;
@@ -1004,18 +1074,7 @@ __device__ __forceinline__ void refine_tile_fast(
     kmin = res;
     kmax = res;
   }
-  // min/max of the masked output for the histogram range (np.histogram's a.min()/a.max())
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    K a = __shfl_xor_sync(0xFFFFFFFFu, kmin, o);
-    K b = __shfl_xor_sync(0xFFFFFFFFu, kmax, o);
-    kmin = a < kmin ? a : kmin;
-    kmax = b > kmax ? b : kmax;
-  }
-  if (lane == 0 && kmin <= kmax) {
-    atomic_min_key(&minmax[0], kmin);
-    atomic_max_key(&minmax[1], kmax);
-  }
+  reduce_minmax(kmin, kmax);
 #ifdef CHIPS_DEBUG_TIMING
   __syncthreads();
   if (tid == 0 && dbg) {

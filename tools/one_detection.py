@@ -5,6 +5,9 @@ import numpy as np, torch
 from pychips_b200 import _lib, engine, synth
 n, k = int(os.environ.get("N", 4096)), int(os.environ.get("K", 51))
 img, r = synth.synthetic_disk(n, 0)
+q = float(os.environ.get("QUANT", 0))
+if q > 0:
+    img = (np.round(img / q) * q).astype(np.float32)      # instrument-like quantised intensities
 dev = engine.require_cuda()
 t = torch.from_numpy(img).to(dev)
 c = n // 2
@@ -14,3 +17,9 @@ for _ in range(int(os.environ.get("REPS", 1))):
     det.detect(t, maps=maps)
 torch.cuda.synchronize()
 print("n_peaks", det.result().n_peaks, "median_errors", det.result().median_errors)
+if os.environ.get("TIME"):
+    ts = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record(); det.medfilt(t); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    print("medfilt ms", sorted(ts)[2])
