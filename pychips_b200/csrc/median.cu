@@ -1119,6 +1119,58 @@ __global__ void __launch_bounds__(kTile* kTile, 4) k_refine_fast_list(
   }
 }
 
+// ------------------------------------------------------------------ small kernels (k <= 5)
+// For a 3x3 or 5x5 window the two-tier machinery is all overhead (the synoptic default is k = 3):
+// one thread per pixel holds the window's ordered keys in registers and runs a fixed selection
+// network (compare-exchange with compile-time indices: after pass i, a[i] is the i-th smallest),
+// stopping at the median's rank (30 / 234 exchanges).  At 7x7 the network (900 exchanges) is
+// already slower than the two-tier path.
+template <typename T, int KS>
+__global__ void __launch_bounds__(256) k_median_small(const T* __restrict__ img, T* __restrict__ out, int H,
+                                                      int W, int rx0, int ry0, int rw, int rh, int cx, int cy,
+                                                      int r, typename Key<T>::type* __restrict__ minmax) {
+  using K = typename Key<T>::type;
+  constexpr int N = KS * KS, R = (N - 1) / 2, HALF = KS / 2;
+  const int x = rx0 + blockIdx.x * 32 + (threadIdx.x & 31), y = ry0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+  const bool active = x < rx0 + rw && y < ry0 + rh && on_disk(x, y, cx, cy, r);
+  K kmin = Key<T>::kMax, kmax = 0;
+  if (active) {
+    K a[N];
+    const K zero = Key<T>::enc((T)0);
+#pragma unroll
+    for (int dy = 0; dy < KS; ++dy) {
+      const int iy = y + dy - HALF;
+#pragma unroll
+      for (int dx = 0; dx < KS; ++dx) {
+        const int ix = x + dx - HALF;
+        a[dy * KS + dx] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? Key<T>::enc(__ldg(&img[(size_t)iy * W + ix]))
+                                                                   : zero;     // medfilt2d zero padding
+      }
+    }
+#pragma unroll
+    for (int i = 0; i <= R; ++i) {
+#pragma unroll
+      for (int j = i + 1; j < N; ++j) {
+        const K lo = a[i] < a[j] ? a[i] : a[j], hi = a[i] < a[j] ? a[j] : a[i];
+        a[i] = lo;
+        a[j] = hi;
+      }
+    }
+    out[(size_t)y * W + x] = Key<T>::dec(a[R]);
+    kmin = kmax = a[R];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    K p = __shfl_xor_sync(0xFFFFFFFFu, kmin, o), q = __shfl_xor_sync(0xFFFFFFFFu, kmax, o);
+    kmin = p < kmin ? p : kmin;
+    kmax = q > kmax ? q : kmax;
+  }
+  if ((threadIdx.x & 31) == 0 && kmin <= kmax) {
+    atomic_min_key(&minmax[0], kmin);
+    atomic_max_key(&minmax[1], kmax);
+  }
+}
+
 // ------------------------------------------------------------------ brute-force checker
 template <typename T>
 __global__ void __launch_bounds__(kHuangThreads) k_median_brute(const T* __restrict__ img,
@@ -1207,6 +1259,18 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
     k_copy_masked<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, H, W, cx, cy, r);
     CHIPS_CHECK_LAUNCH();
     count_launch();
+    return CHIPS_OK;
+  }
+  if (k <= 5) {      // direct selection in registers (all of it counts as stage 1)
+    if (stages & 1) {
+      CHIPS_CUDA(cudaMemsetAsync(&minmax[0], 0xFF, sizeof(K), st));     // running min = kMax
+      CHIPS_CUDA(cudaMemsetAsync(&minmax[1], 0x00, sizeof(K), st));     // running max = 0
+      dim3 grid((rw + 31) / 32, (rh + 7) / 8);
+      if (k == 3) k_median_small<T, 3><<<grid, 256, 0, st>>>(in, out, H, W, rx0, ry0, rw, rh, cx, cy, r, minmax);
+      else k_median_small<T, 5><<<grid, 256, 0, st>>>(in, out, H, W, rx0, ry0, rw, rh, cx, cy, r, minmax);
+      CHIPS_CHECK_LAUNCH();
+      count_launch();
+    }
     return CHIPS_OK;
   }
   if (stages & 1) {  // local quantile boundaries of every block
