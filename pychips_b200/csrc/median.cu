@@ -494,9 +494,11 @@ __device__ __forceinline__ void refine_tile_staged(
       kmin = a < kmin ? a : kmin;
       kmax = b > kmax ? b : kmax;
     }
+    // every warp of the grid would hit the same two addresses: only values that improve on the
+    // (possibly stale, therefore conservative) current bounds go to the L2 atomic unit
     if (lane == 0 && kmin <= kmax) {
-      atomic_min_key(&minmax[0], kmin);
-      atomic_max_key(&minmax[1], kmax);
+      if (kmin < __ldcg(&minmax[0])) atomic_min_key(&minmax[0], kmin);
+      if (kmax > __ldcg(&minmax[1])) atomic_max_key(&minmax[1], kmax);
     }
   };
   if (nactive == 0) {                 // nothing to select: point buckets (or an empty tile) only
@@ -823,9 +825,11 @@ __device__ __forceinline__ void refine_tile_fast(
       kmin = a < kmin ? a : kmin;
       kmax = b > kmax ? b : kmax;
     }
+    // every warp of the grid would hit the same two addresses: only values that improve on the
+    // (possibly stale, therefore conservative) current bounds go to the L2 atomic unit
     if (lane == 0 && kmin <= kmax) {
-      atomic_min_key(&minmax[0], kmin);
-      atomic_max_key(&minmax[1], kmax);
+      if (kmin < __ldcg(&minmax[0])) atomic_min_key(&minmax[0], kmin);
+      if (kmax > __ldcg(&minmax[1])) atomic_max_key(&minmax[1], kmax);
     }
   };
   if (nactive == 0) {                 // nothing to select: point buckets (or an empty tile) only
@@ -1165,9 +1169,9 @@ __global__ void __launch_bounds__(256) k_median_small(const T* __restrict__ img,
     kmin = p < kmin ? p : kmin;
     kmax = q > kmax ? q : kmax;
   }
-  if ((threadIdx.x & 31) == 0 && kmin <= kmax) {
-    atomic_min_key(&minmax[0], kmin);
-    atomic_max_key(&minmax[1], kmax);
+  if ((threadIdx.x & 31) == 0 && kmin <= kmax) {     // (see reduce_minmax in the refine kernels)
+    if (kmin < __ldcg(&minmax[0])) atomic_min_key(&minmax[0], kmin);
+    if (kmax > __ldcg(&minmax[1])) atomic_max_key(&minmax[1], kmax);
   }
 }
 
