@@ -8,7 +8,13 @@ rows = list(csv.reader(open(src)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 h = rows[hi]
 ci, cs, csmp = h.index("Instructions Executed"), h.index("Source"), h.index("# Samples")
-ins = [(r[cs], int(r[ci] or 0), int(r[csmp] or 0)) for r in rows[hi + 1:] if len(r) > ci]
+body = []
+for r in rows[hi + 1:]:
+    if r and r[0] in ("Address", "Kernel Name"):     # next kernel of a multi-kernel export
+        break
+    if len(r) > ci:
+        body.append(r)
+ins = [(r[cs], int(r[ci] or 0), int(r[csmp] or 0)) for r in body]
 # nvdisasm: find function, walk lines, track current "//## File ..., line N"
 lines = open(sass).read().splitlines()
 start = [i for i, l in enumerate(lines) if l.startswith(".text.") and kern in l or (l.strip().startswith(".text.") and kern in l)]
