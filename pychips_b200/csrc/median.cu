@@ -198,11 +198,13 @@ __device__ __forceinline__ int count_bytes_below(uint32_t w, uint32_t m4, uint32
 constexpr int kH4Warps = 2;
 constexpr int kH4Stride = 32 * kH4Warps;   // counters of one bucket, all threads of the CTA
 
+template <int KT>      // compile-time window size (0: run-time k) — lets the byte roles fold
 __global__ void __launch_bounds__(32 * kH4Warps) k_huang4(const uint8_t* __restrict__ Bp, BlockGeom g,
-                                                          int k, int W, int rw, int rh, int cx, int cy,
+                                                          int k_rt, int W, int rw, int rh, int cx, int cy,
                                                           int r, uint8_t* __restrict__ bstar,
                                                           uint32_t* __restrict__ rres, uint32_t* __restrict__ dbg) {
   extern __shared__ __align__(16) uint32_t h4_smem[];
+  const int k = KT ? KT : k_rt;
 #ifdef CHIPS_DEBUG_TIMING
   const long long t_begin = clock64();
   unsigned smid;
@@ -1291,9 +1293,20 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
   if (stages & 4) {  // tier 1: one warp per block, two blocks per CTA
     dim3 grid((p->blk_nbx + kH4Warps - 1) / kH4Warps, p->blk_nby);
     size_t smem = (size_t)kBuckets * kH4Stride * (sizeof(uint16_t) + sizeof(uint32_t));
-    CHIPS_CUDA(cudaFuncSetAttribute(k_huang4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_huang4<<<grid, 32 * kH4Warps, smem, st>>>(Bp, g, k, W, rw, rh, cx, cy, r, bstar, rres,
-                                                reinterpret_cast<uint32_t*>(ws + p->off_parent_c));
+    uint32_t* dbg = reinterpret_cast<uint32_t*>(ws + p->off_parent_c);
+#define CHIPS_LAUNCH_HUANG(KT)                                                                              \
+    do {                                                                                                    \
+      CHIPS_CUDA(cudaFuncSetAttribute(k_huang4<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      k_huang4<KT><<<grid, 32 * kH4Warps, smem, st>>>(Bp, g, k, W, rw, rh, cx, cy, r, bstar, rres, dbg);      \
+    } while (0)
+    switch (k) {       // the kernel sizes the reference's scripts use; anything else runs the generic copy
+      case 11: CHIPS_LAUNCH_HUANG(11); break;
+      case 31: CHIPS_LAUNCH_HUANG(31); break;
+      case 51: CHIPS_LAUNCH_HUANG(51); break;
+      case 71: CHIPS_LAUNCH_HUANG(71); break;
+      default: CHIPS_LAUNCH_HUANG(0); break;
+    }
+#undef CHIPS_LAUNCH_HUANG
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }
