@@ -743,7 +743,7 @@ __device__ __forceinline__ uint32_t sum_u16x8(const uint4 c) {
          (c.w & 0xFFFFu) + (c.w >> 16);
 }
 
-template <typename T>
+template <typename T, int KT>      // KT: compile-time window size (0 = run time)
 __device__ __forceinline__ void refine_tile_fast(
     const int tile_x, const int tile_y, const int gx, const int cap,
     const T* __restrict__ img, const uint8_t* __restrict__ Bp_all, const BlockGeom g,
@@ -783,7 +783,7 @@ __device__ __forceinline__ void refine_tile_fast(
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const int tx = tid & (kTile - 1), ty = tid >> 4;
-  const int half = g.half, pitch = g.LP, rx0 = g.rx0, ry0 = g.ry0;
+  const int half = KT ? KT / 2 : g.half, pitch = g.LP, rx0 = g.rx0, ry0 = g.ry0;
   const int by = (tile_y * kTile) / g.L, blk = by * g.nbx + (tile_x >> 3);
   const K* __restrict__ bounds = bounds_all + (size_t)blk * kBuckets;
   // block-local origin of the tile's region (the +half of the local frame cancels the -half);
@@ -1095,14 +1095,14 @@ __device__ __forceinline__ void refine_tile_fast(
 }
 
 // first pass: one CTA per tile, `cap` candidates (6 CTAs per SM)
-template <typename T>
+template <typename T, int KT>
 __global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
     const int cap, const T* __restrict__ img, const uint8_t* __restrict__ Bp_all, const BlockGeom g,
     const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres,
     const typename Key<T>::type* __restrict__ bounds_all, int H, int W, int rw, int rh, int cx, int cy,
     int r, T* __restrict__ out, typename Key<T>::type* __restrict__ minmax, int* __restrict__ err,
     uint32_t* __restrict__ ovf, int force_overflow, uint32_t* __restrict__ dbg) {
-  refine_tile_fast<T>((int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x, cap, img, Bp_all, g, bstar, rres,
+  refine_tile_fast<T, KT>((int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x, cap, img, Bp_all, g, bstar, rres,
                       bounds_all, H, W, rw, rh, cx, cy, r, out, minmax, err, ovf, force_overflow, dbg);
 }
 
@@ -1118,7 +1118,7 @@ __global__ void __launch_bounds__(kTile* kTile, 4) k_refine_fast_list(
   const uint32_t n = ovf_in[0];
   for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
     const uint32_t t = ovf_in[1 + i];
-    refine_tile_fast<T>((int)(t % (uint32_t)gx), (int)(t / (uint32_t)gx), gx, cap, img, Bp_all, g, bstar,
+    refine_tile_fast<T, 0>((int)(t % (uint32_t)gx), (int)(t / (uint32_t)gx), gx, cap, img, Bp_all, g, bstar,
                         rres, bounds_all, H, W, rw, rh, cx, cy, r, out, minmax, err, ovf_out, force_overflow,
                         nullptr);
     __syncthreads();      // the next tile reuses every shared buffer
@@ -1321,11 +1321,23 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
     };
     uint32_t* ovf2 = ovf + (size_t)gx * gy + 1;          // second-level overflow list
     CHIPS_CUDA(cudaMemsetAsync(ovf2, 0, sizeof(uint32_t), st));
-    CHIPS_CUDA(cudaFuncSetAttribute(k_refine_fast<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)fast_smem(kFastCap)));
-    k_refine_fast<T><<<dim3(gx, gy), kTile * kTile, fast_smem(kFastCap), st>>>(
-        kFastCap, in, Bp, g, bstar, rres, bounds, H, W, rw, rh, cx, cy, r, out, minmax, err, ovf, force_ovf,
-        reinterpret_cast<uint32_t*>(ws + p->off_parent_c));
+    uint32_t* rdbg = reinterpret_cast<uint32_t*>(ws + p->off_parent_c);
+#define CHIPS_LAUNCH_REFINE(KT)                                                                              \
+    do {                                                                                                     \
+      CHIPS_CUDA(cudaFuncSetAttribute(k_refine_fast<T, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                      (int)fast_smem(kFastCap)));                                            \
+      k_refine_fast<T, KT><<<dim3(gx, gy), kTile * kTile, fast_smem(kFastCap), st>>>(                         \
+          kFastCap, in, Bp, g, bstar, rres, bounds, H, W, rw, rh, cx, cy, r, out, minmax, err, ovf, force_ovf, \
+          rdbg);                                                                                             \
+    } while (0)
+    switch (k) {
+      case 11: CHIPS_LAUNCH_REFINE(11); break;
+      case 31: CHIPS_LAUNCH_REFINE(31); break;
+      case 51: CHIPS_LAUNCH_REFINE(51); break;
+      case 71: CHIPS_LAUNCH_REFINE(71); break;
+      default: CHIPS_LAUNCH_REFINE(0); break;
+    }
+#undef CHIPS_LAUNCH_REFINE
     CHIPS_CHECK_LAUNCH();
     const long long ntiles = (long long)gx * gy;
     const int nlist = (int)(ntiles < 4LL * kNumSM ? ntiles : 4LL * kNumSM);
