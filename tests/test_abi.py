@@ -82,3 +82,26 @@ def test_null_pointers_are_rejected_without_touching_the_gpu():
                             None, None, None) == -1
     assert lib.chips_select_threshold(C.byref(p), 5.0, float("nan"), 0, 7, None, None) == -1
     assert lib.chips_medfilt2d_bruteforce(None, None, 8, 8, 3, 4, 0, 0, -1, None) == -1
+
+
+@pytest.mark.parametrize("H,W,k,r", [(4096, 4096, 51, 1577), (1024, 1024, 11, 394), (20, 20, 31, -1),
+                                     (1, 1, 3, -1), (9, 300, 11, -1), (1440, 3600, 3, -1), (300, 9, 75, -1),
+                                     (512, 512, 71, 300)])
+def test_plan_block_geometry_is_consistent(H, W, k, r):
+    """The median's 128 x L blocks tile the ROI, L is a multiple of the 16-pixel refine tile, the
+    block images hold the halo, and every workspace offset is aligned and inside the blob."""
+    from pychips_b200 import _lib
+    lib = _lib.load()
+    p = _lib.Plan()
+    assert lib.chips_plan_init(C.byref(p), H, W, k, 500, 20, 4, W // 2, H // 2, r) == 0
+    half = k // 2
+    assert p.blk_rows % 16 == 0 and p.blk_rows >= 16
+    assert p.blk_nbx * 128 >= p.roi_w and (p.blk_nbx - 1) * 128 < p.roi_w
+    assert p.blk_nby * p.blk_rows >= p.roi_h and (p.blk_nby - 1) * p.blk_rows < p.roi_h
+    assert p.bp_pitch % 16 == 0 and p.bp_pitch >= 128 + 2 * half + 16 and p.bp_rows == p.blk_rows + 2 * half
+    assert 0 <= p.roi_x0 and p.roi_x0 + p.roi_w <= W and 0 <= p.roi_y0 and p.roi_y0 + p.roi_h <= H
+    offs = [getattr(p, f) for f, _ in _lib.Plan._fields_ if f.startswith("off_")]
+    assert all(o % 256 == 0 and o <= p.bytes for o in offs)
+    nblk = p.blk_nbx * p.blk_nby
+    assert p.off_bstar - p.off_bucket >= nblk * p.bp_pitch * p.bp_rows
+    assert p.off_bucket - p.off_bounds >= nblk * 128 * 8
