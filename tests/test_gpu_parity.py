@@ -683,3 +683,36 @@ def test_regional_histograms_vs_oracle(n, xs, ys, hb):
     c2.extract_CHs_CHBs(d2)
     for key, reg in d_or.solar_ch_regions.__dict__.items():
         assert np.array_equal(d2.solar_ch_regions.__dict__[key].map, reg.map)
+
+
+# ----------------------------------------------------------------------------- randomised configurations
+@pytest.mark.parametrize("seed", range(10))
+def test_random_configurations_vs_oracle(seed):
+    """Seeded random (size, kernel, bins, thresholds, quantisation, dtype): every stage output of
+    the drop-in class against the oracle.  Exercises the register network (k <= 5), the generic
+    and the specialised tier-1 / tier-2 kernels and the point buckets inside the full pipeline."""
+    rng = np.random.default_rng(4242 + seed)
+    n = int(rng.integers(96, 360))
+    k = int(rng.choice([3, 5, 7, 9, 11, 21, 31, 51]))
+    hb = int(rng.choice([50, 200, 500, 1500]))
+    t0 = int(rng.integers(-4, 2))
+    tr = [t0, t0 + int(rng.integers(3, 24))]
+    q = float(rng.choice([0.0, 0.0, 0.5, 2.0]))
+    dtype = np.float64 if rng.random() < 0.5 else np.float32
+    img, r = synth.synthetic_disk(n, 300 + seed)
+    if q > 0:
+        img = (np.round(img / q) * q).astype(np.float32)
+    if dtype == np.float64 and rng.random() < 0.5:
+        img = img.astype(np.float64) * (1.0 + 2.0 ** -40)      # not float32-representable
+    d_or = synth.FakeDisk(img.astype(np.float64), r)
+    co.OracleChips(medfilt_kernel=k, h_bins=hb, threshold_range=tr).run(d_or, keep_contours=False)
+    c, d = run_gpu_disk(img.astype(np.float64), r, medfilt_kernel=k, h_bins=hb, threshold_range=tr)
+    if hasattr(d_or, "solar_ch_regions"):
+        regs = list(d_or.solar_ch_regions.__dict__.values())
+        lims, probs = [x.lim for x in regs], [x.prob for x in regs]
+        raw = [x.raw_map.astype(np.uint8) for x in regs]
+        maps = [x.map.astype(np.uint8) for x in regs]
+    else:
+        lims = probs = raw = maps = None
+    compare_disk(d, d_or.solar_filter.filt_disk, d_or.histogram.hbase, d_or.histogram.hbins,
+                 d_or.histogram.bound, np.array(d_or.histogram.peaks), lims, probs, raw, maps, None, c)
