@@ -80,6 +80,7 @@ typedef struct chips_plan {
   size_t off_parent_c;   /* u32 [2][roi_h*roi_w]    component tree: union-find, merge parents */
   size_t off_area;       /* u32 [roi] 2*area at roots; u8 [3][roi] hook level, kept level, W  */
   size_t off_pending;    /* u32 [roi_h*roi_w]  hole-fill work list grouped by level       */
+  size_t off_list2;      /* u32 [roi_h*roi_w]  unsorted list (phase B) / foreground list grouped by W (phase C) */
   size_t off_lvl;        /* u32 [512]          per-level counts / offsets / cursors, phase-C counters */
   size_t off_tiles;      /* (reserved)                                                    */
   size_t off_ovf;        /* u32 [2][1 + #16x16 tiles]  median tier 2: count + list of overflow tiles, two levels */

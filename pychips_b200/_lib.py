@@ -34,7 +34,7 @@ class Plan(C.Structure):
                 ("off_bounds", "off_bucket", "off_bstar", "off_rres", "off_filt", "off_minmax",
                  "off_counts", "off_density", "off_edges", "off_bound", "off_peaks",
                  "off_result", "off_level", "off_fill", "off_keep", "off_probtab",
-                 "off_parent_b", "off_parent_c", "off_area", "off_pending", "off_lvl",
+                 "off_parent_b", "off_parent_c", "off_area", "off_pending", "off_list2", "off_lvl",
                  "off_tiles", "off_ovf", "bytes")]
 
 

@@ -155,11 +155,14 @@ __global__ void __launch_bounds__(256) k_fill_pending(Roi g, const uint8_t* __re
                                                       uint8_t* __restrict__ Wimg,
                                                       uint32_t* __restrict__ parent,
                                                       uint32_t* __restrict__ lvl_count,
-                                                      uint32_t* __restrict__ lvl_cursor,
-                                                      uint32_t* __restrict__ pending) {
+                                                      uint32_t* __restrict__ total,
+                                                      uint32_t* __restrict__ unsorted) {
+  static_assert(PASS == 0, "the scatter pass is k_list_scatter");
   __shared__ uint32_t scnt[CHIPS_MAX_T + 1];
+  __shared__ uint32_t s_total, s_base;
   if (PASS == 0) {
     for (int i = threadIdx.x; i <= T; i += blockDim.x) scnt[i] = 0;
+    if (threadIdx.x == 0) s_total = 0;
     __syncthreads();
   }
   int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -169,12 +172,8 @@ __global__ void __launch_bounds__(256) k_fill_pending(Roi g, const uint8_t* __re
   if (x < g.x0 + g.w && on_disk(x, y, g.cx, g.cy, g.r)) {
     size_t o = (size_t)y * g.W + x;
     int l = lev[o];
-    if (PASS == 0) {
-      if (l == T) bulk = true;
-      else mylev = l;
-    } else {
-      if (!(l == T && Wimg[o] == T)) mylev = l;
-    }
+    if (l == T) bulk = true;
+    else mylev = l;
   }
   if (PASS == 0) {
     // bulk pixels of one row run share their root: the first lane of each run inside the warp's
@@ -193,24 +192,62 @@ __global__ void __launch_bounds__(256) k_fill_pending(Roi g, const uint8_t* __re
       else mylev = T;
     }
   }
-  unsigned act = __ballot_sync(0xFFFFFFFFu, mylev >= 0);
+  // per-level counts, and the pending pixels appended (in no particular order) to `unsorted`:
+  // one shared atomic per warp, one global atomic per CTA
+  const int lane_ = threadIdx.x & 31;
+  const unsigned act = __ballot_sync(0xFFFFFFFFu, mylev >= 0);
+  uint32_t woff = 0;
+  if (act) {
+    const int first = __ffs(act) - 1;
+    if (lane_ == first) woff = atomicAdd(&s_total, (uint32_t)__popc(act));
+    woff = __shfl_sync(0xFFFFFFFFu, woff, first);
+  }
   if (mylev >= 0) {
     unsigned peers = __match_any_sync(act, mylev);
-    int lane = threadIdx.x & 31;
-    int leader = __ffs(peers) - 1;
-    if (PASS == 0) {
-      if (lane == leader) atomicAdd(&scnt[mylev], __popc(peers));
-    } else {
-      uint32_t base = 0;
-      if (lane == leader) base = atomicAdd(&lvl_cursor[mylev], __popc(peers));
-      base = __shfl_sync(peers, base, leader);
-      pending[base + __popc(peers & ((1u << lane) - 1u))] = g.li(x, y);
-    }
+    if (lane_ == __ffs(peers) - 1) atomicAdd(&scnt[mylev], __popc(peers));
   }
-  if (PASS == 0) {
-    __syncthreads();
-    for (int i = threadIdx.x; i <= T; i += blockDim.x)
-      if (scnt[i]) atomicAdd(&lvl_count[i], scnt[i]);
+  __syncthreads();
+  for (int i = threadIdx.x; i <= T; i += blockDim.x)
+    if (scnt[i]) atomicAdd(&lvl_count[i], scnt[i]);
+  if (threadIdx.x == 0 && s_total) s_base = atomicAdd(total, s_total);
+  __syncthreads();
+  if (mylev >= 0) unsorted[s_base + woff + __popc(act & ((1u << lane_) - 1u))] = g.li(x, y);
+}
+
+// B5 / C1b: regroup a pixel list by level: entry -> slot of its level's segment (cursor[] starts
+// at the segment offsets).  `mode` 0: level = lev image value (phase B: pending pixels by lev),
+// 1: level = ROI-local W (phase C: foreground pixels by W; 255 = not foreground, skipped).
+__global__ void __launch_bounds__(256) k_list_scatter(Roi g, const uint8_t* __restrict__ levsrc, int mode,
+                                                      const uint32_t* __restrict__ in,
+                                                      const uint32_t* __restrict__ n_ptr,
+                                                      uint32_t* __restrict__ cursor,
+                                                      uint32_t* __restrict__ out) {
+  const uint32_t n = *n_ptr;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += nthreads) {
+    const uint32_t i = i0 + lane;
+    int level = -1;
+    uint32_t li = 0;
+    if (i < n) {
+      li = in[i];
+      if (mode == 0) {
+        const uint32_t ly = li / (uint32_t)g.w, lx = li - ly * (uint32_t)g.w;
+        level = levsrc[(size_t)(g.y0 + (int)ly) * g.W + (g.x0 + (int)lx)];
+      } else {
+        const int w = levsrc[li];
+        level = w == 255 ? -1 : w;
+      }
+    }
+    const unsigned act = __ballot_sync(0xFFFFFFFFu, level >= 0);
+    if (level >= 0) {
+      const unsigned peers = __match_any_sync(act, level);
+      const int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(&cursor[level], (uint32_t)__popc(peers));
+      base = __shfl_sync(peers, base, leader);
+      out[base + __popc(peers & ((1u << lane) - 1u))] = li;
+    }
   }
 }
 
@@ -341,7 +378,7 @@ __device__ __forceinline__ void uf_unite_rec(const Tree& tr, int t, uint32_t a, 
 
 // C1: ROI-local W, per-level counts of the foreground pixels and singleton initialisation
 // (PASS 0); the list grouped by W (PASS 1).
-template <int PASS>
+template <int PASS>      // (only PASS 0; the list itself is regrouped from phase B's by k_list_scatter)
 __global__ void __launch_bounds__(256) k_tree_list(Roi g, const uint8_t* __restrict__ Wimg, int T, Tree tr,
                                                    uint32_t thr2, uint32_t* __restrict__ lvl_count,
                                                    uint32_t* __restrict__ lvl_cursor) {
@@ -376,11 +413,6 @@ __global__ void __launch_bounds__(256) k_tree_list(Roi g, const uint8_t* __restr
       tr.mlevel[me] = 255;
       tr.klevel[me] = thr2 == 0 ? (uint8_t)w : 255;   // threshold <= 0: kept from birth
       if (lane == leader) atomicAdd(&scnt[w], __popc(peers));
-    } else {
-      uint32_t base = 0;
-      if (lane == leader) base = atomicAdd(&lvl_cursor[w], __popc(peers));
-      base = __shfl_sync(peers, base, leader);
-      tr.plist[base + __popc(peers & ((1u << lane) - 1u))] = me;
     }
   }
   if (PASS == 0) {
@@ -695,7 +727,7 @@ static Tree make_tree(const chips_plan* p, unsigned char* w) {
   t.mlevel = reinterpret_cast<uint8_t*>(t.area + nr);
   t.klevel = t.mlevel + nr;
   t.wl = t.klevel + nr;
-  t.plist = reinterpret_cast<uint32_t*>(w + p->off_pending);
+  t.plist = reinterpret_cast<uint32_t*>(w + p->off_list2);
   t.hooked = reinterpret_cast<uint32_t*>(w + p->off_parent_b);
   uint32_t* lvl = reinterpret_cast<uint32_t*>(w + p->off_lvl);
   t.offset = lvl + 128;
@@ -734,9 +766,10 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
   k_fill_bulk_link<<<grid, blk, 0, st>>>(g, lev, T, Wimg, parent_b);
   dim3 grid4((g.w / 4 + 2 + 255) / 256, g.h);
   k_fill_bulk_union<<<grid4, blk, 0, st>>>(g, lev, T, parent_b);
-  k_fill_pending<0><<<grid, blk, 0, st>>>(g, lev, T, Wimg, parent_b, lvl_count, lvl_cursor, pending);
+  uint32_t* list2 = reinterpret_cast<uint32_t*>(w + plan->off_list2);
+  k_fill_pending<0><<<grid, blk, 0, st>>>(g, lev, T, Wimg, parent_b, lvl_count, &ctr[4], list2);
   k_fill_offsets<<<1, 32, 0, st>>>(T, lvl_count, lvl_offset, lvl_cursor);
-  k_fill_pending<1><<<grid, blk, 0, st>>>(g, lev, T, Wimg, parent_b, lvl_count, lvl_cursor, pending);
+  k_list_scatter<<<4 * kNumSM, blk, 0, st>>>(g, lev, 0, list2, &ctr[4], lvl_cursor, pending);
   CHIPS_CHECK_LAUNCH();
   // the bulk pixels that did not reach the border in round T-1 stay pending at level T and
   // are re-examined by every later round (suffix of the list)
@@ -763,7 +796,8 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
   k_zero_counts<<<1, 128, 0, st>>>(lvl_count);
   k_tree_list<0><<<grid, blk, 0, st>>>(g, Wimg, T, tr, thr2, lvl_count, lvl_cursor);
   k_fill_offsets<<<1, 32, 0, st>>>(T, lvl_count, lvl_offset, lvl_cursor);
-  k_tree_list<1><<<grid, blk, 0, st>>>(g, Wimg, T, tr, thr2, lvl_count, lvl_cursor);
+  // the foreground pixels are exactly phase B's pending pixels: regroup that list by W
+  k_list_scatter<<<4 * kNumSM, blk, 0, st>>>(g, tr.wl, 1, pending, &ctr[4], lvl_cursor, list2);
   CHIPS_CHECK_LAUNCH();
   for (int t = 0; t < T; ++t) {
     k_tree_union<<<gl, blk, 0, st>>>(g, t, tr, thr2, res);

@@ -83,11 +83,12 @@ extern "C" int chips_plan_init(chips_plan* p, int H, int W, int k, int h_bins, i
     p->off_parent_c = take(nr * 4 * 2);       // union-find + merge-tree parents
     p->off_area = take(nr * 4 + nr * 3);      // 2*area accumulators; hook level, kept level, local W
     p->off_pending = take(nr * 4);
+    p->off_list2 = take(nr * 4);
     p->off_lvl = take(512 * 4);
     p->off_tiles = take(256);                  // (reserved)
   } else {   // the synoptic variant has no contour/cleanup step (syn_chips.py:237-251)
     p->off_parent_b = p->off_parent_c = p->off_area = off;
-    p->off_pending = p->off_lvl = p->off_tiles = off;
+    p->off_pending = p->off_list2 = p->off_lvl = p->off_tiles = off;
   }
   p->off_ovf = take(2 * ((size_t)((p->roi_w + 15) / 16) * ((p->roi_h + 15) / 16) + 1) * 4);
   p->bytes = off;
