@@ -350,7 +350,7 @@ def run_b200(a):
             "config": {"workload": workload(a), "images_per_gpu_per_step": a.batch,
                        "storage": "float32 image / uint8 maps; histogram, thresholds, probabilities in fp64",
                        "streams_per_gpu": a.streams,
-                       "l2": f"{a.batch} distinct {in_bytes // a.batch >> 20} MiB inputs + 0.46 GB workspace per "
+                       "l2": f"{a.batch} distinct {in_bytes // a.batch >> 20} MiB inputs + 0.50 GB workspace per "
                              "stream cycle through HBM each step (> 126 MB L2)",
                        "outputs": "T uint8 maps [T,N,N] + level-encoded map + record per image; "
                                   "probability map accumulated per GPU"},
