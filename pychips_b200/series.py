@@ -82,15 +82,28 @@ class SeriesRunner:
         """images: list of host arrays (pinned torch tensors or numpy, dtype matching `elem`);
         radii: per-image pixel_radius.  Copies each image to the device, runs the fused
         detection, copies the record (and the level-encoded map) back."""
+        return self.submit(images, radii, indices, h_thresh).result()
+
+    def submit(self, images, radii, indices=None, h_thresh=None) -> "PendingSeries":
+        """Enqueue a batch without waiting for it: the returned handle's `result()` blocks until the
+        batch's records and maps are on the host.  Batches submitted back to back keep all streams
+        busy (no pipeline drain between them); at most `n_host_sets` (2) may be in flight, each
+        with its own pinned result buffers."""
         n = len(images)
         indices = list(range(n)) if indices is None else list(indices)
         rec_bytes = C.sizeof(_lib.Result)
-        if getattr(self, "_host_n", -1) != n:          # pinned result buffers are reused
-            self._rec_host = torch.empty((n, rec_bytes), dtype=torch.uint8).pin_memory()
-            self._keep_host = [torch.empty((self.H, self.W), dtype=torch.uint8).pin_memory()
-                               for _ in range(n)] if self.want_keep else []
-            self._host_n = n
-        rec_host, keep_host = self._rec_host, self._keep_host
+        sets = self.__dict__.setdefault("_host_sets", {})
+        ring = sets.get(n)
+        if ring is None:                                # pinned result buffers, reused round-robin
+            ring = sets[n] = dict(next=0, bufs=[
+                (torch.empty((n, rec_bytes), dtype=torch.uint8).pin_memory(),
+                 [torch.empty((self.H, self.W), dtype=torch.uint8).pin_memory() for _ in range(n)]
+                 if self.want_keep else [], [None])
+                for _ in range(self.n_host_sets)])
+        rec_host, keep_host, owner = ring["bufs"][ring["next"]]
+        ring["next"] = (ring["next"] + 1) % self.n_host_sets
+        if owner[0] is not None and not owner[0]._done:
+            owner[0].result()                            # the set is still in flight: finish it first
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream()
             for s in self.streams:
@@ -113,23 +126,45 @@ class SeriesRunner:
                         keep_host[i].copy_(det.keep, non_blocking=True)
             for s in self.streams:
                 cur.wait_stream(s)
-            cur.synchronize()
-        recs = [_lib.Result.from_buffer_copy(rec_host[i].numpy().tobytes()) for i in range(n)]
-        T = self.T
+            done = torch.cuda.Event()
+            done.record(cur)
+        handle = PendingSeries(self, indices, rec_host, keep_host, done)
+        owner[0] = handle
+        return handle
+
+    n_host_sets = 2
+
+
+class PendingSeries:
+    """A submitted batch (`SeriesRunner.submit`)."""
+
+    def __init__(self, runner, indices, rec_host, keep_host, done):
+        self._runner, self._indices = runner, indices
+        self._rec_host, self._keep_host, self._event = rec_host, keep_host, done
+        self._done, self._result = False, None
+
+    def result(self) -> SeriesResult:
+        if self._done:
+            return self._result
+        self._event.synchronize()
+        n, T = len(self._indices), self._runner.T
+        recs = [_lib.Result.from_buffer_copy(self._rec_host[i].numpy().tobytes()) for i in range(n)]
         for rc in recs:
             if rc.median_errors:
                 raise _lib.ChipsNativeError("median self-check failed")
-        return SeriesResult(
-            indices=indices,
+        self._result = SeriesResult(
+            indices=self._indices,
             limit_0=np.array([rc.limit_0 for rc in recs]),
             h_thresh=np.array([rc.h_thresh for rc in recs]),
             n_peaks=np.array([rc.n_peaks for rc in recs]),
             limits=np.array([[rc.limits[t] for t in range(T)] for rc in recs]).reshape(n, T),
             probs=np.array([[rc.probs[t] for t in range(T)] for rc in recs]).reshape(n, T),
             n_kept=np.array([[rc.n_kept[t] for t in range(T)] for rc in recs]).reshape(n, T),
-            keep=[k.numpy() for k in keep_host],
-            prob_map_sum=self.prob_sum if self.want_prob_map else None,
+            keep=[k.numpy() for k in self._keep_host],
+            prob_map_sum=self._runner.prob_sum if self._runner.want_prob_map else None,
         )
+        self._done = True
+        return self._result
 
 
 def pack_stats(res: SeriesResult, T: int) -> torch.Tensor:
