@@ -1,6 +1,8 @@
 """Time series / batch detection: one full-disk image per detection, images sharded
-round-robin across ranks (one process per GPU), each rank double-buffered over two CUDA
-streams so the host->device copy of image i+1 overlaps the kernels of image i.
+round-robin across ranks (one process per GPU).  Each rank keeps `n_streams` detections in
+flight on their own compute streams; host->device copies run one image ahead on a copy stream
+(two input buffers per slot) and device->host copies read a device-side snapshot of the outputs
+on another, so neither direction of PCIe traffic stalls a compute stream.
 
 The reference has no batch API (one `Chips` per `RegisterAIA`, `/root/reference/chips/chips.py:
 110-150`); this is the multi-image driver SURVEY.md §8(e) asks for.  The only exchange step is
@@ -106,7 +108,8 @@ class SeriesRunner:
             owner[0].result()                            # the set is still in flight: finish it first
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream()
-            for s in self.streams:
+            self._ensure_copy_pipeline()
+            for s in self.streams + [self._h2d, self._d2h, self._acc]:
                 s.wait_stream(cur)
             for i in range(n):
                 slot = i % self.n_streams
@@ -115,16 +118,43 @@ class SeriesRunner:
                 src = images[i]
                 if isinstance(src, np.ndarray):
                     src = torch.from_numpy(src)
+                par = self._parity[slot]
+                self._parity[slot] ^= 1
+                din = self._dev_in2[slot][par]
+                # host -> device on the copy stream, one image ahead of the slot's compute stream
+                # (two input buffers per slot; a buffer is reused once its detection has read it)
+                with torch.cuda.stream(self._h2d):
+                    self._h2d.wait_event(self._in_free[slot][par])
+                    din.copy_(src, non_blocking=True)
+                    self._in_ready[slot][par].record(self._h2d)
                 with torch.cuda.stream(st):
-                    self.dev_in[slot].copy_(src, non_blocking=True)
-                    det.detect(self.dev_in[slot], self.ratio, h_thresh, self.porb, self.area_thr,
-                               self.maps[slot])
-                    if self.want_prob_map:
+                    st.wait_event(self._in_ready[slot][par])
+                    st.wait_event(self._acc_done[slot])      # the slot's previous map has been summed
+                    # (a CUDA-graph replay: ~200 launches cost the host 1.2 ms otherwise)
+                    det.detect_graphed(din, self.ratio, h_thresh, self.porb, self.area_thr, self.maps[slot])
+                    self._in_free[slot][par].record(st)
+                if self.want_prob_map:
+                    # the batch probability map is summed on ONE stream in image order: no two
+                    # accumulations overlap (race-free) and the sum is reproducible
+                    with torch.cuda.stream(self._acc):
+                        self._acc.wait_event(self._in_free[slot][par])
                         det.prob_stack(0.0, self.prob_sum, accumulate=True)
-                    rec_host[i].copy_(det.result_bytes(), non_blocking=True)
+                        self._acc_done[slot].record(self._acc)
+                with torch.cuda.stream(st):
+                    # snapshot of the outputs (device -> device), so that the slot's next detection
+                    # does not wait for the device -> host copy
+                    st.wait_event(self._stage_free[slot])
+                    self._stage_rec[slot].copy_(det.result_bytes(), non_blocking=True)
                     if self.want_keep:
-                        keep_host[i].copy_(det.keep, non_blocking=True)
-            for s in self.streams:
+                        self._stage_keep[slot].copy_(det.keep, non_blocking=True)
+                    self._snap[slot].record(st)
+                with torch.cuda.stream(self._d2h):
+                    self._d2h.wait_event(self._snap[slot])
+                    rec_host[i].copy_(self._stage_rec[slot], non_blocking=True)
+                    if self.want_keep:
+                        keep_host[i].copy_(self._stage_keep[slot], non_blocking=True)
+                    self._stage_free[slot].record(self._d2h)
+            for s in self.streams + [self._h2d, self._d2h, self._acc]:
                 cur.wait_stream(s)
             done = torch.cuda.Event()
             done.record(cur)
@@ -133,6 +163,32 @@ class SeriesRunner:
         return handle
 
     n_host_sets = 2
+
+    def _ensure_copy_pipeline(self):
+        """Copy streams, double input buffers and output snapshots (created on first use)."""
+        if getattr(self, "_h2d", None) is not None:
+            return
+        ns, dev = self.n_streams, self.device
+        self._h2d = torch.cuda.Stream(device=dev)
+        self._d2h = torch.cuda.Stream(device=dev)
+        self._acc = torch.cuda.Stream(device=dev)
+        self._acc_done = [torch.cuda.Event() for _ in range(ns)]
+        self._dev_in2 = [[self.dev_in[s], torch.empty_like(self.dev_in[s])] for s in range(ns)]
+        self._parity = [0] * ns
+        ev = lambda: torch.cuda.Event()
+        self._in_free = [[ev(), ev()] for _ in range(ns)]
+        self._in_ready = [[ev(), ev()] for _ in range(ns)]
+        self._stage_free = [ev() for _ in range(ns)]
+        self._snap = [ev() for _ in range(ns)]
+        self._stage_rec = [torch.empty(C.sizeof(_lib.Result), dtype=torch.uint8, device=dev) for _ in range(ns)]
+        self._stage_keep = [torch.empty((self.H, self.W), dtype=torch.uint8, device=dev)
+                            if self.want_keep else None for _ in range(ns)]
+        cur = torch.cuda.current_stream()
+        for s in range(ns):                      # events start "signalled"
+            for p in range(2):
+                self._in_free[s][p].record(cur)
+            self._stage_free[s].record(cur)
+            self._acc_done[s].record(cur)
 
 
 class PendingSeries:

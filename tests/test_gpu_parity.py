@@ -716,3 +716,26 @@ def test_random_configurations_vs_oracle(seed):
         lims = probs = raw = maps = None
     compare_disk(d, d_or.solar_filter.filt_disk, d_or.histogram.hbase, d_or.histogram.hbins,
                  d_or.histogram.bound, np.array(d_or.histogram.peaks), lims, probs, raw, maps, None, c)
+
+
+def test_graph_replay_matches_plain_launches():
+    """Detector.detect_graphed: the captured launch sequence, replayed on NEW contents of the same
+    buffers, gives exactly what the plain launches give (records, maps, launch accounting)."""
+    eng = _engine()
+    dev = eng.require_cuda()
+    n = 320
+    imgs = [synth.synthetic_disk(n, 40 + i) for i in range(3)]
+    r = imgs[0][1]
+    buf = torch.empty((n, n), dtype=torch.float32, device=dev)
+    maps = torch.empty((20, n, n), dtype=torch.uint8, device=dev)
+    det = eng.Detector(eng.Geometry(n, n, n // 2, n // 2, r), 11, 500, 0, 20, 4, dev)
+    ref = eng.Detector(eng.Geometry(n, n, n // 2, n // 2, r), 11, 500, 0, 20, 4, dev)
+    rmaps = torch.empty_like(maps)
+    for i, (img, _) in enumerate(imgs):
+        buf.copy_(torch.from_numpy(img))
+        det.detect_graphed(buf, maps=maps)        # first call: plain + capture, then replays
+        ref.detect(buf, maps=rmaps)
+        torch.cuda.synchronize()
+        assert torch.equal(det.keep, ref.keep) and torch.equal(maps, rmaps), i
+        assert torch.equal(det.result_bytes(), ref.result_bytes()), i
+    assert det.graph_launches > 0 and len(det._graphs) == 1
