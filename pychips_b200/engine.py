@@ -55,7 +55,7 @@ class Detector:
     """
 
     def __init__(self, geom: Geometry, k: int, h_bins: int, t0: int, t1: int, elem: int = 4,
-                 device=None):
+                 device=None, ws: torch.Tensor | None = None):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.geom = geom
@@ -75,8 +75,12 @@ class Detector:
                              ("peaks", self.h_bins * 4), ("result", C.sizeof(Result))):
             self._tail[name] = off
             off = (off + nbytes + 255) // 256 * 256
-        with torch.cuda.device(self.device):
-            self.ws = torch.empty(off, dtype=torch.uint8, device=self.device)
+        self.ws_bytes = off
+        if ws is not None and ws.numel() >= off:
+            self.ws = ws            # shared by the caller (detectors of one stream slot run in turn)
+        else:
+            with torch.cuda.device(self.device):
+                self.ws = torch.empty(off, dtype=torch.uint8, device=self.device)
         self._pp = C.byref(self.plan)
         self.dtype = torch.float32 if elem == 4 else torch.float64
         self.graph_launches = 0        # kernels launched through CUDA-graph replays (not seen by the library counter)

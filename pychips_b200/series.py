@@ -61,6 +61,7 @@ class SeriesRunner:
         self.dtype = torch.float32 if elem == 4 else torch.float64
         self.n_streams = n_streams
         self._slots = {}
+        self._slot_ws = {}
         with torch.cuda.device(self.device):
             self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
             self.dev_in = [torch.empty((self.H, self.W), dtype=self.dtype, device=self.device)
@@ -73,10 +74,18 @@ class SeriesRunner:
         key = (slot, r)
         det = self._slots.get(key)
         if det is None:
-            # one workspace per (stream slot, radius); a jittered series reuses a handful
+            # one plan (and one set of captured graphs) per (stream slot, radius), but ONE workspace
+            # per slot, sized for a disk that covers the whole image: a series with a jittered
+            # radius does not multiply the 0.5 GB workspaces
             c = int(self.H / 2)
+            ws = self._slot_ws.get(slot)
+            if ws is None and self.masked:
+                big = Detector(Geometry(self.H, self.W, c, c, self.H + self.W), self.k, self.h_bins,
+                               self.t0, self.t1, self.elem, self.device)
+                ws = self._slot_ws[slot] = big.ws
             g = Geometry(self.H, self.W, c, c, int(r) if self.masked else -1)
-            det = Detector(g, self.k, self.h_bins, self.t0, self.t1, self.elem, self.device)
+            det = Detector(g, self.k, self.h_bins, self.t0, self.t1, self.elem, self.device, ws=ws)
+            self._slot_ws.setdefault(slot, det.ws)
             self._slots[key] = det
         return det
 
@@ -90,7 +99,9 @@ class SeriesRunner:
         """Enqueue a batch without waiting for it: the returned handle's `result()` blocks until the
         batch's records and maps are on the host.  Batches submitted back to back keep all streams
         busy (no pipeline drain between them); at most `n_host_sets` (2) may be in flight, each
-        with its own pinned result buffers."""
+        with its own pinned result buffers.  The `keep` arrays of a result are VIEWS of those
+        pinned buffers: they stay valid until the second following `submit` of the same batch
+        size — copy them if they must live longer."""
         n = len(images)
         indices = list(range(n)) if indices is None else list(indices)
         rec_bytes = C.sizeof(_lib.Result)

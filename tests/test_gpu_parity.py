@@ -475,6 +475,19 @@ def test_config3_time_series_runner_matches_single_image_path():
         st = c.probability_map(d)
         total += np.nan_to_num(st, nan=0.0)
     assert np.allclose(res.prob_map_sum.cpu().numpy(), total, rtol=1e-5, atol=1e-6)
+    # three radii on two stream slots: one workspace per slot, shared by the per-radius plans
+    assert len(runner._slots) > 2
+    assert len({d.ws.data_ptr() for d in runner._slots.values()}) == 2
+    # a second, pipelined pass over the same series (graph replays, submit/result) is identical
+    # (result arrays are views of a ring of two pinned buffer sets: copy before submitting twice more)
+    res.keep = [k.copy() for k in res.keep]
+    h1 = runner.submit([torch.from_numpy(im).pin_memory() for im in imgs], radii)
+    h2 = runner.submit([torch.from_numpy(im).pin_memory() for im in imgs[::-1]], radii[::-1])
+    r1, r2 = h1.result(), h2.result()
+    for i in range(len(imgs)):
+        assert np.array_equal(r1.keep[i], res.keep[i]) and np.array_equal(r1.probs[i], res.probs[i], equal_nan=True)
+        j = len(imgs) - 1 - i
+        assert np.array_equal(r2.keep[j], res.keep[i]) and np.array_equal(r2.limits[j], res.limits[i])
 
 
 def test_h_thresh_is_sticky_across_wavelengths():
