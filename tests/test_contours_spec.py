@@ -63,3 +63,21 @@ def test_area_and_kept_contours_match_the_reference_step():
             assert np.array_equal(a, b)
         assert np.array_equal(np.asarray(reg.hierarchy), khier)
         assert np.array_equal(dx, reg.map)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_parallel_formulation_matches_opencv(seed):
+    """oracle/contours_parallel_spec.py: cycles of the state permutation + event-level start
+    resolution give OpenCV's contours, order and hierarchy."""
+    from oracle import contours_parallel_spec as ps
+    rng = np.random.default_rng(100 + seed)
+    for _ in range(25):
+        h, w = int(rng.integers(1, 34)), int(rng.integers(1, 34))
+        m = (rng.random((h, w)) < rng.choice([0.3, 0.5, 0.7])).astype(np.uint8)
+        for simple in (True, False):
+            ref, hi = cv2.findContours(m, cv2.RETR_TREE,
+                                       cv2.CHAIN_APPROX_SIMPLE if simple else cv2.CHAIN_APPROX_NONE)
+            got, gh = ps.find_contours_parallel(m, simple)
+            assert len(ref) == len(got)
+            assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+            assert len(ref) == 0 or np.array_equal(hi[0], gh)
