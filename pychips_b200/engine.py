@@ -248,7 +248,8 @@ class Detector:
         cap.wait_stream(cur)
         g = torch.cuda.CUDAGraph()
         n0 = self.lib.chips_launch_count()
-        with torch.cuda.graph(g, stream=cap):
+        # thread_local: CUDA calls of other threads (NCCL watchdog, samplers) do not break the capture
+        with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
             self.detect(image, ht_peak_ratio, h_thresh, porb_threshold, area_threshold, maps)
         nodes = int(self.lib.chips_launch_count() - n0)   # counted while capturing, not executed
         cur.wait_stream(cap)
