@@ -200,6 +200,35 @@ int chips_pack_cube(const chips_plan* plan, int which, float* cube, void* ws, vo
 int chips_row_cosine(const void* map, const void* map0, int H, int W, int elem, double* out,
                      void* stream);
 
+/* ---- SURVEY.md §8(f) row 4  replaces: cv2.findContours(tmp_data.astype(np.uint8), cv2.RETR_TREE,
+ *      cv2.CHAIN_APPROX_SIMPLE), chips.py:382-386 — point lists, order of discovery and parents of
+ *      every border (Suzuki-Abe border following as data-parallel passes, csrc/contours_core.h).
+ *      Foreground of `img` ([h] rows of `pitch` bytes): img <= thr (mode 0, e.g. the level image at
+ *      plan->off_level with thr = threshold index) or img != 0 (mode 1).
+ *      recs[b], b = 0 .. n_contours-1 in ORDER OF DISCOVERY (border number b + 2): start pixel,
+ *      hole flag, parent border number (1 = the image frame), number of CHAIN_APPROX_SIMPLE points,
+ *      offset of its first point in `points` (x, y pairs), and the shoelace sum of the border
+ *      (|area2| == 2 * cv2.contourArea).  OpenCV's output order and hierarchy rows follow from the
+ *      parents on the host (pychips_b200/contours.py::output_order).
+ *      counts->overflow: bit 0 more than max_border_px border pixels (nothing else is valid then;
+ *      n_border_px holds the number needed), bit 1 n_contours > max_contours, bit 2 n_points >
+ *      max_points (records / points beyond the capacity are not written).  counts->changed != 0:
+ *      the start positions had not settled after `start_rounds` rounds — call again with more. */
+typedef struct chips_contour_rec {
+  int32_t x, y, is_hole, parent, n_points, offset;
+  int64_t area2;
+} chips_contour_rec;
+
+typedef struct chips_contour_counts {
+  int32_t n_border_px, n_contours, n_points, changed, overflow, pad_;
+} chips_contour_counts;
+
+size_t chips_contours_workspace_bytes(int w, int h, long long max_border_px);
+int chips_contours(const uint8_t* img, int w, int h, int pitch, int mode, int thr,
+                   long long max_border_px, int start_rounds, chips_contour_rec* recs,
+                   long long max_contours, int32_t* points, long long max_points,
+                   chips_contour_counts* counts, void* ws, size_t ws_bytes, void* stream);
+
 /* helper: f64 -> f32 demotion with an exactness flag (1 = every value representable) */
 int chips_demote_f64(const double* in, float* out, size_t n, int32_t* all_exact, void* stream);
 

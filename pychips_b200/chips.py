@@ -344,12 +344,28 @@ class Chips(object):
                         with torch.cuda.device(self.device):
                             return det.expand_map(t, which).cpu().numpy().astype(dt, copy=False)
 
+                    traced = {}
+
+                    def _ctr(which, t=t, traced=traced):
+                        # chips.py:382-400 on demand: every border of the raw mask on the device,
+                        # then the area cut of clean_small_scale_structures (chips.py:421-429)
+                        if not traced:
+                            with torch.cuda.device(self.device):
+                                cs, hier, area2 = det.contours(t)
+                            keep = np.flatnonzero(area2 / 2.0 / det.geom.disk_area >= self.area_threshold)
+                            traced["contours"] = [cs[i] for i in keep]
+                            traced["hierarchy"] = np.array([hier[i] for i in keep])
+                            traced["contour_ids"] = [f"CH_{ix}" for ix in range(len(keep))]
+                        return traced[which]
+
                     dtmp_map[str(lim)] = LazyNamespace(
                         _lazy=dict(map=_map, raw_map=lambda t=t: _map(t, 1),
-                                   filled_map=lambda t=t: _map(t, 2)),
+                                   filled_map=lambda t=t: _map(t, 2),
+                                   contours=lambda f=_ctr: f("contours"),
+                                   hierarchy=lambda f=_ctr: f("hierarchy"),
+                                   contour_ids=lambda f=_ctr: f("contour_ids")),
                         lim=lim, limit_0=limit_0, prob=np.float64(res.probs[t]),
-                        n_components=int(res.n_comp[t]), n_kept=int(res.n_kept[t]),
-                        contours=None, hierarchy=None, contour_ids=None, index=t)
+                        n_components=int(res.n_comp[t]), n_kept=int(res.n_kept[t]), index=t)
                     logger.info(f"Estimated prob.({res.probs[t]}) at lim({lim})")
                 disk.set_value("solar_ch_regions", Namespace(**dtmp_map))
         return

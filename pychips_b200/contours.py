@@ -1,0 +1,74 @@
+"""Host side of the device contour pass.
+
+`chips_contours` (csrc/contours.cu) returns one record per border in ORDER OF DISCOVERY
+(border number NBD = index + 2, Suzuki-Abe) with its parent border number, and the kept points of
+every border.  What is left for the host is the O(#borders) bookkeeping of
+`cv2.findContours(..., RETR_TREE, ...)`'s output order — children of a border are listed in
+reverse order of discovery, the tree in pre-order — and the `[next, prev, first_child, parent]`
+hierarchy rows (/root/reference/chips/chips.py:382-386 consumes both).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+REC_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("is_hole", "<i4"), ("parent", "<i4"),
+                      ("n_points", "<i4"), ("offset", "<i4"), ("area2", "<i8")])
+COUNTS_DTYPE = np.dtype([("n_border_px", "<i4"), ("n_contours", "<i4"), ("n_points", "<i4"),
+                         ("changed", "<i4"), ("overflow", "<i4"), ("pad_", "<i4")])
+
+
+def output_order(parent_nbd: np.ndarray):
+    """parent_nbd[b]: border number of the parent of border b (1 = the frame).  Returns
+    (seq, hierarchy): seq[i] = discovery index of the i-th output contour, hierarchy int32 [n, 4]."""
+    n = len(parent_nbd)
+    hier = np.full((n, 4), -1, dtype=np.int32)
+    if n == 0:
+        return np.zeros(0, dtype=np.int64), hier
+    parent = np.asarray(parent_nbd, dtype=np.int64) - 2          # -1 = frame
+    if (parent < -1).any():
+        raise RuntimeError("contour pass returned a border without a parent")
+    b = np.arange(n)
+    by_parent = np.lexsort((-b, parent))                          # siblings: latest discovered first
+    first_child = np.full(n + 1, -1, dtype=np.int64)              # slot n = frame
+    next_sib = np.full(n, -1, dtype=np.int64)
+    prev_sib = np.full(n, -1, dtype=np.int64)
+    ps = parent[by_parent]
+    head = np.ones(n, dtype=bool)
+    head[1:] = ps[1:] != ps[:-1]
+    first_child[np.where(ps[head] < 0, n, ps[head])] = by_parent[head]
+    same = ~head[1:]
+    next_sib[by_parent[:-1][same]] = by_parent[1:][same]
+    prev_sib[by_parent[1:][same]] = by_parent[:-1][same]
+    seq = np.empty(n, dtype=np.int64)
+    k = 0
+    stack = [int(first_child[n])]
+    fc, ns = first_child.tolist(), next_sib.tolist()
+    while stack:
+        node = stack.pop()
+        if node < 0:
+            continue
+        seq[k] = node
+        k += 1
+        stack.append(ns[node])
+        stack.append(fc[node])
+    if k != n:
+        raise RuntimeError("contour tree is not connected to the frame")
+    pos = np.empty(n, dtype=np.int64)
+    pos[seq] = np.arange(n)
+    look = lambda a: np.where(a >= 0, pos[np.maximum(a, 0)], -1)
+    hier[:, 0] = look(next_sib[seq])
+    hier[:, 1] = look(prev_sib[seq])
+    hier[:, 2] = look(first_child[:n][seq])
+    hier[:, 3] = look(parent[seq])
+    return seq, hier
+
+
+def assemble(recs: np.ndarray, points: np.ndarray):
+    """Records + point buffer -> (contours, hierarchy, twice_area) exactly as
+    cv2.findContours(mask, RETR_TREE, CHAIN_APPROX_SIMPLE) orders them; twice_area[i] =
+    2 * cv2.contourArea(contours[i]) as an exact integer."""
+    seq, hier = output_order(recs["parent"])
+    pts = points.reshape(-1, 2)
+    contours = [pts[o:o + m].reshape(-1, 1, 2) for o, m in zip(recs["offset"][seq].tolist(),
+                                                             recs["n_points"][seq].tolist())]
+    return contours, hier, np.abs(recs["area2"][seq])

@@ -297,6 +297,16 @@ class Detector:
         lab[fg] = inv.astype(np.int32) + 1
         return lab, a[fg][first].astype(np.int64)
 
+    def contours(self, t: int):
+        """Contours of the raw threshold mask `level <= t` exactly as the reference's
+        cv2.findContours call sees it (chips.py:382-386): (contours, hierarchy [n, 4],
+        twice_area [n]) in OpenCV's order, before the area cut."""
+        from . import contours as _c
+        if getattr(self, "_tracer", None) is None:
+            self._tracer = ContourTracer(self.geom.W, self.geom.H, self.device)
+        recs, pts = self._tracer.trace(self.level, 0, int(t))
+        return _c.assemble(recs, pts)
+
     def prob_stack(self, lower_lim: float = 0.0, out: torch.Tensor | None = None,
                    accumulate: bool = False, dtype=torch.float64) -> torch.Tensor:
         if out is None:
@@ -327,6 +337,83 @@ def to_device_image(data: np.ndarray, device, allow_demote: bool = True):
     if int(flag.item()) == 1:
         return t32, 4
     return t64, 8
+
+
+class ContourTracer:
+    """Device buffers of `chips_contours` (csrc/contours.cu) for one image size; capacities grow
+    on demand (the call reports what it needed)."""
+
+    def __init__(self, w: int, h: int, device=None, max_border_px: int = 1 << 18,
+                 max_contours: int = 1 << 15, max_points: int = 1 << 19):
+        from . import contours as _c
+        self._c = _c
+        self.lib = _lib.load()
+        self.device = require_cuda(device)
+        self.w, self.h = int(w), int(h)
+        self.cap, self.max_contours, self.max_points = int(max_border_px), int(max_contours), int(max_points)
+        self.start_rounds = 8
+        self.calls = 0
+        self._alloc()
+
+    def _alloc(self):
+        nbytes = int(self.lib.chips_contours_workspace_bytes(self.w, self.h, self.cap))
+        if nbytes == 0:
+            raise ValueError("bad contour geometry")
+        with torch.cuda.device(self.device):
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self.recs = torch.empty(self.max_contours * self._c.REC_DTYPE.itemsize, dtype=torch.uint8,
+                                    device=self.device)
+            self.points = torch.empty(2 * self.max_points, dtype=torch.int32, device=self.device)
+            self.counts = torch.zeros(self._c.COUNTS_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+
+    def trace(self, img: torch.Tensor, mode: int = 1, thr: int = 0):
+        """img: uint8 [h, w] device tensor (rows contiguous).  Returns (records, points) on the host:
+        records in order of discovery (`contours.REC_DTYPE`), points int32 [n_points, 2]."""
+        if img.dtype != torch.uint8 or img.dim() != 2 or img.shape != (self.h, self.w) or img.stride(1) != 1:
+            raise ValueError("contour input must be a uint8 [h, w] device image")
+        if img.device != self.device:
+            raise ValueError("contour input lives on another device")
+        c = self._c
+        for _ in range(12):
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.chips_contours(
+                    _ptr(img), self.w, self.h, int(img.stride(0)), int(mode), int(thr), self.cap,
+                    self.start_rounds, _ptr(self.recs), self.max_contours, _ptr(self.points),
+                    self.max_points, _ptr(self.counts), _ptr(self.ws), self.ws.numel(), _stream_ptr()),
+                    "chips_contours")
+                self.calls += 1
+                cnt = self.counts.cpu().numpy().view(c.COUNTS_DTYPE)[0]
+            if cnt["overflow"] & 1:
+                self.cap = int(cnt["n_border_px"]) * 5 // 4 + 1024
+            elif cnt["overflow"]:
+                self.max_contours = max(self.max_contours, int(cnt["n_contours"]) * 5 // 4 + 64)
+                self.max_points = max(self.max_points, int(cnt["n_points"]) * 5 // 4 + 64)
+            elif cnt["changed"]:
+                self.start_rounds *= 2
+                continue
+            else:
+                n, m = int(cnt["n_contours"]), int(cnt["n_points"])
+                recs = self.recs[:n * c.REC_DTYPE.itemsize].cpu().numpy().view(c.REC_DTYPE)
+                pts = self.points[:2 * m].cpu().numpy().reshape(-1, 2)
+                return recs, pts
+            self._alloc()
+        raise _lib.ChipsNativeError("chips_contours did not settle")
+
+
+def find_contours(mask: np.ndarray, device=None):
+    """`cv2.findContours(mask, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)` on the GPU: (contours,
+    hierarchy [1, n, 4] or None)."""
+    from . import contours as _c
+    device = require_cuda(device)
+    m = np.ascontiguousarray(mask)
+    if m.ndim != 2 or m.dtype != np.uint8:
+        raise ValueError("mask must be a 2-D uint8 array")
+    with torch.cuda.device(device):
+        img = torch.from_numpy(m).to(device)
+        tracer = ContourTracer(m.shape[1], m.shape[0], device)
+        recs, pts = tracer.trace(img, 1, 0)
+    cs, hier, _ = _c.assemble(recs, pts)
+    return tuple(cs), (hier[None] if len(cs) else None)
 
 
 def row_cosine(map_: np.ndarray, map0: np.ndarray, device=None):

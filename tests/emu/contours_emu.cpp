@@ -1,0 +1,31 @@
+// TEST INFRASTRUCTURE — host emulation of pychips_b200/csrc/contours_core.h.
+// Runs exactly the passes contours.cu launches as kernels, as plain loops over host memory, so
+// tests/test_contours_emu.py can check the pass logic against OpenCV on the CPU-only build box.
+// Built by the test with g++ into a temporary directory; never loaded by the product.
+#include <stdlib.h>
+#include <string.h>
+#include "../../pychips_b200/csrc/contours_core.h"
+
+struct HostExec {
+  template <class F>
+  void each(long n, const F& f) {
+    for (long i = 0; i < n; ++i) f(i);
+  }
+};
+
+extern "C" size_t emu_contours_workspace_bytes(int w, int h, long long cap) {
+  ctr::Ws ws;
+  return ctr::carve(ws, nullptr, w, h, (long)cap);
+}
+
+extern "C" int emu_contours(const uint8_t* img, int w, int h, int pitch, int mode, int thr, long long cap,
+                            int start_rounds, void* recs, long long max_contours, int32_t* points,
+                            long long max_points, void* counts, void* wsmem, size_t ws_bytes) {
+  ctr::Ws ws;
+  if (ctr::carve(ws, (char*)wsmem, w, h, (long)cap) > ws_bytes) return -3;
+  ctr::Args a{img, w, h, pitch, mode, thr, (long)cap, start_rounds, (ctr::Rec*)recs, (long)max_contours,
+              points, (long)max_points, (ctr::Counts*)counts};
+  HostExec ex;
+  ctr::run(ex, a, ws);
+  return 0;
+}

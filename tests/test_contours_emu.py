@@ -1,0 +1,122 @@
+"""CPU: the passes of pychips_b200/csrc/contours_core.h (the code contours.cu launches as CUDA
+kernels), run as host loops by tests/emu/contours_emu.cpp, against the installed OpenCV — contours,
+order, hierarchy and areas of cv2.findContours(RETR_TREE, CHAIN_APPROX_SIMPLE).  The GPU parity
+test of the same entry point is tests/test_gpu_parity.py::test_contours_*."""
+import ctypes
+import os
+import subprocess
+
+import cv2
+import numpy as np
+import pytest
+
+from pychips_b200 import contours as pc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("emu") / "contours_emu.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out,
+                    os.path.join(HERE, "emu", "contours_emu.cpp")], check=True)
+    lib = ctypes.CDLL(out)
+    lib.emu_contours_workspace_bytes.restype = ctypes.c_size_t
+    lib.emu_contours_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong]
+    lib.emu_contours.restype = ctypes.c_int
+    lib.emu_contours.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                 ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p,
+                                 ctypes.c_longlong, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p,
+                                 ctypes.c_void_p, ctypes.c_size_t]
+    return lib
+
+
+def run_emu(lib, img, mode=1, thr=0, cap=None, rounds=12, max_contours=None, max_points=None):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    cap = cap or max(1, h * w)
+    max_contours = max_contours or cap
+    max_points = max_points or 8 * cap
+    nbytes = lib.emu_contours_workspace_bytes(w, h, cap)
+    ws = np.full(nbytes, 0xA5, dtype=np.uint8)               # garbage: the passes must initialise
+    recs = np.zeros(max_contours, dtype=pc.REC_DTYPE)
+    points = np.full(2 * max_points, -7, dtype=np.int32)
+    counts = np.zeros(1, dtype=pc.COUNTS_DTYPE)
+    rc = lib.emu_contours(img.ctypes.data, w, h, w, mode, thr, cap, rounds, recs.ctypes.data, max_contours,
+                          points.ctypes.data, max_points, counts.ctypes.data, ws.ctypes.data, nbytes)
+    assert rc == 0
+    return recs, points, counts[0]
+
+
+def check(lib, mask, **kw):
+    ref, hi = cv2.findContours(mask, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+    recs, points, c = run_emu(lib, mask, **kw)
+    assert c["overflow"] == 0 and c["changed"] == 0
+    assert c["n_contours"] == len(ref)
+    got, hier, area2 = pc.assemble(recs[:c["n_contours"]], points[:2 * c["n_points"]])
+    for k, (a, b) in enumerate(zip(ref, got)):
+        assert np.array_equal(a, b), k
+    if len(ref):
+        assert np.array_equal(hi[0], hier)
+        assert np.array_equal(area2, [int(round(2 * cv2.contourArea(a))) for a in ref])
+    return ref
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_masks(emu, seed):
+    rng = np.random.default_rng(seed)
+    for _ in range(40):
+        h, w = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        m = (rng.random((h, w)) < rng.choice([0.2, 0.5, 0.8])).astype(np.uint8)
+        check(emu, m)
+
+
+def test_structured_masks(emu):
+    full = np.ones((20, 33), np.uint8)
+    check(emu, full)
+    check(emu, np.zeros((5, 9), np.uint8))
+    ring = np.zeros((9, 9), np.uint8)
+    ring[1:8, 1:8] = 1
+    ring[2:7, 2:7] = 0
+    ring[4, 4] = 1
+    check(emu, ring)
+    yy, xx = np.mgrid[:120, :130]
+    blobs = ((np.sin(xx / 7.0) * np.cos(yy / 5.0) > 0.2) | ((xx - 60) ** 2 + (yy - 60) ** 2 < 400)).astype(np.uint8)
+    blobs[50:70, 55:65] = 0
+    blobs[58:62, 58:61] = 1
+    assert len(check(emu, blobs)) > 10
+    rng = np.random.default_rng(5)
+    big = (rng.random((150, 170)) < 0.55).astype(np.uint8)
+    assert len(check(emu, big)) > 1000
+
+
+def test_threshold_mode_and_pitch(emu):
+    rng = np.random.default_rng(9)
+    lev = rng.integers(0, 6, size=(31, 45)).astype(np.uint8)
+    for t in range(6):
+        mask = (lev <= t).astype(np.uint8)
+        ref, hi = cv2.findContours(mask, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+        recs, points, c = run_emu(emu, lev, mode=0, thr=t)
+        got, hier, _ = pc.assemble(recs[:c["n_contours"]], points[:2 * c["n_points"]])
+        assert len(got) == len(ref) and all(np.array_equal(a, b) for a, b in zip(ref, got))
+        assert np.array_equal(hi[0], hier)
+
+
+def test_overflow_is_reported(emu):
+    rng = np.random.default_rng(2)
+    m = (rng.random((40, 40)) < 0.5).astype(np.uint8)
+    _, _, c = run_emu(emu, m, cap=16)
+    assert c["overflow"] & 1 and c["n_contours"] == 0 and c["n_border_px"] > 16
+    _, _, c = run_emu(emu, m, max_contours=3)
+    assert c["overflow"] & 2
+    _, _, c = run_emu(emu, m, max_points=5)
+    assert c["overflow"] & 4
+    _, _, c = run_emu(emu, m, rounds=2)
+    assert c["overflow"] == 0      # `changed` tells whether two rounds were enough
+
+
+def test_output_order_host_logic():
+    # frame -> 2 (outer) -> 3 (hole) -> 4 (outer) ; 5 (outer, top level)
+    seq, hier = pc.output_order(np.array([1, 2, 3, 1]))
+    assert seq.tolist() == [3, 0, 1, 2]
+    assert hier.tolist() == [[1, -1, -1, -1], [-1, 0, 2, -1], [-1, -1, 3, 1], [-1, -1, -1, 2]]

@@ -756,3 +756,99 @@ def test_graph_replay_matches_plain_launches():
         for f in ("limits", "probs", "n_kept", "n_comp"):
             assert np.array_equal(np.array(getattr(a, f)[:20]), np.array(getattr(b, f)[:20]), equal_nan=True), (i, f)
     assert det.graph_launches > 0 and len(det._graphs) == 1
+
+
+# ----------------------------------------------------------------------------- contours (§8(f) row 4)
+def _same_contours(mask, got, hier):
+    import cv2
+    ref, hi = cv2.findContours(mask, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+    assert len(ref) == len(got)
+    for k, (a, b) in enumerate(zip(ref, got)):
+        assert a.dtype == b.dtype and np.array_equal(a, b), k
+    if len(ref):
+        assert np.array_equal(hi, hier)
+    else:
+        assert hier is None
+    return ref
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_contours_random_masks_vs_opencv(seed):
+    """chips_contours (csrc/contours.cu) == cv2.findContours(RETR_TREE, CHAIN_APPROX_SIMPLE): points,
+    order and hierarchy, on noise (thousands of borders, 1-pixel walls), blobs and ragged shapes."""
+    eng = _engine()
+    rng = np.random.default_rng(300 + seed)
+    shapes = [(1, 1), (1, 17), (23, 1), (37, 53), (64, 64), (130, 257), (200, 333)]
+    for h, w in shapes:
+        for p in (0.25, 0.5, 0.75):
+            m = (rng.random((h, w)) < p).astype(np.uint8)
+            _same_contours(m, *eng.find_contours(m))
+    yy, xx = np.mgrid[:300, :410]
+    blobs = ((np.sin(xx / (7.0 + seed)) * np.cos(yy / 5.0) > 0.2) |
+             ((xx - 200) ** 2 + (yy - 150) ** 2 < 90 ** 2)).astype(np.uint8)
+    blobs[120:180, 170:230] = 0
+    blobs[140:160, 190:210] = 255
+    assert len(_same_contours(blobs, *eng.find_contours(blobs))) > 10
+    for m in (np.zeros((9, 12), np.uint8), np.ones((9, 12), np.uint8)):
+        _same_contours(m, *eng.find_contours(m))
+
+
+def test_contours_capacities_grow_on_demand():
+    eng = _engine()
+    dev = eng.require_cuda()
+    from pychips_b200 import contours as pc
+    rng = np.random.default_rng(7)
+    m = (rng.random((150, 170)) < 0.55).astype(np.uint8)
+    tr = eng.ContourTracer(170, 150, dev, max_border_px=64, max_contours=8, max_points=16)
+    tr.start_rounds = 2
+    recs, pts = tr.trace(torch.from_numpy(m).to(dev), 1, 0)
+    got, hier, area2 = pc.assemble(recs, pts)
+    ref = _same_contours(m, got, hier[None])
+    assert len(ref) > 1000 and tr.calls >= 3
+    import cv2
+    assert np.array_equal(area2, [int(round(2 * cv2.contourArea(c))) for c in ref])
+    with pytest.raises(ValueError):
+        tr.trace(torch.zeros((10, 10), dtype=torch.uint8, device=dev))
+
+
+@pytest.mark.parametrize("n,k,seed", [(320, 11, 3), (512, 31, 8)])
+def test_contours_of_the_pipeline_vs_oracle(n, k, seed, tmp_path):
+    """region.contours / hierarchy / contour_ids of Chips.extract_CHs_CHBs (chips.py:382-400) against
+    the reference's cv2 calls (oracle with keep_contours=True), every threshold."""
+    img, r = synth.synthetic_disk(n, seed)
+    d_or = synth.FakeDisk(img.astype(np.float64), r)
+    co.OracleChips(medfilt_kernel=k).run(d_or, keep_contours=True)
+    from pychips_b200 import Chips
+    d = synth.FakeDisk(img.astype(np.float64), r)
+    Chips(synth.FakeAIA(d), base_folder=str(tmp_path) + "/", medfilt_kernel=k).run_CHIPS()
+    want, got = vars(d_or.solar_ch_regions), vars(d.solar_ch_regions)
+    assert list(want) == list(got) and len(want) == 20
+    total = 0
+    for key in want:
+        a, b = want[key], got[key]
+        assert len(a.contours) == len(b.contours), key
+        for x, y in zip(a.contours, b.contours):
+            assert x.dtype == y.dtype and np.array_equal(x, y), key
+        assert np.array_equal(np.asarray(a.hierarchy), np.asarray(b.hierarchy)), key
+        assert a.contour_ids == b.contour_ids
+        total += len(a.contours)
+    assert total > 0
+
+
+def test_contours_full_size_vs_opencv():
+    """4096^2 detection: every border of two threshold masks against OpenCV."""
+    import cv2
+    eng = _engine()
+    dev = eng.require_cuda()
+    n = 4096
+    img, r = synth.synthetic_disk(n, 1)
+    det = eng.Detector(eng.Geometry(n, n, n // 2, n // 2, r), 51, 500, 0, 20, 4, dev)
+    det.detect(torch.from_numpy(img).to(dev))
+    torch.cuda.synchronize()
+    lev = det.level.cpu().numpy()
+    for t in (0, 19):
+        mask = (lev <= t).astype(np.uint8)
+        got, hier, area2 = det.contours(t)
+        ref = _same_contours(mask, got, hier[None] if len(got) else None)
+        assert np.array_equal(area2, [int(round(2 * cv2.contourArea(c))) for c in ref])
+        assert len(ref) > 0
