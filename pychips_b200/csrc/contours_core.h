@@ -28,19 +28,33 @@
 #define CTR_POPC(v) __popc(v)
 #define CTR_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #define CTR_ATOMIC_ADD64(p, v) atomicAdd((unsigned long long*)(p), (unsigned long long)(v))
+// raise a flag many threads may raise: same-address stores serialise in L2 (loads do not), so only
+// while it still reads 0, and one lane per warp
+#define CTR_RAISE(p)                                                           \
+  do {                                                                         \
+    if (__ldcg(p) == 0) {                                                      \
+      const unsigned m__ = __activemask();                                     \
+      if ((int)(threadIdx.x & 31) == __ffs(m__) - 1) *(p) = 1;                 \
+    }                                                                          \
+  } while (0)
 #else
 #define CTR_POPC(v) __builtin_popcount(v)
 #define CTR_ATOMIC_MIN(p, v) (*(p) = (*(p) < (v) ? *(p) : (v)))
 #define CTR_ATOMIC_ADD64(p, v) (*(p) += (v))
+#define CTR_RAISE(p) (*(p) = 1)
 #endif
 
 namespace ctr {
 
 constexpr uint32_t kNone = 0xFFFFFFFFu;
-constexpr int kChunk = 256;          // elements per thread in the three-level scans
+constexpr int kScanTile = 4096;      // elements per CTA of the scan kernels
 
 // counters in Ws::ctr
-enum { C_NB = 0, C_CHANGED = 1, C_NBORDERS = 2, C_NPOINTS = 3, C_OVERFLOW = 4, C_NB_RAW = 5 };
+enum { C_NB = 0, C_NBORDERS = 2, C_NPOINTS = 3, C_OVERFLOW = 4, C_NB_RAW = 5,
+       C_LABEL = 16,      // [32] "round r changed a label"  (a round with no change => converged, both
+       C_START = 80,      // [kMaxStartRounds] "round r moved a start"     buffers equal, later rounds return)
+       C_COUNT = 256 };
+constexpr int kMaxStartRounds = 128;
 
 // directions: 0 = east, then counter-clockwise on the screen (y grows downwards)
 CTR_HD int dx(int s) { return (int)((0x901Au >> (2 * s)) & 3u) - 1; }
@@ -69,7 +83,7 @@ struct Counts {           // == chips_contour_counts
 
 struct Ws {
   int32_t* ctr;
-  uint8_t* gmask;   uint32_t* goff;   uint32_t* s1;   uint32_t* s2;
+  uint8_t* gmask;   uint32_t* goff;   uint32_t* s1;
   uint32_t* px;     uint8_t* nbm;
   uint32_t* nxt;    uint8_t* sfl;
   uint32_t *labA, *labB, *jmpA, *jmpB, *cntA, *cntB, *ecA, *ecB;
@@ -90,11 +104,10 @@ inline size_t carve(Ws& ws, char* base, int w, int h, long cap) {
   const size_t nmax = G > (size_t)cap ? G : (size_t)cap;
   size_t off = 0;
   auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align256(bytes); return p; };
-  ws.ctr = (int32_t*)take(16 * 4);
+  ws.ctr = (int32_t*)take(C_COUNT * 4);
   ws.gmask = (uint8_t*)take(G);
   ws.goff = (uint32_t*)take(G * 4);
-  ws.s1 = (uint32_t*)take((nmax / kChunk + 2) * 4);
-  ws.s2 = (uint32_t*)take((nmax / kChunk / kChunk + 2) * 4);
+  ws.s1 = (uint32_t*)take((nmax / kScanTile + 2) * 4);
   ws.px = (uint32_t*)take((size_t)cap * 4);
   ws.nbm = (uint8_t*)take((size_t)cap);
   ws.nxt = (uint32_t*)take(S * 4);
@@ -129,42 +142,17 @@ struct Fill64 {
   CTR_HD void operator()(long i) const { p[i] = 0; }
 };
 
-// exclusive scan of small counts in independent passes: sums of 256-element chunks, sums of 256 of
-// those, one thread over the (few) top sums, then the chunk scans back down
+// counts fed to Exec::scan (exclusive prefix sums; the CUDA executor has tiled scan kernels for it)
 struct CountGroups { const uint8_t* g; CTR_HD uint32_t operator()(long i) const { return (uint32_t)CTR_POPC((unsigned)g[i]); } };
 struct CountFlags  { const uint8_t* f; CTR_HD uint32_t operator()(long i) const { return f[i]; } };
 struct CountI32    { const int32_t* v; CTR_HD uint32_t operator()(long i) const { return (uint32_t)v[i]; } };
-struct CountU32    { const uint32_t* v; CTR_HD uint32_t operator()(long i) const { return v[i]; } };
 
-template <class Count>
-struct ScanSums {
-  Count c; uint32_t* s1; long n_const; const int32_t* n_ptr;
-  CTR_HD void operator()(long j) const {
-    const long n = n_ptr ? (long)*n_ptr : n_const;
-    uint32_t s = 0;
-    const long e = (j + 1) * kChunk < n ? (j + 1) * kChunk : n;
-    for (long i = j * kChunk; i < e; ++i) s += c(i);
-    s1[j] = s;
-  }
-};
-struct ScanTop {            // one thread; total -> ctr[slot] (clamped to 0 above `limit`, raw -> ctr[raw_slot])
-  uint32_t* s1; long nchunks; int32_t* ctr; int slot, raw_slot, overflow_bit; long limit;
-  CTR_HD void operator()(long) const {
-    uint32_t run = 0;
-    for (long j = 0; j < nchunks; ++j) { const uint32_t v = s1[j]; s1[j] = run; run += v; }
+struct ScanTotal {          // what a scan does with its grand total
+  int32_t* ctr; int slot, raw_slot, overflow_bit; long limit;
+  CTR_HD void operator()(uint32_t run) const {
     if (raw_slot >= 0) ctr[raw_slot] = (int32_t)run;
-    if (limit >= 0 && (long)run > limit) { ctr[C_OVERFLOW] |= overflow_bit; run = 0; }
+    if (limit >= 0 && (long)run > limit) { ctr[C_OVERFLOW] |= overflow_bit; run = 0; }   // clamp: nothing downstream runs
     ctr[slot] = (int32_t)run;
-  }
-};
-template <class Count>
-struct ScanChunks {
-  Count c; const uint32_t* s1; uint32_t* out; long n_const; const int32_t* n_ptr;
-  CTR_HD void operator()(long j) const {
-    const long n = n_ptr ? (long)*n_ptr : n_const;
-    uint32_t run = s1[j];
-    const long e = (j + 1) * kChunk < n ? (j + 1) * kChunk : n;
-    for (long i = j * kChunk; i < e; ++i) { const uint32_t v = c(i); out[i] = run; run += v; }   // out may alias the counts
   }
 };
 
@@ -223,7 +211,7 @@ enum { F_VALID = 1, F_NEG = 2, F_EMIT = 4 };
 struct InitStates {
   Geo g; const uint8_t* gmask; const uint32_t* goff; const int32_t* ctr;
   const uint32_t* px; const uint8_t* nbm;
-  uint32_t* nxt; uint8_t* sfl; uint32_t* lab; uint32_t* jmp;
+  uint32_t* nxt; uint8_t* sfl; uint32_t* lab; uint32_t* jmp; uint32_t *dist, *em, *ew;
   CTR_HD void operator()(long i) const {
     if (i >= 8L * ctr[C_NB]) return;
     const uint32_t bi = (uint32_t)(i >> 3);
@@ -248,36 +236,30 @@ struct InitStates {
       }
     }
     nxt[i] = to; sfl[i] = fl; lab[i] = label; jmp[i] = to;
+    dist[i] = 0; em[i] = 0; ew[i] = (fl & F_EMIT) ? 1u : 0u;
   }
 };
 
-// cycle label = smallest state id of the cycle (kNone absorbs: the walk leaves the border pixels)
+// Pointer doubling over the window W_r(i) = {i, T(i), .., T^(2^r - 1)(i)}; per state
+//   lab  = smallest state id in the window (kNone absorbs: the walk leaves the border pixels),
+//   dist = steps from i to that state, em = kept points among those steps, ew = kept points in W_r(i).
+// Once the window covers the cycle: lab = the cycle's label m, dist / em = list rank of i against m.
+// A round that changes no label has converged (windows at stride 2^r tile the cycle, so equal
+// minima along every stride orbit are the global minimum); both ping-pong buffers then hold the
+// same lab / dist / em and the remaining rounds return at once.
 struct LabelRound {
-  const int32_t* ctr; const uint32_t *lab, *jmp; uint32_t *lab2, *jmp2;
+  int32_t* ctr; int r; const uint32_t *lab, *jmp, *dist, *em, *ew; uint32_t *lab2, *jmp2, *dist2, *em2, *ew2;
   CTR_HD void operator()(long i) const {
-    if (i >= 8L * ctr[C_NB]) return;
+    if (i >= 8L * ctr[C_NB] || (r > 0 && !ctr[C_LABEL + r - 1])) return;
     const uint32_t a = lab[i], j = jmp[i], b = lab[j];
-    lab2[i] = (a == kNone || b == kNone) ? kNone : (a < b ? a : b);
+    uint32_t v = a, d = dist[i], e = em[i];
+    if (a != kNone && (b == kNone || b < a)) {
+      v = b; d = (1u << r) + dist[j]; e = ew[i] + em[j];
+      CTR_RAISE(&ctr[C_LABEL + r]);
+    }
+    lab2[i] = v; dist2[i] = d; em2[i] = e;
+    ew2[i] = ew[i] + ew[j];
     jmp2[i] = jmp[j];
-  }
-};
-
-// list ranking against the label state m: cnt = steps to m, ec = kept points in [k, m)
-struct RankInit {
-  const int32_t* ctr; const uint32_t *lab, *nxt; const uint8_t* sfl; uint32_t *jmp, *cnt, *ec;
-  CTR_HD void operator()(long i) const {
-    if (i >= 8L * ctr[C_NB]) return;
-    const uint32_t l = lab[i];
-    if (l == kNone || l == (uint32_t)i) { jmp[i] = (uint32_t)i; cnt[i] = 0; ec[i] = 0; return; }
-    jmp[i] = nxt[i]; cnt[i] = 1; ec[i] = (sfl[i] & F_EMIT) ? 1u : 0u;
-  }
-};
-struct RankRound {
-  const int32_t* ctr; const uint32_t *jmp, *cnt, *ec; uint32_t *jmp2, *cnt2, *ec2;
-  CTR_HD void operator()(long i) const {
-    if (i >= 8L * ctr[C_NB]) return;
-    const uint32_t j = jmp[i];
-    cnt2[i] = cnt[i] + cnt[j]; ec2[i] = ec[i] + ec[j]; jmp2[i] = jmp[j];
   }
 };
 
@@ -308,10 +290,10 @@ CTR_HD int start_dir(unsigned m, int s0) {
 
 // one Jacobi round of "where does every cycle start": start key = 2 * position + is_hole
 struct StartRound {
-  const int32_t* ctr; const uint32_t* px; const uint8_t* nbm; const uint32_t* lab;
+  const int32_t* ctr; int r; const uint32_t* px; const uint8_t* nbm; const uint32_t* lab;
   const uint8_t* sfl; const uint32_t* stOld; uint32_t* stNew;
   CTR_HD void operator()(long bi) const {
-    if (bi >= ctr[C_NB]) return;
+    if (bi >= ctr[C_NB] || (r > 0 && !ctr[C_START + r - 1])) return;
     const unsigned m = nbm[bi];
     const bool w0 = !((m >> 4) & 1), e0 = !(m & 1);
     if (!w0 && !e0) return;
@@ -338,17 +320,13 @@ struct StartRound {
   }
 };
 struct StartCommit {
-  int32_t* ctr; uint32_t *stOld, *stNew;
+  int32_t* ctr; int r; uint32_t *stOld, *stNew;
   CTR_HD void operator()(long i) const {
-    if (i >= 8L * ctr[C_NB]) return;
+    if (i >= 8L * ctr[C_NB] || (r > 0 && !ctr[C_START + r - 1])) return;
     const uint32_t v = stNew[i];
-    if (v != stOld[i]) { ctr[C_CHANGED] = 1; stOld[i] = v; }
+    if (v != stOld[i]) { CTR_RAISE(&ctr[C_START + r]); stOld[i] = v; }
     stNew[i] = kNone;
   }
-};
-struct ClearChanged {
-  int32_t* ctr;
-  CTR_HD void operator()(long) const { ctr[C_CHANGED] = 0; }
 };
 
 struct MarkStarts {
@@ -487,13 +465,13 @@ struct WriteRecs {
 };
 
 struct Finish {
-  int32_t* ctr; Counts* out; long max_contours, max_points;
+  int32_t* ctr; Counts* out; long max_contours, max_points; int start_rounds;
   CTR_HD void operator()(long) const {
     int ov = ctr[C_OVERFLOW];
     if (ctr[C_NBORDERS] > max_contours) ov |= 2;
     if (ctr[C_NPOINTS] > max_points) ov |= 4;
     out->n_border_px = ctr[C_NB_RAW]; out->n_contours = ctr[C_NBORDERS]; out->n_points = ctr[C_NPOINTS];
-    out->changed = ctr[C_CHANGED]; out->overflow = ov; out->pad_ = 0;
+    out->changed = ctr[C_START + start_rounds - 1]; out->overflow = ov; out->pad_ = 0;
   }
 };
 
@@ -509,65 +487,55 @@ struct Args {
 
 inline int ceil_log2(unsigned long long v) { int r = 0; while ((1ull << r) < v) ++r; return r; }
 
-template <class Exec, class Count>
-void scan(Exec& ex, Count c, long n_max, const int32_t* n_ptr, Ws& ws, uint32_t* out, int slot, int raw_slot,
-          int overflow_bit, long limit) {
-  const long nch = (n_max + kChunk - 1) / kChunk, nch2 = (nch + kChunk - 1) / kChunk;
-  ex.each(nch, ScanSums<Count>{c, ws.s1, n_max, n_ptr});
-  ex.each(nch2, ScanSums<CountU32>{CountU32{ws.s1}, ws.s2, nch, nullptr});
-  ex.each(1, ScanTop{ws.s2, nch2, ws.ctr, slot, raw_slot, overflow_bit, limit});
-  ex.each(nch2, ScanChunks<CountU32>{CountU32{ws.s1}, ws.s2, ws.s1, nch, nullptr});
-  ex.each(nch, ScanChunks<Count>{c, ws.s1, out, n_max, n_ptr});
-}
-
-// the whole pass list; Exec::each(n, functor) applies functor(i) for i in [0, n)
+// The whole pass list.  Exec::each(n, f) applies f(i) for i in [0, n); each_n bounds the range by
+// mult * *n_ptr read on the device (the counts are never known on the host: nothing synchronises);
+// Exec::scan(count, n_max, n_ptr, out, scratch, total) writes exclusive prefix sums of count(i).
 template <class Exec>
 void run(Exec& ex, const Args& a, Ws& ws) {
   Geo g{a.img, a.w, a.h, a.pitch, (a.w + 7) / 8, a.mode, a.thr};
   const long G = (long)g.gw * a.h, cap = a.cap, S = cap * 8;
-  ex.each(16, Fill32{(uint32_t*)ws.ctr, 0u});
+  const int32_t *nB = ws.ctr + C_NB, *nBorders = ws.ctr + C_NBORDERS;
+  ex.each(C_COUNT, Fill32{(uint32_t*)ws.ctr, 0u});
   ex.each(G, FlagGroups{g, ws.gmask});
-  scan(ex, CountGroups{ws.gmask}, G, nullptr, ws, ws.goff, C_NB, C_NB_RAW, 1, cap);
+  ex.scan(CountGroups{ws.gmask}, G, nullptr, ws.goff, ws.s1, ScanTotal{ws.ctr, C_NB, C_NB_RAW, 1, cap});
   ex.each(G, ScatterBorder{g, ws.gmask, ws.goff, ws.ctr, ws.px, ws.nbm});
-  ex.each(S, InitStates{g, ws.gmask, ws.goff, ws.ctr, ws.px, ws.nbm, ws.nxt, ws.sfl, ws.labA, ws.jmpA});
-  const int rounds = ceil_log2((unsigned long long)S) + 1;
+  // ws.stOld / ws.stNew double as the window counts of the doubling rounds (re-filled below)
   uint32_t *lab = ws.labA, *lab2 = ws.labB, *jmp = ws.jmpA, *jmp2 = ws.jmpB;
+  uint32_t *cnt = ws.cntA, *cnt2 = ws.cntB, *ec = ws.ecA, *ec2 = ws.ecB, *ew = ws.stOld, *ew2 = ws.stNew;
+  ex.each_n(S, nB, 8, InitStates{g, ws.gmask, ws.goff, ws.ctr, ws.px, ws.nbm, ws.nxt, ws.sfl, lab, jmp, cnt, ec, ew});
+  int rounds = ceil_log2((unsigned long long)S) + 1;
+  if (rounds > 31) rounds = 31;
   for (int r = 0; r < rounds; ++r) {
-    ex.each(S, LabelRound{ws.ctr, lab, jmp, lab2, jmp2});
+    ex.each_n(S, nB, 8, LabelRound{ws.ctr, r, lab, jmp, cnt, ec, ew, lab2, jmp2, cnt2, ec2, ew2});
     uint32_t* t = lab; lab = lab2; lab2 = t;
     t = jmp; jmp = jmp2; jmp2 = t;
-  }
-  uint32_t *cnt = ws.cntA, *cnt2 = ws.cntB, *ec = ws.ecA, *ec2 = ws.ecB;
-  ex.each(S, RankInit{ws.ctr, lab, ws.nxt, ws.sfl, jmp, cnt, ec});
-  for (int r = 0; r < rounds; ++r) {
-    ex.each(S, RankRound{ws.ctr, jmp, cnt, ec, jmp2, cnt2, ec2});
-    uint32_t* t = jmp; jmp = jmp2; jmp2 = t;
     t = cnt; cnt = cnt2; cnt2 = t;
     t = ec; ec = ec2; ec2 = t;
+    t = ew; ew = ew2; ew2 = t;
   }
-  ex.each(S, Fill64{ws.area});
-  ex.each(S, AreaAccum{g, ws.ctr, lab, ws.nxt, ws.px, ws.area});
-  ex.each(S, Fill32{ws.stOld, kNone});
-  ex.each(S, Fill32{ws.stNew, kNone});
-  ex.each(S, Fill32{ws.nbd, 0u});
-  ex.each(cap, Fill8{ws.sflag, 0});
+  ex.each_n(S, nB, 8, Fill64{ws.area});
+  ex.each_n(S, nB, 8, AreaAccum{g, ws.ctr, lab, ws.nxt, ws.px, ws.area});
+  ex.each_n(S, nB, 8, Fill32{ws.stOld, kNone});
+  ex.each_n(S, nB, 8, Fill32{ws.stNew, kNone});
+  ex.each_n(S, nB, 8, Fill32{ws.nbd, 0u});
+  ex.each_n(cap, nB, 1, Fill8{ws.sflag, 0});
   for (int r = 0; r < a.start_rounds; ++r) {
-    if (r == a.start_rounds - 1) ex.each(1, ClearChanged{ws.ctr});
-    ex.each(cap, StartRound{ws.ctr, ws.px, ws.nbm, lab, ws.sfl, ws.stOld, ws.stNew});
-    ex.each(S, StartCommit{ws.ctr, ws.stOld, ws.stNew});
+    ex.each_n(cap, nB, 1, StartRound{ws.ctr, r, ws.px, ws.nbm, lab, ws.sfl, ws.stOld, ws.stNew});
+    ex.each_n(S, nB, 8, StartCommit{ws.ctr, r, ws.stOld, ws.stNew});
   }
-  ex.each(S, MarkStarts{g, ws.ctr, ws.gmask, ws.goff, ws.stOld, ws.sflag, ws.cyc_at});
-  scan(ex, CountFlags{ws.sflag}, cap, ws.ctr + C_NB, ws, ws.srank, C_NBORDERS, -1, 0, -1);
-  ex.each(cap, BorderTable{ws.ctr, ws.sflag, ws.srank, ws.cyc_at, ws.stOld, ws.nxt, ec, ws.nbm, ws.sfl,
-                           ws.area, ws.nbd, ws.btype, ws.bnpts, ws.bbi, ws.bss, ws.barea});
-  ex.each(cap, LastMark{a.w, ws.ctr, ws.px, ws.nbm, lab, ws.sfl, ws.stOld, ws.nbd, ws.btype, ws.bbi, ws.blnbd});
-  ex.each(cap, Parents{ws.ctr, ws.btype, ws.blnbd, ws.bparent});
-  scan(ex, CountI32{ws.bnpts}, cap, ws.ctr + C_NBORDERS, ws, ws.boff, C_NPOINTS, -1, 0, -1);
-  ex.each(S, EmitPoints{g, ws.ctr, lab, ws.sfl, ws.nbd, ws.bss, ws.boff, ws.bnpts, ec, ws.px, a.points,
-                        a.max_points});
-  ex.each(cap, WriteRecs{a.w, ws.ctr, ws.px, ws.bbi, ws.btype, ws.bparent, ws.bnpts, ws.boff, ws.bss,
-                         ws.barea, a.recs, a.max_contours, a.points, a.max_points});
-  ex.each(1, Finish{ws.ctr, a.counts, a.max_contours, a.max_points});
+  ex.each_n(S, nB, 8, MarkStarts{g, ws.ctr, ws.gmask, ws.goff, ws.stOld, ws.sflag, ws.cyc_at});
+  ex.scan(CountFlags{ws.sflag}, cap, nB, ws.srank, ws.s1, ScanTotal{ws.ctr, C_NBORDERS, -1, 0, -1});
+  ex.each_n(cap, nB, 1, BorderTable{ws.ctr, ws.sflag, ws.srank, ws.cyc_at, ws.stOld, ws.nxt, ec, ws.nbm, ws.sfl,
+                                    ws.area, ws.nbd, ws.btype, ws.bnpts, ws.bbi, ws.bss, ws.barea});
+  ex.each_n(cap, nBorders, 1, LastMark{a.w, ws.ctr, ws.px, ws.nbm, lab, ws.sfl, ws.stOld, ws.nbd, ws.btype,
+                                       ws.bbi, ws.blnbd});
+  ex.each_n(cap, nBorders, 1, Parents{ws.ctr, ws.btype, ws.blnbd, ws.bparent});
+  ex.scan(CountI32{ws.bnpts}, cap, nBorders, ws.boff, ws.s1, ScanTotal{ws.ctr, C_NPOINTS, -1, 0, -1});
+  ex.each_n(S, nB, 8, EmitPoints{g, ws.ctr, lab, ws.sfl, ws.nbd, ws.bss, ws.boff, ws.bnpts, ec, ws.px, a.points,
+                                 a.max_points});
+  ex.each_n(cap, nBorders, 1, WriteRecs{a.w, ws.ctr, ws.px, ws.bbi, ws.btype, ws.bparent, ws.bnpts, ws.boff,
+                                        ws.bss, ws.barea, a.recs, a.max_contours, a.points, a.max_points});
+  ex.each(1, Finish{ws.ctr, a.counts, a.max_contours, a.max_points, a.start_rounds});
 }
 
 }  // namespace ctr

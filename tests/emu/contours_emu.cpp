@@ -11,6 +11,21 @@ struct HostExec {
   void each(long n, const F& f) {
     for (long i = 0; i < n; ++i) f(i);
   }
+  template <class F>
+  void each_n(long n_max, const int32_t* n_ptr, int mult, const F& f) {
+    const long m = (long)mult * *n_ptr;
+    each(m < n_max ? m : n_max, f);
+  }
+  template <class Count, class Total>
+  void scan(Count c, long n_max, const int32_t* n_ptr, uint32_t* out, uint32_t*, Total total) {
+    const long n = n_ptr && *n_ptr < n_max ? *n_ptr : n_max;
+    uint32_t run = 0;
+    for (long i = 0; i < n; ++i) {
+      out[i] = run;
+      run += c(i);
+    }
+    total(run);
+  }
 };
 
 extern "C" size_t emu_contours_workspace_bytes(int w, int h, long long cap) {

@@ -16,7 +16,8 @@ tr = det._tracer
 for t in (0, 10, 19):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lib = tr.lib
-    e0.record()
+    torch.cuda._sleep(20_000_000)                  # ~10 ms of GPU spin: the launches below queue up behind it,
+    e0.record()                                    # so the events bracket device time, not host enqueue time
     for _ in range(5):
         eng._lib.check(lib.chips_contours(eng._ptr(det.level), n, n, n, 0, t, tr.cap, tr.start_rounds,
                                           eng._ptr(tr.recs), tr.max_contours, eng._ptr(tr.points), tr.max_points,
@@ -29,3 +30,15 @@ for t in (0, 10, 19):
     cnt = tr.counts.cpu().numpy().view(pc.COUNTS_DTYPE)[0]
     print(f"t={t}: border px {cnt['n_border_px']}, contours {len(got)}, points {cnt['n_points']}: device {dev_ms:.3f} ms, "
           f"call+download+assemble {wall:.2f} ms, cv2.findContours {cv_ms:.2f} ms, cap {tr.cap}", flush=True)
+
+import time
+t0 = time.perf_counter()
+tot = 0
+for t in range(20):
+    cs, hier, a2 = det.contours(t)
+    tot += len(cs)
+print(f"all 20 thresholds through Detector.contours: {(time.perf_counter() - t0) * 1e3:.1f} ms wall, {tot} contours")
+t0 = time.perf_counter()
+for t in range(20):
+    cv2.findContours((lev <= t).astype(np.uint8), cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+print(f"all 20 thresholds through cv2.findContours (mask build included): {(time.perf_counter() - t0) * 1e3:.1f} ms wall")
