@@ -27,6 +27,19 @@ __global__ void __launch_bounds__(256) k_contour_pass_n(F f, long n_max, const i
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
 }
 
+// each_n for a functor that returns "raise the flag": one store per CTA at most, and only while the
+// flag still reads 0 (same-address stores from every thread serialise in L2: ~10 ns each)
+template <class F>
+__global__ void __launch_bounds__(256) k_contour_pass_flag(F f, long n_max, const int32_t* __restrict__ n_ptr,
+                                                           int mult, int32_t* flag) {
+  const long m = (long)mult * (long)*n_ptr;
+  const long n = m < n_max ? m : n_max;
+  const long stride = (long)gridDim.x * blockDim.x;
+  bool any = false;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) any |= f(i);
+  if (__syncthreads_or(any) && threadIdx.x == 0 && __ldcg(flag) == 0) *flag = 1;
+}
+
 // ---- exclusive prefix sums of count(i): tile sums, one CTA over the tile sums, tile scans ------
 constexpr int kScanThreads = 256, kScanItems = ctr::kScanTile / kScanThreads;
 
@@ -133,6 +146,12 @@ struct CudaExec {
   void each_n(long n_max, const int32_t* n_ptr, int mult, const F& f) {
     if (n_max <= 0 || failed) return;
     k_contour_pass_n<F><<<grid_for(n_max), 256, 0, stream>>>(f, n_max, n_ptr, mult);
+    after();
+  }
+  template <class F>
+  void each_flag(long n_max, const int32_t* n_ptr, int mult, const F& f, int32_t* flag) {
+    if (n_max <= 0 || failed) return;
+    k_contour_pass_flag<F><<<grid_for(n_max), 256, 0, stream>>>(f, n_max, n_ptr, mult, flag);
     after();
   }
   template <class Count, class Total>

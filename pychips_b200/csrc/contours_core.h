@@ -28,20 +28,10 @@
 #define CTR_POPC(v) __popc(v)
 #define CTR_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #define CTR_ATOMIC_ADD64(p, v) atomicAdd((unsigned long long*)(p), (unsigned long long)(v))
-// raise a flag many threads may raise: same-address stores serialise in L2 (loads do not), so only
-// while it still reads 0, and one lane per warp
-#define CTR_RAISE(p)                                                           \
-  do {                                                                         \
-    if (__ldcg(p) == 0) {                                                      \
-      const unsigned m__ = __activemask();                                     \
-      if ((int)(threadIdx.x & 31) == __ffs(m__) - 1) *(p) = 1;                 \
-    }                                                                          \
-  } while (0)
 #else
 #define CTR_POPC(v) __builtin_popcount(v)
 #define CTR_ATOMIC_MIN(p, v) (*(p) = (*(p) < (v) ? *(p) : (v)))
 #define CTR_ATOMIC_ADD64(p, v) (*(p) += (v))
-#define CTR_RAISE(p) (*(p) = 1)
 #endif
 
 namespace ctr {
@@ -249,17 +239,16 @@ struct InitStates {
 // same lab / dist / em and the remaining rounds return at once.
 struct LabelRound {
   int32_t* ctr; int r; const uint32_t *lab, *jmp, *dist, *em, *ew; uint32_t *lab2, *jmp2, *dist2, *em2, *ew2;
-  CTR_HD void operator()(long i) const {
-    if (i >= 8L * ctr[C_NB] || (r > 0 && !ctr[C_LABEL + r - 1])) return;
+  CTR_HD bool operator()(long i) const {          // true: raise ctr[C_LABEL + r] (Exec::each_flag)
+    if (i >= 8L * ctr[C_NB] || (r > 0 && !ctr[C_LABEL + r - 1])) return false;
     const uint32_t a = lab[i], j = jmp[i], b = lab[j];
     uint32_t v = a, d = dist[i], e = em[i];
-    if (a != kNone && (b == kNone || b < a)) {
-      v = b; d = (1u << r) + dist[j]; e = ew[i] + em[j];
-      CTR_RAISE(&ctr[C_LABEL + r]);
-    }
+    const bool better = a != kNone && (b == kNone || b < a);
+    if (better) { v = b; d = (1u << r) + dist[j]; e = ew[i] + em[j]; }
     lab2[i] = v; dist2[i] = d; em2[i] = e;
     ew2[i] = ew[i] + ew[j];
     jmp2[i] = jmp[j];
+    return better;
   }
 };
 
@@ -321,11 +310,13 @@ struct StartRound {
 };
 struct StartCommit {
   int32_t* ctr; int r; uint32_t *stOld, *stNew;
-  CTR_HD void operator()(long i) const {
-    if (i >= 8L * ctr[C_NB] || (r > 0 && !ctr[C_START + r - 1])) return;
+  CTR_HD bool operator()(long i) const {          // true: raise ctr[C_START + r]
+    if (i >= 8L * ctr[C_NB] || (r > 0 && !ctr[C_START + r - 1])) return false;
     const uint32_t v = stNew[i];
-    if (v != stOld[i]) { CTR_RAISE(&ctr[C_START + r]); stOld[i] = v; }
+    const bool moved = v != stOld[i];
+    if (moved) stOld[i] = v;
     stNew[i] = kNone;
+    return moved;
   }
 };
 
@@ -489,6 +480,7 @@ inline int ceil_log2(unsigned long long v) { int r = 0; while ((1ull << r) < v) 
 
 // The whole pass list.  Exec::each(n, f) applies f(i) for i in [0, n); each_n bounds the range by
 // mult * *n_ptr read on the device (the counts are never known on the host: nothing synchronises);
+// each_flag is each_n for a functor returning bool and sets *flag = 1 if any call returned true;
 // Exec::scan(count, n_max, n_ptr, out, scratch, total) writes exclusive prefix sums of count(i).
 template <class Exec>
 void run(Exec& ex, const Args& a, Ws& ws) {
@@ -506,7 +498,8 @@ void run(Exec& ex, const Args& a, Ws& ws) {
   int rounds = ceil_log2((unsigned long long)S) + 1;
   if (rounds > 31) rounds = 31;
   for (int r = 0; r < rounds; ++r) {
-    ex.each_n(S, nB, 8, LabelRound{ws.ctr, r, lab, jmp, cnt, ec, ew, lab2, jmp2, cnt2, ec2, ew2});
+    ex.each_flag(S, nB, 8, LabelRound{ws.ctr, r, lab, jmp, cnt, ec, ew, lab2, jmp2, cnt2, ec2, ew2},
+                 ws.ctr + C_LABEL + r);
     uint32_t* t = lab; lab = lab2; lab2 = t;
     t = jmp; jmp = jmp2; jmp2 = t;
     t = cnt; cnt = cnt2; cnt2 = t;
@@ -521,7 +514,7 @@ void run(Exec& ex, const Args& a, Ws& ws) {
   ex.each_n(cap, nB, 1, Fill8{ws.sflag, 0});
   for (int r = 0; r < a.start_rounds; ++r) {
     ex.each_n(cap, nB, 1, StartRound{ws.ctr, r, ws.px, ws.nbm, lab, ws.sfl, ws.stOld, ws.stNew});
-    ex.each_n(S, nB, 8, StartCommit{ws.ctr, r, ws.stOld, ws.stNew});
+    ex.each_flag(S, nB, 8, StartCommit{ws.ctr, r, ws.stOld, ws.stNew}, ws.ctr + C_START + r);
   }
   ex.each_n(S, nB, 8, MarkStarts{g, ws.ctr, ws.gmask, ws.goff, ws.stOld, ws.sflag, ws.cyc_at});
   ex.scan(CountFlags{ws.sflag}, cap, nB, ws.srank, ws.s1, ScanTotal{ws.ctr, C_NBORDERS, -1, 0, -1});

@@ -16,6 +16,13 @@ struct HostExec {
     const long m = (long)mult * *n_ptr;
     each(m < n_max ? m : n_max, f);
   }
+  template <class F>
+  void each_flag(long n_max, const int32_t* n_ptr, int mult, const F& f, int32_t* flag) {
+    const long m = (long)mult * *n_ptr;
+    const long n = m < n_max ? m : n_max;
+    for (long i = 0; i < n; ++i)
+      if (f(i)) *flag = 1;
+  }
   template <class Count, class Total>
   void scan(Count c, long n_max, const int32_t* n_ptr, uint32_t* out, uint32_t*, Total total) {
     const long n = n_ptr && *n_ptr < n_max ? *n_ptr : n_max;
