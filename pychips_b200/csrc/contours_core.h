@@ -42,9 +42,9 @@ constexpr int kScanTile = 4096;      // elements per CTA of the scan kernels
 // counters in Ws::ctr
 enum { C_NB = 0, C_NBORDERS = 2, C_NPOINTS = 3, C_OVERFLOW = 4, C_NB_RAW = 5,
        C_LABEL = 16,      // [32] "round r changed a label"  (a round with no change => converged, both
-       C_START = 80,      // [kMaxStartRounds] "round r moved a start"     buffers equal, later rounds return)
+       C_START = 80,      // [3] "round r moved a start", slot r % 3           buffers equal, later rounds return)
        C_COUNT = 256 };
-constexpr int kMaxStartRounds = 128;
+constexpr int kMaxStartRounds = 1 << 20;   // lattices of 1-pixel walls need O(image side) rounds
 
 // directions: 0 = east, then counter-clockwise on the screen (y grows downwards)
 CTR_HD int dx(int s) { return (int)((0x901Au >> (2 * s)) & 3u) - 1; }
@@ -279,10 +279,11 @@ CTR_HD int start_dir(unsigned m, int s0) {
 
 // one Jacobi round of "where does every cycle start": start key = 2 * position + is_hole
 struct StartRound {
-  const int32_t* ctr; int r; const uint32_t* px; const uint8_t* nbm; const uint32_t* lab;
+  int32_t* ctr; int r; const uint32_t* px; const uint8_t* nbm; const uint32_t* lab;
   const uint8_t* sfl; const uint32_t* stOld; uint32_t* stNew;
   CTR_HD void operator()(long bi) const {
-    if (bi >= ctr[C_NB] || (r > 0 && !ctr[C_START + r - 1])) return;
+    if (bi == 0) ctr[C_START + (r + 1) % 3] = 0;      // the slot of the next round (nobody reads it now)
+    if (bi >= ctr[C_NB] || (r > 0 && !ctr[C_START + (r - 1) % 3])) return;
     const unsigned m = nbm[bi];
     const bool w0 = !((m >> 4) & 1), e0 = !(m & 1);
     if (!w0 && !e0) return;
@@ -311,7 +312,7 @@ struct StartRound {
 struct StartCommit {
   int32_t* ctr; int r; uint32_t *stOld, *stNew;
   CTR_HD bool operator()(long i) const {          // true: raise ctr[C_START + r]
-    if (i >= 8L * ctr[C_NB] || (r > 0 && !ctr[C_START + r - 1])) return false;
+    if (i >= 8L * ctr[C_NB] || (r > 0 && !ctr[C_START + (r - 1) % 3])) return false;
     const uint32_t v = stNew[i];
     const bool moved = v != stOld[i];
     if (moved) stOld[i] = v;
@@ -462,7 +463,7 @@ struct Finish {
     if (ctr[C_NBORDERS] > max_contours) ov |= 2;
     if (ctr[C_NPOINTS] > max_points) ov |= 4;
     out->n_border_px = ctr[C_NB_RAW]; out->n_contours = ctr[C_NBORDERS]; out->n_points = ctr[C_NPOINTS];
-    out->changed = ctr[C_START + start_rounds - 1]; out->overflow = ov; out->pad_ = 0;
+    out->changed = ctr[C_START + (start_rounds - 1) % 3]; out->overflow = ov; out->pad_ = 0;
   }
 };
 
@@ -514,7 +515,7 @@ void run(Exec& ex, const Args& a, Ws& ws) {
   ex.each_n(cap, nB, 1, Fill8{ws.sflag, 0});
   for (int r = 0; r < a.start_rounds; ++r) {
     ex.each_n(cap, nB, 1, StartRound{ws.ctr, r, ws.px, ws.nbm, lab, ws.sfl, ws.stOld, ws.stNew});
-    ex.each_flag(S, nB, 8, StartCommit{ws.ctr, r, ws.stOld, ws.stNew}, ws.ctr + C_START + r);
+    ex.each_flag(S, nB, 8, StartCommit{ws.ctr, r, ws.stOld, ws.stNew}, ws.ctr + C_START + r % 3);
   }
   ex.each_n(S, nB, 8, MarkStarts{g, ws.ctr, ws.gmask, ws.goff, ws.stOld, ws.sflag, ws.cyc_at});
   ex.scan(CountFlags{ws.sflag}, cap, nB, ws.srank, ws.s1, ScanTotal{ws.ctr, C_NBORDERS, -1, 0, -1});

@@ -374,11 +374,12 @@ class ContourTracer:
         if img.device != self.device:
             raise ValueError("contour input lives on another device")
         c = self._c
-        for _ in range(12):
+        rounds = self.start_rounds        # per call: pipeline masks settle in 2-3 rounds
+        for _ in range(24):
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.chips_contours(
                     _ptr(img), self.w, self.h, int(img.stride(0)), int(mode), int(thr), self.cap,
-                    self.start_rounds, _ptr(self.recs), self.max_contours, _ptr(self.points),
+                    rounds, _ptr(self.recs), self.max_contours, _ptr(self.points),
                     self.max_points, _ptr(self.counts), _ptr(self.ws), self.ws.numel(), _stream_ptr()),
                     "chips_contours")
                 self.calls += 1
@@ -388,8 +389,10 @@ class ContourTracer:
             elif cnt["overflow"]:
                 self.max_contours = max(self.max_contours, int(cnt["n_contours"]) * 5 // 4 + 64)
                 self.max_points = max(self.max_points, int(cnt["n_points"]) * 5 // 4 + 64)
-            elif cnt["changed"]:
-                self.start_rounds *= 2
+            elif cnt["changed"]:          # lattices of 1-pixel walls need O(image side) rounds
+                if rounds >= 1 << 20:
+                    break
+                rounds *= 2
                 continue
             else:
                 n, m = int(cnt["n_contours"]), int(cnt["n_points"])

@@ -120,3 +120,16 @@ def test_output_order_host_logic():
     seq, hier = pc.output_order(np.array([1, 2, 3, 1]))
     assert seq.tolist() == [3, 0, 1, 2]
     assert hier.tolist() == [[1, -1, -1, -1], [-1, 0, 2, -1], [-1, -1, 3, 1], [-1, -1, -1, 2]]
+
+
+def test_lattice_of_one_pixel_walls_needs_many_start_rounds(emu):
+    """The start positions of a lattice settle in O(image side) Jacobi rounds: `changed` says when
+    the enqueued rounds were too few, and any number of rounds is allowed (rotating flag slots)."""
+    n = 80
+    m = np.zeros((n, n), np.uint8)
+    m[::2, :] = 1
+    m[:, ::3] = 1
+    _, _, c = run_emu(emu, m, rounds=8)
+    assert c["changed"] == 1 and c["overflow"] == 0
+    check(emu, m, rounds=64)
+    check(emu, m, rounds=301)

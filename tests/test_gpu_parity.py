@@ -811,6 +811,21 @@ def test_contours_capacities_grow_on_demand():
         tr.trace(torch.zeros((10, 10), dtype=torch.uint8, device=dev))
 
 
+def test_contours_lattice_needs_many_start_rounds():
+    """A lattice of 1-pixel walls: the start positions settle only after O(image side) rounds; the
+    tracer re-enqueues with more rounds until the call reports that nothing moved."""
+    eng = _engine()
+    m = np.zeros((200, 230), np.uint8)
+    m[::2, :] = 1
+    m[:, ::3] = 1
+    dev = eng.require_cuda()
+    tr = eng.ContourTracer(230, 200, dev)
+    from pychips_b200 import contours as pc
+    recs, pts = tr.trace(torch.from_numpy(m).to(dev), 1, 0)
+    got, hier, _ = pc.assemble(recs, pts)
+    assert len(_same_contours(m, got, hier[None])) > 1000 and tr.calls >= 4
+
+
 @pytest.mark.parametrize("n,k,seed", [(320, 11, 3), (512, 31, 8)])
 def test_contours_of_the_pipeline_vs_oracle(n, k, seed, tmp_path):
     """region.contours / hierarchy / contour_ids of Chips.extract_CHs_CHBs (chips.py:382-400) against
