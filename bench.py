@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--t1", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=16)
     return ap.parse_args()
 
 
