@@ -133,3 +133,30 @@ def test_lattice_of_one_pixel_walls_needs_many_start_rounds(emu):
     assert c["changed"] == 1 and c["overflow"] == 0
     check(emu, m, rounds=64)
     check(emu, m, rounds=301)
+
+
+def test_pipeline_masks_every_threshold(emu):
+    """The raw threshold masks of a synthetic detection (what chips.py:382 hands to findContours),
+    through the level image + threshold form of the call (mode 0), and the area cut of
+    clean_small_scale_structures on the traced lists."""
+    from oracle import chips_oracle as co
+    from pychips_b200 import synth
+    n = 256
+    img, r = synth.synthetic_disk(n, 5)
+    d = synth.FakeDisk(img.astype(np.float64), r)
+    co.OracleChips(medfilt_kernel=11).run(d, keep_contours=True)
+    regions = list(vars(d.solar_ch_regions).values())
+    filt = d.solar_filter.filt_disk * d.solar_mask.n_mask          # NaN off-disk
+    level = np.full((n, n), len(regions), dtype=np.uint8)
+    for t in reversed(range(len(regions))):
+        level[np.nan_to_num(filt, nan=np.inf) <= regions[t].lim] = t
+    disk_area = np.pi * r ** 2
+    for t, reg in enumerate(regions):
+        recs, points, c = run_emu(emu, level, mode=0, thr=t)
+        assert c["overflow"] == 0 and c["changed"] == 0
+        got, hier, area2 = pc.assemble(recs[:c["n_contours"]], points[:2 * c["n_points"]])
+        keep = np.flatnonzero(area2 / 2.0 / disk_area >= 1e-3)
+        assert len(keep) == len(reg.contours), t
+        for i, want in zip(keep, reg.contours):
+            assert np.array_equal(got[i], want), t
+        assert np.array_equal(np.array([hier[i] for i in keep]), np.asarray(reg.hierarchy)), t

@@ -81,3 +81,29 @@ def test_parallel_formulation_matches_opencv(seed):
             assert len(ref) == len(got)
             assert all(np.array_equal(a, b) for a, b in zip(ref, got))
             assert len(ref) == 0 or np.array_equal(hi[0], gh)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_fixed_point_start_resolution_matches_opencv(seed):
+    """oracle/contours_parallel_spec.py::find_contours_fixed_point — the start positions as a
+    Jacobi fixed point (the form the device passes use) — against OpenCV, and how many rounds it takes."""
+    from oracle import contours_parallel_spec as ps
+    rng = np.random.default_rng(200 + seed)
+    rounds = []
+    for _ in range(25):
+        h, w = int(rng.integers(1, 34)), int(rng.integers(1, 34))
+        m = (rng.random((h, w)) < rng.choice([0.3, 0.5, 0.7])).astype(np.uint8)
+        ref, hi = cv2.findContours(m, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+        got, gh = ps.find_contours_fixed_point(m, True, rounds)
+        assert len(ref) == len(got)
+        assert all(np.array_equal(a, b) for a, b in zip(ref, got))
+        assert len(ref) == 0 or np.array_equal(hi[0], gh)
+    assert max(rounds) <= 12
+    lattice = np.zeros((30, 31), np.uint8)
+    lattice[::2, :] = 1
+    lattice[:, ::3] = 1
+    ref, hi = cv2.findContours(lattice, cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
+    rounds = []
+    got, gh = ps.find_contours_fixed_point(lattice, True, rounds)
+    assert all(np.array_equal(a, b) for a, b in zip(ref, got)) and np.array_equal(hi[0], gh)
+    assert rounds[0] > 8            # O(image side): the device call reports `changed` and is re-enqueued
