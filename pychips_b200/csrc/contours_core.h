@@ -123,13 +123,13 @@ struct Fill32 {
   uint32_t* p; uint32_t v;
   CTR_HD void operator()(long i) const { p[i] = v; }
 };
-struct Fill8 {
-  uint8_t* p; uint8_t v;
-  CTR_HD void operator()(long i) const { p[i] = v; }
-};
-struct Fill64 {
-  long long* p;
-  CTR_HD void operator()(long i) const { p[i] = 0; }
+// per-state / per-border-pixel tables of the start resolution, in one pass over the states
+struct InitCycles {
+  const int32_t* ctr; long long* area; uint32_t *stOld, *stNew, *nbd; uint8_t* sflag;
+  CTR_HD void operator()(long i) const {
+    area[i] = 0; stOld[i] = kNone; stNew[i] = kNone; nbd[i] = 0u;
+    if (i < ctr[C_NB]) sflag[i] = 0;
+  }
 };
 
 // counts fed to Exec::scan (exclusive prefix sums; the CUDA executor has tiled scan kernels for it)
@@ -148,19 +148,39 @@ struct ScanTotal {          // what a scan does with its grand total
 
 // ------------------------------------------------------------------------------------------
 // border pixels: foreground with a background pixel among the 8 neighbours
+CTR_HD bool fg_value(const Geo& g, unsigned v) { return g.mode ? v != 0 : (int)v <= g.thr; }
+
+// 10 foreground bits of row y for x0-1 .. x0+8; the 8 pixels of the group come from one aligned
+// 64-bit load when the row allows it (`words`: image base and pitch are multiples of 8)
+CTR_HD unsigned row_window(const Geo& g, bool words, int x0, int y) {
+  if ((unsigned)y >= (unsigned)g.h) return 0u;
+  unsigned b = 0;
+  if (words && x0 + 8 <= g.w) {
+    const uint8_t* p = g.img + (size_t)y * g.pitch + x0;
+#ifndef __CUDA_ARCH__
+    if ((uintptr_t)p & 7) __builtin_trap();          // the host emulation checks the alignment rule
+#endif
+    const uint64_t v = *reinterpret_cast<const uint64_t*>(p);
+    for (int k = 0; k < 8; ++k) b |= (unsigned)fg_value(g, (unsigned)(v >> (8 * k)) & 0xFFu) << (k + 1);
+    b |= (unsigned)fg(g, x0 - 1, y);
+    b |= (unsigned)fg(g, x0 + 8, y) << 9;
+    return b;
+  }
+  for (int k = 0; k < 10; ++k) b |= (unsigned)fg(g, x0 - 1 + k, y) << k;
+  return b;
+}
+
 struct FlagGroups {
-  Geo g; uint8_t* gmask;
+  Geo g; uint8_t* gmask; bool words;
   CTR_HD void operator()(long i) const {
     const int y = (int)(i / g.gw), x0 = (int)(i % g.gw) * 8;
-    unsigned row[3];
+    unsigned inner = 0xFFu, mid = 0;
     for (int r = 0; r < 3; ++r) {
-      unsigned b = 0;
-      for (int k = 0; k < 10; ++k) b |= (unsigned)fg(g, x0 - 1 + k, y - 1 + r) << k;
-      row[r] = b;
+      const unsigned row = row_window(g, words, x0, y - 1 + r);
+      if (r == 1) mid = row;
+      inner &= row & (row >> 1) & (row >> 2);
     }
-    unsigned inner = 0xFFu;
-    for (int r = 0; r < 3; ++r) inner &= row[r] & (row[r] >> 1) & (row[r] >> 2);
-    gmask[i] = (uint8_t)((row[1] >> 1) & 0xFFu & ~inner);
+    gmask[i] = (uint8_t)((mid >> 1) & 0xFFu & ~inner);
   }
 };
 
@@ -489,7 +509,8 @@ void run(Exec& ex, const Args& a, Ws& ws) {
   const long G = (long)g.gw * a.h, cap = a.cap, S = cap * 8;
   const int32_t *nB = ws.ctr + C_NB, *nBorders = ws.ctr + C_NBORDERS;
   ex.each(C_COUNT, Fill32{(uint32_t*)ws.ctr, 0u});
-  ex.each(G, FlagGroups{g, ws.gmask});
+  const bool words = ((uintptr_t)a.img & 7) == 0 && (a.pitch & 7) == 0;
+  ex.each(G, FlagGroups{g, ws.gmask, words});
   ex.scan(CountGroups{ws.gmask}, G, nullptr, ws.goff, ws.s1, ScanTotal{ws.ctr, C_NB, C_NB_RAW, 1, cap});
   ex.each(G, ScatterBorder{g, ws.gmask, ws.goff, ws.ctr, ws.px, ws.nbm});
   // ws.stOld / ws.stNew double as the window counts of the doubling rounds (re-filled below)
@@ -507,12 +528,8 @@ void run(Exec& ex, const Args& a, Ws& ws) {
     t = ec; ec = ec2; ec2 = t;
     t = ew; ew = ew2; ew2 = t;
   }
-  ex.each_n(S, nB, 8, Fill64{ws.area});
+  ex.each_n(S, nB, 8, InitCycles{ws.ctr, ws.area, ws.stOld, ws.stNew, ws.nbd, ws.sflag});
   ex.each_n(S, nB, 8, AreaAccum{g, ws.ctr, lab, ws.nxt, ws.px, ws.area});
-  ex.each_n(S, nB, 8, Fill32{ws.stOld, kNone});
-  ex.each_n(S, nB, 8, Fill32{ws.stNew, kNone});
-  ex.each_n(S, nB, 8, Fill32{ws.nbd, 0u});
-  ex.each_n(cap, nB, 1, Fill8{ws.sflag, 0});
   for (int r = 0; r < a.start_rounds; ++r) {
     ex.each_n(cap, nB, 1, StartRound{ws.ctr, r, ws.px, ws.nbm, lab, ws.sfl, ws.stOld, ws.stNew});
     ex.each_flag(S, nB, 8, StartCommit{ws.ctr, r, ws.stOld, ws.stNew}, ws.ctr + C_START + r % 3);
