@@ -105,3 +105,37 @@ def test_plan_block_geometry_is_consistent(H, W, k, r):
     nblk = p.blk_nbx * p.blk_nby
     assert p.off_bstar - p.off_bucket >= nblk * p.bp_pitch * p.bp_rows
     assert p.off_bucket - p.off_bounds >= nblk * 128 * 8
+
+
+def test_contour_structs_and_argument_errors(tmp_path):
+    """chips_contour_rec / chips_contour_counts: the numpy mirrors match the C layout; bad arguments
+    are rejected before anything touches the GPU; the workspace grows with the capacity."""
+    import numpy as np
+    from pychips_b200 import _lib, contours as pc
+    prog = tmp_path / "szc.c"
+    prog.write_text(
+        '#include <stdio.h>\n#include <stddef.h>\n#include "chips_b200.h"\n'
+        'int main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(chips_contour_rec), sizeof(chips_contour_counts),'
+        ' offsetof(chips_contour_rec, area2), offsetof(chips_contour_rec, offset),'
+        ' offsetof(chips_contour_counts, overflow));return 0;}\n')
+    exe = tmp_path / "szc"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
+    out = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert out == [pc.REC_DTYPE.itemsize, pc.COUNTS_DTYPE.itemsize, pc.REC_DTYPE.fields["area2"][1],
+                   pc.REC_DTYPE.fields["offset"][1], pc.COUNTS_DTYPE.fields["overflow"][1]]
+    lib = _lib.load()
+    small, big = (lib.chips_contours_workspace_bytes(4096, 4096, c) for c in (1 << 16, 1 << 18))
+    assert 0 < small < big and big - small >= (3 << 16) * 8 * 4 * 9
+    assert lib.chips_contours_workspace_bytes(0, 10, 100) == 0
+    one = C.c_void_p(256)           # never dereferenced: the checks come first
+    ok = dict(w=64, h=64, pitch=64, mode=1, thr=0, cap=1000, rounds=8, maxc=10, maxp=10, ws_bytes=1 << 30)
+
+    def call(**kw):
+        a = dict(ok, **kw)
+        return lib.chips_contours(one, a["w"], a["h"], a["pitch"], a["mode"], a["thr"], a["cap"], a["rounds"],
+                                  one, a["maxc"], one, a["maxp"], one, one, a["ws_bytes"], None)
+    for bad in (dict(w=0), dict(pitch=63), dict(mode=2), dict(cap=0), dict(cap=1 << 28), dict(rounds=1),
+                dict(rounds=(1 << 20) + 1), dict(maxc=0), dict(maxp=0), dict(w=1 << 15, h=1 << 15, pitch=1 << 15)):
+        assert call(**bad) == -1, bad
+    assert call(ws_bytes=1024) == -3
+    assert lib.chips_contours(None, 64, 64, 64, 1, 0, 1000, 8, one, 10, one, 10, one, one, 1 << 30, None) == -1
