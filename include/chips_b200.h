@@ -229,6 +229,15 @@ int chips_contours(const uint8_t* img, int w, int h, int pitch, int mode, int th
                    long long max_contours, int32_t* points, long long max_points,
                    chips_contour_counts* counts, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- uploads of only what the path reads.  rect = {x0, y0, x1, y1}: the pixels of the input image
+ *      any kernel of a detection with this plan can touch (bounding box of the disk, extended to the
+ *      median's blocks and halo, clipped to the image); everything outside may stay uninitialised.
+ *      chips_copy_rect: cudaMemcpy2DAsync of rows [y0, y0+rows) x bytes [x0_bytes, x0_bytes+width_bytes)
+ *      between two images of the same pitch (to_device: host -> device, else device -> host). */
+int chips_input_rect(const chips_plan* plan, int32_t* rect);
+int chips_copy_rect(void* dst, const void* src, size_t pitch_bytes, size_t x0_bytes, int y0,
+                    size_t width_bytes, int rows, int to_device, void* stream);
+
 /* helper: f64 -> f32 demotion with an exactness flag (1 = every value representable) */
 int chips_demote_f64(const double* in, float* out, size_t n, int32_t* all_exact, void* stream);
 

@@ -131,3 +131,32 @@ extern "C" int chips_detect(const void* image, const chips_plan* plan, int cx, i
   if (maps_or_null && (rc = chips_expand_maps(plan, 0, maps_or_null, ws, stream))) return rc;
   return CHIPS_OK;
 }
+
+// ---- host <-> device copies of only what the path reads ------------------------------------
+// Every kernel that reads the input image stays inside the halo-extended median blocks (bounds
+// samples, bucket images, tile staging, the k <= 5 windows), clipped to the image: that rectangle
+// is all a caller has to upload.  4096^2, r = 1577, k = 51: 3250 x 3218 of 4096 x 4096 = 62 %.
+extern "C" int chips_input_rect(const chips_plan* plan, int32_t* rect) {
+  if (!plan || !rect) return CHIPS_E_ARG;
+  const int half = plan->k / 2;
+  const int bw = plan->blk_nbx * 128 > plan->roi_w ? plan->blk_nbx * 128 : plan->roi_w;
+  const int bh = plan->blk_nby * plan->blk_rows > plan->roi_h ? plan->blk_nby * plan->blk_rows : plan->roi_h;
+  const int x0 = plan->roi_x0 - half, y0 = plan->roi_y0 - half;
+  const int x1 = plan->roi_x0 + bw + half, y1 = plan->roi_y0 + bh + half;
+  rect[0] = x0 < 0 ? 0 : x0;
+  rect[1] = y0 < 0 ? 0 : y0;
+  rect[2] = x1 > plan->W ? plan->W : x1;
+  rect[3] = y1 > plan->H ? plan->H : y1;
+  return CHIPS_OK;
+}
+
+extern "C" int chips_copy_rect(void* dst, const void* src, size_t pitch_bytes, size_t x0_bytes, int y0,
+                               size_t width_bytes, int rows, int to_device, void* stream) {
+  if (!dst || !src || rows < 1 || y0 < 0 || width_bytes < 1 || x0_bytes + width_bytes > pitch_bytes)
+    return CHIPS_E_ARG;
+  const size_t off = (size_t)y0 * pitch_bytes + x0_bytes;
+  CHIPS_CUDA(cudaMemcpy2DAsync((char*)dst + off, pitch_bytes, (const char*)src + off, pitch_bytes, width_bytes,
+                               (size_t)rows, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                               (cudaStream_t)stream));
+  return CHIPS_OK;
+}

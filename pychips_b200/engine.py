@@ -82,8 +82,25 @@ class Detector:
             with torch.cuda.device(self.device):
                 self.ws = torch.empty(off, dtype=torch.uint8, device=self.device)
         self._pp = C.byref(self.plan)
+        rect = (C.c_int32 * 4)()
+        _lib.check(self.lib.chips_input_rect(self._pp, rect), "chips_input_rect")
+        self.input_rect = tuple(int(v) for v in rect)     # x0, y0, x1, y1: all a detection reads of its input
         self.dtype = torch.float32 if elem == 4 else torch.float64
         self.graph_launches = 0        # kernels launched through CUDA-graph replays (not seen by the library counter)
+
+    def upload(self, dst: torch.Tensor, src: torch.Tensor) -> int:
+        """Host image -> device image, only `input_rect` (the rest of `dst` is never read by a
+        detection with this plan).  Enqueued on the current stream; returns the bytes copied."""
+        x0, y0, x1, y1 = self.input_rect
+        H, W = self.geom.H, self.geom.W
+        if (src.dtype != dst.dtype or tuple(src.shape) != (H, W) or tuple(dst.shape) != (H, W)
+                or not src.is_contiguous() or not dst.is_contiguous() or src.is_cuda or not dst.is_cuda):
+            dst.copy_(src, non_blocking=True)
+            return src.numel() * src.element_size()
+        e = src.element_size()
+        _lib.check(self.lib.chips_copy_rect(_ptr(dst), C.c_void_p(src.data_ptr()), W * e, x0 * e, y0,
+                                            (x1 - x0) * e, y1 - y0, 1, _stream_ptr()), "chips_copy_rect")
+        return (x1 - x0) * e * (y1 - y0)
 
     # ------------------------------------------------------------------ workspace views
     def view(self, name: str, dtype, shape) -> torch.Tensor:

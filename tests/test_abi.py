@@ -139,3 +139,25 @@ def test_contour_structs_and_argument_errors(tmp_path):
         assert call(**bad) == -1, bad
     assert call(ws_bytes=1024) == -3
     assert lib.chips_contours(None, 64, 64, 64, 1, 0, 1000, 8, one, 10, one, 10, one, one, 1 << 30, None) == -1
+
+
+def test_input_rect_covers_the_median_blocks():
+    from pychips_b200 import _lib
+    lib = _lib.load()
+    p = _lib.Plan()
+    rect = (C.c_int32 * 4)()
+    assert lib.chips_plan_init(C.byref(p), 4096, 4096, 51, 500, 20, 4, 2048, 2048, 1577) == 0
+    assert lib.chips_input_rect(C.byref(p), rect) == 0
+    x0, y0, x1, y1 = rect
+    assert (x0, y0) == (471 - 25, 471 - 25)
+    assert x1 == min(4096, 471 + p.blk_nbx * 128 + 25) and y1 == min(4096, 471 + p.blk_nby * p.blk_rows + 25)
+    assert x1 >= 471 + 3155 + 25 and y1 >= 471 + 3155 + 25
+    assert (x1 - x0) * (y1 - y0) < 0.66 * 4096 * 4096
+    assert lib.chips_plan_init(C.byref(p), 1440, 3600, 3, 5000, 25, 4, 0, 0, -1) == 0     # unmasked: everything
+    assert lib.chips_input_rect(C.byref(p), rect) == 0 and tuple(rect) == (0, 0, 3600, 1440)
+    assert lib.chips_plan_init(C.byref(p), 100, 100, 5, 10, 3, 8, 50, 50, 80) == 0         # clipped disk
+    assert lib.chips_input_rect(C.byref(p), rect) == 0 and tuple(rect) == (0, 0, 100, 100)
+    assert lib.chips_input_rect(None, rect) == -1
+    one = C.c_void_p(256)
+    assert lib.chips_copy_rect(one, one, 64, 60, 0, 8, 1, 1, None) == -1      # runs past the pitch
+    assert lib.chips_copy_rect(None, one, 64, 0, 0, 8, 1, 1, None) == -1

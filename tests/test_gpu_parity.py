@@ -867,3 +867,35 @@ def test_contours_full_size_vs_opencv():
         ref = _same_contours(mask, got, hier[None] if len(got) else None)
         assert np.array_equal(area2, [int(round(2 * cv2.contourArea(c))) for c in ref])
         assert len(ref) > 0
+
+
+# ----------------------------------------------------------------------------- uploads
+@pytest.mark.parametrize("n,k,rfrac", [(256, 11, 0.385), (320, 31, 0.25), (200, 5, 0.3), (256, 11, 0.6)])
+def test_series_uploads_only_the_rectangle_the_kernels_read(n, k, rfrac):
+    """SeriesRunner.roi_copy: only Detector.input_rect of each host image is uploaded.  With the
+    device input buffers poisoned (NaN) beforehand, records and maps equal the full-copy path —
+    i.e. nothing outside the rectangle is ever read."""
+    from pychips_b200 import series
+    r = int(n * rfrac)
+    imgs = [synth.synthetic_disk(n, seed=70 + i, radius=r)[0] for i in range(3)]
+    pinned = [torch.from_numpy(im).pin_memory() for im in imgs]
+    out = []
+    for roi in (False, True):
+        runner = series.SeriesRunner(n, n, k, 500, (0, 20), n_streams=2, want_maps=False)
+        runner.roi_copy = roi
+        runner._ensure_copy_pipeline()
+        for pair in runner._dev_in2:
+            for buf in pair:
+                buf.fill_(float("nan"))
+        torch.cuda.synchronize()
+        res = runner.run(pinned, [r] * 3)
+        out.append((res, runner.h2d_bytes, next(iter(runner._slots.values())).input_rect))
+    (a, bytes_full, _), (b, bytes_roi, rect) = out
+    x0, y0, x1, y1 = rect
+    assert bytes_full == 3 * n * n * 4 and bytes_roi == 3 * (x1 - x0) * (y1 - y0) * 4
+    assert bytes_roi < bytes_full or r > n // 2
+    assert int(a.n_peaks.min()) > 0
+    for i in range(3):
+        assert np.array_equal(a.keep[i], b.keep[i])
+        assert np.array_equal(a.limits[i], b.limits[i]) and np.array_equal(a.probs[i], b.probs[i], equal_nan=True)
+    assert torch.equal(a.prob_map_sum, b.prob_map_sum)
