@@ -337,6 +337,7 @@ class Chips(object):
                         f"median filter self-check failed for {res.median_errors} pixels")
                 limit_0 = np.float64(res.limit_0)
                 dtmp_map = {}
+                traced_all = {}
                 for t in range(det.T):
                     lim = np.float64(res.limits[t])
 
@@ -344,19 +345,19 @@ class Chips(object):
                         with torch.cuda.device(self.device):
                             return det.expand_map(t, which).cpu().numpy().astype(dt, copy=False)
 
-                    traced = {}
-
-                    def _ctr(which, t=t, traced=traced):
-                        # chips.py:382-400 on demand: every border of the raw mask on the device,
-                        # then the area cut of clean_small_scale_structures (chips.py:421-429)
+                    def _ctr(which, t=t, traced=traced_all):
+                        # chips.py:382-400 on demand: every border of every raw mask on the device
+                        # (one enqueue for all T), then the area cut of clean_small_scale_structures
+                        # (chips.py:421-429)
                         if not traced:
                             with torch.cuda.device(self.device):
-                                cs, hier, area2 = det.contours(t)
-                            keep = np.flatnonzero(area2 / 2.0 / det.geom.disk_area >= self.area_threshold)
-                            traced["contours"] = [cs[i] for i in keep]
-                            traced["hierarchy"] = np.array([hier[i] for i in keep])
-                            traced["contour_ids"] = [f"CH_{ix}" for ix in range(len(keep))]
-                        return traced[which]
+                                per_t = det.contours_all()
+                            for tt, (cs, hier, area2) in enumerate(per_t):
+                                keep = np.flatnonzero(area2 / 2.0 / det.geom.disk_area >= self.area_threshold)
+                                traced[tt] = dict(contours=[cs[i] for i in keep],
+                                                  hierarchy=np.array([hier[i] for i in keep]),
+                                                  contour_ids=[f"CH_{ix}" for ix in range(len(keep))])
+                        return traced[t][which]
 
                     dtmp_map[str(lim)] = LazyNamespace(
                         _lazy=dict(map=_map, raw_map=lambda t=t: _map(t, 1),

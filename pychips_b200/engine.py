@@ -324,6 +324,14 @@ class Detector:
         recs, pts = self._tracer.trace(self.level, 0, int(t))
         return _c.assemble(recs, pts)
 
+    def contours_all(self):
+        """`contours(t)` for every threshold of the detection, enqueued together and synchronised
+        once: [(contours, hierarchy, twice_area)] for t = 0 .. T-1."""
+        from . import contours as _c
+        if getattr(self, "_tracer", None) is None:
+            self._tracer = ContourTracer(self.geom.W, self.geom.H, self.device)
+        return [_c.assemble(recs, pts) for recs, pts in self._tracer.trace_many(self.level, range(self.T), 0)]
+
     def prob_stack(self, lower_lim: float = 0.0, out: torch.Tensor | None = None,
                    accumulate: bool = False, dtype=torch.float64) -> torch.Tensor:
         if out is None:
@@ -418,6 +426,45 @@ class ContourTracer:
                 return recs, pts
             self._alloc()
         raise _lib.ChipsNativeError("chips_contours did not settle")
+
+    def trace_many(self, img: torch.Tensor, thrs, mode: int = 0):
+        """The masks `img <= t` for every t in `thrs` in one enqueue and ONE synchronisation (the
+        passes of the T calls run back to back on the stream and share the workspace; each call has
+        its own output buffers).  A mask whose call reports an overflow or unsettled starts is redone
+        by `trace`.  Returns [(records, points)] in the order of `thrs`."""
+        if img.dtype != torch.uint8 or img.dim() != 2 or img.shape != (self.h, self.w) or img.stride(1) != 1:
+            raise ValueError("contour input must be a uint8 [h, w] device image")
+        c = self._c
+        thrs = [int(t) for t in thrs]
+        T, rb = len(thrs), c.REC_DTYPE.itemsize
+        if T == 0:
+            return []
+        with torch.cuda.device(self.device):
+            recs = torch.empty((T, self.max_contours * rb), dtype=torch.uint8, device=self.device)
+            points = torch.empty((T, 2 * self.max_points), dtype=torch.int32, device=self.device)
+            counts = torch.zeros((T, c.COUNTS_DTYPE.itemsize), dtype=torch.uint8, device=self.device)
+            for i, t in enumerate(thrs):
+                _lib.check(self.lib.chips_contours(
+                    _ptr(img), self.w, self.h, int(img.stride(0)), int(mode), t, self.cap,
+                    self.start_rounds, _ptr(recs[i]), self.max_contours, _ptr(points[i]),
+                    self.max_points, _ptr(counts[i]), _ptr(self.ws), self.ws.numel(), _stream_ptr()),
+                    "chips_contours")
+                self.calls += 1
+            cnt = counts.cpu().numpy().view(c.COUNTS_DTYPE).reshape(T)          # the one synchronisation
+            good = (cnt["overflow"] == 0) & (cnt["changed"] == 0)
+            n_max = int(cnt["n_contours"][good].max()) if good.any() else 0
+            m_max = int(cnt["n_points"][good].max()) if good.any() else 0
+            recs_h = recs[:, :n_max * rb].cpu().numpy()
+            pts_h = points[:, :2 * m_max].cpu().numpy()
+        out = []
+        for i, t in enumerate(thrs):
+            if not good[i]:
+                out.append(self.trace(img, mode, t))
+                continue
+            n, m = int(cnt["n_contours"][i]), int(cnt["n_points"][i])
+            out.append((np.ascontiguousarray(recs_h[i, :n * rb]).view(c.REC_DTYPE),
+                        np.ascontiguousarray(pts_h[i, :2 * m]).reshape(-1, 2)))
+        return out
 
 
 def find_contours(mask: np.ndarray, device=None):

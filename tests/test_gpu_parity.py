@@ -867,6 +867,14 @@ def test_contours_full_size_vs_opencv():
         ref = _same_contours(mask, got, hier[None] if len(got) else None)
         assert np.array_equal(area2, [int(round(2 * cv2.contourArea(c))) for c in ref])
         assert len(ref) > 0
+    # all thresholds in one enqueue == one at a time
+    every = det.contours_all()
+    assert len(every) == 20
+    for t in (0, 7, 19):
+        got, hier, area2 = det.contours(t)
+        g2, h2, a2 = every[t]
+        assert len(got) == len(g2) and all(np.array_equal(a, b) for a, b in zip(got, g2))
+        assert np.array_equal(hier, h2) and np.array_equal(area2, a2)
 
 
 # ----------------------------------------------------------------------------- uploads

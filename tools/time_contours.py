@@ -38,6 +38,10 @@ for t in range(20):
     cs, hier, a2 = det.contours(t)
     tot += len(cs)
 print(f"all 20 thresholds through Detector.contours: {(time.perf_counter() - t0) * 1e3:.1f} ms wall, {tot} contours")
+det.contours_all()
+t0 = time.perf_counter()
+tot = sum(len(cs) for cs, _, _ in det.contours_all())
+print(f"all 20 thresholds through Detector.contours_all (one enqueue, one sync): {(time.perf_counter() - t0) * 1e3:.1f} ms wall, {tot} contours")
 t0 = time.perf_counter()
 for t in range(20):
     cv2.findContours((lev <= t).astype(np.uint8), cv2.RETR_TREE, cv2.CHAIN_APPROX_SIMPLE)
