@@ -160,3 +160,31 @@ def test_pipeline_masks_every_threshold(emu):
         for i, want in zip(keep, reg.contours):
             assert np.array_equal(got[i], want), t
         assert np.array_equal(np.array([hier[i] for i in keep]), np.asarray(reg.hierarchy)), t
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_drawn_shapes_nested_and_touching(emu, seed):
+    """Rectangles, diagonal strokes, rings and punched holes drawn over each other (nesting several
+    levels deep, borders sharing pixels, shapes touching the image frame)."""
+    rng = np.random.default_rng(900 + seed)
+    for _ in range(12):
+        h, w = int(rng.integers(8, 72)), int(rng.integers(8, 72))
+        m = np.zeros((h, w), np.uint8)
+        for _ in range(int(rng.integers(3, 14))):
+            kind = rng.integers(0, 4)
+            y0, x0 = int(rng.integers(0, h)), int(rng.integers(0, w))
+            y1, x1 = int(rng.integers(y0, h)) + 1, int(rng.integers(x0, w)) + 1
+            val = int(rng.integers(0, 2))
+            if kind == 0:
+                m[y0:y1, x0:x1] = val
+            elif kind == 1:                                  # ring, one pixel wide
+                m[y0:y1, x0:x1] = 1
+                m[y0 + 1:y1 - 1, x0 + 1:x1 - 1] = 0
+            elif kind == 2:                                  # diagonal stroke
+                n = min(y1 - y0, x1 - x0)
+                idx = np.arange(n)
+                m[y0 + idx, (x0 + idx) if rng.random() < 0.5 else (x1 - 1 - idx)] = val
+            else:                                            # salt
+                pts = rng.random((y1 - y0, x1 - x0)) < 0.15
+                m[y0:y1, x0:x1][pts] = val
+        check(emu, m, rounds=64)
