@@ -39,6 +39,20 @@ def output_order(parent_nbd: np.ndarray):
     same = ~head[1:]
     next_sib[by_parent[:-1][same]] = by_parent[1:][same]
     prev_sib[by_parent[1:][same]] = by_parent[:-1][same]
+    seq = _preorder_by_levels(parent, by_parent, head)
+    if seq is None:                                               # very deep nesting: plain walk
+        seq = _preorder_walk(first_child, next_sib, n)
+    pos = np.empty(n, dtype=np.int64)
+    pos[seq] = np.arange(n)
+    look = lambda a: np.where(a >= 0, pos[np.maximum(a, 0)], -1)
+    hier[:, 0] = look(next_sib[seq])
+    hier[:, 1] = look(prev_sib[seq])
+    hier[:, 2] = look(first_child[:n][seq])
+    hier[:, 3] = look(parent[seq])
+    return seq, hier
+
+
+def _preorder_walk(first_child, next_sib, n):
     seq = np.empty(n, dtype=np.int64)
     k = 0
     stack = [int(first_child[n])]
@@ -53,14 +67,44 @@ def output_order(parent_nbd: np.ndarray):
         stack.append(fc[node])
     if k != n:
         raise RuntimeError("contour tree is not connected to the frame")
+    return seq
+
+
+def _preorder_by_levels(parent, by_parent, head, max_depth: int = 48):
+    """Pre-order positions without walking the tree: position = parent's position + 1 + sizes of
+    the subtrees of the siblings listed before it.  O(depth) numpy passes; None if deeper than
+    `max_depth` (concentric rings), where the plain walk is used."""
+    n = len(parent)
+    levels = [np.flatnonzero(parent < 0)]
+    seen = len(levels[0])
+    while seen < n:
+        if len(levels) > max_depth or len(levels[-1]) == 0:
+            return None if len(levels) > max_depth else _fail()
+        mark = np.zeros(n, dtype=bool)
+        mark[levels[-1]] = True
+        nxt = np.flatnonzero((parent >= 0) & mark[np.maximum(parent, 0)])
+        levels.append(nxt)
+        seen += len(nxt)
+    size = np.ones(n, dtype=np.int64)
+    for lev in reversed(levels[1:]):
+        np.add.at(size, parent[lev], size[lev])
+    # exclusive sums of the subtree sizes inside every sibling group, in sibling order
+    sz = size[by_parent]
+    run = np.cumsum(sz) - sz
+    group_start = np.maximum.accumulate(np.where(head, np.arange(n), 0))
+    before = np.empty(n, dtype=np.int64)
+    before[by_parent] = run - run[group_start]
     pos = np.empty(n, dtype=np.int64)
-    pos[seq] = np.arange(n)
-    look = lambda a: np.where(a >= 0, pos[np.maximum(a, 0)], -1)
-    hier[:, 0] = look(next_sib[seq])
-    hier[:, 1] = look(prev_sib[seq])
-    hier[:, 2] = look(first_child[:n][seq])
-    hier[:, 3] = look(parent[seq])
-    return seq, hier
+    pos[levels[0]] = before[levels[0]]
+    for lev in levels[1:]:
+        pos[lev] = pos[parent[lev]] + 1 + before[lev]
+    seq = np.empty(n, dtype=np.int64)
+    seq[pos] = np.arange(n)
+    return seq
+
+
+def _fail():
+    raise RuntimeError("contour tree is not connected to the frame")
 
 
 def assemble(recs: np.ndarray, points: np.ndarray):

@@ -188,3 +188,36 @@ def test_drawn_shapes_nested_and_touching(emu, seed):
                 pts = rng.random((y1 - y0, x1 - x0)) < 0.15
                 m[y0:y1, x0:x1][pts] = val
         check(emu, m, rounds=64)
+
+
+def test_output_order_levelwise_equals_walk():
+    """contours.output_order: the level-by-level pre-order (numpy passes) equals the plain tree walk
+    on random forests, including chains deeper than its depth limit (fallback)."""
+    rng = np.random.default_rng(4)
+    for n in (1, 2, 7, 50, 400, 3000):
+        for bias in (0.0, 0.5, 0.95):
+            parent = np.full(n, 1, dtype=np.int64)                  # border numbers; 1 = frame
+            for b in range(1, n):
+                if rng.random() < bias:
+                    parent[b] = b + 1                               # child of the previous border: deep chains
+                elif rng.random() < 0.7:
+                    parent[b] = int(rng.integers(0, b)) + 2
+            seq, hier = pc.output_order(parent)
+            p0 = parent - 2
+            b = np.arange(n)
+            by_parent = np.lexsort((-b, p0))
+            first_child = np.full(n + 1, -1, dtype=np.int64)
+            next_sib = np.full(n, -1, dtype=np.int64)
+            ps = p0[by_parent]
+            head = np.ones(n, dtype=bool)
+            head[1:] = ps[1:] != ps[:-1]
+            first_child[np.where(ps[head] < 0, n, ps[head])] = by_parent[head]
+            same = ~head[1:]
+            next_sib[by_parent[:-1][same]] = by_parent[1:][same]
+            want = pc._preorder_walk(first_child, next_sib, n)
+            assert np.array_equal(seq, want), (n, bias)
+            pos = np.empty(n, dtype=np.int64)
+            pos[seq] = np.arange(n)
+            assert np.array_equal(hier[:, 3], np.where(p0[seq] >= 0, pos[np.maximum(p0[seq], 0)], -1))
+    with pytest.raises(RuntimeError):
+        pc.output_order(np.array([3, 2]))                           # two borders that are each other's parent
