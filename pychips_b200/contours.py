@@ -112,7 +112,7 @@ def assemble(recs: np.ndarray, points: np.ndarray):
     cv2.findContours(mask, RETR_TREE, CHAIN_APPROX_SIMPLE) orders them; twice_area[i] =
     2 * cv2.contourArea(contours[i]) as an exact integer."""
     seq, hier = output_order(recs["parent"])
-    pts = points.reshape(-1, 2)
-    contours = [pts[o:o + m].reshape(-1, 1, 2) for o, m in zip(recs["offset"][seq].tolist(),
-                                                             recs["n_points"][seq].tolist())]
+    pts = points.reshape(-1, 1, 2)                   # OpenCV's [n, 1, 2] layout; the slices are views
+    start = recs["offset"][seq].astype(np.int64)
+    contours = [pts[o:e] for o, e in zip(start.tolist(), (start + recs["n_points"][seq]).tolist())]
     return contours, hier, np.abs(recs["area2"][seq])
