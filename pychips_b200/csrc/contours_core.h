@@ -8,7 +8,8 @@
 //   * whether a visit marks p negative / keeps p under CHAIN_APPROX_SIMPLE is local to a state;
 //   * the raster scan only decides WHERE each cycle starts: the first candidate pixel (west or
 //     east neighbour 0) whose mark condition holds given the starts of the other cycles through
-//     that pixel — a fixed point reached in a handful of Jacobi rounds;
+//     that pixel — a fixed point reached in a handful of Jacobi rounds (O(image side) rounds on
+//     lattices of 1-pixel walls: the call reports `changed`, the caller re-enqueues with more);
 //   * border number = rank of the start position, parent from the nearest earlier mark in the row.
 //
 // Every pass is a functor applied to an index range.  contours.cu runs them as CUDA kernels;
