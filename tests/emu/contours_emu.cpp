@@ -6,10 +6,25 @@
 #include <string.h>
 #include "../../pychips_b200/csrc/contours_core.h"
 
+// Order in which a pass visits its indices: 0 ascending, 1 descending, 2 a fixed pseudo-random
+// permutation.  A pass whose result depended on the order would be a race on the GPU.
+static int g_order = 0;
+extern "C" void emu_set_order(int order) { g_order = order; }
+
 struct HostExec {
   template <class F>
   void each(long n, const F& f) {
-    for (long i = 0; i < n; ++i) f(i);
+    if (g_order == 1) {
+      for (long i = n - 1; i >= 0; --i) f(i);
+    } else if (g_order == 2 && n > 2) {
+      long step = 2654435761L % n;                   // any step coprime to n walks every index once
+      auto gcd = [](long a, long b) { while (b) { long t = a % b; a = b; b = t; } return a; };
+      while (step < 2 || gcd(step, n) != 1) ++step;
+      long i = n / 3;
+      for (long k = 0; k < n; ++k) { f(i); i = (i + step) % n; }
+    } else {
+      for (long i = 0; i < n; ++i) f(i);
+    }
   }
   template <class F>
   void each_n(long n_max, const int32_t* n_ptr, int mult, const F& f) {
@@ -20,8 +35,7 @@ struct HostExec {
   void each_flag(long n_max, const int32_t* n_ptr, int mult, const F& f, int32_t* flag) {
     const long m = (long)mult * *n_ptr;
     const long n = m < n_max ? m : n_max;
-    for (long i = 0; i < n; ++i)
-      if (f(i)) *flag = 1;
+    each(n, [&](long i) { if (f(i)) *flag = 1; });
   }
   template <class Count, class Total>
   void scan(Count c, long n_max, const int32_t* n_ptr, uint32_t* out, uint32_t*, Total total) {
