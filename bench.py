@@ -42,6 +42,12 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=16)
+    ap.add_argument("--no-check", action="store_true", help="skip the exchange check (world > 1)")
+    ap.add_argument("--no-f64", action="store_true", help="skip the float64-storage throughput leg")
+    ap.add_argument("--sweep", action="store_true",
+                    help="BASELINE config 5: medfilt_kernel in {11,31,51,71} x 16 thresholds ([-3,13]) "
+                         "over the batch, on N GPUs (test/test_ROI_plots.py:72-81 of the reference)")
+    ap.add_argument("--out", default=None, help="also write the JSON line to this file")
     return ap.parse_args()
 
 
@@ -173,6 +179,16 @@ def run_reference(a):
         "note": "oracle port of the reference CPU path (numpy/scipy/OpenCV), extrapolated from a "
                 "bounded per-image sample; the reference is single-threaded so cores = processes",
     }
+    vp = os.path.join(ROOT, "profiles", "r02_cpu_full_vs_sample.json")
+    if os.path.exists(vp) and (a.n, a.k, a.h_bins, a.t0, a.t1) == (4096, 51, 500, 0, 20):
+        try:      # how the bounded sample compares with a measured whole-image run (build container)
+            v = json.load(open(vp))
+            line["cpu_baseline"]["measured_full_image_s"] = v["measured_full_image_s"]
+            line["cpu_baseline"]["sample_validation_same_machine"] = {
+                "extrapolated_over_measured": v["extrapolated_over_measured"],
+                "file": "profiles/r02_cpu_full_vs_sample.json"}
+        except Exception:
+            pass
     _emit(line)
 
 
@@ -206,9 +222,11 @@ def run_b200(a):
                                  want_keep=True, want_prob_map=True, want_maps=True)
     stats_dummy = None
 
-    def exchange(res_stats):
+    def exchange(res_stats, prob_map):
+        """the one exchange step of a batch; returns (all statistics, all-reduced map)"""
         if world > 1:
-            series.gather_series(res_stats, runner.prob_sum, a.batch * world, T)
+            return series.gather_series(res_stats, prob_map, a.batch * world, T)
+        return None, None
 
     def step_resident():
         """inputs already in HBM: detect every image of the batch, then the exchange."""
@@ -217,6 +235,8 @@ def run_b200(a):
         acc = runner._acc                                  # the batch map is summed on one stream
         for s in runner.streams + [acc]:
             s.wait_stream(cur)
+        with torch.cuda.stream(acc):
+            runner.prob_sum.zero_()                        # the batch's own probability map
         for i in range(a.batch):
             slot = i % runner.n_streams
             det = runner._detector(slot, radii[i])
@@ -232,7 +252,7 @@ def run_b200(a):
         for s in runner.streams + [acc]:
             cur.wait_stream(s)
         if world > 1:
-            exchange(stats_dev)
+            exchange(stats_dev, runner.prob_sum)
 
     inflight = []
 
@@ -247,7 +267,7 @@ def run_b200(a):
         while len(inflight) > (0 if flush else 1):
             res = inflight.pop(0).result()
             if world > 1:
-                exchange(series.pack_stats(res, T))
+                exchange(series.pack_stats(res, T), res.prob_map_sum)
         return res
 
     stats_dev = torch.zeros((a.batch, 3 + 3 * T), dtype=torch.float64, device=dev)
@@ -309,6 +329,60 @@ def run_b200(a):
                "host_dtype": "float32 (pinned)", "ms_per_step": ms_e / a.steps}
         assert int(res.n_peaks.min()) > 0
 
+    # ---- exchange check (outside every timed region): the all-reduced map against the sum of the
+    # per-rank maps gathered separately, the gathered statistics against each rank's own rows
+    exchange_ok = None
+    if world > 1 and not a.no_check:
+        res = runner.run(host, radii, indices=[rank + world * i for i in range(a.batch)])
+        mine = series.pack_stats(res, T)
+        allstats, total = exchange(mine, res.prob_map_sum)
+        parts = [torch.empty_like(res.prob_map_sum) for _ in range(world)]
+        dist.all_gather(parts, res.prob_map_sum)
+        ref = torch.stack(parts).to(torch.float64).sum(0)
+        ok_map = bool(torch.allclose(total.to(torch.float64), ref, rtol=1e-6, atol=1e-6)) and \
+            bool(torch.equal(parts[rank], res.prob_map_sum)) and float(ref.max()) > 0
+        rows = allstats[rank::world][:a.batch]
+        ok_stats = allstats.shape == (a.batch * world, 3 + 3 * T) and \
+            np.array_equal(rows, mine.numpy(), equal_nan=True) and \
+            np.array_equal(allstats[:, 0], np.arange(a.batch * world))
+        # a second exchange of the same batch must give the same map (no in-place re-summing)
+        _, total2 = exchange(mine, res.prob_map_sum)
+        ok_twice = bool(torch.equal(total, total2))
+        flag = torch.tensor([int(ok_map and ok_stats and ok_twice)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        exchange_ok = bool(flag.item())
+
+    # ---- float64 storage (images that are not float32-representable, e.g. raw aiapy output):
+    # the same resident-input measurement with elem = 8 (8-byte keys, twice the image traffic)
+    f64 = None
+    if not a.no_f64:
+        nb = min(a.batch, 16)
+        imgs64 = [(h.to(torch.float64) * (1.0 + 2.0 ** -40)).to(dev) for h in host[:nb]]
+        run64 = series.SeriesRunner(n, n, a.k, a.h_bins, (a.t0, a.t1), device=dev, n_streams=min(a.streams, 8),
+                                    elem=8, want_keep=False, want_prob_map=False, want_maps=True)
+        run64._ensure_copy_pipeline()
+
+        def step64():
+            cur = torch.cuda.current_stream()
+            for s_ in run64.streams:
+                s_.wait_stream(cur)
+            for i in range(nb):
+                slot = i % run64.n_streams
+                with torch.cuda.stream(run64.streams[slot]):
+                    run64._detector(slot, radii[i]).detect_graphed(imgs64[i], 5, None, 0.8, 1e-3, run64.maps[slot])
+            for s_ in run64.streams:
+                cur.wait_stream(s_)
+        for _ in range(3):
+            step64()
+        s64 = max(2, min(a.steps, 5))
+        ms64 = timed(step64, s64)
+        f64 = {"value": world * nb * s64 / (ms64 / 1e3), "unit": UNIT, "images_per_gpu_per_step": nb,
+               "steps": s64, "streams_per_gpu": run64.n_streams,
+               "note": "resident float64 images that are NOT float32-representable: float64 storage "
+                       "(elem=8) through every kernel"}
+        del run64, imgs64
+        torch.cuda.empty_cache()
+
     line = None
     if rank == 0:
         # ---- per-kernel timing pass (CUDA events on the launching stream, after the timed region)
@@ -355,6 +429,7 @@ def run_b200(a):
             if st_["kernel"].startswith("cleanup"):
                 st_["launches"] = 6 + 2 * (T - 1) + 5 + 2 * T
         dom = max((s_ for s_ in per_stage if "launches" not in s_), key=lambda s_: s_["ms"])
+        big = max(per_stage, key=lambda s_: s_["ms"])          # the largest STAGE (may be many launches)
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
@@ -367,6 +442,9 @@ def run_b200(a):
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["gbs"], "peak": peak,
                     "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
                     "share_of_step": round(dom["ms"] / total_ms, 3),
+                    "largest_stage": {"stage": big["kernel"], "ms": big["ms"], "launches": big.get("launches", 1),
+                                      "alg_bytes": big["alg_bytes"], "gbs": big["gbs"], "frac": big["frac"],
+                                      "share_of_step": round(big["ms"] / total_ms, 3)},
                     "pipeline": {"alg_bytes_per_image": total_bytes, "ms_per_image_serial": round(total_ms, 3),
                                  "gbs": round(total_bytes / (total_ms * 1e-3) / 1e9, 1),
                                  "frac": round(total_bytes / (total_ms * 1e-3) / 1e9 / peak, 4)},
@@ -374,23 +452,41 @@ def run_b200(a):
         cpu = None
         if world == 1 and not a.no_cpu_baseline:
             from oracle import cpu_timing as ct
+            # the threshold loop is timed on the REAL filt_disk of this image: the GPU result, copied
+            # back here, before the timed CPU region (it is only an input of the numpy/OpenCV calls)
+            det.medfilt(dev_imgs[0])
+            filt_host = det.filt.cpu().numpy()
             o = ct.sample_detection_seconds(host[0].numpy(), radii[0], a.k, a.h_bins, (a.t0, a.t1),
-                                            band_rows=16, thr_sample=2)
+                                            band_rows=16, thr_sample=2, filt=filt_host)
             cpu = {"value": 1.0 / o["seconds_per_image"], "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": o["sample"], "seconds_per_image": round(o["seconds_per_image"], 1),
+                   "parts_s": {k_: round(v_, 2) for k_, v_ in o["parts"].items()},
                    "host_cores_available": ct.usable_cores()}
+            vp = os.path.join(ROOT, "profiles", "r02_cpu_full_vs_sample.json")
+            if os.path.exists(vp) and (a.n, a.k, a.h_bins, a.t0, a.t1) == (4096, 51, 500, 0, 20):
+                try:
+                    v = json.load(open(vp))
+                    cpu["measured_full_image_s"] = v["measured_full_image_s"]
+                    cpu["measured_on"] = ("unmodified reference, whole 4096^2 image, one core of the BUILD "
+                                          "container (tests/golden/make_golden_headline.py)")
+                    cpu["extrapolated_over_measured"] = round(o["seconds_per_image"] / v["measured_full_image_s"], 3)
+                    cpu["sample_validation_same_machine"] = {
+                        "extrapolated_over_measured": v["extrapolated_over_measured"],
+                        "file": "profiles/r02_cpu_full_vs_sample.json"}
+                except Exception:
+                    pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": max(a.warmup, 3), "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload(a), "images_per_gpu_per_step": a.batch,
                        "storage": "float32 image / uint8 maps; histogram, thresholds, probabilities in fp64",
-                       "streams_per_gpu": a.streams,
+                       "streams_per_gpu": a.streams, "f64_storage": f64,
                        "l2": f"{a.batch} distinct {in_bytes // a.batch >> 20} MiB inputs + 0.50 GB workspace per "
                              "stream cycle through HBM each step (> 126 MB L2)",
                        "outputs": "T uint8 maps [T,N,N] + level-encoded map + record per image; "
                                   "probability map accumulated per GPU"},
-            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches), "exchange_ok": exchange_ok,
             "roofline": roofline, "cpu_baseline": cpu,
         }
     if world > 1:
@@ -398,6 +494,81 @@ def run_b200(a):
         dist.destroy_process_group()
     if line is not None:
         _emit(line)
+
+
+# --------------------------------------------------------------------------- config-5 sweep
+def run_sweep(a):
+    """BASELINE config 5: the reference's only uncertainty sweep (test/test_ROI_plots.py:72-81) —
+    medfilt_kernel in {11, 31, 51, 71} with h_bins=5000 — at 16 thresholds (threshold_range=[-3,13])
+    over a batch of 4096^2 images; images are sharded over the ranks, every rank runs all four kernel
+    sizes on its images (resident inputs).  One JSON line: per-kernel-size and aggregate detections/s."""
+    import torch
+    import torch.distributed as dist
+    from pychips_b200 import series, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, t0, t1, hb = a.n, -3, 13, 5000
+    nb = min(a.batch, 16)
+    imgs, radii = [], []
+    for i in range(nb):
+        img, r = synth.synthetic_disk(n, seed=rank * 1000 + i)
+        imgs.append(torch.from_numpy(img).to(dev))
+        radii.append(r)
+    per_k, total_ms = [], 0.0
+    for k in (11, 31, 51, 71):
+        runner = series.SeriesRunner(n, n, k, hb, (t0, t1), device=dev, n_streams=a.streams,
+                                     want_keep=False, want_prob_map=False, want_maps=True)
+
+        def step():
+            cur = torch.cuda.current_stream()
+            for s_ in runner.streams:
+                s_.wait_stream(cur)
+            for i in range(nb):
+                slot = i % runner.n_streams
+                with torch.cuda.stream(runner.streams[slot]):
+                    runner._detector(slot, radii[i]).detect_graphed(imgs[i], 5, None, 0.8, 1e-3, runner.maps[slot])
+            for s_ in runner.streams:
+                cur.wait_stream(s_)
+        for _ in range(max(a.warmup, 3)):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = float(ms.item())
+        res = runner._detector(0, radii[0]).result()
+        assert res.median_errors == 0 and res.n_peaks > 0
+        per_k.append({"medfilt_kernel": k, "images_per_s": world * nb * a.steps / (ms / 1e3),
+                      "ms_per_image_per_gpu": ms / (nb * a.steps)})
+        total_ms += ms
+        del runner
+        torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        _emit({"metric": "config-5 sweep: (image, medfilt_kernel) detections/sec, 16 thresholds each",
+               "value": world * nb * a.steps * 4 / (total_ms / 1e3), "unit": "detections/s", "n_gpus": world,
+               "steps": a.steps, "warmup": max(a.warmup, 3), "higher_is_better": True, "scaling": "weak",
+               "dtype": "f64", "data": "synthetic",
+               "config": {"workload": f"configs[4]: medfilt_kernel in {{11,31,51,71}} x threshold_range=[-3,13] "
+                                      f"(T=16), h_bins={hb}, {nb} synthetic {n}x{n} disks per GPU, inputs resident",
+                          "streams_per_gpu": a.streams},
+               "per_kernel_size": per_k})
 
 
 def main():
@@ -408,7 +579,14 @@ def main():
     os.dup2(2, 1)
     sys.stdout = sys.stderr
     global _emit
-    _emit = lambda line: (real_out.write(json.dumps(line) + "\n"), real_out.flush())
+    def _emit(line):
+        real_out.write(json.dumps(line) + "\n")
+        real_out.flush()
+        if a.out:
+            with open(a.out, "w") as fh:
+                json.dump(line, fh, indent=1)
+    if a.sweep:
+        return run_sweep(a)
     if a.impl == "reference":
         run_reference(a)
     else:

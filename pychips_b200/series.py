@@ -68,7 +68,11 @@ class SeriesRunner:
                            for _ in range(n_streams)]
             self.maps = [torch.empty((self.T, self.H, self.W), dtype=torch.uint8, device=self.device)
                          if want_maps else None for _ in range(n_streams)]
-            self.prob_sum = torch.zeros((self.H, self.W), dtype=torch.float32, device=self.device)
+            # one summed probability map per host buffer set: a batch's map is zeroed when the batch
+            # is submitted and belongs to that batch alone (batches overlap by one in flight)
+            self._prob_sums = [torch.zeros((self.H, self.W), dtype=torch.float32, device=self.device)
+                               for _ in range(self.n_host_sets if want_prob_map else 1)]
+            self.prob_sum = self._prob_sums[0]           # the map of the most recently submitted batch
 
     def _detector(self, slot: int, r: int) -> Detector:
         key = (slot, r)
@@ -117,11 +121,18 @@ class SeriesRunner:
         ring["next"] = (ring["next"] + 1) % self.n_host_sets
         if owner[0] is not None and not owner[0]._done:
             owner[0].result()                            # the set is still in flight: finish it first
+        self._prob_turn = (getattr(self, "_prob_turn", -1) + 1) % len(self._prob_sums)
+        prob_sum = self.prob_sum = self._prob_sums[self._prob_turn]
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream()
             self._ensure_copy_pipeline()
             for s in self.streams + [self._h2d, self._d2h, self._acc]:
                 s.wait_stream(cur)
+            if self.want_prob_map:
+                # the batch's own map starts at zero (on the accumulation stream, i.e. after every
+                # accumulation of the batch that used this buffer two submits ago)
+                with torch.cuda.stream(self._acc):
+                    prob_sum.zero_()
             for i in range(n):
                 slot = i % self.n_streams
                 st = self.streams[slot]
@@ -153,7 +164,7 @@ class SeriesRunner:
                     # accumulations overlap (race-free) and the sum is reproducible
                     with torch.cuda.stream(self._acc):
                         self._acc.wait_event(self._in_free[slot][par])
-                        det.prob_stack(0.0, self.prob_sum, accumulate=True)
+                        det.prob_stack(0.0, prob_sum, accumulate=True)
                         self._acc_done[slot].record(self._acc)
                 with torch.cuda.stream(st):
                     # snapshot of the outputs (device -> device), so that the slot's next detection
@@ -173,7 +184,8 @@ class SeriesRunner:
                 cur.wait_stream(s)
             done = torch.cuda.Event()
             done.record(cur)
-        handle = PendingSeries(self, indices, rec_host, keep_host, done)
+        handle = PendingSeries(self, indices, rec_host, keep_host, done,
+                               prob_sum if self.want_prob_map else None)
         owner[0] = handle
         return handle
 
@@ -211,9 +223,10 @@ class SeriesRunner:
 class PendingSeries:
     """A submitted batch (`SeriesRunner.submit`)."""
 
-    def __init__(self, runner, indices, rec_host, keep_host, done):
+    def __init__(self, runner, indices, rec_host, keep_host, done, prob_sum=None):
         self._runner, self._indices = runner, indices
         self._rec_host, self._keep_host, self._event = rec_host, keep_host, done
+        self._prob_sum = prob_sum
         self._done, self._result = False, None
 
     def result(self) -> SeriesResult:
@@ -234,7 +247,7 @@ class PendingSeries:
             probs=np.array([[rc.probs[t] for t in range(T)] for rc in recs]).reshape(n, T),
             n_kept=np.array([[rc.n_kept[t] for t in range(T)] for rc in recs]).reshape(n, T),
             keep=[k.numpy() for k in self._keep_host],
-            prob_map_sum=self._runner.prob_sum if self._runner.want_prob_map else None,
+            prob_map_sum=self._prob_sum,
         )
         self._done = True
         return self._result
@@ -258,7 +271,9 @@ def gather_series(stats: torch.Tensor, prob_sum: torch.Tensor | None, n_total: i
                   group=None):
     """The one exchange step of a batch: all_gather of the per-image statistics (padded to the
     largest shard) and all_reduce(sum) of the probability map.  Works on NCCL (device tensors)
-    and on gloo (CPU tensors; used by the world_size-2 CPU tests)."""
+    and on gloo (CPU tensors; used by the world_size-2 CPU tests).  `prob_sum` (this rank's map)
+    is NOT modified: the reduction runs on a copy, which is returned — reducing in place would
+    re-sum an already reduced map (x world) whenever the caller's buffer lives on."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     per = (n_total + world - 1) // world
@@ -269,9 +284,11 @@ def gather_series(stats: torch.Tensor, prob_sum: torch.Tensor | None, n_total: i
     pad[:stats.shape[0]] = stats
     bucket = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bucket, pad, group=group)
+    total = None
     if prob_sum is not None:
-        dist.all_reduce(prob_sum, op=dist.ReduceOp.SUM, group=group)
+        total = prob_sum.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
     allstats = torch.cat(bucket).cpu().numpy()
     allstats = allstats[~np.isnan(allstats[:, 0])]
     order = np.argsort(allstats[:, 0], kind="stable")
-    return allstats[order], prob_sum
+    return allstats[order], total

@@ -119,9 +119,12 @@ def _gloo_worker(rank, world, port, n_total, T, H, W, q):
         n_peaks=np.ones(n), limits=np.array([[i + t for t in range(T)] for i in idx], dtype=float).reshape(n, T),
         probs=np.array([[0.01 * i * t for t in range(T)] for i in idx]).reshape(n, T),
         n_kept=np.array([[i % 3 + t for t in range(T)] for i in idx]).reshape(n, T))
-    psum = torch.full((H, W), float(rank + 1))
-    allstats, psum = series.gather_series(series.pack_stats(res, T), psum, n_total, T)
-    q.put((rank, allstats, psum.numpy()))
+    local = torch.full((H, W), float(rank + 1))
+    allstats, psum = series.gather_series(series.pack_stats(res, T), local, n_total, T)
+    # a second batch's exchange with the same per-rank buffer: the first reduction must not have
+    # been folded into it (the round-1 code all-reduced in place: 3, then 6)
+    _, psum2 = series.gather_series(series.pack_stats(res, T), local, n_total, T)
+    q.put((rank, allstats, psum.numpy(), psum2.numpy(), local.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -142,7 +145,9 @@ def test_series_exchange_gloo_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, allstats, psum in outs:
+    for rank, allstats, psum, psum2, local in outs:
+        assert np.all(local == rank + 1.0)                                  # this rank's map is untouched
+        assert np.all(psum2 == 3.0)                                         # two batches: 3 and 3, not 3 and 6
         assert allstats.shape == (n_total, 3 + 3 * T)
         assert np.array_equal(allstats[:, 0], np.arange(n_total))          # ordered by image index
         assert np.array_equal(allstats[:, 1], 20.0 + np.arange(n_total))

@@ -114,3 +114,59 @@ def test_cleanfl_oracle_matches_reference_golden():
         assert np.array_equal(maps[t], reg.map.astype(np.uint8))
         assert np.array_equal(raw[t], reg.raw_map.astype(np.uint8))
         assert np.array_equal(g["probs"][t], reg.prob, equal_nan=True)
+
+
+def test_headline_config1_oracle_matches_reference_golden():
+    """BASELINE config 1 (1024^2, k=51, h_bins=500, [0,20]): the oracle's stages after the median on
+    the reference's own filt_disk, and the median itself on 48 sampled windows (the full
+    scipy.signal.medfilt2d call costs 29 s; make_golden_headline.py asserted it in full)."""
+    import hashlib
+    g = load_golden("disk_n1024_k51")
+    n, r = 1024, int(g["pixel_radius"])
+    img, r2 = synth.synthetic_disk(n, int(g["seed"]))
+    assert r2 == r
+    if hashlib.sha256(img.tobytes()).hexdigest() != str(g["image_sha256"]):
+        pytest.skip("synthetic generator not bit-reproducible on this host")
+    filt = g["filt_disk"].astype(np.float64)
+    n_mask, i_mask = co.solar_masks(img.astype(np.float64), n, r)
+    rng = np.random.default_rng(0)
+    ys, xs = np.nonzero(i_mask)
+    pad = np.pad(img, 25)
+    for i in rng.integers(0, len(ys), 48):
+        w = np.sort(pad[ys[i]:ys[i] + 51, xs[i]:xs[i] + 51].ravel())
+        assert filt[ys[i], xs[i]] == w[1300]
+    assert np.all(filt[i_mask == 0] == 0)
+    hd = co.extract_histogram(filt * n_mask, 500, None, 5)
+    for f in ("hbase", "hbins", "bound", "h_thresh"):
+        assert np.array_equal(g[f], hd[f]), f
+    assert np.array_equal(g["peaks"], np.array(hd["peaks"]))
+    regs = co.extract_CHs_CHBs(filt, n_mask, n, r, hd["peaks"], [0, 20])
+    assert list(regs.keys()) == list(g["keys"])
+    T = len(regs)
+    maps, raw = unpack(g["maps"], T, n, n), unpack(g["raw_maps"], T, n, n)
+    for t, (k, reg) in enumerate(regs.items()):
+        assert np.array_equal(maps[t], reg.map.astype(np.uint8))
+        assert np.array_equal(raw[t], reg.raw_map.astype(np.uint8))
+        assert g["probs"][t] == reg.prob and g["limits"][t] == reg.lim
+        assert g["n_contours"][t] == len(reg.contours)
+        assert g["map_counts"][t] == int(reg.map.sum()) and g["raw_counts"][t] == int(reg.raw_map.sum())
+
+
+def test_headline_config2_fixture_is_self_consistent():
+    """The 4096^2 digest fixture: keys / limits / histogram are consistent with each other and the
+    recorded reference stage times are there (bench.py validates its bounded CPU sample with them)."""
+    import json
+    import os
+    from conftest import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, "disk_n4096_k51.npz")):
+        pytest.skip("fixture not generated yet")
+    g = load_golden("disk_n4096_k51")
+    assert len(g["keys"]) == 20 and len(g["map_sha256"]) == 20 and len(g["raw_sha256"]) == 20
+    assert np.array_equal(g["limits"], np.round(g["limit_0"] + np.arange(0, 20), 4))
+    assert [str(v) for v in g["limits"]] == list(g["keys"])
+    assert g["limit_0"] == g["peaks"][0]
+    assert np.array_equal(g["bound"], g["hbins"][:-1] + np.diff(g["hbins"]))
+    assert np.all(np.diff(g["raw_counts"]) >= 0) and np.all(g["map_counts"] >= 0)
+    secs = json.loads(str(g["stage_seconds"]))
+    assert set(secs) == {"extract_solar_masks", "run_filters", "extract_histogram", "extract_CHs_CHBs"}
+    assert secs["run_filters"] > 60
