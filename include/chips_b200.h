@@ -31,7 +31,11 @@ extern "C" {
 #define CHIPS_E_WS (-3)       /* workspace too small                                  */
 
 #define CHIPS_MAX_T 64        /* max number of thresholds per detection               */
-#define CHIPS_MAX_K 75        /* max median kernel size of the tiled fast path        */
+#define CHIPS_MAX_K 73        /* max median kernel size (block sort: a 16-row block with its halo fits shared memory) */
+/* pixels of one halo-extended median block that the block sort holds in shared memory
+ * (keys + two index arrays): float32 / float64 storage                                  */
+#define CHIPS_MAX_BLOCK_ELEMS_F32 26624
+#define CHIPS_MAX_BLOCK_ELEMS_F64 17664
 #define CHIPS_PROB_BINS 20    /* chips.py:445 np.linspace(0,1,21)                     */
 
 /* Per-image result record written by the device epilogues (one per detection). */
@@ -56,11 +60,12 @@ typedef struct chips_plan {
   int32_t H, W, k, h_bins, T, elem, masked, pad_;
   int32_t roi_x0, roi_y0, roi_w, roi_h;   /* bounding box of the disk (whole image if unmasked) */
   /* median blocks: the ROI is cut into blk_nbx x blk_nby blocks of 128 columns x blk_rows rows
-   * (blk_rows a multiple of 16); each block has its own 256 quantile boundaries and a bucket
-   * image of its halo-extended region, bp_rows x bp_pitch bytes                            */
+   * (blk_rows a multiple of 16).  Each block sorts its halo-extended region ((128+k-1) x bp_rows
+   * pixels, zero padding outside the image) and keeps every pixel's RANK in that order (u16) and
+   * its bucket = rank / blk_bucket (u8, < 128), images of bp_rows x bp_pitch elements           */
   int32_t bp_pitch, bp_rows;
-  int32_t blk_rows, blk_nbx, blk_nby, pad2_;
-  size_t off_bounds;     /* [blocks][256] bucket boundaries (ordered keys, 8 B each)      */
+  int32_t blk_rows, blk_nbx, blk_nby, blk_bucket;
+  size_t off_rank;       /* u16 [blocks][bp_rows][bp_pitch]   block-local rank images     */
   size_t off_bucket;     /* u8  [blocks][bp_rows][bp_pitch]   block-local bucket images   */
   size_t off_bstar;      /* u8  [H][W]   median bucket per pixel                          */
   size_t off_rres;       /* u32 [H][W]   residual rank | (bucket population << 16)        */
@@ -83,7 +88,7 @@ typedef struct chips_plan {
   size_t off_list2;      /* u32 [roi_h*roi_w]  unsorted list (phase B) / foreground list grouped by W (phase C) */
   size_t off_lvl;        /* u32 [512]          per-level counts / offsets / cursors, phase-C counters */
   size_t off_tiles;      /* (reserved)                                                    */
-  size_t off_ovf;        /* u32 [2][1 + #16x16 tiles]  median tier 2: count + list of overflow tiles, two levels */
+  size_t off_ovf;        /* (reserved)                                                    */
   size_t bytes;          /* total workspace size                                          */
 } chips_plan;
 

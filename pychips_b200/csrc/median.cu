@@ -2,36 +2,37 @@
 //
 // Replaces scipy.signal.medfilt2d at /root/reference/chips/chips.py:214-216 and
 // /root/reference/chips/syn_chips.py:106.  A median is a pure order statistic, so any
-// exact selection reproduces scipy to the bit.  The B200 design is a two-tier selection:
+// exact selection reproduces scipy to the bit.  The B200 design is a block sort followed by a
+// two-tier selection on RANKS:
 //
 //   0. the ROI is cut into blocks of 128 columns x L rows (L a multiple of the 16-pixel
-//      refine tile, chosen by chips_plan_init so that one wave of tier-1 CTAs covers the ROI).
-//   1. k_bounds      one CTA per block: 1024 samples of the block's halo-extended region,
-//                    bitonic sort in shared memory, 127 LOCAL quantile boundaries -> 128 value
-//                    buckets of equal local mass (a window's median bucket then holds ~1-2 % of
-//                    the window instead of ~6 % with image-wide quantiles: tier 2 shrinks).
-//   2. k_bucketize   per block: uint8 bucket image of the extended region (zero padding
-//                    outside the image = bucket of 0.0).
-//   3. k_huang4      tier 1: one warp per block, every thread slides FOUR adjacent columns
+//      select tile, chosen by chips_plan_init so that one wave of tier-1 warps covers the ROI).
+//   1. k_block_sort  one CTA per block: the block's halo-extended region (zero padding outside
+//                    the image) is radix-sorted in shared memory (LSD, 8-bit digits over the
+//                    significant bits of key - min, warp-private counters, match.any for the
+//                    stable in-warp order).  Output: every pixel's RANK in its block (u16, unique
+//                    - ties are broken by the sort) and its bucket = rank / S (u8, 128 buckets
+//                    of exactly equal population).  From here on no kernel compares values.
+//   2. k_huang4      tier 1: one warp per block, every thread slides FOUR adjacent columns
 //                    down the block (Huang's O(k) update) with a shared core histogram of the
 //                    common window columns plus packed per-column fringe counters, private to
 //                    the thread, in shared memory (bank-conflict-free interleaved layout).
 //                    Output per pixel: the bucket that holds the median, the residual rank
-//                    inside that bucket and the bucket's population.
-//   4. k_refine_fast tier 2: one CTA per 16x16 output tile streams the bucket bytes of the
-//                    tile's (16+k-1)^2 region, keeps the pixels that fall in a bucket some
-//                    pixel of the tile needs, fetches only those values, counting-sorts them
-//                    by (bucket, key digits) and rank-sorts inside the sub-groups; every
-//                    thread walks its bucket's sorted candidates counting in-window ones
-//                    until it reaches its residual rank.  The fused epilogue applies the disk
-//                    mask and reduces min/max for the histogram.  Tiles with too many
-//                    candidates are retried with larger buffers (k_refine_fast_list) and, if
-//                    they still overflow (flat areas), refined with the whole region staged
-//                    in shared memory (k_refine_list).
+//                    inside that bucket and the bucket's population in the window.
+//   3. k_select      tier 2: one CTA per 16x16 output tile streams the ranks of the tile's
+//                    (16+k-1)^2 region (128-bit loads).  Ranks are unique, so "sorting the
+//                    candidates" is a direct-address store: table[rank - rank_lo] = position for
+//                    the ranks inside the span of buckets the tile's pixels need, plus a bitmap
+//                    of the filled slots (warp ballots, no atomics).  Every thread then walks the
+//                    set bits of ITS bucket's slot range from the nearer end, counting the
+//                    candidates inside its own k x k window until it reaches its residual rank,
+//                    and fetches that one value.  Buckets are walked in rounds of at most
+//                    kSelSlots ranks, so there is no overflow path: flat or quantised images
+//                    cost the same as continuous ones.  The fused epilogue applies the disk mask
+//                    and reduces min/max for the histogram.
 //
 // k_median_brute is an independent per-thread radix-select used only as the at-scale
 // checker in the tests.
-#include <cuda_pipeline.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -40,39 +41,13 @@
 namespace chips {
 
 constexpr int kBuckets = 128;   // 8 resident tier-1 warps per SM (24 KB of counters each)
-constexpr int kSamples = 1024;   // per block
 constexpr int kHuangThreads = 128;
 constexpr int kTile = 16;
 
-// ------------------------------------------------------------------ shared bitonic sort
-template <typename K, bool HAS_POS>
-__device__ __forceinline__ void bitonic_sort(K* key, uint16_t* pos, int n, int tid, int nthreads) {
-  for (int k2 = 2; k2 <= n; k2 <<= 1) {
-    for (int j = k2 >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < (n >> 1); t += nthreads) {
-        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        int l = i | j;
-        K a = key[i], b = key[l];
-        bool up = (i & k2) == 0;
-        if ((a > b) == up) {
-          key[i] = b;
-          key[l] = a;
-          if (HAS_POS) {
-            uint16_t pa = pos[i];
-            pos[i] = pos[l];
-            pos[l] = pa;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
 // ------------------------------------------------------------------ 0. block geometry
 // Block b = (bx, by) covers image columns [rx0 + 128 bx, +128) and rows [ry0 + L by, +L); its
-// bucket image holds the block extended by `half` on every side: image (x, y) lives at local
-// (x - X0b + half, y - Y0b + half), pitch LP (multiple of 16), LR rows.
+// rank / bucket images hold the block extended by `half` on every side: image (x, y) lives at
+// local (x - X0b + half, y - Y0b + half), pitch LP elements (multiple of 16), LR rows.
 struct BlockGeom {
   int rx0, ry0, L, nbx, LP, LR, half;
 };
@@ -84,83 +59,180 @@ __device__ __forceinline__ bool rect_on_disk(int x0, int y0, int w, int h, int c
   return on_disk(nx, ny, cx, cy, r);
 }
 
-// ------------------------------------------------------------------ 1. boundaries
+template <typename K>
+__device__ __forceinline__ int bit_length(K v) {
+  return (sizeof(K) == 8) ? 64 - __clzll((long long)v) : 32 - __clz((int)v);
+}
+
+// ------------------------------------------------------------------ 1. block sort
+// Shared memory: keys[n] (ordered keys of the region, row-major, never moved), two index arrays
+// (the current order and the one being scattered) and 32 x 256 u16 warp-private digit counters.
+// A warp owns a contiguous segment of the current order; inside a round of 32 elements
+// match.any groups equal digits, the lowest lane of a group adds the group's size to the warp's
+// counter (count phase) / advances the warp's cursor (scatter phase), every lane's slot is the
+// cursor plus the number of lower lanes of its group: the scatter is stable without atomics.
+constexpr int kSortThreads = 1024;
+constexpr int kSortWarps = kSortThreads / 32;
+
+static size_t block_sort_smem(int n, int key_bytes) {
+  const size_t npad = ((size_t)n + 15) & ~(size_t)7;
+  return npad * (key_bytes + 4) + (size_t)kSortWarps * 256 * sizeof(uint16_t);
+}
+
 template <typename T>
-__global__ void __launch_bounds__(256) k_bounds(const T* __restrict__ img, int H, int W, BlockGeom g,
-                                                int cx, int cy, int r,
-                                                typename Key<T>::type* __restrict__ bounds,
-                                                typename Key<T>::type* __restrict__ minmax) {
+__global__ void __launch_bounds__(kSortThreads, 1) k_block_sort(
+    const T* __restrict__ img, int H, int W, BlockGeom g, int cx, int cy, int r, int S,
+    uint16_t* __restrict__ Rk, uint8_t* __restrict__ Bp, typename Key<T>::type* __restrict__ minmax) {
   using K = typename Key<T>::type;
-  __shared__ K s[kSamples];
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  __shared__ K s_min[kSortWarps], s_max[kSortWarps];
+  __shared__ uint32_t s_wsum[8];
+  __shared__ int s_skip;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   const int blk = blockIdx.x, bx = blk % g.nbx, by = blk / g.nbx;
-  if (blk == 0 && threadIdx.x == 0) {
-    minmax[0] = Key<T>::kMax;   // running min
+  if (blk == 0 && tid == 0) {
+    minmax[0] = Key<T>::kMax;   // running min of the masked output (k_select epilogue)
     minmax[1] = 0;              // running max
   }
   const int X = g.rx0 + kHuangThreads * bx, Y = g.ry0 + g.L * by;
   if (!rect_on_disk(X, Y, kHuangThreads, g.L, cx, cy, r)) return;
-  const int ew = kHuangThreads + 2 * g.half, eh = g.L + 2 * g.half;
-  for (int i = threadIdx.x; i < kSamples; i += blockDim.x) {
-    int sy = i >> 5, sx = i & 31;
-    int y = Y - g.half + (((2 * sy + 1) * eh) >> 6);
-    int x = X - g.half + (((2 * sx + 1) * ew) >> 6);
-    T v = (y >= 0 && y < H && x >= 0 && x < W) ? img[(size_t)y * W + x] : (T)0;
-    s[i] = Key<T>::enc(v);
-  }
-  __syncthreads();
-  bitonic_sort<K, false>(s, nullptr, kSamples, threadIdx.x, blockDim.x);
-  // Quantised intensities (instrument counts, exposure-normalised data) repeat: a value that
-  // fills more than one quantile step yields a run of equal boundaries, i.e. empty buckets.  The
-  // last boundary of such a run is raised by one key so that the bucket below it becomes a POINT
-  // bucket [v, v+1): a median that falls into it is v, known after tier 1 (no candidates, no walk).
-  constexpr int kStep = kSamples / kBuckets;
-  for (int i = threadIdx.x; i < kBuckets; i += blockDim.x) {
-    K b = Key<T>::kMax;
-    if (i < kBuckets - 1) {
-      b = s[(i + 1) * kStep];
-      const bool dup_prev = i > 0 && s[i * kStep] == b;
-      const bool last_of_run = i == kBuckets - 2 || s[(i + 2) * kStep] != b;
-      if (dup_prev && last_of_run && b != Key<T>::kMax) b += 1;
+  const int ew = kHuangThreads + 2 * g.half, eh = g.LR, n = ew * eh;
+  const int npad = (n + 15) & ~7;
+  K* keys = reinterpret_cast<K*>(sort_smem);
+  uint16_t* ia = reinterpret_cast<uint16_t*>(keys + npad);
+  uint16_t* ib = ia + npad;
+  uint16_t* cnt = ib + npad;                 // [kSortWarps][256]
+
+  // ---- load the region as ordered keys (coalesced rows), identity order, key range
+  K lmin = Key<T>::kMax, lmax = 0;
+  for (int row = warp; row < eh; row += kSortWarps) {
+    const int y = Y - g.half + row;
+    const bool yin = y >= 0 && y < H;
+    const T* irow = img + (size_t)(yin ? y : 0) * W;
+    for (int lx = lane; lx < ew; lx += 32) {
+      const int x = X - g.half + lx;
+      const T v = (yin && x >= 0 && x < W) ? __ldg(irow + x) : (T)0;   // medfilt2d zero padding
+      const K key = Key<T>::enc(v);
+      const int e = row * ew + lx;
+      keys[e] = key;
+      ia[e] = (uint16_t)e;
+      lmin = key < lmin ? key : lmin;
+      lmax = key > lmax ? key : lmax;
     }
-    bounds[(size_t)blk * kBuckets + i] = b;
   }
-}
-
-template <typename K>
-__device__ __forceinline__ int bucket_of(const K* __restrict__ bnd, K key) {
-  // number of boundaries bnd[0..254] that are <= key  (bnd sorted ascending)
-  int b = 0;
 #pragma unroll
-  for (int step = kBuckets / 2; step > 0; step >>= 1)
-    if (bnd[b + step - 1] <= key) b += step;
-  return b;
-}
-
-// ------------------------------------------------------------------ 2. bucket image
-// grid (ceil(LR / 4), blocks), 64 x 4 threads: one thread = 4 bytes of one local row
-template <typename T>
-__global__ void __launch_bounds__(256) k_bucketize(const T* __restrict__ img, int H, int W, BlockGeom g,
-                                                   int cx, int cy, int r,
-                                                   const typename Key<T>::type* __restrict__ bounds,
-                                                   uint8_t* __restrict__ Bp) {
-  using K = typename Key<T>::type;
-  __shared__ K sb[kBuckets];
-  const int blk = blockIdx.y, bx = blk % g.nbx, by = blk / g.nbx;
-  const int X = g.rx0 + kHuangThreads * bx, Y = g.ry0 + g.L * by;
-  if (!rect_on_disk(X, Y, kHuangThreads, g.L, cx, cy, r)) return;
-  if (threadIdx.x < kBuckets) sb[threadIdx.x] = bounds[(size_t)blk * kBuckets + threadIdx.x];
+  for (int o = 16; o > 0; o >>= 1) {
+    const K a = __shfl_xor_sync(0xFFFFFFFFu, lmin, o), b = __shfl_xor_sync(0xFFFFFFFFu, lmax, o);
+    lmin = a < lmin ? a : lmin;
+    lmax = b > lmax ? b : lmax;
+  }
+  if (lane == 0) {
+    s_min[warp] = lmin;
+    s_max[warp] = lmax;
+  }
+  if (tid == 0) s_skip = 0;
   __syncthreads();
-  const int word = threadIdx.x & 63, row = blockIdx.x * 4 + (threadIdx.x >> 6);
-  if (word * 4 >= g.LP || row >= g.LR) return;
-  const int y = Y - g.half + row;
-  uint32_t out = 0;
+  K kmin = s_min[lane], kmax = s_max[lane];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int x = X - g.half + word * 4 + i;
-    T v = (y >= 0 && y < H && x >= 0 && x < W) ? img[(size_t)y * W + x] : (T)0;
-    out |= (uint32_t)bucket_of<K>(sb, Key<T>::enc(v)) << (8 * i);
+  for (int o = 16; o > 0; o >>= 1) {
+    const K a = __shfl_xor_sync(0xFFFFFFFFu, kmin, o), b = __shfl_xor_sync(0xFFFFFFFFu, kmax, o);
+    kmin = a < kmin ? a : kmin;
+    kmax = b > kmax ? b : kmax;
   }
-  *reinterpret_cast<uint32_t*>(Bp + ((size_t)blk * g.LR + row) * g.LP + word * 4) = out;
+  const int npass = (bit_length<K>(kmax - kmin) + 7) >> 3;   // only the bits that differ in this block
+
+  const int seg = (n + kSortWarps - 1) / kSortWarps;
+  const int wbeg = min(n, warp * seg), wend = min(n, wbeg + seg);
+  uint16_t* mycnt = cnt + warp * 256;
+  uint16_t *in = ia, *out = ib;
+  for (int pass = 0; pass < npass; ++pass) {
+    const int shift = 8 * pass;
+    {
+      uint32_t* c32 = reinterpret_cast<uint32_t*>(cnt);
+      for (int i = tid; i < kSortWarps * 128; i += kSortThreads) c32[i] = 0;
+      if (tid == 0) s_skip = 0;
+    }
+    __syncthreads();
+    // count: digits of my segment
+    for (int i0 = wbeg; i0 < wend; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < wend;
+      unsigned d = 256u;
+      if (valid) d = (unsigned)((keys[in[i]] - kmin) >> shift) & 255u;
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+      if (valid && (peers & lt_mask) == 0) mycnt[d] = (uint16_t)(mycnt[d] + __popc(peers));
+      __syncwarp();
+    }
+    __syncthreads();
+    // exclusive scan in (digit, warp) order
+    uint32_t total = 0, inc = 0;
+    if (tid < 256) {
+      uint32_t run = 0;
+      for (int w = 0; w < kSortWarps; ++w) {
+        const uint32_t c = cnt[w * 256 + tid];
+        cnt[w * 256 + tid] = (uint16_t)run;
+        run += c;
+      }
+      total = inc = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      if (lane == 31) s_wsum[warp] = inc;
+      if (total == (uint32_t)n) s_skip = 1;   // every key has the same digit: the order stands
+    }
+    __syncthreads();
+    const bool skip = s_skip != 0;
+    if (!skip && tid < 256) {
+      uint32_t base = inc - total;
+      for (int w = 0; w < warp; ++w) base += s_wsum[w];
+      for (int w = 0; w < kSortWarps; ++w) cnt[w * 256 + tid] = (uint16_t)(cnt[w * 256 + tid] + base);
+    }
+    __syncthreads();
+    if (skip) continue;
+    // stable scatter
+    for (int i0 = wbeg; i0 < wend; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < wend;
+      unsigned d = 256u, e = 0;
+      if (valid) {
+        e = in[i];
+        d = (unsigned)((keys[e] - kmin) >> shift) & 255u;
+      }
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+      uint32_t base = 0;
+      if (valid) base = mycnt[d];
+      __syncwarp();
+      if (valid) {
+        out[base + __popc(peers & lt_mask)] = (uint16_t)e;
+        if ((peers & lt_mask) == 0) mycnt[d] = (uint16_t)(base + __popc(peers));
+      }
+      __syncwarp();
+    }
+    uint16_t* t = in;
+    in = out;
+    out = t;
+    __syncthreads();   // the next pass zeroes every warp's counters
+  }
+  // ---- rank of every element (by position), then coalesced copy-out of the rank / bucket images
+  for (int i = tid; i < n; i += kSortThreads) out[in[i]] = (uint16_t)i;
+  __syncthreads();
+  uint16_t* rk = Rk + (size_t)blk * g.LR * g.LP;
+  uint8_t* bp = Bp + (size_t)blk * g.LR * g.LP;
+  const int groups = g.LP >> 2;
+  for (int row = warp; row < eh; row += kSortWarps) {
+    for (int gq = lane; gq < groups; gq += 32) {
+      const int lx = 4 * gq;
+      uint32_t rr[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rr[j] = lx + j < ew ? (uint32_t)out[row * ew + lx + j] : 0xFFFFu;   // slack: no rank
+      *reinterpret_cast<uint2*>(rk + (size_t)row * g.LP + lx) = make_uint2(rr[0] | (rr[1] << 16), rr[2] | (rr[3] << 16));
+      *reinterpret_cast<uint32_t*>(bp + (size_t)row * g.LP + lx) =
+          ((rr[0] / S) & 255u) | (((rr[1] / S) & 255u) << 8) | (((rr[2] / S) & 255u) << 16) | (((rr[3] / S) & 255u) << 24);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ 3. tier 1: Huang
@@ -405,24 +477,7 @@ __global__ void __launch_bounds__(32 * kH4Warps) k_huang4(const uint8_t* __restr
 #endif
 }
 
-// ------------------------------------------------------------------ 4. tier 2: tile refine
-// Staged slow path (k_refine_list).  One CTA per 16x16 output tile.
-//   a. bitmap of the buckets the tile's pixels need (tier-1 output);
-//   b. the tile's (16+k-1)^2 input region (bucket bytes + ordered keys) is staged in shared
-//      memory with coalesced, mutually independent loads;
-//   c. a counting sort collects the positions of the region pixels whose bucket is needed,
-//      grouped by (bucket, leading digit of the key inside the bucket's key range);
-//   d. each warp finishes the sort inside the small sub-groups (shuffle rank sort, in place);
-//   e. every thread walks the sorted candidates of ITS bucket from the nearer end, counting
-//      those inside its own k x k window, until it reaches its residual rank.
-// Epilogue: masked store + min/max reduction (histogram range).
-constexpr int kMaxSub = 2048;   // sub-group counters per tile: groups * digits <= kMaxSub
-
-template <typename K>
-__device__ __forceinline__ int bit_length(K v) {
-  return (sizeof(K) == 8) ? 64 - __clzll((long long)v) : 32 - __clz((int)v);
-}
-
+// ------------------------------------------------------------------ 3. tier 2: select
 __device__ __forceinline__ bool in_window(unsigned p, unsigned bias, unsigned win) {
   // p = (ry << 8) | rx, bias = (ty << 8) | tx.  A borrow out of the low byte (rx < tx) leaves a
   // low byte >= 256 - 15 > win, a negative row difference wraps the whole word: both rejected.
@@ -430,700 +485,193 @@ __device__ __forceinline__ bool in_window(unsigned p, unsigned bias, unsigned wi
   return ((t >> 8) <= win) & ((t & 255u) <= win);
 }
 
-template <typename T>
-__device__ __forceinline__ void refine_tile_staged(
-    const int tile_x, const int tile_y, const T* __restrict__ img, const uint8_t* __restrict__ Bp_all,
-    const BlockGeom g, const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres,
-    const typename Key<T>::type* __restrict__ bounds_all, int H, int W, int rw, int rh, int cx, int cy,
-    int r, int cap, T* __restrict__ out, typename Key<T>::type* __restrict__ minmax,
+constexpr int kSelSlots = 8192;   // ranks per round (16 KB table + 1 KB bitmap per CTA)
+
+// lowest set bit of the 128-bit mask nd with index >= from (-1: none)
+__device__ __forceinline__ int next_set128(const uint32_t (&nd)[4], int from) {
+#pragma unroll
+  for (int wi = 0; wi < 4; ++wi) {
+    if (wi < (from >> 5)) continue;
+    uint32_t m = nd[wi];
+    if (wi == (from >> 5)) m &= 0xFFFFFFFFu << (from & 31);
+    if (m) return wi * 32 + __ffs(m) - 1;
+  }
+  return -1;
+}
+// highest set bit with index < end (the caller guarantees there is one)
+__device__ __forceinline__ int last_set128(const uint32_t (&nd)[4], int end) {
+  const int top = end - 1;
+#pragma unroll
+  for (int wi = 3; wi >= 0; --wi) {
+    if (wi > (top >> 5)) continue;
+    uint32_t m = nd[wi];
+    if (wi == (top >> 5)) m &= 0xFFFFFFFFu >> (31 - (top & 31));
+    if (m) return wi * 32 + 31 - __clz(m);
+  }
+  return -1;
+}
+
+template <typename T, int KT>      // KT: compile-time window size (0 = run time)
+__global__ void __launch_bounds__(kTile* kTile, 6) k_select(
+    const T* __restrict__ img, const uint16_t* __restrict__ Rk_all, const BlockGeom g, const int S,
+    const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres, int H, int W, int rw, int rh,
+    int cx, int cy, int r, T* __restrict__ out, typename Key<T>::type* __restrict__ minmax,
     int* __restrict__ err) {
   using K = typename Key<T>::type;
   constexpr int NT = kTile * kTile;
   constexpr int NW = NT / 32;
-  extern __shared__ __align__(128) unsigned char smem_tile[];
-  K* skey = reinterpret_cast<K*>(smem_tile);                                    // [RS*vpitch] keys
-  uint16_t* rsg = reinterpret_cast<uint16_t*>(smem_tile + (size_t)cap * sizeof(K));   // [RS*RS] sub-group of a region pixel
-  uint16_t* cpos = rsg + cap;      // [C] candidate positions grouped by sub-group (unsorted)
-  uint16_t* csg = cpos + cap;      // [C] sub-group of a candidate
-  uint16_t* spos = rsg;            // [C] candidate positions, fully sorted (aliases rsg)
-  __shared__ uint32_t need[8], needpfx[9];
-  __shared__ uint16_t glut[kBuckets];          // bucket -> group (0xFFFF: not needed by this tile)
-  __shared__ K gklo[kBuckets];
-  __shared__ uint8_t gshift[kBuckets];
-  __shared__ uint32_t sgstart[kMaxSub], sgcur[kMaxSub];
-  __shared__ uint32_t wsum[NW];
-  __shared__ int nactive;
+  __shared__ __align__(16) uint16_t table[kSelSlots];
+  __shared__ uint32_t bitmap[kSelSlots / 32];
+  __shared__ uint32_t need[4];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx = tid & (kTile - 1), ty = tid >> 4;
-  const int half = g.half, pitch = g.LP, rx0 = g.rx0, ry0 = g.ry0;
-  const int by = (tile_y * kTile) / g.L, blk = by * g.nbx + (tile_x >> 3);
-  const typename Key<T>::type* __restrict__ bounds = bounds_all + (size_t)blk * kBuckets;
-  // block-local origin of the tile's region (the +half of the local frame cancels the -half)
-  const uint8_t* __restrict__ Bp = Bp_all + ((size_t)blk * g.LR + (tile_y * kTile - by * g.L)) * pitch +
-                                   (tile_x & 7) * kTile;
-  const int X0 = rx0 + tile_x * kTile, Y0 = ry0 + tile_y * kTile;
-  const int x = X0 + tx, y = Y0 + ty;
-  const bool active = (x < rx0 + rw) && (y < ry0 + rh) && on_disk(x, y, cx, cy, r);
-  if (tid < 8) need[tid] = 0;
-  if (tid == 0) nactive = 0;
-  __syncthreads();
-  int bs = 0, rr = 0, mpop = 0;
-  bool walk = false;                  // this pixel needs the candidates of its bucket
-  K point = 0;                        // ... or its median is the only key of a point bucket
-  if (active) {
-    size_t o = (size_t)y * W + x;
-    bs = bstar[o];
-    uint32_t pk = rres[o];
-    rr = (int)(pk & 0xFFFFu);
-    mpop = (int)(pk >> 16);
-    const K klo = bs ? bounds[bs - 1] : (K)0;
-    if (bs > 0 && bounds[bs] - klo == 1) {
-      point = klo;
-    } else {
-      walk = true;
-      atomicOr(&need[bs >> 5], 1u << (bs & 31));
-      nactive = 1;
-    }
-  }
-  __syncthreads();
-  // min/max of the masked output for the histogram range (np.histogram's a.min()/a.max())
-  auto reduce_minmax = [&](K kmin, K kmax) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      K a = __shfl_xor_sync(0xFFFFFFFFu, kmin, o);
-      K b = __shfl_xor_sync(0xFFFFFFFFu, kmax, o);
-      kmin = a < kmin ? a : kmin;
-      kmax = b > kmax ? b : kmax;
-    }
-    // every warp of the grid would hit the same two addresses: only values that improve on the
-    // (possibly stale, therefore conservative) current bounds go to the L2 atomic unit
-    if (lane == 0 && kmin <= kmax) {
-      if (kmin < __ldcg(&minmax[0])) atomic_min_key(&minmax[0], kmin);
-      if (kmax > __ldcg(&minmax[1])) atomic_max_key(&minmax[1], kmax);
-    }
-  };
-  if (nactive == 0) {                 // nothing to select: point buckets (or an empty tile) only
-    K kmin = Key<T>::kMax, kmax = 0;
-    if (active) {
-      out[(size_t)y * W + x] = Key<T>::dec(point);
-      kmin = kmax = point;
-    }
-    reduce_minmax(kmin, kmax);
-    return;
-  }
-  if (tid < 9) {
-    uint32_t p = 0;
-    for (int i = 0; i < tid; ++i) p += __popc(need[i]);
-    needpfx[tid] = p;
-  }
-  __syncthreads();
-  const int ngroups = (int)needpfx[8];
-  // digits per group: as many as the counter budget allows (64 for <= 32 buckets, the common
-  // case): finer sub-groups make the rank sort below cheaper
-  const int dlog = ngroups <= kMaxSub / 64 ? 6 : ngroups <= kMaxSub / 32 ? 5
-                 : ngroups <= kMaxSub / 16 ? 4 : 3;
-  const int nsg = ngroups << dlog;
-  const int ndm1 = (1 << dlog) - 1;
-  {   // key range of bucket `tid` -> digit shift of its group; clear the sub-group counters
-    const int b = tid;
-    uint16_t gl = 0xFFFF;
-    if (b < kBuckets && ((need[b >> 5] >> (b & 31)) & 1u)) {
-      K klo = (b == 0) ? (K)0 : bounds[b - 1];
-      K span = bounds[b] - klo;               // bucket = [klo, bounds[b]) ; the last bound is kMax
-      if (b == kBuckets - 1 && span != Key<T>::kMax) span += 1;   // the last bucket is closed
-      int g = (int)(needpfx[b >> 5] + __popc(need[b >> 5] & ((1u << (b & 31)) - 1u)));
-      gl = (uint16_t)g;
-      gklo[g] = klo;
-      gshift[g] = (uint8_t)max(0, bit_length<K>(span - 1) - dlog);
-    }
-    if (b < kBuckets) glut[b] = gl;
-    for (int i = tid; i < nsg; i += NT) sgstart[i] = 0;
-  }
-  __syncthreads();
-
-  // ---- b. stage the region (values + bucket bytes) with per-lane LDGSTS copies, then one
-  //         shared-memory pass turns values into ordered keys, looks up each pixel's sub-group
-  //         and counts the members.
-  const int RS = kTile + 2 * half;
-  constexpr int EPA = 16 / (int)sizeof(T);          // elements per 16 bytes
-  const int vpitch = (RS + 2 * EPA - 2) & ~(EPA - 1);
-  constexpr int vmis = 0, bmis = 0;
-  const int bpitch = (RS + 6) & ~3;
-  {
-    T* sraw = reinterpret_cast<T*>(skey);           // raw values first, keys in place afterwards
-    uint8_t* sbyte = reinterpret_cast<uint8_t*>(csg);   // dead before csg is written
-    {
-      const bool interior = (X0 - half >= 0) && (Y0 - half >= 0) && (X0 - half + RS <= W) &&
-                            (Y0 - half + RS <= H);
-      const int bwords = (RS + 3) >> 2;
-      for (int ry = warp; ry < RS; ry += NW) {
-        const int iy = Y0 + ry - half;
-        const T* irow = img + ((long long)iy * W + (X0 - half));
-        for (int rx = lane; rx < RS; rx += 32) {
-          int ix = X0 + rx - half;
-          if (interior || (iy >= 0 && iy < H && ix >= 0 && ix < W))
-            __pipeline_memcpy_async(&sraw[ry * vpitch + rx], &irow[rx], sizeof(T));
-          else
-            sraw[ry * vpitch + rx] = (T)0;          // zero padding of medfilt2d
-        }
-        const uint32_t* bw = reinterpret_cast<const uint32_t*>(Bp + (size_t)ry * pitch);
-        if (lane < bwords) __pipeline_memcpy_async(sbyte + ry * bpitch + 4 * lane, bw + lane, 4);
-      }
-      __pipeline_commit();
-      __pipeline_wait_prior(0);
-      __syncthreads();
-    }
-    for (int ry = ty; ry < RS; ry += kTile) {
-      for (int rx = tx; rx < RS; rx += kTile) {
-        const int ri = ry * vpitch + vmis + rx;
-        K key = Key<T>::enc(sraw[ri]);
-        skey[ri] = key;
-        const int g = glut[sbyte[ry * bpitch + bmis + rx]];
-        uint16_t sg = 0xFFFF;
-        if (g != 0xFFFF) {
-          K dg = (key - gklo[g]) >> gshift[g];
-          sg = (uint16_t)((g << dlog) + (int)(dg < (K)ndm1 ? dg : (K)ndm1));
-          atomicAdd(&sgstart[sg], 1u);
-        }
-        rsg[ri] = sg;
-      }
-    }
-  }
-  __syncthreads();
-  {   // exclusive scan of the nsg counters (contiguous chunk per thread)
-    const int per = (nsg + NT - 1) / NT;
-    const int lo = tid * per, hi = min(lo + per, nsg);
-    uint32_t s = 0;
-    for (int i = lo; i < hi; ++i) s += sgstart[i];
-    uint32_t inc = s;
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-      if (lane >= o) inc += n;
-    }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    uint32_t base = 0;
-    for (int wv = 0; wv < warp; ++wv) base += wsum[wv];
-    uint32_t run = base + inc - s;
-    for (int i = lo; i < hi; ++i) {
-      uint32_t c = sgstart[i];
-      sgstart[i] = run;
-      sgcur[i] = run;
-      run += c;
-    }
-  }
-  __syncthreads();
-  // ---- c. scatter candidate positions into their sub-groups
-  for (int ry = ty; ry < RS; ry += kTile) {
-    for (int rx = tx; rx < RS; rx += kTile) {
-      const unsigned sg = rsg[ry * vpitch + vmis + rx];
-      if (sg != 0xFFFFu) {
-        uint32_t slot = atomicAdd(&sgcur[sg], 1u);
-        cpos[slot] = (uint16_t)((ry << 8) | rx);
-        csg[slot] = (uint16_t)sg;
-      }
-    }
-  }
-  __syncthreads();
-  auto key_at = [&](unsigned p) -> K { return skey[(p >> 8) * vpitch + vmis + (p & 255u)]; };
-  const int C = (int)sgcur[nsg - 1];
-
-  // ---- d. finish the sort: every candidate finds its rank inside its sub-group (rsg is dead
-  //         from here on; spos aliases it)
-  for (int e = tid; e < C; e += NT) {
-    const unsigned sg = csg[e];
-    const int s0 = (int)sgstart[sg], s1 = (int)sgcur[sg];
-    const unsigned p = cpos[e];
-    const K key = key_at(p);
-    int rank = s0;
-    for (int j = s0; j < s1; ++j) {
-      const K o = key_at(cpos[j]);
-      rank += (o < key || (o == key && j < e)) ? 1 : 0;
-    }
-    spos[rank] = (uint16_t)p;
-  }
-  __syncthreads();
-
-  // ---- e. walk the sorted candidates of my bucket from the nearer end
-  K kmin = Key<T>::kMax, kmax = 0;
-  if (active && !walk) {
-    out[(size_t)y * W + x] = Key<T>::dec(point);
-    kmin = kmax = point;
-  }
-  if (walk) {
-    const int g = glut[bs];
-    const int beg = (int)sgstart[g << dlog], end = (int)sgcur[(g << dlog) + ndm1];
-    const unsigned win = 2u * (unsigned)half;
-    const unsigned bias = ((unsigned)ty << 8) | (unsigned)tx;
-    const bool fwd = 2 * rr < mpop;
-    const int want = fwd ? rr : mpop - 1 - rr;     // in-window candidates to skip
-    const int step = fwd ? 1 : -1;
-    int i = fwd ? beg : end - 1;
-    int left = end - beg;
-    int cnt = 0, found = -1;
-    for (; left >= 4; left -= 4, i += 4 * step) {
-      unsigned p0 = spos[i], p1 = spos[i + step], p2 = spos[i + 2 * step], p3 = spos[i + 3 * step];
-      int c0 = in_window(p0, bias, win), c1 = in_window(p1, bias, win);
-      int c2 = in_window(p2, bias, win), c3 = in_window(p3, bias, win);
-      int c = c0 + c1 + c2 + c3;
-      if (cnt + c > want) {                        // the target is one of these four
-        if (c0 && cnt == want) found = i;
-        cnt += c0;
-        if (found < 0 && c1 && cnt == want) found = i + step;
-        cnt += c1;
-        if (found < 0 && c2 && cnt == want) found = i + 2 * step;
-        cnt += c2;
-        if (found < 0) found = i + 3 * step;
-        break;
-      }
-      cnt += c;
-    }
-    if (found < 0) {
-      for (; left > 0; --left, i += step) {
-        if (in_window(spos[i], bias, win)) {
-          if (cnt == want) {
-            found = i;
-            break;
-          }
-          ++cnt;
-        }
-      }
-    }
-    K res;
-    if (found >= 0) {
-      res = key_at(spos[found]);
-    } else {                                   // inconsistent tier-1 data: must never happen
-      atomicAdd(err, 1);
-      res = Key<T>::enc((T)0);
-    }
-    out[(size_t)y * W + x] = Key<T>::dec(res);
-    kmin = res;
-    kmax = res;
-  }
-  reduce_minmax(kmin, kmax);
-}
-
-// Slow path of tier 2: tiles whose candidate set does not fit the fast path's fixed buffers
-// (large flat areas: every region pixel shares the median's bucket) are refined with the whole
-// region staged in shared memory.  A fixed grid walks the overflow list left by k_refine_fast.
-template <typename T>
-__global__ void __launch_bounds__(kTile* kTile) k_refine_list(
-    const uint32_t* __restrict__ ovf, int gx, const T* __restrict__ img,
-    const uint8_t* __restrict__ Bp, BlockGeom g, const uint8_t* __restrict__ bstar,
-    const uint32_t* __restrict__ rres, const typename Key<T>::type* __restrict__ bounds, int H, int W,
-    int rw, int rh, int cx, int cy, int r, int cap, T* __restrict__ out,
-    typename Key<T>::type* __restrict__ minmax, int* __restrict__ err) {
-  const uint32_t n = ovf[0];
-  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-    const uint32_t t = ovf[1 + i];
-    refine_tile_staged<T>((int)(t % (uint32_t)gx), (int)(t / (uint32_t)gx), img, Bp, g, bstar, rres,
-                          bounds, H, W, rw, rh, cx, cy, r, cap, out, minmax, err);
-    __syncthreads();      // the next tile reuses every shared buffer
-  }
-}
-
-// Fast path of tier 2.  One CTA per 16x16 output tile:
-//   a. bitmap + range [bmin, bmax] of the buckets the tile's pixels need (tier-1 output);
-//   b. the bucket bytes of the tile's (16+k-1)^2 region are streamed from the padded bucket
-//      image with aligned 128-bit loads; bytes in a needed bucket become candidates
-//      (position + group), typically ~5 % of the region;
-//   c. only the candidates' values are fetched (zero padding outside the image), keyed and
-//      counting-sorted by (bucket, leading key digits); a rank sort finishes each sub-group;
-//   d. every thread walks the sorted candidates of ITS bucket from the nearer end, counting
-//      those inside its own k x k window, until it reaches its residual rank.
-// Tiles with more than kFastCap candidates are retried with kFastCap2 (k_refine_fast_list); what
-// still overflows (flat areas) goes to the staged slow path (k_refine_list).
-constexpr int kFastCap = 1280;   // candidates per tile, first pass (6 CTAs per SM)
-constexpr int kFastCap2 = 2560;  // second pass over the overflow list (4 CTAs per SM)
-constexpr int kFastSub = 512;    // (bucket, digit) sub-groups per tile
-
-__device__ __forceinline__ uint32_t sum_u16x8(const uint4 c) {
-  return (c.x & 0xFFFFu) + (c.x >> 16) + (c.y & 0xFFFFu) + (c.y >> 16) + (c.z & 0xFFFFu) + (c.z >> 16) +
-         (c.w & 0xFFFFu) + (c.w >> 16);
-}
-
-template <typename T, int KT>      // KT: compile-time window size (0 = run time)
-__device__ __forceinline__ void refine_tile_fast(
-    const int tile_x, const int tile_y, const int gx, const int cap,
-    const T* __restrict__ img, const uint8_t* __restrict__ Bp_all, const BlockGeom g,
-    const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres,
-    const typename Key<T>::type* __restrict__ bounds_all, int H, int W, int rw, int rh, int cx, int cy,
-    int r, T* __restrict__ out,
-    typename Key<T>::type* __restrict__ minmax, int* __restrict__ err, uint32_t* __restrict__ ovf,
-    int force_overflow, uint32_t* __restrict__ dbg) {
-  using K = typename Key<T>::type;
-  constexpr int NT = kTile * kTile;
-  constexpr int NW = NT / 32;
-  static_assert(NW == 8, "one uint4 of u16 counters per sub-group");
-  extern __shared__ __align__(128) unsigned char smem_tile[];
-  K* tkey = reinterpret_cast<K*>(smem_tile);
-  K* ckey = tkey + cap;
-  uint16_t* tpos = reinterpret_cast<uint16_t*>(ckey + cap);
-  uint16_t* cpos = tpos + cap;
-  uint16_t* tsg = cpos + cap;
-  uint16_t* csg = tsg + cap;
-  K* skey = tkey;               // sorted keys / positions reuse the unsorted first-pass arrays
-  uint16_t* spos = tpos;
-  __shared__ uint32_t need[8], needpfx[9];
-  __shared__ uint16_t glut[kBuckets];          // bucket -> group (0xFFFF: not needed by this tile)
-  __shared__ K gklo[kBuckets];
-  __shared__ uint8_t gshift[kBuckets];
-  // warp-private sub-group counters [sub-group][warp] (shared-memory atomics cost 2 cycles per
-  // lane on the one LSU of the SM; a warp resolves its own collisions with match.any instead)
-  uint16_t* wcnt = csg + cap;                 // [kFastSub][NW], 16-byte aligned
-  __shared__ uint16_t sgoff[kFastSub + 1];
-  __shared__ uint32_t wsum[NW];
-  __shared__ int nactive;
-  __shared__ uint32_t ncand;
-#ifdef CHIPS_DEBUG_TIMING
-  long long t_0 = clock64(), t_1 = 0, t_2 = 0;
-#endif
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   const int tx = tid & (kTile - 1), ty = tid >> 4;
   const int half = KT ? KT / 2 : g.half, pitch = g.LP, rx0 = g.rx0, ry0 = g.ry0;
+  const int tile_x = blockIdx.x, tile_y = blockIdx.y;
   const int by = (tile_y * kTile) / g.L, blk = by * g.nbx + (tile_x >> 3);
-  const K* __restrict__ bounds = bounds_all + (size_t)blk * kBuckets;
   // block-local origin of the tile's region (the +half of the local frame cancels the -half);
-  // 16-byte aligned: LP and the tile's column offset are multiples of 16
-  const uint8_t* __restrict__ Bp = Bp_all + ((size_t)blk * g.LR + (tile_y * kTile - by * g.L)) * pitch +
-                                   (tile_x & 7) * kTile;
+  // 32-byte aligned: LP and the tile's column offset are multiples of 16 elements
+  const uint16_t* __restrict__ Rk = Rk_all + ((size_t)blk * g.LR + (tile_y * kTile - by * g.L)) * pitch +
+                                    (tile_x & 7) * kTile;
+  const int nelem = (kHuangThreads + 2 * half) * g.LR;       // ranks of one block
   const int X0 = rx0 + tile_x * kTile, Y0 = ry0 + tile_y * kTile;
   const int x = X0 + tx, y = Y0 + ty;
   const bool active = (x < rx0 + rw) && (y < ry0 + rh) && on_disk(x, y, cx, cy, r);
-  if (tid < 8) need[tid] = 0;
-  if (tid == 0) {
-    nactive = 0;
-    ncand = 0;
-  }
+  if (tid < 4) need[tid] = 0;
   __syncthreads();
   int bs = 0, rr = 0, mpop = 0;
-  bool walk = false;                  // this pixel needs the candidates of its bucket
-  K point = 0;                        // ... or its median is the only key of a point bucket
-  if (active) {
-    size_t o = (size_t)y * W + x;
-    bs = bstar[o];
-    uint32_t pk = rres[o];
-    rr = (int)(pk & 0xFFFFu);
-    mpop = (int)(pk >> 16);
-    const K klo = bs ? bounds[bs - 1] : (K)0;
-    if (bs > 0 && bounds[bs] - klo == 1) {
-      point = klo;
-    } else {
-      walk = true;
-      atomicOr(&need[bs >> 5], 1u << (bs & 31));
-      nactive = 1;
-    }
-  }
-  __syncthreads();
-  // min/max of the masked output for the histogram range (np.histogram's a.min()/a.max())
-  auto reduce_minmax = [&](K kmin, K kmax) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      K a = __shfl_xor_sync(0xFFFFFFFFu, kmin, o);
-      K b = __shfl_xor_sync(0xFFFFFFFFu, kmax, o);
-      kmin = a < kmin ? a : kmin;
-      kmax = b > kmax ? b : kmax;
-    }
-    // every warp of the grid would hit the same two addresses: only values that improve on the
-    // (possibly stale, therefore conservative) current bounds go to the L2 atomic unit
-    if (lane == 0 && kmin <= kmax) {
-      if (kmin < __ldcg(&minmax[0])) atomic_min_key(&minmax[0], kmin);
-      if (kmax > __ldcg(&minmax[1])) atomic_max_key(&minmax[1], kmax);
-    }
-  };
-  if (nactive == 0) {                 // nothing to select: point buckets (or an empty tile) only
-    K kmin = Key<T>::kMax, kmax = 0;
-    if (active) {
-      out[(size_t)y * W + x] = Key<T>::dec(point);
-      kmin = kmax = point;
-    }
-    reduce_minmax(kmin, kmax);
-    return;
-  }
-  if (tid < 9) {
-    uint32_t p = 0;
-    for (int i = 0; i < tid; ++i) p += __popc(need[i]);
-    needpfx[tid] = p;
-  }
-  __syncthreads();
-  const int ngroups = (int)needpfx[8];
-  {   // key range of bucket `tid` -> group tables (gshift holds the span's bit length for now)
-    const int b = tid;
-    uint16_t gl = 0xFFFF;
-    if (b < kBuckets && ((need[b >> 5] >> (b & 31)) & 1u)) {
-      K klo = (b == 0) ? (K)0 : bounds[b - 1];
-      K span = bounds[b] - klo;               // bucket = [klo, bounds[b]) ; the last bound is kMax
-      if (b == kBuckets - 1 && span != Key<T>::kMax) span += 1;   // the last bucket is closed
-      int g = (int)(needpfx[b >> 5] + __popc(need[b >> 5] & ((1u << (b & 31)) - 1u)));
-      gl = (uint16_t)g;
-      gklo[g] = klo;
-      gshift[g] = (uint8_t)bit_length<K>(span - 1);
-    }
-    if (b < kBuckets) glut[b] = gl;
-  }
-  __syncthreads();
-
-  // ---- b. stream the region's bucket bytes; collect (position, group) of the candidates
-  const int RS = kTile + 2 * half;
   {
-    const int nseg = (RS + 15) >> 4;
-    const int ntask = RS * nseg;
-    const uint8_t* base = Bp;
-    for (int t0 = 0; t0 < ntask; t0 += NT) {
-      const int task = t0 + tid;
-      uint32_t m = 0;
-      uint64_t wlo = 0, whi = 0;
-      int ry = 0, rxb = 0;
-      if (task < ntask) {
-        ry = task / nseg;
-        const int seg = task - ry * nseg;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)ry * pitch + 16 * seg));
-        wlo = ((uint64_t)v.y << 32) | v.x;
-        whi = ((uint64_t)v.w << 32) | v.z;
-        rxb = 16 * seg;                                      // region column of byte 0
-        const int hi = min(16, RS - rxb);
+    uint32_t m[4] = {0, 0, 0, 0};
+    if (active) {
+      const size_t o = (size_t)y * W + x;
+      bs = bstar[o];
+      const uint32_t pk = rres[o];
+      rr = (int)(pk & 0xFFFFu);
+      mpop = (int)(pk >> 16);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const unsigned b = (unsigned)((i < 8 ? wlo : whi) >> (8 * (i & 7))) & 255u;
-          m |= ((need[b >> 5] >> (b & 31)) & 1u) << i;       // 8 words, 8 banks: conflict-free
-        }
-        m &= 0xFFFFu >> (16 - hi);
-      }
-      // one shared-memory atomic per warp: exclusive scan of the hit counts
-      const uint32_t n = (uint32_t)__popc(m);
-      uint32_t inc = n;
+      for (int wi = 0; wi < 4; ++wi) m[wi] = (bs >> 5) == wi ? 1u << (bs & 31) : 0u;
+    }
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc += u;
-      }
-      uint32_t wbase = 0;
-      if (lane == 31 && inc) wbase = atomicAdd(&ncand, inc);
-      wbase = __shfl_sync(0xFFFFFFFFu, wbase, 31);
-      uint32_t slot = wbase + inc - n;
-      while (m) {
-        const int i = __ffs(m) - 1;
-        m &= m - 1;
-        if (slot < (uint32_t)cap) tpos[slot] = (uint16_t)((ry << 8) | (rxb + i));
-        ++slot;
-      }
+    for (int wi = 0; wi < 4; ++wi) {
+      const uint32_t v = __reduce_or_sync(0xFFFFFFFFu, m[wi]);
+      if (lane == 0 && v) atomicOr(&need[wi], v);
     }
   }
   __syncthreads();
-  const int C = (int)ncand;
-  if (C > cap || force_overflow) {
-    if (tid == 0) {
-      uint32_t i = atomicAdd(&ovf[0], 1u);
-      ovf[1 + i] = (uint32_t)(tile_y * gx + tile_x);
-    }
-    return;
-  }
-  // digits per group: enough sub-groups that the rank sort below sees ~1 candidate each
-  int dlog = 0;
-  while (dlog < 6 && (ngroups << (dlog + 1)) <= kFastSub && (ngroups << dlog) < C) ++dlog;
-  const int nsg = ngroups << dlog;
-  const int ndm1 = (1 << dlog) - 1;
-  if (tid < ngroups) gshift[tid] = (uint8_t)max(0, (int)gshift[tid] - dlog);
-  uint4* wcnt4 = reinterpret_cast<uint4*>(wcnt);
-  for (int i = tid; i < nsg; i += NT) wcnt4[i] = make_uint4(0, 0, 0, 0);
-  __syncthreads();
+  const uint32_t nd[4] = {need[0], need[1], need[2], need[3]};
+  if ((nd[0] | nd[1] | nd[2] | nd[3]) == 0) return;           // no on-disk pixel in this tile
 
-  // ---- c. fetch + key the candidates, count the sub-groups (warp-private counters)
-  for (int e0 = warp * 32; e0 < C; e0 += NT) {
-    const int e = e0 + lane;
-    unsigned sg = 0xFFFFu;
-    if (e < C) {
-      const unsigned p = tpos[e];
-      const int iy = Y0 + (int)(p >> 8) - half, ix = X0 + (int)(p & 255u) - half;
-      const T v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(&img[(size_t)iy * W + ix]) : (T)0;
-      const K key = Key<T>::enc(v);
-      const int g = glut[__ldg(Bp + (size_t)(p >> 8) * pitch + (p & 255u))];   // bucket byte: L1 hit
-      const K dg = (key - gklo[g]) >> gshift[g];
-      sg = (unsigned)((g << dlog) + (int)(dg < (K)ndm1 ? dg : (K)ndm1));
-      tkey[e] = key;
-      tsg[e] = (uint16_t)sg;
+  const int RS = kTile + 2 * half;
+  const int nseg = (RS + 7) >> 3;
+  const int ntask = RS * nseg;
+  const int CB = kSelSlots / S;                                // buckets per round
+  const unsigned win = 2u * (unsigned)half;
+  const unsigned bias = ((unsigned)ty << 8) | (unsigned)tx;
+  bool done = !active;
+  unsigned found = 0xFFFFFFFFu;
+  int cursor = 0;
+  while (true) {
+    const int cb = next_set128(nd, cursor);
+    if (cb < 0) break;
+    const int hb = last_set128(nd, min(cb + CB, kBuckets));
+    const int rlo = cb * S, rlen = min((hb + 1) * S, nelem) - rlo;
+    if (cursor > 0) __syncthreads();                           // the previous round's walks are over
+    // ---- a. empty table
+    {
+      uint4* t4 = reinterpret_cast<uint4*>(table);
+      const uint4 ff = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      for (int i = tid; i < ((rlen + 7) >> 3); i += NT) t4[i] = ff;
     }
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, sg);
-    if (e < C && (peers & lt_mask) == 0) {
-      uint16_t* c = &wcnt[sg * NW + warp];
-      *c = (uint16_t)(*c + __popc(peers));
-    }
-    __syncwarp();
-  }
-  __syncthreads();
-  {   // exclusive scan over (sub-group, warp): contiguous sub-groups per thread
-    const int per = (nsg + NT - 1) / NT;
-    const int lo = tid * per, hi = min(lo + per, nsg);
-    uint32_t s = 0;
-    for (int i = lo; i < hi; ++i) s += sum_u16x8(wcnt4[i]);
-    uint32_t inc = s;
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t n = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-      if (lane >= o) inc += n;
-    }
-    if (lane == 31) wsum[warp] = inc;
     __syncthreads();
-    uint32_t base = 0;
-    for (int wv = 0; wv < warp; ++wv) base += wsum[wv];
-    uint32_t run = base + inc - s;
-    for (int i = lo; i < hi; ++i) {
-      const uint4 c = wcnt4[i];
-      sgoff[i] = (uint16_t)run;
-      uint4 o;
-      uint32_t a0 = run, a1 = a0 + (c.x & 0xFFFFu), a2 = a1 + (c.x >> 16), a3 = a2 + (c.y & 0xFFFFu);
-      uint32_t a4 = a3 + (c.y >> 16), a5 = a4 + (c.z & 0xFFFFu), a6 = a5 + (c.z >> 16);
-      uint32_t a7 = a6 + (c.w & 0xFFFFu);
-      run = a7 + (c.w >> 16);
-      o.x = a0 | (a1 << 16);
-      o.y = a2 | (a3 << 16);
-      o.z = a4 | (a5 << 16);
-      o.w = a6 | (a7 << 16);
-      wcnt4[i] = o;
-    }
-    if (tid == 0) sgoff[nsg] = (uint16_t)C;
-  }
-  __syncthreads();
-  for (int e0 = warp * 32; e0 < C; e0 += NT) {     // scatter into the sub-groups
-    const int e = e0 + lane;
-    const unsigned sg = e < C ? (unsigned)tsg[e] : 0xFFFFu;
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, sg);
-    uint32_t slot = 0;
-    if (e < C) slot = wcnt[sg * NW + warp];
-    __syncwarp();
-    if (e < C) {
-      if ((peers & lt_mask) == 0) wcnt[sg * NW + warp] = (uint16_t)(slot + __popc(peers));
-      slot += __popc(peers & lt_mask);
-      cpos[slot] = tpos[e];
-      ckey[slot] = tkey[e];
-      csg[slot] = (uint16_t)sg;
-    }
-    __syncwarp();
-  }
-  __syncthreads();
-#ifdef CHIPS_DEBUG_TIMING
-  t_1 = clock64();
-#endif
-  // rank sort inside each sub-group -> fully sorted (skey, spos)
-  for (int e = tid; e < C; e += NT) {
-    const unsigned sg = csg[e];
-    const int s0 = (int)sgoff[sg], s1 = (int)sgoff[sg + 1];
-    const K key = ckey[e];
-    int rank = s0;
-    for (int j = s0; j < s1; ++j) {
-      const K o = ckey[j];
-      rank += (o < key || (o == key && j < e)) ? 1 : 0;
-    }
-    spos[rank] = cpos[e];
-    skey[rank] = key;
-  }
-  __syncthreads();
-#ifdef CHIPS_DEBUG_TIMING
-  t_2 = clock64();
-#endif
-
-  // ---- d. walk the sorted candidates of my bucket from the nearer end
-  K kmin = Key<T>::kMax, kmax = 0;
-  if (active && !walk) {
-    out[(size_t)y * W + x] = Key<T>::dec(point);
-    kmin = kmax = point;
-  }
-  if (walk) {
-    const int g = glut[bs];
-    const int beg = (int)sgoff[g << dlog], end = (int)sgoff[(g + 1) << dlog];
-    const unsigned win = 2u * (unsigned)half;
-    const unsigned bias = ((unsigned)ty << 8) | (unsigned)tx;
-    const bool fwd = 2 * rr < mpop;
-    const int want = fwd ? rr : mpop - 1 - rr;     // in-window candidates to skip
-    const int step = fwd ? 1 : -1;
-    int i = fwd ? beg : end - 1;
-    int left = end - beg;
-    int cnt = 0, found = -1;
-    for (; left >= 4; left -= 4, i += 4 * step) {
-      unsigned p0 = spos[i], p1 = spos[i + step], p2 = spos[i + 2 * step], p3 = spos[i + 3 * step];
-      int c0 = in_window(p0, bias, win), c1 = in_window(p1, bias, win);
-      int c2 = in_window(p2, bias, win), c3 = in_window(p3, bias, win);
-      int c = c0 + c1 + c2 + c3;
-      if (cnt + c > want) {                        // the target is one of these four
-        if (c0 && cnt == want) found = i;
-        cnt += c0;
-        if (found < 0 && c1 && cnt == want) found = i + step;
-        cnt += c1;
-        if (found < 0 && c2 && cnt == want) found = i + 2 * step;
-        cnt += c2;
-        if (found < 0) found = i + 3 * step;
-        break;
+    // ---- b. stream the region's ranks: a rank inside [rlo, rlo + rlen) owns slot rank - rlo
+    //         (columns past the region are real block pixels outside every window, or slack = 0xFFFF)
+    for (int task = tid; task < ntask; task += NT) {
+      const int ry = task / nseg;
+      const int seg = task - ry * nseg;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(Rk + (size_t)ry * pitch + 8 * seg));
+      const unsigned pos0 = ((unsigned)ry << 8) | (unsigned)(8 * seg);
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const unsigned rho = (j & 1) ? (wv[j >> 1] >> 16) : (wv[j >> 1] & 0xFFFFu);
+        const unsigned d = rho - (unsigned)rlo;
+        if (d < (unsigned)rlen) table[d] = (uint16_t)(pos0 + j);
       }
-      cnt += c;
     }
-    if (found < 0) {
-      for (; left > 0; --left, i += step) {
-        if (in_window(spos[i], bias, win)) {
-          if (cnt == want) {
-            found = i;
-            break;
+    __syncthreads();
+    // ---- c. bitmap of the filled slots
+    for (int wd = warp; wd < ((rlen + 31) >> 5); wd += NW) {
+      const int slot = wd * 32 + lane;
+      const bool filled = slot < rlen && table[slot] != 0xFFFFu;
+      const uint32_t b = __ballot_sync(0xFFFFFFFFu, filled);
+      if (lane == 0) bitmap[wd] = b;
+    }
+    __syncthreads();
+    // ---- d. walk the filled slots of my bucket from the nearer end
+    if (!done && bs >= cb && bs <= hb) {
+      done = true;
+      const int s = bs * S - rlo, e1 = min(s + S, rlen) - 1;  // my slots [s, e1]
+      const bool fwd = 2 * rr < mpop;
+      const int want = fwd ? rr : mpop - 1 - rr;              // in-window candidates to skip
+      const int wfirst = s >> 5, wlast = e1 >> 5;
+      const uint32_t mfirst = 0xFFFFFFFFu << (s & 31), mlast = 0xFFFFFFFFu >> (31 - (e1 & 31));
+      int w = fwd ? wfirst : wlast;
+      const int wstop = fwd ? wlast : wfirst;
+      int cnt = 0;
+      if (want >= 0) {
+        while (true) {
+          uint32_t word = bitmap[w];
+          if (w == wfirst) word &= mfirst;
+          if (w == wlast) word &= mlast;
+          if (!fwd) word = __brev(word);
+          while (word) {
+            const int b = __ffs(word) - 1;
+            word &= word - 1;
+            const unsigned p = table[(w << 5) + (fwd ? b : 31 - b)];
+            if (in_window(p, bias, win)) {
+              if (cnt == want) {
+                found = p;
+                break;
+              }
+              ++cnt;
+            }
           }
-          ++cnt;
+          if (found != 0xFFFFFFFFu || w == wstop) break;
+          w += fwd ? 1 : -1;
         }
       }
     }
+    cursor = hb + 1;
+  }
+  // ---- epilogue: fetch the one value, mask, min/max of the masked output
+  K kmin = Key<T>::kMax, kmax = 0;
+  if (active) {
     K res;
-    if (found >= 0) {
-      res = skey[found];
+    if (found != 0xFFFFFFFFu) {
+      const int iy = Y0 + (int)(found >> 8) - half, ix = X0 + (int)(found & 255u) - half;
+      const T v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(&img[(size_t)iy * W + ix]) : (T)0;
+      res = Key<T>::enc(v);
     } else {                                   // inconsistent tier-1 data: must never happen
       atomicAdd(err, 1);
       res = Key<T>::enc((T)0);
     }
     out[(size_t)y * W + x] = Key<T>::dec(res);
-    kmin = res;
-    kmax = res;
+    kmin = kmax = res;
   }
-  reduce_minmax(kmin, kmax);
-#ifdef CHIPS_DEBUG_TIMING
-  __syncthreads();
-  if (tid == 0 && dbg) {
-    uint32_t* d = dbg + 4 * (size_t)(tile_y * gx + tile_x);
-    long long t_3 = clock64();
-    d[0] = (uint32_t)(t_1 - t_0);
-    d[1] = (uint32_t)(t_2 - t_1);
-    d[2] = (uint32_t)(t_3 - t_2);
-    d[3] = (uint32_t)C;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const K a = __shfl_xor_sync(0xFFFFFFFFu, kmin, o), b = __shfl_xor_sync(0xFFFFFFFFu, kmax, o);
+    kmin = a < kmin ? a : kmin;
+    kmax = b > kmax ? b : kmax;
   }
-#endif
+  // every warp of the grid would hit the same two addresses: only values that improve on the
+  // (possibly stale, therefore conservative) current bounds go to the L2 atomic unit
+  if (lane == 0 && kmin <= kmax) {
+    if (kmin < __ldcg(&minmax[0])) atomic_min_key(&minmax[0], kmin);
+    if (kmax > __ldcg(&minmax[1])) atomic_max_key(&minmax[1], kmax);
+  }
 }
 
-// first pass: one CTA per tile, `cap` candidates (6 CTAs per SM)
-template <typename T, int KT>
-__global__ void __launch_bounds__(kTile* kTile, 6) k_refine_fast(
-    const int cap, const T* __restrict__ img, const uint8_t* __restrict__ Bp_all, const BlockGeom g,
-    const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres,
-    const typename Key<T>::type* __restrict__ bounds_all, int H, int W, int rw, int rh, int cx, int cy,
-    int r, T* __restrict__ out, typename Key<T>::type* __restrict__ minmax, int* __restrict__ err,
-    uint32_t* __restrict__ ovf, int force_overflow, uint32_t* __restrict__ dbg) {
-  refine_tile_fast<T, KT>((int)blockIdx.x, (int)blockIdx.y, (int)gridDim.x, cap, img, Bp_all, g, bstar, rres,
-                      bounds_all, H, W, rw, rh, cx, cy, r, out, minmax, err, ovf, force_overflow, dbg);
-}
-
-// second pass: the tiles that overflowed the first one, with larger buffers (a fixed grid walks
-// the list `ovf_in`); what still does not fit goes to `ovf_out` and the staged slow path
-template <typename T>
-__global__ void __launch_bounds__(kTile* kTile, 4) k_refine_fast_list(
-    const uint32_t* __restrict__ ovf_in, const int gx, const int cap, const T* __restrict__ img,
-    const uint8_t* __restrict__ Bp_all, const BlockGeom g, const uint8_t* __restrict__ bstar,
-    const uint32_t* __restrict__ rres, const typename Key<T>::type* __restrict__ bounds_all, int H, int W,
-    int rw, int rh, int cx, int cy, int r, T* __restrict__ out, typename Key<T>::type* __restrict__ minmax,
-    int* __restrict__ err, uint32_t* __restrict__ ovf_out, int force_overflow) {
-  const uint32_t n = ovf_in[0];
-  for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-    const uint32_t t = ovf_in[1 + i];
-    refine_tile_fast<T, 0>((int)(t % (uint32_t)gx), (int)(t / (uint32_t)gx), gx, cap, img, Bp_all, g, bstar,
-                        rres, bounds_all, H, W, rw, rh, cx, cy, r, out, minmax, err, ovf_out, force_overflow,
-                        nullptr);
-    __syncthreads();      // the next tile reuses every shared buffer
-  }
-}
 
 // ------------------------------------------------------------------ small kernels (k <= 5)
 // For a 3x3 or 5x5 window the two-tier machinery is all overhead (the synoptic default is k = 3):
@@ -1231,22 +779,13 @@ __global__ void k_copy_masked(const T* __restrict__ in, T* __restrict__ out, int
 }
 
 // ------------------------------------------------------------------ host-side launchers
-static int refine_vpitch(int k, int elem) {
-  int rs = kTile + (k - 1), epa = 16 / elem;
-  return (rs + 2 * epa - 2) & ~(epa - 1);
-}
-static int refine_cap(int k, int elem) {
-  int rs = kTile + (k - 1);
-  return (rs * refine_vpitch(k, elem) + 31) & ~31;
-}
-
 template <typename T>
 static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy, int r,
                         unsigned char* ws, cudaStream_t st, int stages) {
   using K = typename Key<T>::type;
   const int H = p->H, W = p->W, k = p->k, half = k >> 1;
-  K* bounds = reinterpret_cast<K*>(ws + p->off_bounds);
   K* minmax = reinterpret_cast<K*>(ws + p->off_minmax);
+  uint16_t* Rk = reinterpret_cast<uint16_t*>(ws + p->off_rank);
   uint8_t* Bp = ws + p->off_bucket;
   uint8_t* bstar = ws + p->off_bstar;
   uint32_t* rres = reinterpret_cast<uint32_t*>(ws + p->off_rres);
@@ -1279,14 +818,13 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
     }
     return CHIPS_OK;
   }
-  if (stages & 1) {  // local quantile boundaries of every block
-    k_bounds<T><<<nblocks, 256, 0, st>>>(in, H, W, g, cx, cy, r, bounds, minmax);
-    CHIPS_CHECK_LAUNCH();
-    count_launch();
-  }
-  if (stages & 2) {  // bucket image of every block's halo-extended region
-    dim3 grid((p->bp_rows + 3) / 4, nblocks);
-    k_bucketize<T><<<grid, 256, 0, st>>>(in, H, W, g, cx, cy, r, bounds, Bp);
+  const int nelem = (kHuangThreads + 2 * half) * p->bp_rows;
+  const int S = p->blk_bucket;
+  if (S < 1 || (nelem + S - 1) / S > kBuckets || nelem > 65535 || S > kSelSlots) return CHIPS_E_ARG;
+  if (stages & 1) {  // rank + bucket images of every block's halo-extended region
+    const size_t smem = block_sort_smem(nelem, (int)sizeof(K));
+    CHIPS_CUDA(cudaFuncSetAttribute(k_block_sort<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_block_sort<T><<<nblocks, kSortThreads, smem, st>>>(in, H, W, g, cx, cy, r, S, Rk, Bp, minmax);
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }
@@ -1310,49 +848,19 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }
-  if (stages & 8) {  // tier 2: fast path over every tile, then the overflow list
-    uint32_t* ovf = reinterpret_cast<uint32_t*>(ws + p->off_ovf);
-    const int gx = (rw + kTile - 1) / kTile, gy = (rh + kTile - 1) / kTile;
-    static const int force_ovf = getenv("CHIPS_REFINE_STAGED") ? 1 : 0;   // tests: slow path only
-    CHIPS_CUDA(cudaMemsetAsync(ovf, 0, sizeof(uint32_t), st));
-    auto fast_smem = [](int c) {
-      return (size_t)c * (2 * sizeof(K) + 4 * sizeof(uint16_t)) +
-             (size_t)kFastSub * (kTile * kTile / 32) * sizeof(uint16_t);
-    };
-    uint32_t* ovf2 = ovf + (size_t)gx * gy + 1;          // second-level overflow list
-    CHIPS_CUDA(cudaMemsetAsync(ovf2, 0, sizeof(uint32_t), st));
-    uint32_t* rdbg = reinterpret_cast<uint32_t*>(ws + p->off_parent_c);
-#define CHIPS_LAUNCH_REFINE(KT)                                                                              \
-    do {                                                                                                     \
-      CHIPS_CUDA(cudaFuncSetAttribute(k_refine_fast<T, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                      (int)fast_smem(kFastCap)));                                            \
-      k_refine_fast<T, KT><<<dim3(gx, gy), kTile * kTile, fast_smem(kFastCap), st>>>(                         \
-          kFastCap, in, Bp, g, bstar, rres, bounds, H, W, rw, rh, cx, cy, r, out, minmax, err, ovf, force_ovf, \
-          rdbg);                                                                                             \
-    } while (0)
+  if (stages & 8) {  // tier 2: one CTA per 16x16 tile
+    const dim3 grid((rw + kTile - 1) / kTile, (rh + kTile - 1) / kTile);
+#define CHIPS_LAUNCH_SELECT(KT)                                                                             \
+    k_select<T, KT><<<grid, kTile * kTile, 0, st>>>(in, Rk, g, S, bstar, rres, H, W, rw, rh, cx, cy, r, out, \
+                                                    minmax, err)
     switch (k) {
-      case 11: CHIPS_LAUNCH_REFINE(11); break;
-      case 31: CHIPS_LAUNCH_REFINE(31); break;
-      case 51: CHIPS_LAUNCH_REFINE(51); break;
-      case 71: CHIPS_LAUNCH_REFINE(71); break;
-      default: CHIPS_LAUNCH_REFINE(0); break;
+      case 11: CHIPS_LAUNCH_SELECT(11); break;
+      case 31: CHIPS_LAUNCH_SELECT(31); break;
+      case 51: CHIPS_LAUNCH_SELECT(51); break;
+      case 71: CHIPS_LAUNCH_SELECT(71); break;
+      default: CHIPS_LAUNCH_SELECT(0); break;
     }
-#undef CHIPS_LAUNCH_REFINE
-    CHIPS_CHECK_LAUNCH();
-    const long long ntiles = (long long)gx * gy;
-    const int nlist = (int)(ntiles < 4LL * kNumSM ? ntiles : 4LL * kNumSM);
-    CHIPS_CUDA(cudaFuncSetAttribute(k_refine_fast_list<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)fast_smem(kFastCap2)));
-    k_refine_fast_list<T><<<nlist, kTile * kTile, fast_smem(kFastCap2), st>>>(
-        ovf, gx, kFastCap2, in, Bp, g, bstar, rres, bounds, H, W, rw, rh, cx, cy, r, out, minmax, err, ovf2,
-        force_ovf);
-    CHIPS_CHECK_LAUNCH();
-    count_launch(2);
-    int cap = refine_cap(k, (int)sizeof(T));
-    size_t smem = (size_t)cap * (sizeof(K) + 3 * sizeof(uint16_t));
-    CHIPS_CUDA(cudaFuncSetAttribute(k_refine_list<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_refine_list<T><<<nlist, kTile * kTile, smem, st>>>(ovf2, gx, in, Bp, g, bstar, rres, bounds, H, W, rw,
-                                                         rh, cx, cy, r, cap, out, minmax, err);
+#undef CHIPS_LAUNCH_SELECT
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }
@@ -1360,6 +868,7 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
 }
 
 }  // namespace chips
+
 
 extern "C" int chips_medfilt2d_stages(const void* in, void* out, const chips_plan* plan, int cx,
                                       int cy, int r, void* ws, void* stream, int stages);

@@ -33,15 +33,23 @@ extern "C" int chips_plan_init(chips_plan* p, int H, int W, int k, int h_bins, i
     p->roi_x0 = 0; p->roi_y0 = 0; p->roi_w = W; p->roi_h = H;
   }
   const int half = k >> 1;
-  {  // median blocks (median.cu): 128 columns x L rows, L a multiple of the 16-pixel refine tile.
+  {  // median blocks (median.cu): 128 columns x L rows, L a multiple of the 16-pixel select tile.
      // Every tier-1 run pays a (k-1)-row warm-up; one warp owns one block and 8 warps (24 KB of
-     // histograms each) are resident per SM: minimise waves(L) * (L + k).
+     // histograms each) are resident per SM: minimise waves(L) * (L + k).  The block sort holds a
+     // block's halo-extended region in shared memory: (128 + k - 1) * (L + k - 1) pixels at most
+     // CHIPS_MAX_BLOCK_ELEMS_F32 / _F64.
     const int nbx = (p->roi_w + 127) / 128;
     const long long resident = 8LL * kNumSM;
-    const int lmax = (int)align_up((size_t)p->roi_h, 16);
+    const int emax = elem == 4 ? CHIPS_MAX_BLOCK_ELEMS_F32 : CHIPS_MAX_BLOCK_ELEMS_F64;
+    int lcap = (emax / (128 + 2 * half) - 2 * half) & ~15;
+    if (lcap < 16) return CHIPS_E_ARG;
+    int lmax = (int)align_up((size_t)p->roi_h, 16);
+    if (lmax > lcap) lmax = lcap;
     int L = lmax;
     long long best = -1;
-    for (int cand = (int)align_up((size_t)(k < 16 ? 16 : k), 16); cand <= lmax; cand += 16) {
+    int cand0 = (int)align_up((size_t)(k < 16 ? 16 : k), 16);
+    if (cand0 > lmax) cand0 = lmax;
+    for (int cand = cand0; cand <= lmax; cand += 16) {
       long long blocks = (long long)nbx * ((p->roi_h + cand - 1) / cand);
       long long waves = (blocks + resident - 1) / resident;
       long long cost = waves * (cand + k);
@@ -53,16 +61,17 @@ extern "C" int chips_plan_init(chips_plan* p, int H, int W, int k, int h_bins, i
     p->blk_rows = L;
     p->blk_nbx = nbx;
     p->blk_nby = (p->roi_h + L - 1) / L;
-    p->pad2_ = 0;
-    // + 16 bytes of slack: 128-bit row reads of the last refine tile / funnel loads of tier 1
+    // + 16 elements of slack: funnel loads of tier 1, 8-element row reads of tier 2
     p->bp_pitch = (int)align_up((size_t)128 + 2 * half + 16, 16);
     p->bp_rows = L + 2 * half;
+    // 128 buckets of equal population: bucket = rank / blk_bucket
+    p->blk_bucket = ((128 + 2 * half) * (L + 2 * half) + 127) / 128;
   }
   const size_t nblk = (size_t)p->blk_nbx * p->blk_nby;
   const size_t n = (size_t)H * W, nr = (size_t)p->roi_w * p->roi_h;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  p->off_bounds = take(nblk * 256 * 8);
+  p->off_rank = take(nblk * p->bp_pitch * p->bp_rows * 2);
   p->off_bucket = take(nblk * p->bp_pitch * p->bp_rows);
   p->off_bstar = take(n);
   p->off_rres = take(n * 4);
@@ -90,7 +99,7 @@ extern "C" int chips_plan_init(chips_plan* p, int H, int W, int k, int h_bins, i
     p->off_parent_b = p->off_parent_c = p->off_area = off;
     p->off_pending = p->off_list2 = p->off_lvl = p->off_tiles = off;
   }
-  p->off_ovf = take(2 * ((size_t)((p->roi_w + 15) / 16) * ((p->roi_h + 15) / 16) + 1) * 4);
+  p->off_ovf = take(256);                      // (reserved)
   p->bytes = off;
   return CHIPS_OK;
 }
@@ -133,8 +142,8 @@ extern "C" int chips_detect(const void* image, const chips_plan* plan, int cx, i
 }
 
 // ---- host <-> device copies of only what the path reads ------------------------------------
-// Every kernel that reads the input image stays inside the halo-extended median blocks (bounds
-// samples, bucket images, tile staging, the k <= 5 windows), clipped to the image: that rectangle
+// Every kernel that reads the input image stays inside the halo-extended median blocks (block
+// sort, the selected medians, the k <= 5 windows), clipped to the image: that rectangle
 // is all a caller has to upload.  4096^2, r = 1577, k = 51: 3250 x 3218 of 4096 x 4096 = 62 %.
 extern "C" int chips_input_rect(const chips_plan* plan, int32_t* rect) {
   if (!plan || !rect) return CHIPS_E_ARG;

@@ -265,9 +265,20 @@ class Detector:
         cap.wait_stream(cur)
         g = torch.cuda.CUDAGraph()
         n0 = self.lib.chips_launch_count()
-        # thread_local: CUDA calls of other threads (NCCL watchdog, samplers) do not break the capture
-        with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
-            self.detect(image, ht_peak_ratio, h_thresh, porb_threshold, area_threshold, maps)
+        # Python's cycle collector must not run inside the capture: finalising an unrelated CUDA
+        # graph / tensor there (cudaGraphDestroy, cudaFree) is an operation that invalidates it.
+        # Collect before, keep the collector off while capturing.
+        import gc
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            # thread_local: CUDA calls of other threads (NCCL watchdog, samplers) do not break the capture
+            with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
+                self.detect(image, ht_peak_ratio, h_thresh, porb_threshold, area_threshold, maps)
+        finally:
+            if gc_was_on:
+                gc.enable()
         nodes = int(self.lib.chips_launch_count() - n0)   # counted while capturing, not executed
         cur.wait_stream(cap)
         graphs[key] = (g, nodes)

@@ -224,7 +224,9 @@ class PendingSeries:
     """A submitted batch (`SeriesRunner.submit`)."""
 
     def __init__(self, runner, indices, rec_host, keep_host, done, prob_sum=None):
-        self._runner, self._indices = runner, indices
+        # no strong reference to the runner: the runner keeps this handle (its pinned buffers are
+        # still in flight), a reference back would make a cycle that only the cycle collector frees
+        self._T, self._indices = runner.T, indices
         self._rec_host, self._keep_host, self._event = rec_host, keep_host, done
         self._prob_sum = prob_sum
         self._done, self._result = False, None
@@ -233,7 +235,7 @@ class PendingSeries:
         if self._done:
             return self._result
         self._event.synchronize()
-        n, T = len(self._indices), self._runner.T
+        n, T = len(self._indices), self._T
         recs = [_lib.Result.from_buffer_copy(self._rec_host[i].numpy().tobytes()) for i in range(n)]
         for rc in recs:
             if rc.median_errors:

@@ -53,14 +53,14 @@ def med(mask):
 
 
 STAGES = {
-    "bounds": med(1), "bucketize": med(2), "huang": med(4), "refine": med(8), "median": med(15),
+    "sort": med(1), "huang": med(4), "select": med(8), "median": med(15),
     "hist": lambda s: (dets[s].histogram(), dets[s].select_threshold(5, None)),
     "thr": lambda s: dets[s].threshold_prob(0.8),
     "cleanup": lambda s: dets[s].cleanup(1e-3),
     "expand": lambda s: dets[s].expand_maps(0, maps[s]),
     "all": lambda s: dets[s].detect(imgs[s], maps=maps[s]),
 }
-SUBSETS = [["bounds"], ["bucketize"], ["huang"], ["refine"], ["median"], ["hist", "thr"], ["cleanup"], ["expand"],
+SUBSETS = [["sort"], ["huang"], ["select"], ["median"], ["hist", "thr"], ["cleanup"], ["expand"],
            ["median", "hist", "thr"], ["hist", "thr", "cleanup", "expand"], ["all"]]
 if a.subsets:
     SUBSETS = [x.split("+") for x in a.subsets.split(",")]
