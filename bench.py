@@ -400,7 +400,7 @@ def run_b200(a):
             # kernels is quoted against that figure
             ("median.k_block_sort", k_stage(1), 7 * n * n),   # image in, u16 rank + u8 bucket out
             ("median.k_huang4", k_stage(4), 8 * n * n),
-            ("median.k_select", k_stage(8), 8 * n * n),
+            ("median.k_rank_select", k_stage(8), 8 * n * n),
             ("k_hist", lambda: det.histogram(), 4 * n * n),
             ("k_select", lambda: det.select_threshold(5, None), 0),
             ("k_threshold_prob", lambda: det.threshold_prob(0.8), 5 * n * n),

@@ -34,7 +34,7 @@ extern "C" {
 #define CHIPS_MAX_K 73        /* max median kernel size (block sort: a 16-row block with its halo fits shared memory) */
 /* pixels of one halo-extended median block that the block sort holds in shared memory
  * (keys + two index arrays): float32 / float64 storage                                  */
-#define CHIPS_MAX_BLOCK_ELEMS_F32 26624
+#define CHIPS_MAX_BLOCK_ELEMS_F32 24576
 #define CHIPS_MAX_BLOCK_ELEMS_F64 17664
 #define CHIPS_PROB_BINS 20    /* chips.py:445 np.linspace(0,1,21)                     */
 
@@ -61,11 +61,11 @@ typedef struct chips_plan {
   int32_t roi_x0, roi_y0, roi_w, roi_h;   /* bounding box of the disk (whole image if unmasked) */
   /* median blocks: the ROI is cut into blk_nbx x blk_nby blocks of 128 columns x blk_rows rows
    * (blk_rows a multiple of 16).  Each block sorts its halo-extended region ((128+k-1) x bp_rows
-   * pixels, zero padding outside the image) and keeps every pixel's RANK in that order (u16) and
-   * its bucket = rank / blk_bucket (u8, < 128), images of bp_rows x bp_pitch elements           */
+   * pixels, zero padding outside the image) and keeps the pixels' positions in key order (u16
+   * lists) and every pixel's bucket = rank / blk_bucket (u8, < 128; images of bp_rows x bp_pitch) */
   int32_t bp_pitch, bp_rows;
   int32_t blk_rows, blk_nbx, blk_nby, blk_bucket;
-  size_t off_rank;       /* u16 [blocks][bp_rows][bp_pitch]   block-local rank images     */
+  size_t off_order;      /* u16 [blocks][align8(pixels per block)]  the block's pixels in key order, (ly << 8 | lx) */
   size_t off_bucket;     /* u8  [blocks][bp_rows][bp_pitch]   block-local bucket images   */
   size_t off_bstar;      /* u8  [H][W]   median bucket per pixel                          */
   size_t off_rres;       /* u32 [H][W]   residual rank | (bucket population << 16)        */

@@ -31,7 +31,7 @@ class Plan(C.Structure):
                  "roi_x0", "roi_y0", "roi_w", "roi_h", "bp_pitch", "bp_rows",
                  "blk_rows", "blk_nbx", "blk_nby", "blk_bucket")] + \
                [(n, C.c_size_t) for n in
-                ("off_rank", "off_bucket", "off_bstar", "off_rres", "off_filt", "off_minmax",
+                ("off_order", "off_bucket", "off_bstar", "off_rres", "off_filt", "off_minmax",
                  "off_counts", "off_density", "off_edges", "off_bound", "off_peaks",
                  "off_result", "off_level", "off_fill", "off_keep", "off_probtab",
                  "off_parent_b", "off_parent_c", "off_area", "off_pending", "off_list2", "off_lvl",

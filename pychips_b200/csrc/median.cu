@@ -8,28 +8,28 @@
 //   0. the ROI is cut into blocks of 128 columns x L rows (L a multiple of the 16-pixel
 //      select tile, chosen by chips_plan_init so that one wave of tier-1 warps covers the ROI).
 //   1. k_block_sort  one CTA per block: the block's halo-extended region (zero padding outside
-//                    the image) is radix-sorted in shared memory (LSD, 8-bit digits over the
-//                    significant bits of key - min, warp-private counters, match.any for the
-//                    stable in-warp order).  Output: every pixel's RANK in its block (u16, unique
-//                    - ties are broken by the sort) and its bucket = rank / S (u8, 128 buckets
-//                    of exactly equal population).  From here on no kernel compares values.
+//                    the image) is radix-sorted in shared memory (LSD, 4-bit digits over the
+//                    significant bits of key - min, thread-private counters, no atomics).
+//                    Output: the block's pixel POSITIONS in key order (u16 list; a pixel's index in
+//                    it is its rank, unique - ties are broken by the sort) and every pixel's bucket
+//                    = rank / S (u8 image, 128 buckets of exactly equal population).  From here on
+//                    no kernel compares values.
 //   2. k_huang4      tier 1: one warp per block, every thread slides FOUR adjacent columns
 //                    down the block (Huang's O(k) update) with a shared core histogram of the
 //                    common window columns plus packed per-column fringe counters, private to
 //                    the thread, in shared memory (bank-conflict-free interleaved layout).
 //                    Output per pixel: the bucket that holds the median, the residual rank
 //                    inside that bucket and the bucket's population in the window.
-//   3. k_select      tier 2: one CTA per 16x16 output tile streams the ranks of the tile's
-//                    (16+k-1)^2 region (128-bit loads).  Ranks are unique, so "sorting the
-//                    candidates" is a direct-address store: table[rank - rank_lo] = position for
-//                    the ranks inside the span of buckets the tile's pixels need, plus a bitmap
-//                    of the filled slots (warp ballots, no atomics).  Every thread then walks the
-//                    set bits of ITS bucket's slot range from the nearer end, counting the
-//                    candidates inside its own k x k window until it reaches its residual rank,
-//                    and fetches that one value.  Buckets are walked in rounds of at most
-//                    kSelSlots ranks, so there is no overflow path: flat or quantised images
-//                    cost the same as continuous ones.  The fused epilogue applies the disk mask
-//                    and reduces min/max for the histogram.
+//   3. k_rank_select tier 2: one CTA per 16x16 output tile.  A bucket is a contiguous slice of S
+//                    entries of the block's sorted list, so "the sorted candidates of a bucket"
+//                    need no sort: one warp per bucket some pixel of the tile needs streams the
+//                    slice and keeps the positions inside the tile's (16+k-1)^2 region (ballot
+//                    compaction, order preserved).  Every thread then walks the candidates of ITS
+//                    bucket from the nearer end, counting those inside its own k x k window until
+//                    it reaches its residual rank, and fetches that one value.  At most
+//                    kSelSlots / S buckets per round, so there is no overflow path: flat or
+//                    quantised images cost the same as continuous ones.  The fused epilogue applies
+//                    the disk mask and reduces min/max for the histogram.
 //
 // k_median_brute is an independent per-thread radix-select used only as the at-scale
 // checker in the tests.
@@ -65,34 +65,41 @@ __device__ __forceinline__ int bit_length(K v) {
 }
 
 // ------------------------------------------------------------------ 1. block sort
-// Shared memory: keys[n] (ordered keys of the region, row-major, never moved), two index arrays
-// (the current order and the one being scattered) and 32 x 256 u16 warp-private digit counters.
-// A warp owns a contiguous segment of the current order; inside a round of 32 elements
-// match.any groups equal digits, the lowest lane of a group adds the group's size to the warp's
-// counter (count phase) / advances the warp's cursor (scatter phase), every lane's slot is the
-// cursor plus the number of lower lanes of its group: the scatter is stable without atomics.
-constexpr int kSortThreads = 1024;
-constexpr int kSortWarps = kSortThreads / 32;
+// LSD radix sort of one block's halo-extended region in shared memory, 4-bit digits over the
+// significant bits of key - min.  Shared memory: keys[n] (ordered keys, row-major, never moved),
+// two u16 index arrays (the current order and the one being scattered) and 16 x NT u16 counters.
+// Every thread owns a CONTIGUOUS chunk of the current order and private digit counters, so a
+// pass needs no cross-lane matching and no atomics:
+//   1. walk my chunk: digit d, my running count of d (= rank among my own elements with digit d),
+//      kept packed in a register per element;
+//   2. exclusive scan of all counters in (digit, thread) order: packed warp scans + one scan of the
+//      16 x warps warp totals; my counters become my start offsets;
+//   3. scatter: slot = start[d] + my running count.  Stable, hence LSD-correct.
+// (A first version used 8-bit digits with warp-private counters and match.any / eight ballots per
+// round of 32 elements: 700 instructions per element against ~250 here.)
+template <typename T> struct SortCfg;
+template <> struct SortCfg<float> { static constexpr int NT = 1024, IT = CHIPS_MAX_BLOCK_ELEMS_F32 / 1024; };
+template <> struct SortCfg<double> { static constexpr int NT = 512, IT = (CHIPS_MAX_BLOCK_ELEMS_F64 + 511) / 512; };
 
-static size_t block_sort_smem(int n, int key_bytes) {
+template <typename T>
+static size_t block_sort_smem(int n) {
   const size_t npad = ((size_t)n + 15) & ~(size_t)7;
-  return npad * (key_bytes + 4) + (size_t)kSortWarps * 256 * sizeof(uint16_t);
+  return npad * (sizeof(T) + 4) + (size_t)16 * SortCfg<T>::NT * sizeof(uint16_t);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(kSortThreads, 1) k_block_sort(
+__global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
     const T* __restrict__ img, int H, int W, BlockGeom g, int cx, int cy, int r, int S,
-    uint16_t* __restrict__ Rk, uint8_t* __restrict__ Bp, typename Key<T>::type* __restrict__ minmax) {
+    uint16_t* __restrict__ Ord, uint8_t* __restrict__ Bp, typename Key<T>::type* __restrict__ minmax) {
   using K = typename Key<T>::type;
+  constexpr int NT = SortCfg<T>::NT, IT = SortCfg<T>::IT, NW = NT / 32;
   extern __shared__ __align__(16) unsigned char sort_smem[];
-  __shared__ K s_min[kSortWarps], s_max[kSortWarps];
-  __shared__ uint32_t s_wsum[8];
-  __shared__ int s_skip;
+  __shared__ K s_min[NW], s_max[NW];
+  __shared__ uint16_t s_wtot[16 * NW];          // [digit][warp] totals, then exclusive starts
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   const int blk = blockIdx.x, bx = blk % g.nbx, by = blk / g.nbx;
   if (blk == 0 && tid == 0) {
-    minmax[0] = Key<T>::kMax;   // running min of the masked output (k_select epilogue)
+    minmax[0] = Key<T>::kMax;   // running min of the masked output (k_rank_select epilogue)
     minmax[1] = 0;              // running max
   }
   const int X = g.rx0 + kHuangThreads * bx, Y = g.ry0 + g.L * by;
@@ -102,11 +109,12 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_block_sort(
   K* keys = reinterpret_cast<K*>(sort_smem);
   uint16_t* ia = reinterpret_cast<uint16_t*>(keys + npad);
   uint16_t* ib = ia + npad;
-  uint16_t* cnt = ib + npad;                 // [kSortWarps][256]
+  uint16_t* cnt = ib + npad;                 // [16][NT]
+  uint16_t* mycnt = cnt + tid;
 
   // ---- load the region as ordered keys (coalesced rows), identity order, key range
   K lmin = Key<T>::kMax, lmax = 0;
-  for (int row = warp; row < eh; row += kSortWarps) {
+  for (int row = warp; row < eh; row += NW) {
     const int y = Y - g.half + row;
     const bool yin = y >= 0 && y < H;
     const T* irow = img + (size_t)(yin ? y : 0) * W;
@@ -131,106 +139,120 @@ __global__ void __launch_bounds__(kSortThreads, 1) k_block_sort(
     s_min[warp] = lmin;
     s_max[warp] = lmax;
   }
-  if (tid == 0) s_skip = 0;
   __syncthreads();
-  K kmin = s_min[lane], kmax = s_max[lane];
+  K kmin = s_min[lane % NW], kmax = s_max[lane % NW];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const K a = __shfl_xor_sync(0xFFFFFFFFu, kmin, o), b = __shfl_xor_sync(0xFFFFFFFFu, kmax, o);
     kmin = a < kmin ? a : kmin;
     kmax = b > kmax ? b : kmax;
   }
-  const int npass = (bit_length<K>(kmax - kmin) + 7) >> 3;   // only the bits that differ in this block
+  const int npass = (bit_length<K>(kmax - kmin) + 3) >> 2;   // only the bits that differ in this block
 
-  const int seg = (n + kSortWarps - 1) / kSortWarps;
-  const int wbeg = min(n, warp * seg), wend = min(n, wbeg + seg);
-  uint16_t* mycnt = cnt + warp * 256;
+  const int chunk = (n + NT - 1) / NT;                       // <= IT
+  const int beg = min(n, tid * chunk), cnt_items = min(n, beg + chunk) - beg;
   uint16_t *in = ia, *out = ib;
   for (int pass = 0; pass < npass; ++pass) {
-    const int shift = 8 * pass;
-    {
-      uint32_t* c32 = reinterpret_cast<uint32_t*>(cnt);
-      for (int i = tid; i < kSortWarps * 128; i += kSortThreads) c32[i] = 0;
-      if (tid == 0) s_skip = 0;
-    }
-    __syncthreads();
-    // count: digits of my segment
-    for (int i0 = wbeg; i0 < wend; i0 += 32) {
-      const int i = i0 + lane;
-      const bool valid = i < wend;
-      unsigned d = 256u;
-      if (valid) d = (unsigned)((keys[in[i]] - kmin) >> shift) & 255u;
-      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-      if (valid && (peers & lt_mask) == 0) mycnt[d] = (uint16_t)(mycnt[d] + __popc(peers));
-      __syncwarp();
-    }
-    __syncthreads();
-    // exclusive scan in (digit, warp) order
-    uint32_t total = 0, inc = 0;
-    if (tid < 256) {
-      uint32_t run = 0;
-      for (int w = 0; w < kSortWarps; ++w) {
-        const uint32_t c = cnt[w * 256 + tid];
-        cnt[w * 256 + tid] = (uint16_t)run;
-        run += c;
+    const int shift = 4 * pass;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) mycnt[d * NT] = 0;
+    // 1. my chunk: element | digit << 16 | my running count of that digit << 20
+    uint32_t item[IT];
+#pragma unroll
+    for (int j = 0; j < IT; ++j) {
+      if (j < cnt_items) {
+        const unsigned e = in[beg + j];
+        const unsigned d = (unsigned)((keys[e] - kmin) >> shift) & 15u;
+        const unsigned c = mycnt[d * NT];
+        mycnt[d * NT] = (uint16_t)(c + 1);
+        item[j] = e | (d << 16) | (c << 20);
       }
-      total = inc = run;
+    }
+    // 2. exclusive scan in (digit, thread) order; two digits per 32-bit word (warp sums < 2^16)
+    uint32_t inc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      inc[q] = (uint32_t)mycnt[(2 * q) * NT] | ((uint32_t)mycnt[(2 * q + 1) * NT] << 16);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc[q], o);
+        if (lane >= o) inc[q] += u;
+      }
+    }
+    if (lane == 31) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        s_wtot[(2 * q) * NW + warp] = (uint16_t)(inc[q] & 0xFFFFu);
+        s_wtot[(2 * q + 1) * NW + warp] = (uint16_t)(inc[q] >> 16);
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {   // 16 * NW totals, NW / 2 consecutive entries per lane
+      constexpr int E = 16 * NW / 32;
+      uint32_t v[E], sum = 0;
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        v[i] = s_wtot[lane * E + i];
+        sum += v[i];
+      }
+      uint32_t incl = sum;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc += u;
+        const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += u;
       }
-      if (lane == 31) s_wsum[warp] = inc;
-      if (total == (uint32_t)n) s_skip = 1;   // every key has the same digit: the order stands
+      uint32_t run = incl - sum;
+#pragma unroll
+      for (int i = 0; i < E; ++i) {
+        s_wtot[lane * E + i] = (uint16_t)run;
+        run += v[i];
+      }
     }
     __syncthreads();
-    const bool skip = s_skip != 0;
-    if (!skip && tid < 256) {
-      uint32_t base = inc - total;
-      for (int w = 0; w < warp; ++w) base += s_wsum[w];
-      for (int w = 0; w < kSortWarps; ++w) cnt[w * 256 + tid] = (uint16_t)(cnt[w * 256 + tid] + base);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t c0 = mycnt[(2 * q) * NT], c1 = mycnt[(2 * q + 1) * NT];      // my own counts
+      mycnt[(2 * q) * NT] = (uint16_t)(s_wtot[(2 * q) * NW + warp] + (inc[q] & 0xFFFFu) - c0);
+      mycnt[(2 * q + 1) * NT] = (uint16_t)(s_wtot[(2 * q + 1) * NW + warp] + (inc[q] >> 16) - c1);
     }
-    __syncthreads();
-    if (skip) continue;
-    // stable scatter
-    for (int i0 = wbeg; i0 < wend; i0 += 32) {
-      const int i = i0 + lane;
-      const bool valid = i < wend;
-      unsigned d = 256u, e = 0;
-      if (valid) {
-        e = in[i];
-        d = (unsigned)((keys[e] - kmin) >> shift) & 255u;
+    // 3. stable scatter
+#pragma unroll
+    for (int j = 0; j < IT; ++j) {
+      if (j < cnt_items) {
+        const uint32_t it = item[j];
+        out[mycnt[((it >> 16) & 15u) * NT] + (it >> 20)] = (uint16_t)(it & 0xFFFFu);
       }
-      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
-      uint32_t base = 0;
-      if (valid) base = mycnt[d];
-      __syncwarp();
-      if (valid) {
-        out[base + __popc(peers & lt_mask)] = (uint16_t)e;
-        if ((peers & lt_mask) == 0) mycnt[d] = (uint16_t)(base + __popc(peers));
-      }
-      __syncwarp();
     }
+    __syncthreads();   // `out` is complete; s_wtot and the counters are free again
     uint16_t* t = in;
     in = out;
     out = t;
-    __syncthreads();   // the next pass zeroes every warp's counters
   }
-  // ---- rank of every element (by position), then coalesced copy-out of the rank / bucket images
-  for (int i = tid; i < n; i += kSortThreads) out[in[i]] = (uint16_t)i;
-  __syncthreads();
-  uint16_t* rk = Rk + (size_t)blk * g.LR * g.LP;
-  uint8_t* bp = Bp + (size_t)blk * g.LR * g.LP;
-  const int groups = g.LP >> 2;
-  for (int row = warp; row < eh; row += kSortWarps) {
-    for (int gq = lane; gq < groups; gq += 32) {
-      const int lx = 4 * gq;
-      uint32_t rr[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) rr[j] = lx + j < ew ? (uint32_t)out[row * ew + lx + j] : 0xFFFFu;   // slack: no rank
-      *reinterpret_cast<uint2*>(rk + (size_t)row * g.LP + lx) = make_uint2(rr[0] | (rr[1] << 16), rr[2] | (rr[3] << 16));
-      *reinterpret_cast<uint32_t*>(bp + (size_t)row * g.LP + lx) =
-          ((rr[0] / S) & 255u) | (((rr[1] / S) & 255u) << 8) | (((rr[2] / S) & 255u) << 16) | (((rr[3] / S) & 255u) << 24);
+  // ---- outputs: the block's pixels in key order as (ly << 8 | lx) (coalesced), and the bucket
+  //      image: bucket = rank / S by position (scattered in shared memory, copied out by rows)
+  {
+    uint16_t* ord = Ord + (size_t)blk * ((n + 7) & ~7);
+    uint8_t* bkt = reinterpret_cast<uint8_t*>(out);          // [n] bucket by position
+    // e / ew == umulhi(e, magic) for e < 2^16 (ew, S < 2^16)
+    const uint32_t magic = 0xFFFFFFFFu / (uint32_t)ew + 1u, magic_s = 0xFFFFFFFFu / (uint32_t)S + 1u;
+    for (int i = tid; i < n; i += NT) {
+      const uint32_t e = in[i];
+      const uint32_t ly = __umulhi(e, magic), lx = e - ly * ew;
+      ord[i] = (uint16_t)((ly << 8) | lx);
+      bkt[e] = (uint8_t)__umulhi((uint32_t)i, magic_s);
+    }
+    __syncthreads();
+    uint8_t* bp = Bp + (size_t)blk * g.LR * g.LP;
+    const int groups = (ew + 3) >> 2;
+    for (int row = warp; row < eh; row += NW) {
+      for (int gq = lane; gq < groups; gq += 32) {
+        const int lx = 4 * gq;
+        const uint8_t* src = bkt + row * ew + lx;                // (reads <= 3 bytes past a row: slack columns)
+        *reinterpret_cast<uint32_t*>(bp + (size_t)row * g.LP + lx) =
+            (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24);
+      }
     }
   }
 }
@@ -485,55 +507,32 @@ __device__ __forceinline__ bool in_window(unsigned p, unsigned bias, unsigned wi
   return ((t >> 8) <= win) & ((t & 255u) <= win);
 }
 
-constexpr int kSelSlots = 8192;   // ranks per round (16 KB table + 1 KB bitmap per CTA)
-
-// lowest set bit of the 128-bit mask nd with index >= from (-1: none)
-__device__ __forceinline__ int next_set128(const uint32_t (&nd)[4], int from) {
-#pragma unroll
-  for (int wi = 0; wi < 4; ++wi) {
-    if (wi < (from >> 5)) continue;
-    uint32_t m = nd[wi];
-    if (wi == (from >> 5)) m &= 0xFFFFFFFFu << (from & 31);
-    if (m) return wi * 32 + __ffs(m) - 1;
-  }
-  return -1;
-}
-// highest set bit with index < end (the caller guarantees there is one)
-__device__ __forceinline__ int last_set128(const uint32_t (&nd)[4], int end) {
-  const int top = end - 1;
-#pragma unroll
-  for (int wi = 3; wi >= 0; --wi) {
-    if (wi > (top >> 5)) continue;
-    uint32_t m = nd[wi];
-    if (wi == (top >> 5)) m &= 0xFFFFFFFFu >> (31 - (top & 31));
-    if (m) return wi * 32 + 31 - __clz(m);
-  }
-  return -1;
-}
+constexpr int kSelSlots = 8192;   // candidate slots per round (16 KB per CTA)
 
 template <typename T, int KT>      // KT: compile-time window size (0 = run time)
-__global__ void __launch_bounds__(kTile* kTile, 6) k_select(
-    const T* __restrict__ img, const uint16_t* __restrict__ Rk_all, const BlockGeom g, const int S,
-    const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres, int H, int W, int rw, int rh,
+__global__ void __launch_bounds__(kTile* kTile, 8) k_rank_select(
+    const T* __restrict__ img, const uint16_t* __restrict__ Ord_all, const BlockGeom g, const int S,
+    const int per_round, const uint32_t magic_L, const uint8_t* __restrict__ bstar, const uint32_t* __restrict__ rres, int H, int W, int rw, int rh,
     int cx, int cy, int r, T* __restrict__ out, typename Key<T>::type* __restrict__ minmax,
     int* __restrict__ err) {
   using K = typename Key<T>::type;
   constexpr int NT = kTile * kTile;
   constexpr int NW = NT / 32;
-  __shared__ __align__(16) uint16_t table[kSelSlots];
-  __shared__ uint32_t bitmap[kSelSlots / 32];
+  __shared__ uint16_t cand[kSelSlots];          // [needed bucket of this round][S] candidates in key order
+  __shared__ uint16_t ncand[kBuckets];          // candidates per needed bucket of this round
+  __shared__ uint8_t blist[kBuckets];           // the needed buckets, ascending
   __shared__ uint32_t need[4];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   const int tx = tid & (kTile - 1), ty = tid >> 4;
-  const int half = KT ? KT / 2 : g.half, pitch = g.LP, rx0 = g.rx0, ry0 = g.ry0;
+  const int half = KT ? KT / 2 : g.half, rx0 = g.rx0, ry0 = g.ry0;
   const int tile_x = blockIdx.x, tile_y = blockIdx.y;
-  const int by = (tile_y * kTile) / g.L, blk = by * g.nbx + (tile_x >> 3);
-  // block-local origin of the tile's region (the +half of the local frame cancels the -half);
-  // 32-byte aligned: LP and the tile's column offset are multiples of 16 elements
-  const uint16_t* __restrict__ Rk = Rk_all + ((size_t)blk * g.LR + (tile_y * kTile - by * g.L)) * pitch +
-                                    (tile_x & 7) * kTile;
-  const int nelem = (kHuangThreads + 2 * half) * g.LR;       // ranks of one block
+  const int by = (int)__umulhi((uint32_t)(tile_y * kTile), magic_L), blk = by * g.nbx + (tile_x >> 3);   // / g.L
+  const int nelem = (kHuangThreads + 2 * half) * g.LR;       // pixels of one block
+  const uint16_t* __restrict__ ord = Ord_all + (size_t)blk * ((nelem + 7) & ~7);
+  // block-frame position of the tile region's corner (the +half of the frame cancels the -half)
+  const unsigned origin = ((unsigned)(tile_y * kTile - by * g.L) << 8) | (unsigned)((tile_x & 7) * kTile);
   const int X0 = rx0 + tile_x * kTile, Y0 = ry0 + tile_y * kTile;
   const int x = X0 + tx, y = Y0 + ty;
   const bool active = (x < rx0 + rw) && (y < ry0 + rh) && on_disk(x, y, cx, cy, r);
@@ -559,89 +558,97 @@ __global__ void __launch_bounds__(kTile* kTile, 6) k_select(
   }
   __syncthreads();
   const uint32_t nd[4] = {need[0], need[1], need[2], need[3]};
-  if ((nd[0] | nd[1] | nd[2] | nd[3]) == 0) return;           // no on-disk pixel in this tile
+  const int nneeded = __popc(nd[0]) + __popc(nd[1]) + __popc(nd[2]) + __popc(nd[3]);
+  if (nneeded == 0) return;                                   // no on-disk pixel in this tile
+  // ordinal of bucket b among the needed ones
+  auto ordinal = [&](int b) {
+    int o = 0;
+#pragma unroll
+    for (int wi = 0; wi < 4; ++wi)
+      o += (wi < (b >> 5)) ? __popc(nd[wi]) : (wi == (b >> 5)) ? __popc(nd[wi] & ((1u << (b & 31)) - 1u)) : 0;
+    return o;
+  };
+  const int myord = ordinal(bs);
+  if (tid < kBuckets && ((nd[tid >> 5] >> (tid & 31)) & 1u)) blist[ordinal(tid)] = (uint8_t)tid;
 
-  const int RS = kTile + 2 * half;
-  const int nseg = (RS + 7) >> 3;
-  const int ntask = RS * nseg;
-  const int CB = kSelSlots / S;                                // buckets per round
+  const unsigned RSm1 = (unsigned)(kTile + 2 * half - 1);
   const unsigned win = 2u * (unsigned)half;
   const unsigned bias = ((unsigned)ty << 8) | (unsigned)tx;
-  bool done = !active;
   unsigned found = 0xFFFFFFFFu;
-  int cursor = 0;
-  while (true) {
-    const int cb = next_set128(nd, cursor);
-    if (cb < 0) break;
-    const int hb = last_set128(nd, min(cb + CB, kBuckets));
-    const int rlo = cb * S, rlen = min((hb + 1) * S, nelem) - rlo;
-    if (cursor > 0) __syncthreads();                           // the previous round's walks are over
-    // ---- a. empty table
-    {
-      uint4* t4 = reinterpret_cast<uint4*>(table);
-      const uint4 ff = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-      for (int i = tid; i < ((rlen + 7) >> 3); i += NT) t4[i] = ff;
-    }
-    __syncthreads();
-    // ---- b. stream the region's ranks: a rank inside [rlo, rlo + rlen) owns slot rank - rlo
-    //         (columns past the region are real block pixels outside every window, or slack = 0xFFFF)
-    for (int task = tid; task < ntask; task += NT) {
-      const int ry = task / nseg;
-      const int seg = task - ry * nseg;
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(Rk + (size_t)ry * pitch + 8 * seg));
-      const unsigned pos0 = ((unsigned)ry << 8) | (unsigned)(8 * seg);
-      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const unsigned rho = (j & 1) ? (wv[j >> 1] >> 16) : (wv[j >> 1] & 0xFFFFu);
-        const unsigned d = rho - (unsigned)rlo;
-        if (d < (unsigned)rlen) table[d] = (uint16_t)(pos0 + j);
+  for (int o0 = 0; o0 < nneeded; o0 += per_round) {
+    const int o1 = min(o0 + per_round, nneeded);
+    __syncthreads();                           // blist is written / the previous round's walks are over
+    // ---- a. one warp per needed bucket: stream the bucket's S block pixels in key order (two per
+    //         lane and load), keep the ones inside the tile's (16+k-1)^2 region (ballot compaction:
+    //         still in key order)
+    for (int o = o0 + warp; o < o1; o += NW) {
+      const int b = blist[o];
+      const int rb = b * S, re = min(rb + S, nelem);
+      uint16_t* dst = cand + (o - o0) * S;
+      int nout = 0;
+      for (int i0 = rb & ~1; i0 < re; i0 += 64) {
+        const int i = i0 + 2 * lane;
+        unsigned ta = 0, tb = 0;
+        bool ha = false, hb = false;
+        if (i < re) {                                     // (the list is padded to an even length)
+          const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(ord + i));
+          ta = (w & 0xFFFFu) - origin;
+          tb = (w >> 16) - origin;
+          ha = (i >= rb) & ((ta >> 8) <= RSm1) & ((ta & 255u) <= RSm1);
+          hb = (i + 1 < re) & ((tb >> 8) <= RSm1) & ((tb & 255u) <= RSm1);
+        }
+        const uint32_t ma = __ballot_sync(0xFFFFFFFFu, ha), mb = __ballot_sync(0xFFFFFFFFu, hb);
+        // key order: a0 b0 a1 b1 ...: before my a come the a's and b's of the lower lanes
+        const int before = __popc(ma & lt_mask) + __popc(mb & lt_mask);
+        if (ha) dst[nout + before] = (uint16_t)ta;
+        if (hb) dst[nout + before + (ha ? 1 : 0)] = (uint16_t)tb;
+        nout += __popc(ma) + __popc(mb);
       }
+      if (lane == 0) ncand[o - o0] = (uint16_t)nout;
     }
     __syncthreads();
-    // ---- c. bitmap of the filled slots
-    for (int wd = warp; wd < ((rlen + 31) >> 5); wd += NW) {
-      const int slot = wd * 32 + lane;
-      const bool filled = slot < rlen && table[slot] != 0xFFFFu;
-      const uint32_t b = __ballot_sync(0xFFFFFFFFu, filled);
-      if (lane == 0) bitmap[wd] = b;
-    }
-    __syncthreads();
-    // ---- d. walk the filled slots of my bucket from the nearer end
-    if (!done && bs >= cb && bs <= hb) {
-      done = true;
-      const int s = bs * S - rlo, e1 = min(s + S, rlen) - 1;  // my slots [s, e1]
+    // ---- b. walk the candidates of my bucket from the nearer end, counting those inside my window
+    if (active && myord >= o0 && myord < o1) {
+      const uint16_t* spos = cand + (myord - o0) * S;
+      const int end = ncand[myord - o0];
       const bool fwd = 2 * rr < mpop;
-      const int want = fwd ? rr : mpop - 1 - rr;              // in-window candidates to skip
-      const int wfirst = s >> 5, wlast = e1 >> 5;
-      const uint32_t mfirst = 0xFFFFFFFFu << (s & 31), mlast = 0xFFFFFFFFu >> (31 - (e1 & 31));
-      int w = fwd ? wfirst : wlast;
-      const int wstop = fwd ? wlast : wfirst;
-      int cnt = 0;
+      const int want = fwd ? rr : mpop - 1 - rr;     // in-window candidates to skip
+      const int step = fwd ? 1 : -1;
+      int i = fwd ? 0 : end - 1;
+      int left = end;
+      int cnt = 0, fi = -1;
       if (want >= 0) {
-        while (true) {
-          uint32_t word = bitmap[w];
-          if (w == wfirst) word &= mfirst;
-          if (w == wlast) word &= mlast;
-          if (!fwd) word = __brev(word);
-          while (word) {
-            const int b = __ffs(word) - 1;
-            word &= word - 1;
-            const unsigned p = table[(w << 5) + (fwd ? b : 31 - b)];
-            if (in_window(p, bias, win)) {
+        for (; left >= 4; left -= 4, i += 4 * step) {
+          unsigned p0 = spos[i], p1 = spos[i + step], p2 = spos[i + 2 * step], p3 = spos[i + 3 * step];
+          int c0 = in_window(p0, bias, win), c1 = in_window(p1, bias, win);
+          int c2 = in_window(p2, bias, win), c3 = in_window(p3, bias, win);
+          int c = c0 + c1 + c2 + c3;
+          if (cnt + c > want) {                        // the target is one of these four
+            if (c0 && cnt == want) fi = i;
+            cnt += c0;
+            if (fi < 0 && c1 && cnt == want) fi = i + step;
+            cnt += c1;
+            if (fi < 0 && c2 && cnt == want) fi = i + 2 * step;
+            cnt += c2;
+            if (fi < 0) fi = i + 3 * step;
+            break;
+          }
+          cnt += c;
+        }
+        if (fi < 0) {
+          for (; left > 0; --left, i += step) {
+            if (in_window(spos[i], bias, win)) {
               if (cnt == want) {
-                found = p;
+                fi = i;
                 break;
               }
               ++cnt;
             }
           }
-          if (found != 0xFFFFFFFFu || w == wstop) break;
-          w += fwd ? 1 : -1;
         }
       }
+      if (fi >= 0) found = spos[fi];
     }
-    cursor = hb + 1;
   }
   // ---- epilogue: fetch the one value, mask, min/max of the masked output
   K kmin = Key<T>::kMax, kmax = 0;
@@ -671,7 +678,6 @@ __global__ void __launch_bounds__(kTile* kTile, 6) k_select(
     if (kmax > __ldcg(&minmax[1])) atomic_max_key(&minmax[1], kmax);
   }
 }
-
 
 // ------------------------------------------------------------------ small kernels (k <= 5)
 // For a 3x3 or 5x5 window the two-tier machinery is all overhead (the synoptic default is k = 3):
@@ -785,7 +791,7 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
   using K = typename Key<T>::type;
   const int H = p->H, W = p->W, k = p->k, half = k >> 1;
   K* minmax = reinterpret_cast<K*>(ws + p->off_minmax);
-  uint16_t* Rk = reinterpret_cast<uint16_t*>(ws + p->off_rank);
+  uint16_t* Ord = reinterpret_cast<uint16_t*>(ws + p->off_order);
   uint8_t* Bp = ws + p->off_bucket;
   uint8_t* bstar = ws + p->off_bstar;
   uint32_t* rres = reinterpret_cast<uint32_t*>(ws + p->off_rres);
@@ -822,9 +828,10 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
   const int S = p->blk_bucket;
   if (S < 1 || (nelem + S - 1) / S > kBuckets || nelem > 65535 || S > kSelSlots) return CHIPS_E_ARG;
   if (stages & 1) {  // rank + bucket images of every block's halo-extended region
-    const size_t smem = block_sort_smem(nelem, (int)sizeof(K));
+    const size_t smem = block_sort_smem<T>(nelem);
+    if (nelem > SortCfg<T>::NT * SortCfg<T>::IT) return CHIPS_E_ARG;
     CHIPS_CUDA(cudaFuncSetAttribute(k_block_sort<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_block_sort<T><<<nblocks, kSortThreads, smem, st>>>(in, H, W, g, cx, cy, r, S, Rk, Bp, minmax);
+    k_block_sort<T><<<nblocks, SortCfg<T>::NT, smem, st>>>(in, H, W, g, cx, cy, r, S, Ord, Bp, minmax);
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }
@@ -851,7 +858,8 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
   if (stages & 8) {  // tier 2: one CTA per 16x16 tile
     const dim3 grid((rw + kTile - 1) / kTile, (rh + kTile - 1) / kTile);
 #define CHIPS_LAUNCH_SELECT(KT)                                                                             \
-    k_select<T, KT><<<grid, kTile * kTile, 0, st>>>(in, Rk, g, S, bstar, rres, H, W, rw, rh, cx, cy, r, out, \
+    k_rank_select<T, KT><<<grid, kTile * kTile, 0, st>>>(in, Ord, g, S, kSelSlots / S,                     \
+                                                         0xFFFFFFFFu / (uint32_t)p->blk_rows + 1u, bstar, rres, H, W, rw, rh, cx, cy, r, out, \
                                                     minmax, err)
     switch (k) {
       case 11: CHIPS_LAUNCH_SELECT(11); break;

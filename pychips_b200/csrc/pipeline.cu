@@ -71,7 +71,7 @@ extern "C" int chips_plan_init(chips_plan* p, int H, int W, int k, int h_bins, i
   const size_t n = (size_t)H * W, nr = (size_t)p->roi_w * p->roi_h;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
-  p->off_rank = take(nblk * p->bp_pitch * p->bp_rows * 2);
+  p->off_order = take(nblk * align_up((size_t)(128 + 2 * half) * p->bp_rows, 8) * 2);
   p->off_bucket = take(nblk * p->bp_pitch * p->bp_rows);
   p->off_bstar = take(n);
   p->off_rres = take(n * 4);

@@ -37,12 +37,12 @@ def test_struct_layouts_match_c(tmp_path):
         '#include <stdio.h>\n#include <stddef.h>\n#include "chips_b200.h"\n'
         'int main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(chips_result), sizeof(chips_plan),'
         ' offsetof(chips_result, n_samples), offsetof(chips_result, median_errors),'
-        ' offsetof(chips_plan, off_rank), offsetof(chips_plan, bytes));return 0;}\n')
+        ' offsetof(chips_plan, off_order), offsetof(chips_plan, bytes));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
     got = [C.sizeof(_lib.Result), C.sizeof(_lib.Plan), _lib.Result.n_samples.offset,
-           _lib.Result.median_errors.offset, _lib.Plan.off_rank.offset, _lib.Plan.bytes.offset]
+           _lib.Result.median_errors.offset, _lib.Plan.off_order.offset, _lib.Plan.bytes.offset]
     assert [int(v) for v in out] == got
 
 
@@ -104,10 +104,10 @@ def test_plan_block_geometry_is_consistent(H, W, k, r):
     assert all(o % 256 == 0 and o <= p.bytes for o in offs)
     nblk = p.blk_nbx * p.blk_nby
     assert p.off_bstar - p.off_bucket >= nblk * p.bp_pitch * p.bp_rows
-    assert p.off_bucket - p.off_rank >= nblk * p.bp_pitch * p.bp_rows * 2
+    assert p.off_bucket - p.off_order >= nblk * (128 + 2 * half) * p.bp_rows * 2
     # the block sort holds a halo-extended block in shared memory; 128 buckets of blk_bucket ranks
     nelem = (128 + 2 * half) * p.bp_rows
-    assert nelem <= 26624 and p.blk_bucket * 128 >= nelem > p.blk_bucket * 127 - 128
+    assert nelem <= 24576 and p.blk_bucket * 128 >= nelem > p.blk_bucket * 127 - 128
 
 
 def test_contour_structs_and_argument_errors(tmp_path):
