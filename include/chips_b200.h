@@ -35,7 +35,7 @@ extern "C" {
 /* pixels of one halo-extended median block that the block sort holds in shared memory
  * (keys + two index arrays): float32 / float64 storage                                  */
 #define CHIPS_MAX_BLOCK_ELEMS_F32 24576
-#define CHIPS_MAX_BLOCK_ELEMS_F64 17664
+#define CHIPS_MAX_BLOCK_ELEMS_F64 17600
 #define CHIPS_PROB_BINS 20    /* chips.py:445 np.linspace(0,1,21)                     */
 
 /* Per-image result record written by the device epilogues (one per detection). */
