@@ -122,8 +122,8 @@ def test_median_fast_vs_bruteforce_full_size(n, k):
 @pytest.mark.parametrize("q,k,dtype", [(0.5, 31, np.float32), (4.0, 51, np.float32), (1.0, 11, np.float64),
                                        (25.0, 51, np.float64)])
 def test_median_fast_quantised_intensities(q, k, dtype):
-    """Instrument-like quantised data: heavy duplicates turn quantile boundaries into point
-    buckets (median known after tier 1).  Bit-exact against scipy and the brute-force kernel."""
+    """Instrument-like quantised data: heavy duplicates (ties are broken by the block sort, every
+    pixel still has a unique rank).  Bit-exact against scipy and the brute-force kernel."""
     img, r = synth.synthetic_disk(600, 5)
     img = (np.round(img / q) * q).astype(dtype)
     got, res = gpu_medfilt(img, k)
@@ -133,6 +133,54 @@ def test_median_fast_quantised_intensities(q, k, dtype):
     fast, res = gpu_medfilt(img, k, c, c, r)
     slow, _ = gpu_medfilt(img, k, c, c, r, brute=True)
     assert res.median_errors == 0 and np.array_equal(fast, slow)
+
+
+@pytest.mark.parametrize("k", [11, 51])
+def test_median_float64_keys_that_agree_in_their_top_32_bits(k):
+    """float64 storage: the block sort first orders the top 32 significant key bits only and
+    re-sorts a block on all its bits when that order is not exact.  Values that differ in the
+    last mantissa bits only, next to zeros and a huge outlier (so that the 32-bit window sits far
+    above those bits), force the second attempt; plain noise takes the first."""
+    rng = np.random.default_rng(k)
+    close = 1.0 + rng.integers(0, 1 << 20, size=(180, 210)).astype(np.float64) * 2.0 ** -52
+    img = close.copy()
+    img[rng.random(img.shape) < 0.2] = 0.0
+    img[7, 9] = 1e9
+    assert len(np.unique(img)) > 10000 and not np.array_equal(img.astype(np.float32), img)
+    for a in (img, rng.normal(100.0, 30.0, size=(180, 210))):
+        got, res = gpu_medfilt(a, k)
+        assert res.median_errors == 0
+        assert np.array_equal(got, signal.medfilt2d(a, k))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("k", [7, 31, 73])
+def test_median_flat_two_valued_and_maximum_kernel(k, dtype):
+    """Inputs that used to take the overflow paths of the tile refinement (every pixel of a region
+    in one bucket): constant, two-valued, a step edge; and the largest supported kernel (73)."""
+    rng = np.random.default_rng(5 * k)
+    flat = np.full((140, 170), 12.5, dtype)
+    two = np.where(rng.random((140, 170)) < 0.5, 3.0, 4.0).astype(dtype)
+    step = np.zeros((140, 170), dtype)
+    step[:, 85:] = 1.0 + (rng.random((140, 85)) * (1e-3 if dtype == np.float64 else 0)).astype(dtype)
+    for img in (flat, two, step):
+        got, res = gpu_medfilt(img, k)
+        assert res.median_errors == 0
+        assert np.array_equal(got, signal.medfilt2d(img, k))
+        got, res = gpu_medfilt(img, k, 85, 70, 60)
+        ref = signal.medfilt2d(img, k)
+        yy, xx = np.mgrid[:140, :170]
+        on = (xx - 85) ** 2 + (yy - 70) ** 2 <= 60 ** 2
+        assert res.median_errors == 0 and np.array_equal(got[on], ref[on]) and not got[~on].any()
+
+
+def test_median_rejects_kernels_beyond_the_block_sort():
+    from pychips_b200 import _lib
+    import ctypes as C
+    p = _lib.Plan()
+    lib = _lib.load()
+    assert lib.chips_plan_init(C.byref(p), 512, 512, 75, 8, 1, 4, 0, 0, -1) == -1
+    assert lib.chips_plan_init(C.byref(p), 512, 512, 73, 8, 1, 8, 0, 0, -1) == 0 and p.blk_rows == 16
 
 
 def test_median_quantised_full_size_is_not_slower():
