@@ -52,7 +52,9 @@ typedef struct chips_result {
   int32_t n_kept[CHIPS_MAX_T];/* kept top-level components per threshold                  */
   int32_t n_comp[CHIPS_MAX_T];/* top-level components per threshold before the area cut   */
   int32_t median_errors;      /* internal consistency counter of the median (must be 0)  */
-  int32_t pad_;
+  int32_t n_nonfinite;        /* NaN / +-Inf pixels met by the median's input pass (the reference's
+                               * scipy.signal.medfilt2d result is undefined for them): the host
+                               * classes raise when it is not 0                               */
 } chips_result;
 
 /* Byte offsets of every buffer inside one workspace blob (all 256-byte aligned). */
@@ -125,9 +127,11 @@ int chips_minmax(const void* filt, const chips_plan* plan, int cx, int cy, int r
 int chips_histogram(const void* filt, const chips_plan* plan, int cx, int cy, int r, void* ws,
                     void* stream);
 /* replaces: density, h_thresh, scipy.signal.find_peaks, bound, peaks, limits
- *           chips.py:239-244, :356-357.  h_thresh_in: NaN = compute max(h)/ratio. */
+ *           chips.py:239-244, :356-357.  h_thresh_in: NaN = compute max(h)/ratio.
+ * offsets: plan->T HOST doubles = np.arange(threshold_range[0], threshold_range[1]) (chips.py:352;
+ *           List[float] in the reference: any start, unit steps), read before the call returns. */
 int chips_select_threshold(const chips_plan* plan, double ht_peak_ratio, double h_thresh_in,
-                           int t0, int t1, void* ws, void* stream);
+                           const double* offsets, void* ws, void* stream);
 
 /* ---- rows F+G  replaces: the `for lim in limits` mask assigns chips.py:360-375 and
  *                calculate_prob chips.py:378,432-450 (all T in one pass) ------------- */
@@ -159,9 +163,28 @@ int chips_prob_stack(const chips_plan* plan, double lower_lim, void* out, int ou
 
 /* ---- rows B..I fused: one full detection enqueued on `stream` --------------------- */
 int chips_detect(const void* image, const chips_plan* plan, int cx, int cy, int r,
-                 double ht_peak_ratio, double h_thresh_in, int t0, int t1,
+                 double ht_peak_ratio, double h_thresh_in, const double* offsets,
                  double porb_threshold, double area_threshold, uint8_t* maps_or_null,
                  void* ws, void* stream);
+
+/* ---- batched detections (SURVEY.md §8(b) "batched variants", §8(e) time series).  The reference has
+ *      no batching: one Chips object handles one RegisterAIA (chips.py:110-150) and the caller
+ *      loops over dates; this is that loop for a non-Python host.  The handle owns n_slots
+ *      in-flight detections (stream, device image, workspace, one instantiated CUDA graph per
+ *      geometry).  images[i]: H x W x elem bytes, host (pinned for asynchronous copies) or device;
+ *      only chips_input_rect of each is read.  results[i]: the record.  keep_or_null[i] (may be
+ *      NULL per image): H x W bytes, the level-encoded final map (map_t = keep <= t).
+ *      prob_sum_or_null: H x W floats, sum over the batch of the plots.py:305-322 probability
+ *      maps (prob_lower_lim as in chips_prob_stack), accumulated in image order.
+ *      Returns when every output is on the host.  masked handles take r[i] >= 0, others r[i] < 0. */
+int chips_batch_create(void** handle, int H, int W, int k, int h_bins, int T, int elem, int masked,
+                       int n_slots);
+int chips_detect_batch(void* handle, int B, const void* const* images, int images_on_device,
+                       const int32_t* cx, const int32_t* cy, const int32_t* r,
+                       double ht_peak_ratio, double h_thresh_in, const double* offsets,
+                       double porb_threshold, double area_threshold, chips_result* results,
+                       uint8_t* const* keep_or_null, float* prob_sum_or_null, double prob_lower_lim);
+int chips_batch_destroy(void* handle);
 
 /* ---- SURVEY.md §8(f) row 1  replaces: CleanFl.create_coronal_hole_candidates,
  *      cleanup.py:69-200 (three co-registered wavelengths of the same size; the reference's

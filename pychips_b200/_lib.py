@@ -20,7 +20,7 @@ class Result(C.Structure):
         ("limit_0", C.c_double), ("limits", C.c_double * MAX_T), ("probs", C.c_double * MAX_T),
         ("n_samples", C.c_int64), ("n_peaks", C.c_int32), ("n_thresholds", C.c_int32),
         ("n_kept", C.c_int32 * MAX_T), ("n_comp", C.c_int32 * MAX_T),
-        ("median_errors", C.c_int32), ("pad_", C.c_int32),
+        ("median_errors", C.c_int32), ("n_nonfinite", C.c_int32),
     ]
 
 
@@ -36,6 +36,16 @@ class Plan(C.Structure):
                  "off_result", "off_level", "off_fill", "off_keep", "off_probtab",
                  "off_parent_b", "off_parent_c", "off_area", "off_pending", "off_list2", "off_lvl",
                  "off_tiles", "off_ovf", "bytes")]
+
+
+def check_record(res) -> None:
+    """Raise for a detection record that must not be used (median self-check, non-finite input)."""
+    if res.n_nonfinite:
+        raise ChipsNativeError(
+            f"the image holds NaN/Inf inside the region the detection reads ({res.n_nonfinite} hits): "
+            "scipy.signal.medfilt2d is undefined there (chips.py:214-216); fill or mask the data first")
+    if res.median_errors:
+        raise ChipsNativeError(f"median filter self-check failed for {res.median_errors} pixels")
 
 
 class FlParams(C.Structure):
@@ -66,14 +76,17 @@ SIGNATURES = {
     "chips_medfilt2d_bruteforce": ([_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp], C.c_int),
     "chips_minmax": ([_vp, _PP, _i, _i, _i, _vp, _vp], C.c_int),
     "chips_histogram": ([_vp, _PP, _i, _i, _i, _vp, _vp], C.c_int),
-    "chips_select_threshold": ([_PP, _d, _d, _i, _i, _vp, _vp], C.c_int),
+    "chips_select_threshold": ([_PP, _d, _d, _vp, _vp, _vp], C.c_int),
     "chips_threshold_prob": ([_vp, _PP, _i, _i, _i, _d, _vp, _vp], C.c_int),
     "chips_cleanup": ([_PP, _i, _i, _i, _d, _d, _vp, _vp], C.c_int),
     "chips_expand_maps": ([_PP, _i, _vp, _vp, _vp], C.c_int),
     "chips_expand_map": ([_PP, _i, _i, _vp, _i, _vp, _vp], C.c_int),
     "chips_roots": ([_PP, _i, _i, _i, _i, _vp, _vp, _vp, _vp], C.c_int),
     "chips_prob_stack": ([_PP, _d, _vp, _i, _i, _vp, _vp], C.c_int),
-    "chips_detect": ([_vp, _PP, _i, _i, _i, _d, _d, _i, _i, _d, _d, _vp, _vp, _vp], C.c_int),
+    "chips_detect": ([_vp, _PP, _i, _i, _i, _d, _d, _vp, _d, _d, _vp, _vp, _vp], C.c_int),
+    "chips_batch_create": ([_vp, _i, _i, _i, _i, _i, _i, _i, _i], C.c_int),
+    "chips_detect_batch": ([_vp, _i, _vp, _i, _vp, _vp, _vp, _d, _d, _vp, _d, _d, _vp, _vp, _vp, _d], C.c_int),
+    "chips_batch_destroy": ([_vp], C.c_int),
     "chips_demote_f64": ([_vp, _vp, _sz, _vp, _vp], C.c_int),
     "chips_fl_workspace_bytes": ([_i, _i], C.c_size_t),
     "chips_fl_candidates": ([_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, C.POINTER(FlParams), _vp, _vp, _vp, _vp],

@@ -84,6 +84,7 @@ class Chips(object):
         self.device = engine.require_cuda(device)
         self._det = {}                   # id(disk) -> Detector
         self._img = {}                   # id(disk) -> device image
+        self._disks = {}                 # id(disk) -> disk: keeps the id alive as long as its detector
         if make_folder:
             self.get_base_folder()
 
@@ -99,6 +100,7 @@ class Chips(object):
                 delattr(disk, key)
         self._det.pop(id(disk), None)
         self._img.pop(id(disk), None)
+        self._disks.pop(id(disk), None)
 
     # ---- chips.py:110-150
     def run_CHIPS(self, wavelength: int = None, resolution: int = None,
@@ -159,22 +161,28 @@ class Chips(object):
         # np.zeros_like(raw.data) * np.nan: float32 stays float32, everything else -> float64
         return np.float32 if np.asarray(disk.raw.data).dtype == np.float32 else np.float64
 
+    def _filt_dtype(self, disk):
+        # chips.py:213-216 i_mask * medfilt2d(normalized.data): the mask follows raw.data, the median
+        # its input (float32 stays float32, everything else is float64)
+        nd = np.asarray(disk.normalized.data).dtype
+        return np.result_type(self._out_dtype(disk), np.float32 if nd == np.float32 else np.float64)
+
     def _detector(self, disk) -> Detector:
         det = self._det.get(id(disk))
         if det is None:
             with torch.cuda.device(self.device):
                 img, elem = engine.to_device_image(np.asarray(disk.normalized.data), self.device)
-                tr = np.arange(self.threshold_range[0], self.threshold_range[1])
-                if len(tr) < 1:
-                    raise ValueError("threshold_range selects no threshold")
-                t0 = int(tr[0])
-                if not np.array_equal(tr, t0 + np.arange(len(tr))):
-                    raise ValueError("threshold_range must produce unit-spaced integer offsets")
-                det = Detector(self._geometry(disk), self.medfilt_kernel, self.h_bins, t0,
-                               t0 + len(tr), elem, self.device)
+                # chips.py:352: List[float], any start, unit steps.  An empty range yields no
+                # regions in the reference: the stages before the thresholds still run (T = 1 plan)
+                t0, t1 = self.threshold_range[0], self.threshold_range[1]
+                self._no_thresholds = len(np.arange(t0, t1)) == 0
+                if self._no_thresholds:
+                    t0, t1 = 0, 1
+                det = Detector(self._geometry(disk), self.medfilt_kernel, self.h_bins, t0, t1, elem, self.device)
                 det.state = set()
             self._det[id(disk)] = det
             self._img[id(disk)] = img
+            self._disks[id(disk)] = disk
         return det
 
     def _ensure_filt(self, disk, det) -> None:
@@ -224,7 +232,7 @@ class Chips(object):
         if not hasattr(disk, "solar_filter"):
             det = self._detector(disk)
             img = self._img[id(disk)]
-            dt = self._out_dtype(disk)
+            dt = self._filt_dtype(disk)
             with torch.cuda.device(self.device):
                 det.medfilt(img)
             det.state.add("filt")
@@ -251,6 +259,7 @@ class Chips(object):
                 det.select_threshold(self.ht_peak_ratio, self.h_thresh)
                 det.state.add("hist")
                 res = det.result()
+                engine._lib.check_record(res)
                 if self.h_thresh is None:
                     self.h_thresh = np.float64(res.h_thresh)       # sticky, chips.py:240-241
                 npk = int(res.n_peaks)
@@ -318,6 +327,9 @@ class Chips(object):
         if not hasattr(disk, "solar_ch_regions"):
             if len(disk.histogram.peaks) > 0:
                 det = self._detector(disk)
+                if self._no_thresholds:              # np.arange(...) empty: `for lim in limits` never runs
+                    disk.set_value("solar_ch_regions", Namespace())
+                    return
                 dt = self._out_dtype(disk)
                 with torch.cuda.device(self.device):
                     if "hist" not in det.state:      # results memoised on `disk` by another object
@@ -331,10 +343,9 @@ class Chips(object):
                             det._pp, engine._ptr(self.cf.bits), engine._ptr(det.ws),
                             engine._stream_ptr()), "chips_apply_candidates")
                     det.cleanup(self.area_threshold)
+                    det.state.add("maps")
                     res = det.result()
-                if res.median_errors:
-                    raise engine._lib.ChipsNativeError(
-                        f"median filter self-check failed for {res.median_errors} pixels")
+                engine._lib.check_record(res)
                 limit_0 = np.float64(res.limit_0)
                 dtmp_map = {}
                 traced_all = {}
@@ -380,7 +391,16 @@ class Chips(object):
     def labels(self, disk, lim_index: int):
         """Canonical component labels (raster order of first pixel) of the hole-filled mask
         at threshold `lim_index`, and 2*contourArea per label."""
-        return self._detector(disk).labels(lim_index)
+        return self._device_results(disk).labels(lim_index)
+
+    def _device_results(self, disk) -> Detector:
+        """The detector of `disk`, with the final maps of THIS object's run resident (a disk whose
+        results were memoised by another object has nothing on this object's device workspace)."""
+        det = self._detector(disk)
+        if "maps" not in det.state:
+            raise RuntimeError("no detection of this disk has run on this Chips object: call "
+                               "run_CHIPS(clear_prev_runs=True) / extract_CHs_CHBs first")
+        return det
 
     # ---- chips.py:512-590.  The region cube is packed on the device (chips_pack_cube); the file
     # is written with netCDF4 in the reference's group layout when that package is importable,
@@ -427,7 +447,7 @@ class Chips(object):
     def region_cube(self, disk):
         """(float32 [res, res, L] cube with cube[:, :, i] = map of the i-th threshold, probs) —
         the arrays `to_netcdf` stores (chips.py:570-586)."""
-        det = self._detector(disk)
+        det = self._device_results(disk)
         with torch.cuda.device(self.device):
             cube = det.pack_cube(0).cpu().numpy()
         probs = [r.prob for r in disk.solar_ch_regions.__dict__.values()]

@@ -25,7 +25,8 @@ static inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory
 
 constexpr int kNumSM = 148;   // B200: 2 dies x 74 SMs
 
-// ---- order-preserving integer keys of IEEE floats (NaN-free input assumed) ----------
+// ---- order-preserving integer keys of IEEE floats (NaN-free input: the median's input pass
+//      counts non-finite pixels in chips_result.n_nonfinite and the host classes raise) ----------
 template <typename T> struct Key;
 template <> struct Key<float> {
   using type = uint32_t;
@@ -51,6 +52,12 @@ template <> struct Key<double> {
   }
   static constexpr uint64_t kMax = 0xFFFFFFFFFFFFFFFFull;
 };
+
+// NaN / +-Inf: all exponent bits set
+__device__ __forceinline__ bool nonfinite(float v) { return (__float_as_uint(v) & 0x7F800000u) == 0x7F800000u; }
+__device__ __forceinline__ bool nonfinite(double v) {
+  return ((uint32_t)((uint64_t)__double_as_longlong(v) >> 32) & 0x7FF00000u) == 0x7FF00000u;
+}
 
 // filled cv2.circle == integer test
 __device__ __forceinline__ bool on_disk(int x, int y, int cx, int cy, int r) {

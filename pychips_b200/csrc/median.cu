@@ -96,7 +96,8 @@ static size_t block_sort_smem(int n) {   // keys[n] + two orders of NT * chunk s
 template <typename T>
 __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
     const T* __restrict__ img, int H, int W, BlockGeom g, int cx, int cy, int r, int S,
-    uint16_t* __restrict__ Ord, uint8_t* __restrict__ Bp, typename Key<T>::type* __restrict__ minmax) {
+    uint16_t* __restrict__ Ord, uint8_t* __restrict__ Bp, typename Key<T>::type* __restrict__ minmax,
+    int* __restrict__ n_nonfinite) {
   using K = typename Key<T>::type;
   constexpr int NT = SortCfg<T>::NT, IT = SortCfg<T>::IT, VEC = SortCfg<T>::VEC, NW = NT / 32;
   constexpr int DB = SortCfg<T>::DB, ND = 1 << DB;
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
 
   // ---- load the region as ordered keys (coalesced rows), identity order, key range
   K lmin = Key<T>::kMax, lmax = 0;
+  bool bad_value = false;
   for (int row = warp; row < eh; row += NW) {
     const int y = Y - g.half + row;
     const bool yin = y >= 0 && y < H;
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
     for (int lx = lane; lx < ew; lx += 32) {
       const int x = X - g.half + lx;
       const T v = (yin && x >= 0 && x < W) ? __ldg(irow + x) : (T)0;   // medfilt2d zero padding
+      bad_value |= nonfinite(v);
       const K key = Key<T>::enc(v);
       const int e = row * ew + lx;
       keys[e] = key;
@@ -147,6 +150,7 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
     s_min[warp] = lmin;
     s_max[warp] = lmax;
   }
+  if (bad_value) atomicAdd(n_nonfinite, 1);     // (pixels in block halos are met more than once)
   __syncthreads();
   K kmin = s_min[lane % NW], kmax = s_max[lane % NW];
 #pragma unroll
@@ -760,7 +764,8 @@ __global__ void __launch_bounds__(kTile* kTile, 8) k_rank_select(
 template <typename T, int KS>
 __global__ void __launch_bounds__(256) k_median_small(const T* __restrict__ img, T* __restrict__ out, int H,
                                                       int W, int rx0, int ry0, int rw, int rh, int cx, int cy,
-                                                      int r, typename Key<T>::type* __restrict__ minmax) {
+                                                      int r, typename Key<T>::type* __restrict__ minmax,
+                                                      int* __restrict__ n_nonfinite) {
   using K = typename Key<T>::type;
   constexpr int N = KS * KS, R = (N - 1) / 2, HALF = KS / 2;
   const int x = rx0 + blockIdx.x * 32 + (threadIdx.x & 31), y = ry0 + blockIdx.y * 8 + (threadIdx.x >> 5);
@@ -768,17 +773,19 @@ __global__ void __launch_bounds__(256) k_median_small(const T* __restrict__ img,
   K kmin = Key<T>::kMax, kmax = 0;
   if (active) {
     K a[N];
-    const K zero = Key<T>::enc((T)0);
+    bool bad_value = false;
 #pragma unroll
     for (int dy = 0; dy < KS; ++dy) {
       const int iy = y + dy - HALF;
 #pragma unroll
       for (int dx = 0; dx < KS; ++dx) {
         const int ix = x + dx - HALF;
-        a[dy * KS + dx] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? Key<T>::enc(__ldg(&img[(size_t)iy * W + ix]))
-                                                                   : zero;     // medfilt2d zero padding
+        const T v = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(&img[(size_t)iy * W + ix]) : (T)0;   // zero padding
+        bad_value |= nonfinite(v);
+        a[dy * KS + dx] = Key<T>::enc(v);
       }
     }
+    if (bad_value) atomicAdd(n_nonfinite, 1);
 #pragma unroll
     for (int i = 0; i <= R; ++i) {
 #pragma unroll
@@ -849,11 +856,14 @@ __global__ void __launch_bounds__(kHuangThreads) k_median_brute(const T* __restr
 
 template <typename T>
 __global__ void k_copy_masked(const T* __restrict__ in, T* __restrict__ out, int H, int W, int cx,
-                              int cy, int r) {
+                              int cy, int r, int* __restrict__ n_nonfinite) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)H * W) return;
   int y = (int)(i / W), x = (int)(i % W);
-  out[i] = on_disk(x, y, cx, cy, r) ? in[i] : (T)0;
+  const bool on = on_disk(x, y, cx, cy, r);
+  const T v = on ? in[i] : (T)0;
+  if (nonfinite(v)) atomicAdd(n_nonfinite, 1);
+  out[i] = v;
 }
 
 // ------------------------------------------------------------------ host-side launchers
@@ -874,12 +884,12 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
 
   if (stages & 1) {
     CHIPS_CUDA(cudaMemsetAsync(out, 0, (size_t)H * W * sizeof(T), st));
-    CHIPS_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+    CHIPS_CUDA(cudaMemsetAsync(err, 0, 2 * sizeof(int), st));   // median_errors, n_nonfinite
   }
   if (k == 1) {
     // medfilt2d with a 1x1 kernel is the identity (then masked); min/max via k_minmax later
     size_t n = (size_t)H * W;
-    k_copy_masked<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, H, W, cx, cy, r);
+    k_copy_masked<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, H, W, cx, cy, r, err + 1);
     CHIPS_CHECK_LAUNCH();
     count_launch();
     return CHIPS_OK;
@@ -889,8 +899,8 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
       CHIPS_CUDA(cudaMemsetAsync(&minmax[0], 0xFF, sizeof(K), st));     // running min = kMax
       CHIPS_CUDA(cudaMemsetAsync(&minmax[1], 0x00, sizeof(K), st));     // running max = 0
       dim3 grid((rw + 31) / 32, (rh + 7) / 8);
-      if (k == 3) k_median_small<T, 3><<<grid, 256, 0, st>>>(in, out, H, W, rx0, ry0, rw, rh, cx, cy, r, minmax);
-      else k_median_small<T, 5><<<grid, 256, 0, st>>>(in, out, H, W, rx0, ry0, rw, rh, cx, cy, r, minmax);
+      if (k == 3) k_median_small<T, 3><<<grid, 256, 0, st>>>(in, out, H, W, rx0, ry0, rw, rh, cx, cy, r, minmax, err + 1);
+      else k_median_small<T, 5><<<grid, 256, 0, st>>>(in, out, H, W, rx0, ry0, rw, rh, cx, cy, r, minmax, err + 1);
       CHIPS_CHECK_LAUNCH();
       count_launch();
     }
@@ -907,7 +917,7 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
       if (sort_chunk<T>(nelem) > SortCfg<T>::IT || smem + kStatic > 227 * 1024) return CHIPS_E_ARG;
     }
     CHIPS_CUDA(cudaFuncSetAttribute(k_block_sort<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_block_sort<T><<<nblocks, SortCfg<T>::NT, smem, st>>>(in, H, W, g, cx, cy, r, S, Ord, Bp, minmax);
+    k_block_sort<T><<<nblocks, SortCfg<T>::NT, smem, st>>>(in, H, W, g, cx, cy, r, S, Ord, Bp, minmax, err + 1);
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }

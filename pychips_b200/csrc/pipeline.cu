@@ -115,17 +115,17 @@ __global__ void k_copy_level_to_keep(const uint8_t* __restrict__ lev, uint8_t* _
 }
 
 extern "C" int chips_detect(const void* image, const chips_plan* plan, int cx, int cy, int r,
-                            double ht_peak_ratio, double h_thresh_in, int t0, int t1,
+                            double ht_peak_ratio, double h_thresh_in, const double* offsets,
                             double porb_threshold, double area_threshold, uint8_t* maps_or_null,
                             void* ws, void* stream) {
-  if (!image || !plan || !ws) return CHIPS_E_ARG;
+  if (!image || !plan || !ws || !offsets) return CHIPS_E_ARG;
   unsigned char* w = (unsigned char*)ws;
   void* filt = w + plan->off_filt;
   int rc;
   if ((rc = chips_medfilt2d(image, filt, plan, cx, cy, r, ws, stream))) return rc;
   if (plan->k == 1 && (rc = chips_minmax(filt, plan, cx, cy, r, ws, stream))) return rc;
   if ((rc = chips_histogram(filt, plan, cx, cy, r, ws, stream))) return rc;
-  if ((rc = chips_select_threshold(plan, ht_peak_ratio, h_thresh_in, t0, t1, ws, stream))) return rc;
+  if ((rc = chips_select_threshold(plan, ht_peak_ratio, h_thresh_in, offsets, ws, stream))) return rc;
   if ((rc = chips_threshold_prob(filt, plan, cx, cy, r, porb_threshold, ws, stream))) return rc;
   if (plan->masked) {
     double disk_area = 3.141592653589793 * (double)((long long)r * r);   // np.pi * r**2

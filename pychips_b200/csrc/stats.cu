@@ -155,8 +155,13 @@ __global__ void __launch_bounds__(256) k_hist(const T* __restrict__ filt, int W,
 }
 
 // ------------------------------------------------------------------ threshold selection
+struct ThresholdOffsets {   // np.arange(threshold_range[0], threshold_range[1]) (chips.py:352), by value
+  double v[CHIPS_MAX_T];
+};
+
 __global__ void __launch_bounds__(1024) k_select(const long long* __restrict__ counts, int nbins,
-                                                 double ratio, double h_thresh_in, int t0, int T,
+                                                 double ratio, double h_thresh_in,
+                                                 const ThresholdOffsets offs, int T,
                                                  double* __restrict__ density,
                                                  double* __restrict__ edges,
                                                  double* __restrict__ bound, int* __restrict__ peaks,
@@ -249,8 +254,8 @@ __global__ void __launch_bounds__(1024) k_select(const long long* __restrict__ c
     if (res->n_peaks > 0) {
       double l0 = bound[peaks[0]];
       if (tid == 0) res->limit_0 = l0;
-      // np.round(limit_0 + arange(t0,t1), 4) = rint(x * 1e4) / 1e4
-      double xv = __dadd_rn(l0, (double)(t0 + tid));
+      // np.round(limit_0 + threshold_range, 4) = rint(x * 1e4) / 1e4
+      double xv = __dadd_rn(l0, offs.v[tid]);
       res->limits[tid] = __ddiv_rn(rint(__dmul_rn(xv, 10000.0)), 10000.0);
     } else {
       if (tid == 0) res->limit_0 = nan("");
@@ -497,15 +502,16 @@ extern "C" int chips_histogram(const void* filt, const chips_plan* plan, int cx,
 }
 
 extern "C" int chips_select_threshold(const chips_plan* plan, double ht_peak_ratio,
-                                      double h_thresh_in, int t0, int t1, void* ws, void* stream) {
-  if (!plan || !ws) return CHIPS_E_ARG;
-  int T = t1 - t0;
-  if (T < 0) T = 0;
-  if (T != plan->T || T > CHIPS_MAX_T) return CHIPS_E_ARG;
+                                      double h_thresh_in, const double* offsets, void* ws, void* stream) {
+  if (!plan || !ws || !offsets) return CHIPS_E_ARG;
+  const int T = plan->T;
+  if (T < 1 || T > CHIPS_MAX_T) return CHIPS_E_ARG;
+  ThresholdOffsets offs;
+  for (int i = 0; i < CHIPS_MAX_T; ++i) offs.v[i] = i < T ? offsets[i] : 0.0;
   unsigned char* w = (unsigned char*)ws;
   k_select<<<1, 1024, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const long long*>(w + plan->off_counts), plan->h_bins, ht_peak_ratio,
-      h_thresh_in, t0, T, reinterpret_cast<double*>(w + plan->off_density),
+      h_thresh_in, offs, T, reinterpret_cast<double*>(w + plan->off_density),
       reinterpret_cast<double*>(w + plan->off_edges), reinterpret_cast<double*>(w + plan->off_bound),
       reinterpret_cast<int*>(w + plan->off_peaks), reinterpret_cast<chips_result*>(w + plan->off_result));
   CHIPS_CHECK_LAUNCH();

@@ -54,13 +54,17 @@ class Detector:
     (`chips_detect`).  All calls only enqueue on the current torch stream.
     """
 
-    def __init__(self, geom: Geometry, k: int, h_bins: int, t0: int, t1: int, elem: int = 4,
+    def __init__(self, geom: Geometry, k: int, h_bins: int, t0, t1, elem: int = 4,
                  device=None, ws: torch.Tensor | None = None):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.geom = geom
-        self.k, self.h_bins, self.t0, self.t1, self.elem = int(k), int(h_bins), int(t0), int(t1), elem
-        self.T = max(0, self.t1 - self.t0)
+        self.k, self.h_bins, self.t0, self.t1, self.elem = int(k), int(h_bins), t0, t1, elem
+        # chips.py:352 np.arange(threshold_range[0], threshold_range[1]): List[float] in the
+        # reference, any start, unit steps; the offsets go to the device as they are
+        self.offsets = np.ascontiguousarray(np.arange(t0, t1), dtype=np.float64)
+        self._offp = self.offsets.ctypes.data
+        self.T = len(self.offsets)
         if self.T < 1:
             raise ValueError("threshold_range must span at least one threshold")
         self.plan = Plan()
@@ -198,7 +202,7 @@ class Detector:
         for fn, args in ((self.lib.chips_minmax, (_ptr(self.filt), qp, *self._g())),
                          (self.lib.chips_histogram, (_ptr(self.filt), qp, *self._g()))):
             _lib.check(fn(*args, _ptr(self.ws), _stream_ptr()), fn.__name__)
-        _lib.check(self.lib.chips_select_threshold(qp, float(ht_peak_ratio), h_in, self.t0, self.t1,
+        _lib.check(self.lib.chips_select_threshold(qp, float(ht_peak_ratio), h_in, self._offp,
                                                    _ptr(self.ws), _stream_ptr()), "chips_select_threshold")
 
         def tail(name, dtype, count):
@@ -217,8 +221,8 @@ class Detector:
 
     def select_threshold(self, ht_peak_ratio: float, h_thresh):
         h_in = float("nan") if h_thresh is None else float(h_thresh)
-        _lib.check(self.lib.chips_select_threshold(self._pp, float(ht_peak_ratio), h_in, self.t0,
-                                                   self.t1, _ptr(self.ws), _stream_ptr()),
+        _lib.check(self.lib.chips_select_threshold(self._pp, float(ht_peak_ratio), h_in, self._offp,
+                                                   _ptr(self.ws), _stream_ptr()),
                    "chips_select_threshold")
 
     def threshold_prob(self, porb_threshold: float, filt: torch.Tensor | None = None):
@@ -239,7 +243,7 @@ class Detector:
                area_threshold=1e-3, maps: torch.Tensor | None = None):
         h_in = float("nan") if h_thresh is None else float(h_thresh)
         _lib.check(self.lib.chips_detect(_ptr(image), self._pp, *self._g(), float(ht_peak_ratio),
-                                         h_in, self.t0, self.t1, float(porb_threshold),
+                                         h_in, self._offp, float(porb_threshold),
                                          float(area_threshold), _ptr(maps), _ptr(self.ws),
                                          _stream_ptr()), "chips_detect")
 

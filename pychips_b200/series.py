@@ -52,8 +52,8 @@ class SeriesRunner:
         self.device = engine.require_cuda(device)
         self.H, self.W = int(H), int(W)
         self.k, self.h_bins = int(medfilt_kernel), int(h_bins)
-        self.t0, self.t1 = int(threshold_range[0]), int(threshold_range[1])
-        self.T = self.t1 - self.t0
+        self.t0, self.t1 = threshold_range[0], threshold_range[1]
+        self.T = len(np.arange(self.t0, self.t1))
         self.ratio, self.porb, self.area_thr = ht_peak_ratio, porb_threshold, area_threshold
         self.masked = masked
         self.elem = elem
@@ -238,8 +238,7 @@ class PendingSeries:
         n, T = len(self._indices), self._T
         recs = [_lib.Result.from_buffer_copy(self._rec_host[i].numpy().tobytes()) for i in range(n)]
         for rc in recs:
-            if rc.median_errors:
-                raise _lib.ChipsNativeError("median self-check failed")
+            _lib.check_record(rc)
         self._result = SeriesResult(
             indices=self._indices,
             limit_0=np.array([rc.limit_0 for rc in recs]),

@@ -1,8 +1,9 @@
 """`SynopticChips` — drop-in for `syn_chips.SynopticChips` of the reference
 (`/root/reference/chips/syn_chips.py:24-274`): same constructor defaults (`:40-52`),
 `run_CHIPS()` (`:79-93`) and stage methods; no disk mask and no contour/cleanup step — the
-per-threshold map is the raw threshold mask (`:237-251`).  NaN-free maps are assumed (the
-reference's own median is order-dependent on NaNs)."""
+per-threshold map is the raw threshold mask (`:237-251`).  A map with NaN/Inf inside a median
+window raises `ChipsNativeError` (scipy's medfilt2d is undefined there: its selection depends on
+the visiting order of the NaNs)."""
 from __future__ import annotations
 
 import os
@@ -66,11 +67,14 @@ class SynopticChips(object):
             data = np.asarray(syn.raw.data)
             with torch.cuda.device(self.device):
                 img, elem = engine.to_device_image(data, self.device)
-                tr = np.arange(self.threshold_range[0], self.threshold_range[1])
-                t0 = int(tr[0])
+                # syn_chips.py:229: List[float], any start, unit steps; an empty range yields no regions
+                t0, t1 = self.threshold_range[0], self.threshold_range[1]
+                self._no_thresholds = len(np.arange(t0, t1)) == 0
+                if self._no_thresholds:
+                    t0, t1 = 0, 1
                 H, W = data.shape
                 self._det = Detector(Geometry(int(H), int(W), 0, 0, -1), self.medfilt_kernel,
-                                     self.h_bins, t0, t0 + len(tr), elem, self.device)
+                                     self.h_bins, t0, t1, elem, self.device)
                 self._det.state = set()
             self._img = img
         return self._det
@@ -96,16 +100,9 @@ class SynopticChips(object):
         if not hasattr(synoptic_map, "histogram"):
             det = self._detector(synoptic_map)
             with torch.cuda.device(self.device):
-                if "filt" not in det.state:
-                    host = np.ascontiguousarray(synoptic_map.solar_filter)
-                    det.filt.copy_(torch.from_numpy(host).to(self.device).to(det.dtype))
-                    det.state.add("filt")
-                    det.histogram(recompute_minmax=True)
-                else:
-                    det.histogram()
-                det.select_threshold(self.ht_peak_ratio, self.h_thresh)
-                det.state.add("hist")
+                self._histogram_on_device(synoptic_map, det, self.h_thresh)
                 res = det.result()
+                engine._lib.check_record(res)
                 if self.h_thresh is None:
                     self.h_thresh = np.float64(res.h_thresh)
                 npk = int(res.n_peaks)
@@ -119,20 +116,36 @@ class SynopticChips(object):
                 peak_indexs=pidx))
         return
 
+    def _histogram_on_device(self, synoptic_map, det, h_thresh) -> None:
+        """Histogram + threshold selection of `solar_filter`; a filter memoised on the map by another
+        object (syn_chips.py:105 `hasattr` guard) is uploaded first."""
+        if "filt" not in det.state:
+            host = np.ascontiguousarray(synoptic_map.solar_filter)
+            det.filt.copy_(torch.from_numpy(host).to(self.device).to(det.dtype))
+            det.state.add("filt")
+            det.histogram(recompute_minmax=True)
+        else:
+            det.histogram()
+        det.select_threshold(self.ht_peak_ratio, h_thresh)
+        det.state.add("hist")
+
     # ---- syn_chips.py:218-254
     def extract_CHs_CHBs(self, synoptic_map) -> None:
         logger.info(f"Extract CHs and CHBs for different regions {synoptic_map.wavelength}")
         if not hasattr(synoptic_map, "solar_ch_regions"):
             if len(synoptic_map.histogram.peaks) > 0:
                 det = self._detector(synoptic_map)
+                if self._no_thresholds:              # np.arange(...) empty: `for lim in limits` never runs
+                    synoptic_map.set_value("solar_ch_regions", Namespace())
+                    return
                 dt = self._out_dtype(synoptic_map)
                 with torch.cuda.device(self.device):
+                    if "hist" not in det.state:      # results memoised on the map by another object
+                        self._histogram_on_device(synoptic_map, det, synoptic_map.histogram.h_thresh)
                     det.threshold_prob(self.porb_threshold)
                     det.cleanup(0.0)
                     res = det.result()
-                if res.median_errors:
-                    raise engine._lib.ChipsNativeError(
-                        f"median filter self-check failed for {res.median_errors} pixels")
+                engine._lib.check_record(res)
                 limit_0 = np.float64(res.limit_0)
                 dtmp_map = {}
                 for t in range(det.T):

@@ -28,10 +28,13 @@ DISK_CASES = {
     "disk_n192_k51": (192, 2, 1.0, dict(medfilt_kernel=51, h_bins=500, threshold_range=[0, 20])),
     "disk_n256_k5_t28": (256, 3, 1.0, dict(medfilt_kernel=5, h_bins=5000, threshold_range=[-3, 25])),
     "disk_n200_k7_wiped": (200, 4, 0.02, dict(medfilt_kernel=7, h_bins=500, threshold_range=[-3, 5])),
+    # List[float] threshold_range (chips.py:56): np.arange(-2.5, 6.25) = -2.5, -1.5, ..., 5.5
+    "disk_n192_k11_frange": (192, 6, 1.0, dict(medfilt_kernel=11, h_bins=500, threshold_range=[-2.5, 6.25])),
 }
 SYN_CASES = {
     "syn_180x360_k3": (180, 360, 0, dict(medfilt_kernel=3, h_bins=5000, threshold_range=[-5, 20])),
     "syn_96x240_k11": (96, 240, 1, dict(medfilt_kernel=11, h_bins=500, threshold_range=[-5, 20])),
+    "syn_90x200_k5_frange": (90, 200, 2, dict(medfilt_kernel=5, h_bins=1000, threshold_range=[0.1, 7.3])),
 }
 
 
@@ -179,9 +182,13 @@ if __name__ == "__main__":
         for name, (n, seed, kw) in FL_CASES.items():
             make_fl(name, n, seed, kw)
         sys.exit(0)
+    only = set(sys.argv[1:])             # optional: names of the cases to (re)generate
     for name, (n, seed, scale, kw) in DISK_CASES.items():
-        make_disk(name, n, seed, scale, kw)
+        if not only or name in only:
+            make_disk(name, n, seed, scale, kw)
     for name, (h, w, seed, kw) in SYN_CASES.items():
-        make_syn(name, h, w, seed, kw)
+        if not only or name in only:
+            make_syn(name, h, w, seed, kw)
     for name, (n, seed, kw) in FL_CASES.items():
-        make_fl(name, n, seed, kw)
+        if not only or name in only:
+            make_fl(name, n, seed, kw)

@@ -78,9 +78,11 @@ def test_null_pointers_are_rejected_without_touching_the_gpu():
     assert lib.chips_histogram(None, C.byref(p), 32, 32, 20, None, None) == -1
     assert lib.chips_threshold_prob(None, C.byref(p), 32, 32, 20, 0.8, None, None) == -1
     assert lib.chips_cleanup(C.byref(p), 32, 32, 20, 1.0, 1e-3, None, None) == -1
-    assert lib.chips_detect(None, C.byref(p), 32, 32, 20, 5.0, float("nan"), 0, 3, 0.8, 1e-3,
+    offs = (C.c_double * 3)(0.0, 1.0, 2.0)
+    assert lib.chips_detect(None, C.byref(p), 32, 32, 20, 5.0, float("nan"), offs, 0.8, 1e-3,
                             None, None, None) == -1
-    assert lib.chips_select_threshold(C.byref(p), 5.0, float("nan"), 0, 7, None, None) == -1
+    assert lib.chips_select_threshold(C.byref(p), 5.0, float("nan"), None, None, None) == -1
+    assert lib.chips_select_threshold(C.byref(p), 5.0, float("nan"), offs, None, None) == -1
     assert lib.chips_medfilt2d_bruteforce(None, None, 8, 8, 3, 4, 0, 0, -1, None) == -1
 
 

@@ -245,13 +245,13 @@ def compare_disk(d, g_filt, g_hbase, g_hbins, g_bound, g_peaks, g_lims, g_probs,
 
 
 @pytest.mark.parametrize("name", ["disk_n256_k11", "disk_n256_k31_211", "disk_n192_k51",
-                                  "disk_n256_k5_t28", "disk_n200_k7_wiped"])
+                                  "disk_n256_k5_t28", "disk_n200_k7_wiped", "disk_n192_k11_frange"])
 def test_disk_pipeline_vs_reference_golden(name):
     g = load_golden(name)
     n = g["image"].shape[0]
     c, d = run_gpu_disk(g["image"], int(g["pixel_radius"]),
                         medfilt_kernel=int(g["kw_medfilt_kernel"]), h_bins=int(g["kw_h_bins"]),
-                        threshold_range=[int(v) for v in g["kw_threshold_range"]])
+                        threshold_range=[v.item() for v in g["kw_threshold_range"]])
     T = len(g["limits"])
     maps = np.unpackbits(g["maps"])[:T * n * n].reshape(T, n, n)
     raw = np.unpackbits(g["raw_maps"])[:T * n * n].reshape(T, n, n)
@@ -264,7 +264,8 @@ def test_disk_pipeline_vs_reference_golden(name):
 
 
 @pytest.mark.parametrize("n,k,hb,tr,seed", [(512, 11, 500, [0, 20], 7), (384, 31, 1000, [-3, 11], 8),
-                                            (320, 51, 500, [0, 20], 9), (512, 3, 20000, [-3, 25], 10)])
+                                            (320, 51, 500, [0, 20], 9), (512, 3, 20000, [-3, 25], 10),
+                                            (256, 7, 500, [-0.75, 9.5], 11), (256, 7, 500, [3, 3], 12)])
 def test_disk_pipeline_vs_oracle_seeded(n, k, hb, tr, seed):
     img, r = synth.synthetic_disk(n, seed)
     d_or = synth.FakeDisk(img.astype(np.float64), r)
@@ -287,6 +288,39 @@ def test_disk_pipeline_vs_oracle_seeded(n, k, hb, tr, seed):
                  d_or.histogram.bound, np.array(d_or.histogram.peaks), lims, probs, raw, maps, st, c)
 
 
+def test_nan_and_inf_inputs_raise_instead_of_returning_garbage():
+    """scipy.signal.medfilt2d is undefined for NaN inside a window (its selection depends on the
+    visiting order), so the reference's result cannot be matched: the drop-in classes raise.  A
+    NaN that no on-disk window reads (far outside the disk) changes nothing."""
+    from pychips_b200 import Chips, SynopticChips
+    from pychips_b200._lib import ChipsNativeError
+    from pychips_b200 import series
+    img, r = synth.synthetic_disk(256, 3)
+    c = 128
+    for bad, k in ((np.nan, 11), (np.inf, 11), (np.nan, 3), (-np.inf, 1)):
+        a = img.astype(np.float64)
+        a[c + 5, c - 7] = bad
+        d = synth.FakeDisk(a, r)
+        with pytest.raises(ChipsNativeError, match="NaN/Inf"):
+            Chips(synth.FakeAIA(d), base_folder="/tmp/chips_b200_test/", medfilt_kernel=k).run_CHIPS()
+    a = img.astype(np.float64)
+    a[0, 0] = np.nan                                     # outside every window the detection reads
+    _, d = run_gpu_disk(a, r, medfilt_kernel=11)
+    _, d0 = run_gpu_disk(img, r, medfilt_kernel=11)
+    assert np.array_equal(d.solar_filter.filt_disk, d0.solar_filter.filt_disk)
+    assert list(d.solar_ch_regions.__dict__) == list(d0.solar_ch_regions.__dict__)
+    syn = synth.synthetic_synoptic(96, 240, 1).astype(np.float32)
+    syn[3, 100] = np.nan                                  # an unfilled polar pixel
+    sm = synth.FakeSynoptic(syn)
+    with pytest.raises(ChipsNativeError, match="NaN/Inf"):
+        SynopticChips(sm, base_folder="/tmp/chips_b200_test/").run_CHIPS()
+    run = series.SeriesRunner(256, 256, 11, n_streams=2)
+    b = img.copy()
+    b[c, c] = np.nan
+    with pytest.raises(ChipsNativeError, match="NaN/Inf"):
+        run.run([img, b], [r, r])
+
+
 def test_float64_storage_path_not_f32_representable():
     img, r = synth.synthetic_disk(256, 21)
     img64 = img.astype(np.float64) * (1.0 + 1e-9) + 1e-7       # needs real float64 storage
@@ -301,7 +335,7 @@ def test_float64_storage_path_not_f32_representable():
                  [x.map.astype(np.uint8) for x in regs])
 
 
-@pytest.mark.parametrize("name", ["syn_180x360_k3", "syn_96x240_k11"])
+@pytest.mark.parametrize("name", ["syn_180x360_k3", "syn_96x240_k11", "syn_90x200_k5_frange"])
 def test_synoptic_pipeline_vs_reference_golden(name):
     from pychips_b200 import SynopticChips
     g = load_golden(name)
@@ -310,7 +344,7 @@ def test_synoptic_pipeline_vs_reference_golden(name):
     s = synth.FakeSynoptic(img.astype(np.float64))
     sc = SynopticChips(s, base_folder="/tmp/chips_b200_test/", medfilt_kernel=int(g["kw_medfilt_kernel"]),
                        h_bins=int(g["kw_h_bins"]),
-                       threshold_range=[int(v) for v in g["kw_threshold_range"]])
+                       threshold_range=[v.item() for v in g["kw_threshold_range"]])
     sc.run_CHIPS()
     assert np.array_equal(s.solar_filter, g["solar_filter"].astype(np.float64))
     assert np.array_equal(s.histogram.hbase, g["hbase"])
@@ -605,6 +639,86 @@ def test_config3_time_series_runner_matches_single_image_path():
         assert np.array_equal(r2.keep[j], res.keep[i]) and np.array_equal(r2.limits[j], res.limits[i])
 
 
+def test_batched_c_abi_entry_matches_the_per_image_path():
+    """chips_detect_batch (SURVEY.md §8(b) batched variant; no Python between the images): 7 host
+    images with three radii through 3 slots == chips_detect one image at a time (records, level
+    maps), the summed probability map == sum of the per-image stacks; also an unmasked handle, a
+    float64 handle, and a NaN image reported through its record."""
+    import ctypes as C
+    from pychips_b200 import _lib
+    eng = _engine()
+    dev = eng.require_cuda()
+    lib = _lib.load()
+    n, k, T = 256, 11, 20
+    offs = np.arange(0, T).astype(np.float64)
+
+    def run_batch(imgs, cxs, radii, masked, elem, keep=True, psum=True, slots=3):
+        h = C.c_void_p()
+        H, W = imgs[0].shape
+        _lib.check(lib.chips_batch_create(C.byref(h), H, W, k, 500, T, elem, int(masked), slots), "create")
+        B = len(imgs)
+        pin = [torch.from_numpy(np.ascontiguousarray(im)).pin_memory() for im in imgs]
+        ptrs = (C.c_void_p * B)(*[p.data_ptr() for p in pin])
+        ci = (C.c_int32 * B)(*[c[0] for c in cxs])
+        cj = (C.c_int32 * B)(*[c[1] for c in cxs])
+        rr = (C.c_int32 * B)(*radii)
+        recs = (_lib.Result * B)()
+        keeps = [np.zeros((H, W), np.uint8) for _ in range(B)]
+        kp = (C.c_void_p * B)(*[a.ctypes.data for a in keeps]) if keep else None
+        ps = np.zeros((H, W), np.float32)
+        for _ in range(2):                                   # the second call replays the slot graphs
+            rc = lib.chips_detect_batch(h, B, ptrs, 0, ci, cj, rr, 5.0, float("nan"), offs.ctypes.data, 0.8,
+                                        1e-3, recs, kp, ps.ctypes.data if psum else None, 0.0)
+            _lib.check(rc, "chips_detect_batch")
+        lib.chips_batch_destroy(h)
+        return recs, keeps, ps
+
+    imgs, radii = [], []
+    for i in range(7):
+        r = int(synth.pixel_radius_for(n) * (1.0 + 0.02 * ((i % 3) - 1)))
+        im, _ = synth.synthetic_disk(n, seed=10 + i, radius=r, drift=0.3 * i)
+        imgs.append(im)
+        radii.append(r)
+    c = n // 2
+    recs, keeps, ps = run_batch(imgs, [(c, c)] * 7, radii, True, 4)
+    total = np.zeros((n, n))
+    for i, (im, r) in enumerate(zip(imgs, radii)):
+        det = eng.Detector(eng.Geometry(n, n, c, c, r), k, 500, 0, T, 4, dev)
+        det.detect(torch.from_numpy(im).to(dev))
+        ref = det.result()
+        assert recs[i].median_errors == 0 and recs[i].n_nonfinite == 0 and recs[i].n_peaks == ref.n_peaks > 0
+        for f in ("first_edge", "last_edge", "h_thresh", "limit_0", "n_samples"):
+            assert getattr(recs[i], f) == getattr(ref, f), (i, f)
+        assert list(recs[i].limits[:T]) == list(ref.limits[:T])
+        assert np.array_equal(np.array(recs[i].probs[:T]), np.array(ref.probs[:T]), equal_nan=True)
+        assert list(recs[i].n_kept[:T]) == list(ref.n_kept[:T])
+        assert np.array_equal(keeps[i], det.keep.cpu().numpy())
+        total += np.nan_to_num(det.prob_stack(0.0).cpu().numpy(), nan=0.0)
+    assert np.allclose(ps, total, rtol=1e-5, atol=1e-6)
+    # float64 storage, no outputs but the records
+    imgs64 = [im.astype(np.float64) * (1 + 1e-9) for im in imgs[:2]]
+    recs64, _, _ = run_batch(imgs64, [(c, c)] * 2, radii[:2], True, 8, keep=False, psum=False, slots=1)
+    for i in range(2):
+        det = eng.Detector(eng.Geometry(n, n, c, c, radii[i]), k, 500, 0, T, 8, dev)
+        det.detect(torch.from_numpy(imgs64[i]).to(dev))
+        assert recs64[i].limit_0 == det.result().limit_0 and list(recs64[i].limits[:T]) == list(det.result().limits[:T])
+    # unmasked (synoptic) handle
+    syn = [synth.synthetic_synoptic(96, 240, s).astype(np.float32) for s in range(2)]
+    recs_s, keeps_s, _ = run_batch(syn, [(0, 0)] * 2, [-1, -1], False, 4, psum=False, slots=2)
+    for i in range(2):
+        det = eng.Detector(eng.Geometry(96, 240, 0, 0, -1), k, 500, 0, T, 4, dev)
+        det.detect(torch.from_numpy(syn[i]).to(dev))
+        assert recs_s[i].limit_0 == det.result().limit_0
+        assert np.array_equal(keeps_s[i], det.keep.cpu().numpy())
+    # a NaN is reported in the image's record; a masked handle rejects r < 0
+    bad = imgs[0].copy()
+    bad[c, c] = np.nan
+    recs_b, _, _ = run_batch([imgs[1], bad], [(c, c)] * 2, radii[:2], True, 4, keep=False, psum=False)
+    assert recs_b[0].n_nonfinite == 0 and recs_b[1].n_nonfinite > 0
+    with pytest.raises(_lib.ChipsNativeError):
+        run_batch([imgs[0]], [(c, c)], [-1], True, 4)
+
+
 def test_h_thresh_is_sticky_across_wavelengths():
     """chips.py:240-241: the first disk's h_thresh is reused for later disks of the same Chips."""
     from pychips_b200 import Chips
@@ -676,7 +790,7 @@ def test_fl_pipeline_vs_reference_golden():
     aia = synth.FakeAIA(disks)
     c = Chips(aia, base_folder="/tmp/chips_b200_test/", run_fl_cleanup=True,
               medfilt_kernel=int(g["kw_medfilt_kernel"]), h_bins=int(g["kw_h_bins"]),
-              threshold_range=[int(v) for v in g["kw_threshold_range"]])
+              threshold_range=[v.item() for v in g["kw_threshold_range"]])
     c.run_CHIPS(wavelength=193, resolution=n)
     planes = np.unpackbits(g["planes"])[:5 * n * n].reshape(5, n, n)
     assert np.array_equal(c.cf.candidate_bitmap.astype(np.uint8), planes[4])

@@ -8,8 +8,8 @@ from oracle import chips_oracle as co
 from pychips_b200 import synth
 
 DISK = ["disk_n256_k11", "disk_n256_k31_211", "disk_n192_k51", "disk_n256_k5_t28",
-        "disk_n200_k7_wiped"]
-SYN = ["syn_180x360_k3", "syn_96x240_k11"]
+        "disk_n200_k7_wiped", "disk_n192_k11_frange"]
+SYN = ["syn_180x360_k3", "syn_96x240_k11", "syn_90x200_k5_frange"]
 
 
 def unpack(bits, T, H, W):
