@@ -167,6 +167,25 @@ int chips_detect(const void* image, const chips_plan* plan, int cx, int cy, int 
                  double porb_threshold, double area_threshold, uint8_t* maps_or_null,
                  void* ws, void* stream);
 
+/* ---- SURVEY.md §8(f) row 3 / sliding windows.  replaces: the loop body of Chips.extract_histograms,
+ *      chips.py:282-300, for nwin windows at once (extract_sliding_histograms, chips.py:321-339, is
+ *      an empty stub in the reference: PARITY UNPINNED, pinned to oracle/chips_oracle.py).
+ *      rects: HOST [nwin][4] = x0, y0, x1, y1 (half-open) inside the image; per window the
+ *      histogram of its on-disk pixels over its own min/max range, density, bound = be[:-1] +
+ *      diff(be), find_peaks(height = h_thresh) indices (first n_peaks of row w of `peaks`).
+ *      h_thresh_in = NaN: max(density of window 0) / ht_peak_ratio for every window (sticky).
+ *      counts/density/bound/peaks: device [nwin][h_bins]; recs: device [nwin]. ------------- */
+typedef struct chips_window_rec {
+  double first_edge, last_edge, h_thresh;
+  int64_t n_samples;
+  int32_t n_peaks, pad_;
+} chips_window_rec;
+size_t chips_window_workspace_bytes(int nwin);
+int chips_window_histograms(const void* filt, int H, int W, int elem, int cx, int cy, int r, int nwin,
+                            const int32_t* rects, int h_bins, double ht_peak_ratio, double h_thresh_in,
+                            long long* counts, double* density, double* bound, int32_t* peaks,
+                            chips_window_rec* recs, void* ws, void* stream);
+
 /* ---- batched detections (SURVEY.md §8(b) "batched variants", §8(e) time series).  The reference has
  *      no batching: one Chips object handles one RegisterAIA (chips.py:110-150) and the caller
  *      loops over dates; this is that loop for a non-Python host.  The handle owns n_slots

@@ -293,3 +293,41 @@ def extract_histograms(filt_disk, n_mask, resolution, hist_xsplit, hist_ysplit, 
                                    h_bins=h_bins)
             k += 1
     return regions, r_peaks, h_thresh
+
+
+def sliding_windows(resolution, hist_xsplit, hist_ysplit, overlap=0.5):
+    """Window rectangles (row0, row1, col0, col1) of `extract_sliding_histograms`: windows of
+    (resolution/hist_xsplit) rows x (resolution/hist_ysplit) columns - the units of
+    chips.py:276-279, first index = rows as in :282-289 - slid in raster order with a step of
+    (1 - overlap) of the window (at least one pixel), every window fully inside the image."""
+    xunit, yunit = int(resolution / hist_xsplit), int(resolution / hist_ysplit)
+    sx, sy = max(1, int(round(xunit * (1.0 - overlap)))), max(1, int(round(yunit * (1.0 - overlap))))
+    out = []
+    for r0 in range(0, resolution - xunit + 1, sx):
+        for c0 in range(0, resolution - yunit + 1, sy):
+            out.append((r0, r0 + xunit, c0, c0 + yunit))
+    return out
+
+
+def sliding_histograms(filt_disk, n_mask, resolution, hist_xsplit, hist_ysplit, h_bins, h_thresh,
+                       ht_peak_ratio, overlap=0.5):
+    """`Chips.extract_sliding_histograms`, chips.py:321-339.  PARITY UNPINNED: the reference method
+    is an empty stub (`pass`); its docstring ("sliding a window (size determined by xsplit, ysplit)
+    through the solar disk") and docs/tutorial/workings.md:36-39 give the intent.  This restatement
+    applies the loop body of `extract_histograms` (chips.py:282-310, with the repairs described
+    there) to every window of `sliding_windows`.  Returns (regions dict, fpeak list, sticky h_thresh)."""
+    regions, r_peaks, k = {}, [], 0
+    for (r0, r1, c0, c1) in sliding_windows(resolution, hist_xsplit, hist_ysplit, overlap):
+        r_disk_data = (filt_disk[r0:r1, c0:c1] * n_mask[r0:r1, c0:c1]).ravel()
+        with np.errstate(invalid="ignore", divide="ignore"):
+            h, be = np.histogram(r_disk_data[~np.isnan(r_disk_data.ravel())], bins=h_bins, density=True)
+        if h_thresh is None:
+            h_thresh = np.max(h) / ht_peak_ratio
+        peaks, _ = signal.find_peaks(h, height=h_thresh)
+        bc = be[:-1] + np.diff(be)
+        if len(peaks) > 1:
+            r_peaks.extend(peaks[:2])
+        regions[k] = Namespace(peaks=peaks, hbase=h, bound=bc, data=r_disk_data, h_thresh=h_thresh,
+                               h_bins=h_bins, window=(r0, r1, c0, c1))
+        k += 1
+    return regions, r_peaks, h_thresh

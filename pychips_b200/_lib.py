@@ -38,6 +38,11 @@ class Plan(C.Structure):
                  "off_tiles", "off_ovf", "bytes")]
 
 
+class WindowRec(C.Structure):
+    _fields_ = [("first_edge", C.c_double), ("last_edge", C.c_double), ("h_thresh", C.c_double),
+                ("n_samples", C.c_int64), ("n_peaks", C.c_int32), ("pad_", C.c_int32)]
+
+
 def check_record(res) -> None:
     """Raise for a detection record that must not be used (median self-check, non-finite input)."""
     if res.n_nonfinite:
@@ -84,6 +89,9 @@ SIGNATURES = {
     "chips_roots": ([_PP, _i, _i, _i, _i, _vp, _vp, _vp, _vp], C.c_int),
     "chips_prob_stack": ([_PP, _d, _vp, _i, _i, _vp, _vp], C.c_int),
     "chips_detect": ([_vp, _PP, _i, _i, _i, _d, _d, _vp, _d, _d, _vp, _vp, _vp], C.c_int),
+    "chips_window_workspace_bytes": ([_i], C.c_size_t),
+    "chips_window_histograms": ([_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp], C.c_int),
     "chips_batch_create": ([_vp, _i, _i, _i, _i, _i, _i, _i, _i], C.c_int),
     "chips_detect_batch": ([_vp, _i, _vp, _i, _vp, _vp, _vp, _d, _d, _vp, _d, _d, _vp, _vp, _vp, _d], C.c_int),
     "chips_batch_destroy": ([_vp], C.c_int),

@@ -316,9 +316,42 @@ class Chips(object):
             disk.set_value("histograms", Namespace(**dict(reg=regions, fpeak=r_peaks, keys=range(k))))
         return
 
-    # ---- chips.py:321-339: an empty stub in the reference (`pass`)
-    def extract_sliding_histograms(self, disk) -> None:
+    # ---- chips.py:321-339: an empty stub in the reference (`pass`).  Built from its docstring
+    # ("sliding a window (size determined by `xsplit`, `ysplit`) through the solar disk") and
+    # docs/tutorial/workings.md:36-39: windows of the regional unit size, slid in raster order
+    # with `overlap` (default one half), each processed like a region of extract_histograms
+    # (chips.py:282-310).  All windows go through the device at once (chips_window_histograms:
+    # one warp per window for the selection).  PARITY UNPINNED; pinned to
+    # oracle/chips_oracle.py::sliding_histograms.  Sets `disk.histograms` like extract_histograms.
+    def extract_sliding_histograms(self, disk, overlap: float = 0.5) -> None:
         logger.info(f"Extract solar histograms for different regions {disk.wavelength}/{disk.resolution}")
+        if (not hasattr(disk, "histograms") and (self.hist_xsplit is not None)
+                and (self.hist_ysplit is not None)):
+            det = self._detector(disk)
+            res = int(disk.resolution)
+            xunit, yunit = int(res / self.hist_xsplit), int(res / self.hist_ysplit)
+            sx = max(1, int(round(xunit * (1.0 - overlap))))
+            sy = max(1, int(round(yunit * (1.0 - overlap))))
+            windows = [(r0, r0 + xunit, c0, c0 + yunit)
+                       for r0 in range(0, res - xunit + 1, sx) for c0 in range(0, res - yunit + 1, sy)]
+            regions, r_peaks = {}, []
+            if windows:
+                with torch.cuda.device(self.device):
+                    self._ensure_filt(disk, det)
+                    dens, bnd, pks, hthr, _ = det.window_histograms(windows, self.ht_peak_ratio, self.h_thresh)
+                if self.h_thresh is None:
+                    self.h_thresh = hthr
+                for k, (r0, r1, c0, c1) in enumerate(windows):
+                    if len(pks[k]) > 1:
+                        r_peaks.extend(pks[k][:2])
+
+                    def data(r0=r0, r1=r1, c0=c0, c1=c1):
+                        return (disk.solar_filter.filt_disk[r0:r1, c0:c1] *
+                                disk.solar_mask.n_mask[r0:r1, c0:c1]).ravel()
+
+                    regions[k] = LazyNamespace(_lazy=dict(data=data), peaks=pks[k], hbase=dens[k], bound=bnd[k],
+                                               h_thresh=self.h_thresh, h_bins=self.h_bins, window=(r0, r1, c0, c1))
+            disk.set_value("histograms", Namespace(**dict(reg=regions, fpeak=r_peaks, keys=range(len(windows)))))
         return
 
     # ---- chips.py:341-403

@@ -481,9 +481,250 @@ static int thr_impl(const T* filt, const chips_plan* p, int cx, int cy, int r, d
   return CHIPS_OK;
 }
 
+// ------------------------------------------------------------------ sliding-window histograms
+// SURVEY.md §8(f) row 3 / north_star (2)-(3): the reference's extract_sliding_histograms
+// (chips.py:321-339) is an empty stub ("sliding a window (size determined by xsplit, ysplit)
+// through the solar disk"); the per-window arithmetic is the loop body of extract_histograms
+// (chips.py:282-300): np.histogram(bins, density=True) of the window's on-disk pixels over the
+// window's OWN min/max range, a sticky h_thresh fixed by the first window, find_peaks, bound.
+// PARITY UNPINNED (no reference output exists); pinned to oracle/chips_oracle.py::sliding_histograms.
+// All windows in three launches: min/max (grid.y = window), histogram (warp-private shared-memory
+// sub-histograms, grid.y = window), selection (ONE WARP per window).
+struct WinRect { int x0, y0, x1, y1; };
+
+template <typename T>
+__global__ void k_win_init(typename Key<T>::type* minmax, int nwin) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nwin) {
+    minmax[2 * i] = Key<T>::kMax;
+    minmax[2 * i + 1] = 0;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_win_minmax(const T* __restrict__ filt, int W, const WinRect* __restrict__ rects,
+                                                    int cx, int cy, int r,
+                                                    typename Key<T>::type* __restrict__ minmax) {
+  using K = typename Key<T>::type;
+  const WinRect q = rects[blockIdx.y];
+  K kmin = Key<T>::kMax, kmax = 0;
+  for (int y = q.y0 + blockIdx.x; y < q.y1; y += gridDim.x) {
+    int xa, xb;
+    if (!row_chord(y, cx, cy, r, q.x0, q.x1 - q.x0, xa, xb)) continue;
+    const T* row = filt + (size_t)y * W;
+    for (int x = xa + threadIdx.x; x < xb; x += blockDim.x) {
+      const K key = Key<T>::enc(row[x]);
+      kmin = key < kmin ? key : kmin;
+      kmax = key > kmax ? key : kmax;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const K a = __shfl_xor_sync(0xFFFFFFFFu, kmin, o), b = __shfl_xor_sync(0xFFFFFFFFu, kmax, o);
+    kmin = a < kmin ? a : kmin;
+    kmax = b > kmax ? b : kmax;
+  }
+  if ((threadIdx.x & 31) == 0 && kmin <= kmax) {
+    atomic_min_key(&minmax[2 * blockIdx.y], kmin);
+    atomic_max_key(&minmax[2 * blockIdx.y + 1], kmax);
+  }
+}
+
+// np.histogram's outer edges of a selection with ordered min / max keys k0, k1
+template <typename T>
+__device__ __forceinline__ void outer_edges(typename Key<T>::type k0, typename Key<T>::type k1, double& first,
+                                            double& last) {
+  if (k0 > k1) {          // empty selection: np.histogram uses the range (0, 1)
+    first = 0.0;
+    last = 1.0;
+  } else {
+    first = (double)Key<T>::dec(k0);
+    last = (double)Key<T>::dec(k1);
+  }
+  if (first == last) {
+    first = first - 0.5;
+    last = last + 0.5;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_win_hist(const T* __restrict__ filt, int W, const WinRect* __restrict__ rects,
+                                                  int cx, int cy, int r,
+                                                  const typename Key<T>::type* __restrict__ minmax, int nbins,
+                                                  int copies, unsigned long long* __restrict__ counts) {
+  extern __shared__ __align__(16) uint32_t sh[];
+  const WinRect q = rects[blockIdx.y];
+  for (int i = threadIdx.x; i < copies * nbins; i += blockDim.x) sh[i] = 0;
+  double first, last;
+  outer_edges<T>(minmax[2 * blockIdx.y], minmax[2 * blockIdx.y + 1], first, last);
+  const double denom = __dsub_rn(last, first);
+  const double step = __ddiv_rn(denom, (double)nbins);
+  const float first_f = (float)first, scale_f = (float)((double)nbins / denom);
+  __syncthreads();
+  uint32_t* mine = sh + ((threadIdx.x >> 5) % copies) * nbins;      // warp-private bins
+  for (int y = q.y0 + blockIdx.x; y < q.y1; y += gridDim.x) {
+    int xa, xb;
+    if (!row_chord(y, cx, cy, r, q.x0, q.x1 - q.x0, xa, xb)) continue;
+    const T* row = filt + (size_t)y * W;
+    for (int x0 = xa; x0 < xb; x0 += blockDim.x) {
+      const int x = x0 + threadIdx.x;
+      int bin = -1;
+      if (x < xb) bin = hist_bin((double)row[x], nbins, first, last, step, first_f, scale_f);
+      // neighbouring pixels of the filtered image mostly share a bin: one shared-memory add per
+      // run of equal bins inside the warp (shuffle with the left neighbour, ballot of run starts)
+      const int left = __shfl_up_sync(0xFFFFFFFFu, bin, 1);
+      const bool head = bin >= 0 && ((threadIdx.x & 31) == 0 || left != bin);
+      const uint32_t heads = __ballot_sync(0xFFFFFFFFu, head);
+      const uint32_t valid = __ballot_sync(0xFFFFFFFFu, bin >= 0);
+      if (head) {
+        const int lane = threadIdx.x & 31;
+        const uint32_t later = heads & (0xFFFFFFFEu << lane);          // run heads after me
+        const int end = later ? __ffs(later) - 1 : 32;
+        const uint32_t run = valid & (0xFFFFFFFFu >> (32 - end)) & (0xFFFFFFFFu << lane);
+        atomicAdd(&mine[bin], (unsigned)__popc(run));
+      }
+    }
+  }
+  __syncthreads();
+  unsigned long long* out = counts + (size_t)blockIdx.y * nbins;
+  for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
+    unsigned long long s = 0;
+    for (int c = 0; c < copies; ++c) s += sh[c * nbins + i];
+    if (s) atomicAdd(&out[i], s);
+  }
+}
+
+// one warp per window
+template <typename T>
+__global__ void __launch_bounds__(128) k_win_select(const unsigned long long* __restrict__ counts,
+                                                    const typename Key<T>::type* __restrict__ minmax, int nwin,
+                                                    int nbins, double ratio, double h_thresh_in,
+                                                    double* __restrict__ density, double* __restrict__ bound,
+                                                    int* __restrict__ peaks, chips_window_rec* __restrict__ recs) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= nwin) return;
+  // density of window `v` into `dst` (or nowhere); returns max density and the sample count
+  auto fill = [&](int v, double* dst, double* bnd, double& first, double& last, long long& total) {
+    outer_edges<T>(minmax[2 * v], minmax[2 * v + 1], first, last);
+    const double step = __ddiv_rn(__dsub_rn(last, first), (double)nbins);
+    const unsigned long long* c = counts + (size_t)v * nbins;
+    long long part = 0;
+    for (int i = lane; i < nbins; i += 32) part += (long long)c[i];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, o);
+    total = part;
+    double dmax = -INFINITY;
+    for (int i = lane; i < nbins; i += 32) {
+      const double e0 = linspace_edge(i, nbins, first, last, step);
+      const double e1 = linspace_edge(i + 1, nbins, first, last, step);
+      const double db = __dsub_rn(e1, e0);
+      const double d = __ddiv_rn(__ddiv_rn((double)c[i], db), (double)part);   // n / db / n.sum()
+      if (dst) {
+        dst[i] = d;
+        bnd[i] = __dadd_rn(e0, db);                                             // be[:-1] + diff(be)
+      }
+      dmax = fmax(dmax, d);          // NaN densities (empty window: 0 / 0) are skipped, as np.max would not
+    }
+    for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(0xFFFFFFFFu, dmax, o));
+    return dmax;
+  };
+  double first, last;
+  long long total;
+  double hthr = h_thresh_in;
+  if (isnan(hthr)) {     // sticky: fixed by the first window of the loop (chips.py:295-296)
+    double f0, l0;
+    long long t0;
+    const double m0 = fill(0, nullptr, nullptr, f0, l0, t0);
+    hthr = t0 > 0 ? __ddiv_rn(m0, ratio) : nan("");    // np.max of an all-NaN density is NaN
+  }
+  double* dst = density + (size_t)w * nbins;
+  double* bnd = bound + (size_t)w * nbins;
+  fill(w, dst, bnd, first, last, total);
+  __syncwarp();
+  if (lane == 0) {       // scipy.signal.find_peaks(h, height=hthr): plateau midpoints, in order
+    int np_ = 0;
+    int* pk = peaks + (size_t)w * nbins;
+    int i = 1;
+    const int imax = nbins - 1;
+    while (i < imax) {
+      const double di = dst[i];
+      if (dst[i - 1] < di) {
+        int ia = i + 1;
+        while (ia < imax && dst[ia] == di) ++ia;
+        if (dst[ia] < di) {
+          const int p = (i + ia - 1) / 2;
+          if (dst[p] >= hthr) pk[np_++] = p;
+          i = ia;
+        }
+      }
+      ++i;
+    }
+    chips_window_rec rc;
+    rc.first_edge = first;
+    rc.last_edge = last;
+    rc.h_thresh = hthr;
+    rc.n_samples = total;
+    rc.n_peaks = np_;
+    rc.pad_ = 0;
+    recs[w] = rc;
+  }
+}
+
+template <typename T>
+static int windows_impl(const T* filt, int H, int W, int cx, int cy, int r, int nwin, const int32_t* rects_host,
+                        int nbins, double ratio, double h_in, unsigned long long* counts, double* density,
+                        double* bound, int32_t* peaks, chips_window_rec* recs, unsigned char* ws, cudaStream_t st) {
+  using K = typename Key<T>::type;
+  K* minmax = reinterpret_cast<K*>(ws);
+  WinRect* rects = reinterpret_cast<WinRect*>(ws + (size_t)nwin * 16);
+  for (int i = 0; i < nwin; ++i) {
+    const int32_t* q = rects_host + 4 * i;
+    if (q[0] < 0 || q[1] < 0 || q[2] > W || q[3] > H || q[2] < q[0] || q[3] < q[1]) return CHIPS_E_ARG;
+  }
+  CHIPS_CUDA(cudaMemcpyAsync(rects, rects_host, (size_t)nwin * sizeof(WinRect), cudaMemcpyHostToDevice, st));
+  CHIPS_CUDA(cudaMemsetAsync(counts, 0, (size_t)nwin * nbins * sizeof(long long), st));
+  k_win_init<T><<<(nwin + 127) / 128, 128, 0, st>>>(minmax, nwin);
+  CHIPS_CHECK_LAUNCH();
+  int copies = hist_copies(nbins);
+  size_t smem = (size_t)copies * nbins * sizeof(uint32_t);
+  if (smem > 200 * 1024) return CHIPS_E_ARG;
+  int gx = (4 * kNumSM + nwin - 1) / nwin;
+  if (gx > H) gx = H;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)nwin);
+  k_win_minmax<T><<<grid, 256, 0, st>>>(filt, W, rects, cx, cy, r, minmax);
+  CHIPS_CHECK_LAUNCH();
+  CHIPS_CUDA(cudaFuncSetAttribute(k_win_hist<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_win_hist<T><<<grid, 256, smem, st>>>(filt, W, rects, cx, cy, r, minmax, nbins, copies, counts);
+  CHIPS_CHECK_LAUNCH();
+  k_win_select<T><<<(nwin + 3) / 4, 128, 0, st>>>(counts, minmax, nwin, nbins, ratio, h_in, density, bound, peaks,
+                                                  recs);
+  CHIPS_CHECK_LAUNCH();
+  count_launch(4);
+  return CHIPS_OK;
+}
+
 }  // namespace chips
 
 using namespace chips;
+
+extern "C" size_t chips_window_workspace_bytes(int nwin) { return (size_t)(nwin > 0 ? nwin : 0) * 32 + 256; }
+
+extern "C" int chips_window_histograms(const void* filt, int H, int W, int elem, int cx, int cy, int r, int nwin,
+                                       const int32_t* rects, int h_bins, double ht_peak_ratio, double h_thresh_in,
+                                       long long* counts, double* density, double* bound, int32_t* peaks,
+                                       chips_window_rec* recs, void* ws, void* stream) {
+  if (!filt || !rects || !counts || !density || !bound || !peaks || !recs || !ws) return CHIPS_E_ARG;
+  if (H < 1 || W < 1 || nwin < 1 || nwin > 65535 || h_bins < 1) return CHIPS_E_ARG;
+  unsigned long long* c = reinterpret_cast<unsigned long long*>(counts);
+  if (elem == 4)
+    return windows_impl<float>((const float*)filt, H, W, cx, cy, r, nwin, rects, h_bins, ht_peak_ratio, h_thresh_in,
+                               c, density, bound, peaks, recs, (unsigned char*)ws, (cudaStream_t)stream);
+  if (elem == 8)
+    return windows_impl<double>((const double*)filt, H, W, cx, cy, r, nwin, rects, h_bins, ht_peak_ratio,
+                                h_thresh_in, c, density, bound, peaks, recs, (unsigned char*)ws, (cudaStream_t)stream);
+  return CHIPS_E_ARG;
+}
 
 extern "C" int chips_minmax(const void* filt, const chips_plan* plan, int cx, int cy, int r,
                             void* ws, void* stream) {

@@ -219,6 +219,33 @@ class Detector:
                 tail("peaks", torch.int32, self.h_bins)[:npk].cpu().numpy().astype(np.int64),
                 np.float64(res.h_thresh))
 
+    def window_histograms(self, windows, ht_peak_ratio: float, h_thresh):
+        """Histogram + find_peaks of the on-disk pixels of `filt[r0:r1, c0:c1]` for every window
+        (r0, r1, c0, c1) at once (`chips_window_histograms`: three launches, one warp per window for
+        the selection).  Returns (density [n, h_bins], bound [n, h_bins], list of peak-index arrays,
+        h_thresh) as host arrays; h_thresh = None lets the first window fix it (sticky)."""
+        n = len(windows)
+        rects = np.ascontiguousarray([[c0, r0, c1, r1] for (r0, r1, c0, c1) in windows], dtype=np.int32)
+        hb = self.h_bins
+        dev = self.device
+        counts = torch.empty((n, hb), dtype=torch.int64, device=dev)
+        density = torch.empty((n, hb), dtype=torch.float64, device=dev)
+        bound = torch.empty((n, hb), dtype=torch.float64, device=dev)
+        peaks = torch.empty((n, hb), dtype=torch.int32, device=dev)
+        recs = torch.empty((n, C.sizeof(_lib.WindowRec)), dtype=torch.uint8, device=dev)
+        ws = torch.empty(int(self.lib.chips_window_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+        h_in = float("nan") if h_thresh is None else float(h_thresh)
+        _lib.check(self.lib.chips_window_histograms(
+            _ptr(self.filt), self.geom.H, self.geom.W, self.elem, *self._g(), n, rects.ctypes.data, hb,
+            float(ht_peak_ratio), h_in, _ptr(counts), _ptr(density), _ptr(bound), _ptr(peaks), _ptr(recs),
+            _ptr(ws), _stream_ptr()), "chips_window_histograms")
+        rec_host = recs.cpu().numpy()
+        rl = [_lib.WindowRec.from_buffer_copy(rec_host[i].tobytes()) for i in range(n)]
+        pk = peaks.cpu().numpy()
+        return (density.cpu().numpy(), bound.cpu().numpy(),
+                [pk[i, :rl[i].n_peaks].astype(np.int64) for i in range(n)],
+                np.float64(rl[0].h_thresh) if n else None, counts.cpu().numpy())
+
     def select_threshold(self, ht_peak_ratio: float, h_thresh):
         h_in = float("nan") if h_thresh is None else float(h_thresh)
         _lib.check(self.lib.chips_select_threshold(self._pp, float(ht_peak_ratio), h_in, self._offp,

@@ -927,6 +927,69 @@ def test_regional_histograms_vs_oracle(n, xs, ys, hb):
         assert np.array_equal(d2.solar_ch_regions.__dict__[key].map, reg.map)
 
 
+@pytest.mark.parametrize("n,xs,ys,hb,overlap,sticky", [(512, 2, 2, 500, 0.5, True), (384, 3, 2, 200, 0.75, False),
+                                                        (320, 4, 4, 1000, 0.0, True), (256, 1, 1, 5000, 0.5, False)])
+def test_sliding_window_histograms_vs_oracle(n, xs, ys, hb, overlap, sticky):
+    """Chips.extract_sliding_histograms (an empty stub in the reference, chips.py:321-339 - parity
+    unpinned, pinned to the oracle restatement): every window's density, bound, peak indices and
+    data, the sticky h_thresh (fixed by the full-disk histogram, or by the first window when the
+    method runs on its own), fpeak; all windows in one chips_window_histograms call."""
+    from pychips_b200 import Chips
+    img, r = synth.synthetic_disk(n, 13)
+    d_or = synth.FakeDisk(img.astype(np.float64), r)
+    o = co.OracleChips(medfilt_kernel=11, h_bins=hb)
+    o.run(d_or, keep_contours=False)
+    regs, fpeak, hthr = co.sliding_histograms(d_or.solar_filter.filt_disk, d_or.solar_mask.n_mask, n, xs, ys,
+                                              hb, o.h_thresh if sticky else None, 5, overlap)
+    d = synth.FakeDisk(img.astype(np.float64), r)
+    c = Chips(synth.FakeAIA(d), base_folder="/tmp/chips_b200_test/", medfilt_kernel=11, h_bins=hb,
+              hist_xsplit=xs, hist_ysplit=ys)
+    if sticky:
+        c.run_CHIPS()
+    else:
+        c.extract_solar_masks(d)
+        c.run_filters(d)
+    c.extract_sliding_histograms(d, overlap=overlap)
+    assert len(regs) == len(co.sliding_windows(n, xs, ys, overlap)) >= 1
+    assert list(d.histograms.keys) == list(range(len(regs))) and len(d.histograms.reg) == len(regs)
+    assert [int(v) for v in d.histograms.fpeak] == [int(v) for v in fpeak]
+    assert c.h_thresh == hthr
+    for k, ref in regs.items():
+        got = d.histograms.reg[k]
+        assert got.window == ref.window
+        assert np.array_equal(got.hbase, ref.hbase, equal_nan=True), k
+        assert np.array_equal(got.bound, ref.bound), k
+        assert np.array_equal(np.asarray(got.peaks), np.asarray(ref.peaks)), k
+        assert np.array_equal(got.data, ref.data, equal_nan=True), k
+        assert got.h_thresh == ref.h_thresh and got.h_bins == hb
+
+
+def test_window_histograms_counts_and_empty_windows():
+    """chips_window_histograms through the Detector: integer counts of every window == np.histogram,
+    a window with no on-disk pixel gives NaN densities and no peaks (numpy on an empty array)."""
+    eng = _engine()
+    dev = eng.require_cuda()
+    n = 384
+    img, r = synth.synthetic_disk(n, 4)
+    c = n // 2
+    det = eng.Detector(eng.Geometry(n, n, c, c, r), 7, 300, 0, 1, 4, dev)
+    det.medfilt(torch.from_numpy(img).to(dev))
+    filt = det.filt.cpu().numpy().astype(np.float64)
+    yy, xx = np.mgrid[:n, :n]
+    on = (xx - c) ** 2 + (yy - c) ** 2 <= r * r
+    wins = [(0, 40, 0, 40), (100, 300, 50, 384), (0, 384, 0, 384), (191, 193, 10, 380), (300, 384, 300, 384)]
+    dens, bnd, pks, hthr, counts = det.window_histograms(wins, 5, None)
+    for k, (r0, r1, c0, c1) in enumerate(wins):
+        v = filt[r0:r1, c0:c1][on[r0:r1, c0:c1]]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            h, be = np.histogram(v, bins=300, density=True)
+        cnt, _ = np.histogram(v, bins=300)
+        assert np.array_equal(counts[k], cnt), k
+        assert np.array_equal(dens[k], h, equal_nan=True), k
+        assert np.array_equal(bnd[k], be[:-1] + np.diff(be)), k
+    assert not on[0:40, 0:40].any() and np.isnan(dens[0]).all() and len(pks[0]) == 0 and np.isnan(hthr)
+
+
 # ----------------------------------------------------------------------------- randomised configurations
 @pytest.mark.parametrize("seed", range(10))
 def test_random_configurations_vs_oracle(seed):

@@ -170,3 +170,22 @@ def test_headline_config2_fixture_is_self_consistent():
     secs = json.loads(str(g["stage_seconds"]))
     assert set(secs) == {"extract_solar_masks", "run_filters", "extract_histogram", "extract_CHs_CHBs"}
     assert secs["run_filters"] > 60
+
+
+def test_sliding_windows_restatement_is_the_regional_one_without_overlap():
+    """oracle.sliding_histograms (parity unpinned: the reference method is a stub) with overlap 0 on
+    square splits visits the regions of oracle.extract_histograms in the same order with the same
+    outputs; with overlap the windows tile the image with the stated step."""
+    from pychips_b200 import synth
+    img, r = synth.synthetic_disk(256, 3)
+    d = synth.FakeDisk(img.astype(np.float64), r)
+    o = co.OracleChips(medfilt_kernel=5, h_bins=200)
+    o.run(d, keep_contours=False)
+    a, fa, ha = co.extract_histograms(d.solar_filter.filt_disk, d.solar_mask.n_mask, 256, 2, 2, 200, None, 5)
+    b, fb, hb = co.sliding_histograms(d.solar_filter.filt_disk, d.solar_mask.n_mask, 256, 2, 2, 200, None, 5, 0.0)
+    assert len(a) == len(b) == 4 and ha == hb and [int(v) for v in fa] == [int(v) for v in fb]
+    for k in a:
+        assert np.array_equal(a[k].hbase, b[k].hbase, equal_nan=True) and np.array_equal(a[k].bound, b[k].bound)
+        assert np.array_equal(a[k].peaks, b[k].peaks)
+    w = co.sliding_windows(256, 2, 2, 0.5)
+    assert len(w) == 9 and w[0] == (0, 128, 0, 128) and w[1] == (0, 128, 64, 192) and w[-1] == (128, 256, 128, 256)
