@@ -186,6 +186,18 @@ int chips_window_histograms(const void* filt, int H, int W, int elem, int cx, in
                             long long* counts, double* density, double* bound, int32_t* peaks,
                             chips_window_rec* recs, void* ws, void* stream);
 
+/* ---- BASELINE config 4 "wrap-around CCL": 8-connected components of a threshold mask whose
+ *      longitude axis is periodic (column W-1 is adjacent to column 0).  The reference's
+ *      SynopticChips has no labelling step (syn_chips.py:237-251): an extension, PARITY UNPINNED,
+ *      pinned to scipy.ndimage.label + a seam merge in the tests.  Foreground: img <= thr (mode 0,
+ *      e.g. the level image with thr = threshold index) or img != 0 (mode 1).  labels: int32 [H][W],
+ *      0 = background, components numbered 1.. in raster order of their first pixel; areas
+ *      (optional, max_labels ints) = pixel counts; *n_labels = number of components. ------------ */
+size_t chips_label_workspace_bytes(int H, int W);
+int chips_label_periodic(const uint8_t* img, int H, int W, int mode, int thr, int periodic,
+                         int32_t* labels, int32_t* areas, long long max_labels, int32_t* n_labels,
+                         void* ws, void* stream);
+
 /* ---- batched detections (SURVEY.md §8(b) "batched variants", §8(e) time series).  The reference has
  *      no batching: one Chips object handles one RegisterAIA (chips.py:110-150) and the caller
  *      loops over dates; this is that loop for a non-Python host.  The handle owns n_slots

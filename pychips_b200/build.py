@@ -8,7 +8,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("CHIPS_LIB", os.path.join(HERE, "libchips_b200.so"))   # override: diagnostics only
-SOURCES = ["median.cu", "stats.cu", "ccl.cu", "fl.cu", "export.cu", "contours.cu", "pipeline.cu", "batch.cu"]
+SOURCES = ["median.cu", "stats.cu", "ccl.cu", "fl.cu", "export.cu", "contours.cu", "pipeline.cu", "batch.cu", "synccl.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--use_fast_math=false", "-Xcompiler", "-fPIC", "-shared",

@@ -356,6 +356,23 @@ class Detector:
         lab[fg] = inv.astype(np.int32) + 1
         return lab, a[fg][first].astype(np.int64)
 
+    def labels_periodic(self, t: int, periodic: bool = True):
+        """8-connected components of the final map of threshold t (`keep <= t`) with the x axis
+        periodic (synoptic maps: longitude wraps) - `chips_label_periodic`.  Returns (labels int32
+        [H, W] numbered in raster order of the first pixel, pixel counts per label) on the host."""
+        H, W = self.geom.H, self.geom.W
+        dev = self.device
+        lab = torch.empty((H, W), dtype=torch.int32, device=dev)
+        cap = ((H + 1) // 2) * ((W + 1) // 2)
+        areas = torch.empty(cap, dtype=torch.int32, device=dev)
+        nlab = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = torch.empty(int(self.lib.chips_label_workspace_bytes(H, W)), dtype=torch.uint8, device=dev)
+        _lib.check(self.lib.chips_label_periodic(_ptr(self.keep), H, W, 0, int(t), int(periodic), _ptr(lab),
+                                                 _ptr(areas), cap, _ptr(nlab), _ptr(ws), _stream_ptr()),
+                   "chips_label_periodic")
+        n = int(nlab.item())
+        return lab.cpu().numpy(), areas[:n].cpu().numpy().astype(np.int64)
+
     def contours(self, t: int):
         """Contours of the raw threshold mask `level <= t` exactly as the reference's
         cv2.findContours call sees it (chips.py:382-386): (contours, hierarchy [n, 4],

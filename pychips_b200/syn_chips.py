@@ -144,6 +144,7 @@ class SynopticChips(object):
                         self._histogram_on_device(synoptic_map, det, synoptic_map.histogram.h_thresh)
                     det.threshold_prob(self.porb_threshold)
                     det.cleanup(0.0)
+                    det.state.add("maps")
                     res = det.result()
                 engine._lib.check_record(res)
                 limit_0 = np.float64(res.limit_0)
@@ -161,6 +162,16 @@ class SynopticChips(object):
                     logger.info(f"Estimated prob.({res.probs[t]}) at lim({lim})")
                 synoptic_map.set_value("solar_ch_regions", Namespace(**dtmp_map))
         return
+
+    # ---- BASELINE config 4 "wrap-around CCL" (no counterpart in syn_chips.py: the reference's
+    # synoptic map is the raw threshold mask, :237-251).  Extension, parity unpinned.
+    def labels(self, lim_index: int, periodic: bool = True):
+        """Connected regions (8-connectivity, longitude periodic) of the map of threshold
+        `lim_index`: (labels int32 [H, W], 0 = background, numbered in raster order; pixels per label)."""
+        if self._det is None or "maps" not in self._det.state:
+            raise RuntimeError("run_CHIPS() / extract_CHs_CHBs() first")
+        with torch.cuda.device(self.device):
+            return self._det.labels_periodic(lim_index, periodic)
 
     # ---- plots.py:624-641 (the arithmetic only)
     def probability_map(self, prob_lower_lim: float = 0.0) -> np.ndarray:

@@ -990,6 +990,102 @@ def test_window_histograms_counts_and_empty_windows():
     assert not on[0:40, 0:40].any() and np.isnan(dens[0]).all() and len(pks[0]) == 0 and np.isnan(hthr)
 
 
+def _periodic_labels_spec(mask):
+    """8-connected components on a cylinder (column W-1 adjacent to column 0), numbered in raster
+    order of their first pixel: scipy.ndimage.label + a union of the labels that touch across the seam."""
+    H, W = mask.shape
+    lab, n = ndimage.label(mask, structure=np.ones((3, 3)))
+    parent = list(range(n + 1))
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+    if W >= 2:
+        for y in range(H):
+            if not mask[y, 0]:
+                continue
+            for dy in (-1, 0, 1):
+                yy = y + dy
+                if 0 <= yy < H and mask[yy, W - 1]:
+                    a, b = find(lab[y, 0]), find(lab[yy, W - 1])
+                    if a != b:
+                        parent[max(a, b)] = min(a, b)
+    root = np.array([find(i) for i in range(n + 1)])
+    merged = root[lab]
+    fg = merged > 0
+    flat = merged.ravel()
+    order = {}
+    for v in flat[fg.ravel()]:
+        if v not in order:
+            order[v] = len(order) + 1
+    lut = np.zeros(n + 1, dtype=np.int32)
+    for v, k in order.items():
+        lut[v] = k
+    out = lut[merged]
+    return out, np.bincount(out.ravel(), minlength=len(order) + 1)[1:]
+
+
+@pytest.mark.parametrize("shape,density,seed", [((96, 240), 0.45, 0), ((64, 64), 0.6, 1), ((33, 2), 0.5, 2),
+                                                ((40, 1), 0.5, 3), ((1, 77), 0.5, 4), ((180, 360), 0.3, 5)])
+def test_periodic_labels_on_random_masks(shape, density, seed):
+    """chips_label_periodic (BASELINE config 4 "wrap-around CCL"; parity unpinned - the reference's
+    SynopticChips has no labelling step) against scipy.ndimage.label + a seam merge, and the plain
+    (non-periodic) mode against scipy.ndimage.label itself."""
+    import ctypes as C
+    from pychips_b200 import _lib
+    eng = _engine()
+    dev = eng.require_cuda()
+    lib = _lib.load()
+    rng = np.random.default_rng(seed)
+    mask = rng.random(shape) < density
+    mask[:, 0] |= rng.random(shape[0]) < 0.5          # plenty of contacts across the seam
+    mask[:, -1] |= rng.random(shape[0]) < 0.5
+    H, W = shape
+    img = torch.from_numpy(mask.astype(np.uint8)).to(dev)
+    for periodic in (1, 0):
+        lab = torch.empty((H, W), dtype=torch.int32, device=dev)
+        cap = ((H + 1) // 2) * ((W + 1) // 2)
+        areas = torch.empty(cap, dtype=torch.int32, device=dev)
+        nlab = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = torch.empty(int(lib.chips_label_workspace_bytes(H, W)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.chips_label_periodic(eng._ptr(img), H, W, 1, 0, periodic, eng._ptr(lab), eng._ptr(areas),
+                                            cap, eng._ptr(nlab), eng._ptr(ws), eng._stream_ptr()), "label")
+        if periodic:
+            ref, ref_areas = _periodic_labels_spec(mask)
+        else:
+            ref, n = ndimage.label(mask, structure=np.ones((3, 3)))
+            ref_areas = np.bincount(ref.ravel(), minlength=n + 1)[1:]
+        n = int(nlab.item())
+        assert n == len(ref_areas)
+        assert np.array_equal(lab.cpu().numpy(), ref)
+        assert np.array_equal(areas[:n].cpu().numpy(), ref_areas)
+
+
+def test_synoptic_regions_wrap_around_the_seam():
+    """SynopticChips.labels: a dark region that straddles longitude 0 / 360 is ONE region with the
+    periodic labelling and two without; labels follow the final map of the chosen threshold."""
+    from pychips_b200 import SynopticChips
+    syn = synth.synthetic_synoptic(180, 360, 0).astype(np.float32)
+    syn[60:90, :14] *= 0.05
+    syn[60:90, -11:] *= 0.05
+    sm = synth.FakeSynoptic(syn)
+    c = SynopticChips(sm, base_folder="/tmp/chips_b200_test/")
+    c.run_CHIPS()
+    regs = list(sm.solar_ch_regions.__dict__.values())
+    t = len(regs) // 2
+    mask = regs[t].map > 0
+    assert mask[75, 0] and mask[75, -1]
+    lab, areas = c.labels(t)
+    ref, ref_areas = _periodic_labels_spec(mask)
+    assert np.array_equal(lab, ref) and np.array_equal(areas, ref_areas)
+    assert lab[75, 0] == lab[75, -1] > 0
+    lab0, areas0 = c.labels(t, periodic=False)
+    assert lab0[75, 0] != lab0[75, -1] and len(areas0) > len(areas)
+    assert int(areas.sum()) == int(mask.sum()) == int(areas0.sum())
+
+
 # ----------------------------------------------------------------------------- randomised configurations
 @pytest.mark.parametrize("seed", range(10))
 def test_random_configurations_vs_oracle(seed):
