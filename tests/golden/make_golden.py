@@ -176,8 +176,32 @@ def make_fl(name, n, seed, kw):
     print(name, "candidate fill on disk", float(o.candidate[on].mean()), "T", len(keys))
 
 
+def make_netcdf_layout(name="netcdf_layout_n256", src="disk_n256_k11"):
+    """The NETCDF4 group layout of the UNMODIFIED reference's Chips.to_netcdf (chips.py:512-590),
+    recorded call by call (netCDF4 itself is absent from this image: oracle/nc_recorder.py)."""
+    import json
+    import sys as _sys
+    from oracle import nc_recorder as ncr
+    n, seed, scale, kw = DISK_CASES[src]
+    img, r = synth.synthetic_disk(n, seed)
+    img = (img * np.float32(scale)).astype(np.float32)
+    d = synth.FakeDisk(img.astype(np.float64), r)
+    aia = synth.FakeAIA(d)
+    c = rh.run_disk(d, aia, **kw)
+    mod = _sys.modules[type(c).__module__]
+    mod.Dataset = ncr.Dataset                      # the name chips.py:526 `nc = Dataset(...)` resolves
+    c.to_netcdf(193, n)
+    log = ncr.LAST[-1].log
+    with open(os.path.join(HERE, name + ".json"), "w") as f:
+        json.dump(dict(source=src, n=n, log=log), f, indent=1)
+    print(name, len(log), "calls:", [x[:3] for x in log if x[0] in ("group", "var")])
+
+
 if __name__ == "__main__":
     assert rh.available(), "reference tree missing"
+    if len(sys.argv) > 1 and sys.argv[1] == "netcdf":
+        make_netcdf_layout()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fl":
         for name, (n, seed, kw) in FL_CASES.items():
             make_fl(name, n, seed, kw)

@@ -858,6 +858,33 @@ def test_region_cube_and_netcdf_file(tmp_path):
     assert np.array_equal(np.asarray(filt), d_or.solar_filter.filt_disk.astype(np.float32))
 
 
+def test_netcdf4_group_layout_matches_the_reference_call_for_call(tmp_path, monkeypatch):
+    """The NETCDF4 branch of Chips.to_netcdf (chips.py:528-588: groups fits / filter / ch_regions,
+    their dimensions, variables, dtypes and values) against the call log of the UNMODIFIED
+    reference, recorded by tests/golden/make_golden.py with the same stand-in for the absent
+    netCDF4 package (oracle/nc_recorder.py)."""
+    import json
+    import os
+    import sys
+    from oracle import nc_recorder as ncr
+    from pychips_b200 import Chips
+    here = os.path.dirname(os.path.abspath(__file__))
+    want = json.load(open(os.path.join(here, "golden", "netcdf_layout_n256.json")))
+    g = load_golden(want["source"])
+    monkeypatch.setitem(sys.modules, "netCDF4", ncr.as_module())
+    d = synth.FakeDisk(g["image"].astype(np.float64), int(g["pixel_radius"]))
+    c = Chips(synth.FakeAIA(d), base_folder=str(tmp_path) + "/", medfilt_kernel=int(g["kw_medfilt_kernel"]),
+              h_bins=int(g["kw_h_bins"]), threshold_range=[v.item() for v in g["kw_threshold_range"]])
+    c.run_CHIPS()
+    before = len(ncr.LAST)
+    c.to_netcdf(193, want["n"])
+    assert len(ncr.LAST) == before + 1
+    got = json.loads(json.dumps(ncr.LAST[-1].log))
+    assert len(got) == len(want["log"])
+    for a, b in zip(got, want["log"]):
+        assert a == b, (a, b)
+
+
 @pytest.mark.parametrize("T", [1, 3, 20, 25])
 def test_pack_cube_ragged_sizes(T):
     eng = _engine()
