@@ -297,6 +297,14 @@ int chips_input_rect(const chips_plan* plan, int32_t* rect);
 int chips_copy_rect(void* dst, const void* src, size_t pitch_bytes, size_t x0_bytes, int y0,
                     size_t width_bytes, int rows, int to_device, void* stream);
 
+/* ---- downloads of only what carries information.  The level-encoded result map (plan->off_keep)
+ *      is T ("in no map") almost everywhere: chips_pack_keep appends one word per pixel with
+ *      keep < T, (y * W + x) << 6 | keep, in arbitrary order, to `entries` (device memory or
+ *      mapped pinned host memory, `cap` words) and leaves their number in *count (device; entries
+ *      beyond cap are counted, not written).  Needs H * W <= 2^26, T <= 64, W % 4 == 0. -------- */
+int chips_pack_keep(const chips_plan* plan, uint32_t* entries, uint32_t cap, uint32_t* count, void* ws,
+                    void* stream);
+
 /* helper: f64 -> f32 demotion with an exactness flag (1 = every value representable) */
 int chips_demote_f64(const double* in, float* out, size_t n, int32_t* all_exact, void* stream);
 

@@ -94,6 +94,7 @@ SIGNATURES = {
                                  _vp], C.c_int),
     "chips_label_workspace_bytes": ([_i, _i], C.c_size_t),
     "chips_label_periodic": ([_vp, _i, _i, _i, _i, _i, _vp, _vp, C.c_longlong, _vp, _vp, _vp], C.c_int),
+    "chips_pack_keep": ([_PP, _vp, C.c_uint32, _vp, _vp, _vp], C.c_int),
     "chips_batch_create": ([_vp, _i, _i, _i, _i, _i, _i, _i, _i], C.c_int),
     "chips_detect_batch": ([_vp, _i, _vp, _i, _vp, _vp, _vp, _d, _d, _vp, _d, _d, _vp, _vp, _vp, _d], C.c_int),
     "chips_batch_destroy": ([_vp], C.c_int),

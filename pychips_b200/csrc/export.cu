@@ -128,6 +128,55 @@ __global__ void __launch_bounds__(1024) k_cosine_mean(double* __restrict__ out, 
   }
 }
 
+// ------------------------------------------------------------------ sparse result map
+// The level-encoded result `keep` is T ("in no map") on ~97 % of a 4096^2 image; only the
+// pixels with keep < T are worth a device -> host copy.  entry = (pixel index << 6) | keep.
+// Warp-aggregated append (one atomic per warp that has anything); the order of the entries is
+// arbitrary, the decoder scatters them.  `entries` may be mapped pinned host memory: the appends
+// are coalesced runs of up to 32 words.
+__global__ void __launch_bounds__(256) k_pack_keep(const uint8_t* __restrict__ keep, int W, int rx0, int ry0,
+                                                   int rw, int rh, int T, uint32_t* __restrict__ entries,
+                                                   uint32_t cap, uint32_t* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const int words = (rw + (rx0 & 3) + 3) >> 2;               // aligned 4-pixel words per ROI row
+  const long long total = (long long)words * rh;
+  for (long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < total;
+       i0 += (long long)gridDim.x * blockDim.x) {
+    const long long i = i0 + lane;
+    uint32_t m = 0, v = 0;
+    int x = 0, y = 0;
+    if (i < total) {
+      y = ry0 + (int)(i / words);
+      x = (rx0 & ~3) + 4 * (int)(i % words);
+      v = *reinterpret_cast<const uint32_t*>(keep + (size_t)y * W + x);   // W % 4 == 0 is checked by the host
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int xb = x + b;
+        if (xb >= rx0 && xb < rx0 + rw && ((v >> (8 * b)) & 255u) < (uint32_t)T) m |= 1u << b;
+      }
+    }
+    const uint32_t any = __ballot_sync(0xFFFFFFFFu, m != 0);
+    if (!any) continue;
+    const int c = __popc(m);
+    int inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    uint32_t base = 0;
+    if (lane == 31) base = atomicAdd(count, (uint32_t)inc);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31) + (uint32_t)(inc - c);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (m & (1u << b)) {
+        if (base < cap) entries[base] = ((uint32_t)(y * W + x + b) << 6) | ((v >> (8 * b)) & 255u);
+        ++base;
+      }
+    }
+  }
+}
+
 }  // namespace chips
 
 using namespace chips;
@@ -158,5 +207,19 @@ extern "C" int chips_row_cosine(const void* map, const void* map0, int H, int W,
   k_cosine_mean<<<1, 1024, 0, st>>>(out, H);
   CHIPS_CHECK_LAUNCH();
   count_launch(2);
+  return CHIPS_OK;
+}
+
+extern "C" int chips_pack_keep(const chips_plan* plan, uint32_t* entries, uint32_t cap, uint32_t* count,
+                               void* ws, void* stream) {
+  if (!plan || !entries || !count || !ws) return CHIPS_E_ARG;
+  if ((long long)plan->H * plan->W > (1LL << 26) || plan->T > 64 || (plan->W & 3)) return CHIPS_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  CHIPS_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), st));
+  const uint8_t* keep = (const uint8_t*)ws + plan->off_keep;
+  k_pack_keep<<<4 * chips::kNumSM, 256, 0, st>>>(keep, plan->W, plan->roi_x0, plan->roi_y0, plan->roi_w,
+                                                plan->roi_h, plan->T, entries, cap, count);
+  CHIPS_CHECK_LAUNCH();
+  chips::count_launch();
   return CHIPS_OK;
 }

@@ -356,6 +356,14 @@ class Detector:
         lab[fg] = inv.astype(np.int32) + 1
         return lab, a[fg][first].astype(np.int64)
 
+    def pack_keep(self, entries: torch.Tensor, count: torch.Tensor) -> None:
+        """Append (pixel index << 6 | keep) of every pixel with keep < T to `entries` (uint32/int32
+        tensor on the device, or PINNED host memory: the kernel writes through the mapping, no
+        device -> host copy of the 16.8 MB map) and leave their number in `count` (device)."""
+        ptr = entries.data_ptr()
+        _lib.check(self.lib.chips_pack_keep(self._pp, ptr, int(entries.numel()), _ptr(count), _ptr(self.ws),
+                                            _stream_ptr()), "chips_pack_keep")
+
     def labels_periodic(self, t: int, periodic: bool = True):
         """8-connected components of the final map of threshold t (`keep <= t`) with the x axis
         periodic (synoptic maps: longitude wraps) - `chips_label_periodic`.  Returns (labels int32

@@ -37,8 +37,48 @@ class SeriesResult:
     limits: np.ndarray             # [n, T]
     probs: np.ndarray              # [n, T]
     n_kept: np.ndarray             # [n, T]
-    keep: list = field(default_factory=list)   # per image uint8 [H,W] level-encoded maps (host)
+    keep: list = field(default_factory=list)   # per image uint8 [H,W] level-encoded maps (host; decoded
+                                               # on first access when the runner downloads them sparse)
     prob_map_sum: torch.Tensor | None = None   # device fp32 [H,W], summed over the batch
+
+
+def decode_keep(entries: np.ndarray, H: int, W: int, T: int) -> np.ndarray:
+    """Dense level-encoded map from the words of `chips_pack_keep` ((pixel index << 6) | keep)."""
+    out = np.full(H * W, T, dtype=np.uint8)
+    e = np.asarray(entries).view(np.uint32)
+    out[e >> 6] = (e & 63).astype(np.uint8)
+    return out.reshape(H, W)
+
+
+class SparseKeepList:
+    """`SeriesResult.keep` of a runner with `sparse_keep=True`: list-like, image i is decoded from
+    its packed words on first access (`packed(i)` returns the words themselves)."""
+
+    def __init__(self, entries_host, counts_host, H, W, T):
+        self._e, self._c, self._shape, self._T = entries_host, counts_host, (H, W), T
+        self._cache = {}
+
+    def __len__(self):
+        return len(self._e)
+
+    def packed(self, i) -> np.ndarray:
+        n = int(self._c[i])
+        if n > self._e[i].numel():
+            raise _lib.ChipsNativeError(f"sparse result map of image {i} overflowed ({n} entries): "
+                                        "use SeriesRunner(sparse_keep=False)")
+        return self._e[i].numpy()[:n].view(np.uint32)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if i not in self._cache:
+            self._cache[i] = decode_keep(self.packed(i), *self._shape, self._T)
+        return self._cache[i]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
 
 
 class SeriesRunner:
@@ -48,7 +88,7 @@ class SeriesRunner:
                  threshold_range=(0, 20), ht_peak_ratio=5, porb_threshold=0.8,
                  area_threshold=1e-3, masked: bool = True, device=None, n_streams: int = 2,
                  elem: int = 4, want_keep: bool = True, want_prob_map: bool = True,
-                 want_maps: bool = False):
+                 want_maps: bool = False, sparse_keep: bool = True):
         self.device = engine.require_cuda(device)
         self.H, self.W = int(H), int(W)
         self.k, self.h_bins = int(medfilt_kernel), int(h_bins)
@@ -58,6 +98,11 @@ class SeriesRunner:
         self.masked = masked
         self.elem = elem
         self.want_keep, self.want_prob_map, self.want_maps = want_keep, want_prob_map, want_maps
+        # the result map travels as one word per pixel that is in some map (~3 % of a disk image)
+        # instead of H*W bytes; needs the word format of chips_pack_keep
+        self.sparse_keep = bool(sparse_keep and want_keep and self.H * self.W <= (1 << 26)
+                                and self.T <= 64 and self.W % 4 == 0)
+        self.sparse_cap = max(4096, self.H * self.W // 8)
         self.dtype = torch.float32 if elem == 4 else torch.float64
         self.n_streams = n_streams
         self._slots = {}
@@ -112,12 +157,17 @@ class SeriesRunner:
         sets = self.__dict__.setdefault("_host_sets", {})
         ring = sets.get(n)
         if ring is None:                                # pinned result buffers, reused round-robin
+            def keep_bufs():
+                if not self.want_keep:
+                    return []
+                if self.sparse_keep:        # packed words, written by the kernel through the mapping
+                    return [torch.empty(self.sparse_cap, dtype=torch.int32).pin_memory() for _ in range(n)]
+                return [torch.empty((self.H, self.W), dtype=torch.uint8).pin_memory() for _ in range(n)]
             ring = sets[n] = dict(next=0, bufs=[
-                (torch.empty((n, rec_bytes), dtype=torch.uint8).pin_memory(),
-                 [torch.empty((self.H, self.W), dtype=torch.uint8).pin_memory() for _ in range(n)]
-                 if self.want_keep else [], [None])
+                (torch.empty((n, rec_bytes), dtype=torch.uint8).pin_memory(), keep_bufs(), [None],
+                 torch.zeros(n, dtype=torch.int32).pin_memory())
                 for _ in range(self.n_host_sets)])
-        rec_host, keep_host, owner = ring["bufs"][ring["next"]]
+        rec_host, keep_host, owner, cnt_host = ring["bufs"][ring["next"]]
         ring["next"] = (ring["next"] + 1) % self.n_host_sets
         if owner[0] is not None and not owner[0]._done:
             owner[0].result()                            # the set is still in flight: finish it first
@@ -171,13 +221,17 @@ class SeriesRunner:
                     # does not wait for the device -> host copy
                     st.wait_event(self._stage_free[slot])
                     self._stage_rec[slot].copy_(det.result_bytes(), non_blocking=True)
-                    if self.want_keep:
+                    if self.sparse_keep:
+                        det.pack_keep(keep_host[i], self._stage_cnt[slot])
+                    elif self.want_keep:
                         self._stage_keep[slot].copy_(det.keep, non_blocking=True)
                     self._snap[slot].record(st)
                 with torch.cuda.stream(self._d2h):
                     self._d2h.wait_event(self._snap[slot])
                     rec_host[i].copy_(self._stage_rec[slot], non_blocking=True)
-                    if self.want_keep:
+                    if self.sparse_keep:
+                        cnt_host[i:i + 1].copy_(self._stage_cnt[slot], non_blocking=True)
+                    elif self.want_keep:
                         keep_host[i].copy_(self._stage_keep[slot], non_blocking=True)
                     self._stage_free[slot].record(self._d2h)
             for s in self.streams + [self._h2d, self._d2h, self._acc]:
@@ -185,7 +239,8 @@ class SeriesRunner:
             done = torch.cuda.Event()
             done.record(cur)
         handle = PendingSeries(self, indices, rec_host, keep_host, done,
-                               prob_sum if self.want_prob_map else None)
+                               prob_sum if self.want_prob_map else None,
+                               cnt_host if self.sparse_keep else None)
         owner[0] = handle
         return handle
 
@@ -211,7 +266,8 @@ class SeriesRunner:
         self._snap = [ev() for _ in range(ns)]
         self._stage_rec = [torch.empty(C.sizeof(_lib.Result), dtype=torch.uint8, device=dev) for _ in range(ns)]
         self._stage_keep = [torch.empty((self.H, self.W), dtype=torch.uint8, device=dev)
-                            if self.want_keep else None for _ in range(ns)]
+                            if self.want_keep and not self.sparse_keep else None for _ in range(ns)]
+        self._stage_cnt = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(ns)]
         cur = torch.cuda.current_stream()
         for s in range(ns):                      # events start "signalled"
             for p in range(2):
@@ -223,12 +279,13 @@ class SeriesRunner:
 class PendingSeries:
     """A submitted batch (`SeriesRunner.submit`)."""
 
-    def __init__(self, runner, indices, rec_host, keep_host, done, prob_sum=None):
+    def __init__(self, runner, indices, rec_host, keep_host, done, prob_sum=None, cnt_host=None):
         # no strong reference to the runner: the runner keeps this handle (its pinned buffers are
         # still in flight), a reference back would make a cycle that only the cycle collector frees
         self._T, self._indices = runner.T, indices
         self._rec_host, self._keep_host, self._event = rec_host, keep_host, done
         self._prob_sum = prob_sum
+        self._cnt_host, self._shape = cnt_host, (runner.H, runner.W)
         self._done, self._result = False, None
 
     def result(self) -> SeriesResult:
@@ -247,7 +304,8 @@ class PendingSeries:
             limits=np.array([[rc.limits[t] for t in range(T)] for rc in recs]).reshape(n, T),
             probs=np.array([[rc.probs[t] for t in range(T)] for rc in recs]).reshape(n, T),
             n_kept=np.array([[rc.n_kept[t] for t in range(T)] for rc in recs]).reshape(n, T),
-            keep=[k.numpy() for k in self._keep_host],
+            keep=(SparseKeepList(self._keep_host, self._cnt_host.numpy(), *self._shape, T)
+                  if self._cnt_host is not None else [k.numpy() for k in self._keep_host]),
             prob_map_sum=self._prob_sum,
         )
         self._done = True

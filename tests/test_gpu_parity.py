@@ -624,6 +624,13 @@ def test_config3_time_series_runner_matches_single_image_path():
         st = c.probability_map(d)
         total += np.nan_to_num(st, nan=0.0)
     assert np.allclose(res.prob_map_sum.cpu().numpy(), total, rtol=1e-5, atol=1e-6)
+    # the maps above came back sparse (one word per pixel that is in some map, written by the kernel
+    # through the pinned mapping); the dense download gives the same arrays
+    assert runner.sparse_keep and 0 < res.keep.packed(0).size < n * n // 8
+    dense = series.SeriesRunner(n, n, k, 500, (0, 20), n_streams=2, want_maps=False, sparse_keep=False)
+    rd = dense.run([torch.from_numpy(im).pin_memory() for im in imgs], radii)
+    for i in range(len(imgs)):
+        assert np.array_equal(rd.keep[i], res.keep[i])
     # three radii on two stream slots: one workspace per slot, shared by the per-radius plans
     assert len(runner._slots) > 2
     assert len({d.ws.data_ptr() for d in runner._slots.values()}) == 2
