@@ -325,7 +325,8 @@ def run_b200(a):
             down_note = ("per image the 1.6 kB record and the result map as one 32-bit word per pixel that is in "
                          "some map (chips_pack_keep writes them through the pinned mapping; "
                          f"{down / a.batch / 1e6:.2f} MB per image instead of {n * n / 1e6:.1f} MB dense)")
-            assert np.array_equal(res.keep[0], series.decode_keep(res.keep.packed(0), n, n, T))
+            assert not res.keep.is_dense(0) and np.array_equal(
+                res.keep[0], series.decode_keep(res.keep.packed(0), n, n, T))
         else:
             down = a.batch * (n * n + rec)
             down_note = "per image the 1.6 kB record and the dense level-encoded result map"
@@ -416,14 +417,33 @@ def run_b200(a):
             ("cleanup(fill+ccl)", lambda: det.cleanup(1e-3), 2 * T * n * n),
             ("k_expand_all", lambda: det.expand_maps(0, runner.maps[0]), (T + 1) * n * n),
         ]
+        # every stage is captured in a CUDA graph and the REPLAY is timed: that is how the timed
+        # region above runs them (Detector.detect_graphed), and a stage of many small launches
+        # (the cleanup) costs less per launch inside a graph than enqueued one by one
         reps = 5
         times = {name: 0.0 for name, _, _ in stages}
+        nodes = {}
+        graphs = {}
+        cap = torch.cuda.Stream(device=dev)
+        import gc
+        gc.collect()
+        gc.disable()                                           # no finaliser may run inside a capture
+        for name, fn, _b in stages:
+            fn()                                               # warm (function attributes, lazy state)
+            torch.cuda.synchronize()
+            gph = torch.cuda.CUDAGraph()
+            l_before = lib.chips_launch_count()
+            with torch.cuda.graph(gph, stream=cap, capture_error_mode="thread_local"):
+                fn()
+            nodes[name] = int(lib.chips_launch_count() - l_before)
+            graphs[name] = gph
+        gc.enable()
         for _ in range(reps):
             for name, fn, _b in stages:
                 flush.fill_(1)                                 # evict L2 between kernels
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                fn()
+                graphs[name].replay()
                 e1.record()
                 torch.cuda.synchronize()
                 times[name] += e0.elapsed_time(e1) / reps
@@ -436,8 +456,8 @@ def run_b200(a):
         # the cleanup entry is a stage of ~90 small, latency-bound launches (not one kernel): the
         # dominant KERNEL is chosen among the single-kernel entries
         for st_ in per_stage:
-            if st_["kernel"].startswith("cleanup"):
-                st_["launches"] = 6 + 2 * (T - 1) + 5 + 2 * T
+            if nodes.get(st_["kernel"], 1) > 1:
+                st_["launches"] = nodes[st_["kernel"]]
         dom = max((s_ for s_ in per_stage if "launches" not in s_), key=lambda s_: s_["ms"])
         big = max(per_stage, key=lambda s_: s_["ms"])          # the largest STAGE (may be many launches)
         traffic = None

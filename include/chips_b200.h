@@ -59,7 +59,10 @@ typedef struct chips_result {
 
 /* Byte offsets of every buffer inside one workspace blob (all 256-byte aligned). */
 typedef struct chips_plan {
-  int32_t H, W, k, h_bins, T, elem, masked, pad_;
+  int32_t H, W, k, h_bins, T, elem, masked;
+  int32_t f32_math;   /* 1: the caller's arrays are float32 and numpy would keep float32 for the bin edges,
+                       * bound / limit_0 and the sigmoid of calculate_prob (np.histogram's bin_type,
+                       * chips.py:235-244, :446); 0 (chips_plan_init): float64 arithmetic.  elem must be 4. */
   int32_t roi_x0, roi_y0, roi_w, roi_h;   /* bounding box of the disk (whole image if unmasked) */
   /* median blocks: the ROI is cut into blk_nbx x blk_nby blocks of 128 columns x blk_rows rows
    * (blk_rows a multiple of 16).  Each block sorts its halo-extended region ((128+k-1) x bp_rows
@@ -181,8 +184,8 @@ typedef struct chips_window_rec {
   int32_t n_peaks, pad_;
 } chips_window_rec;
 size_t chips_window_workspace_bytes(int nwin);
-int chips_window_histograms(const void* filt, int H, int W, int elem, int cx, int cy, int r, int nwin,
-                            const int32_t* rects, int h_bins, double ht_peak_ratio, double h_thresh_in,
+int chips_window_histograms(const void* filt, int H, int W, int elem, int f32_math, int cx, int cy, int r,
+                            int nwin, const int32_t* rects, int h_bins, double ht_peak_ratio, double h_thresh_in,
                             long long* counts, double* density, double* bound, int32_t* peaks,
                             chips_window_rec* recs, void* ws, void* stream);
 
@@ -301,9 +304,17 @@ int chips_copy_rect(void* dst, const void* src, size_t pitch_bytes, size_t x0_by
  *      is T ("in no map") almost everywhere: chips_pack_keep appends one word per pixel with
  *      keep < T, (y * W + x) << 6 | keep, in arbitrary order, to `entries` (device memory or
  *      mapped pinned host memory, `cap` words) and leaves their number in *count (device; entries
- *      beyond cap are counted, not written).  Needs H * W <= 2^26, T <= 64, W % 4 == 0. -------- */
+ *      beyond cap are counted, not written).  When *count > cap and cap * 4 >= H * W (entries
+ *      16-byte aligned), the buffer receives the dense H * W bytes of the map instead: the reader
+ *      tells the two apart by *count > cap.  Needs H * W <= 2^26, T <= 64, W % 4 == 0. -------- */
 int chips_pack_keep(const chips_plan* plan, uint32_t* entries, uint32_t cap, uint32_t* count, void* ws,
                     void* stream);
+/* copy of min(*count, cap) 32-bit words whose number only the device knows (count: device memory),
+ * e.g. the entries of chips_pack_keep into mapped pinned host memory, by 8 CTAs on `stream` (a copy
+ * stream: it takes no SMs worth mentioning from the detections); *count_out (optional, may be
+ * mapped host memory) = *count.  src, dst 16-byte aligned. */
+int chips_copy_words(const uint32_t* src, uint32_t* dst, const uint32_t* count, uint32_t cap,
+                     uint32_t* count_out, void* stream);
 
 /* helper: f64 -> f32 demotion with an exactness flag (1 = every value representable) */
 int chips_demote_f64(const double* in, float* out, size_t n, int32_t* all_exact, void* stream);

@@ -27,7 +27,7 @@ class Result(C.Structure):
 class Plan(C.Structure):
     """Mirror of `chips_plan`."""
     _fields_ = [(n, C.c_int32) for n in
-                ("H", "W", "k", "h_bins", "T", "elem", "masked", "pad_",
+                ("H", "W", "k", "h_bins", "T", "elem", "masked", "f32_math",
                  "roi_x0", "roi_y0", "roi_w", "roi_h", "bp_pitch", "bp_rows",
                  "blk_rows", "blk_nbx", "blk_nby", "blk_bucket")] + \
                [(n, C.c_size_t) for n in
@@ -90,11 +90,12 @@ SIGNATURES = {
     "chips_prob_stack": ([_PP, _d, _vp, _i, _i, _vp, _vp], C.c_int),
     "chips_detect": ([_vp, _PP, _i, _i, _i, _d, _d, _vp, _d, _d, _vp, _vp, _vp], C.c_int),
     "chips_window_workspace_bytes": ([_i], C.c_size_t),
-    "chips_window_histograms": ([_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp,
-                                 _vp], C.c_int),
+    "chips_window_histograms": ([_vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _d, _d, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _vp], C.c_int),
     "chips_label_workspace_bytes": ([_i, _i], C.c_size_t),
     "chips_label_periodic": ([_vp, _i, _i, _i, _i, _i, _vp, _vp, C.c_longlong, _vp, _vp, _vp], C.c_int),
     "chips_pack_keep": ([_PP, _vp, C.c_uint32, _vp, _vp, _vp], C.c_int),
+    "chips_copy_words": ([_vp, _vp, _vp, C.c_uint32, _vp, _vp], C.c_int),
     "chips_batch_create": ([_vp, _i, _i, _i, _i, _i, _i, _i, _i], C.c_int),
     "chips_detect_batch": ([_vp, _i, _vp, _i, _vp, _vp, _vp, _d, _d, _vp, _d, _d, _vp, _vp, _vp, _d], C.c_int),
     "chips_batch_destroy": ([_vp], C.c_int),

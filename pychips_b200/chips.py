@@ -178,7 +178,12 @@ class Chips(object):
                 self._no_thresholds = len(np.arange(t0, t1)) == 0
                 if self._no_thresholds:
                     t0, t1 = 0, 1
-                det = Detector(self._geometry(disk), self.medfilt_kernel, self.h_bins, t0, t1, elem, self.device)
+                # float32 raw AND normalized arrays: h_data = filt_disk * n_mask stays float32 and numpy
+                # keeps float32 bin edges (np.histogram's bin_type), bound, limit_0 and sigmoid
+                f32 = (np.asarray(disk.normalized.data).dtype == np.float32
+                       and np.asarray(disk.raw.data).dtype == np.float32)
+                det = Detector(self._geometry(disk), self.medfilt_kernel, self.h_bins, t0, t1, elem, self.device,
+                               f32_math=f32)
                 det.state = set()
             self._det[id(disk)] = det
             self._img[id(disk)] = img
@@ -264,11 +269,12 @@ class Chips(object):
                     self.h_thresh = np.float64(res.h_thresh)       # sticky, chips.py:240-241
                 npk = int(res.n_peaks)
                 pidx = det.peak_index[:npk].cpu().numpy()
-                bound = det.bound.cpu().numpy()
+                edt = np.float32 if det.f32_math else np.float64      # dtype of np.histogram's edges
+                bound = det.bound.cpu().numpy().astype(edt, copy=False)
             peaks = [bound[p] for p in pidx]
             disk.set_value("histogram", LazyNamespace(
                 _lazy=dict(hbase=lambda: det.density.cpu().numpy(),
-                           hbins=lambda: det.edges.cpu().numpy(),
+                           hbins=lambda: det.edges.cpu().numpy().astype(edt, copy=False),
                            counts=lambda: det.counts.cpu().numpy()),
                 peaks=peaks, bound=bound, h_thresh=self.h_thresh, h_bins=self.h_bins,
                 peak_indexs=pidx))
@@ -301,6 +307,7 @@ class Chips(object):
                                               np.zeros(0, dtype=np.int64), np.float64(np.nan))
                     else:
                         h, bc, peaks, hthr = out
+                        bc = bc.astype(np.float32 if det.f32_math else np.float64, copy=False)
                     if self.h_thresh is None:
                         self.h_thresh = hthr
                     if len(peaks) > 1:
@@ -339,6 +346,7 @@ class Chips(object):
                 with torch.cuda.device(self.device):
                     self._ensure_filt(disk, det)
                     dens, bnd, pks, hthr, _ = det.window_histograms(windows, self.ht_peak_ratio, self.h_thresh)
+                    bnd = bnd.astype(np.float32 if det.f32_math else np.float64, copy=False)
                 if self.h_thresh is None:
                     self.h_thresh = hthr
                 for k, (r0, r1, c0, c1) in enumerate(windows):
@@ -379,7 +387,7 @@ class Chips(object):
                     det.state.add("maps")
                     res = det.result()
                 engine._lib.check_record(res)
-                limit_0 = np.float64(res.limit_0)
+                limit_0 = (np.float32 if det.f32_math else np.float64)(res.limit_0)    # = histogram.peaks[0]
                 dtmp_map = {}
                 traced_all = {}
                 for t in range(det.T):

@@ -98,6 +98,62 @@ __device__ __forceinline__ double linspace_edge(int i, int nbins, double first, 
   return __dadd_rn(__dmul_rn((double)i, step), first);
 }
 
+// Bin edges of np.histogram(bins=n): np.linspace(first, last, n + 1) in the dtype of the data.
+// float64 data (and everything widened to it): fp64.  float32 DATA (f32 = 1: numpy keeps
+// bin_type = float32, numpy/lib/_histograms_impl.py `_get_bin_edges`): every operation of
+// linspace in float32 - delta = last - first, step = delta / n, edge_i = i * step + first, last
+// edge forced - and the values returned widened (exactly) to double.
+struct Edges {
+  int nbins, f32;
+  double first, last, step;
+  float ffirst, flast, fstep, fdelta;
+  __device__ __forceinline__ double operator()(int i) const {
+    if (!f32) return linspace_edge(i, nbins, first, last, step);
+    if (i >= nbins) return (double)flast;
+    const float y = (fstep == 0.0f) ? __fmul_rn(__fdiv_rn((float)i, (float)nbins), fdelta)
+                                    : __fmul_rn((float)i, fstep);
+    return (double)__fadd_rn(y, ffirst);
+  }
+  // np.diff(edges)[i] as float64 (numpy subtracts in the edge dtype, then converts)
+  __device__ __forceinline__ double width(double e0, double e1) const {
+    return f32 ? (double)__fsub_rn((float)e1, (float)e0) : __dsub_rn(e1, e0);
+  }
+  // edges[:-1] + np.diff(edges) in the edge dtype
+  __device__ __forceinline__ double upper(double e0, double db) const {
+    return f32 ? (double)__fadd_rn((float)e0, (float)db) : __dadd_rn(e0, db);
+  }
+};
+
+// outer edges of a selection with minimum `first` and maximum `last` (np.histogram's
+// _get_outer_edges: a.min(), a.max(), widened by 0.5 on both sides when they are equal; (0, 1)
+// for an empty selection: empty = true)
+__device__ __forceinline__ Edges make_edges(double first, double last, bool empty, int nbins, int f32) {
+  Edges e;
+  e.nbins = nbins;
+  e.f32 = f32;
+  if (empty) {
+    first = 0.0;
+    last = 1.0;
+  }
+  if (first == last) {
+    if (f32) {
+      first = (double)__fsub_rn((float)first, 0.5f);
+      last = (double)__fadd_rn((float)last, 0.5f);
+    } else {
+      first = first - 0.5;
+      last = last + 0.5;
+    }
+  }
+  e.first = first;
+  e.last = last;
+  e.step = __ddiv_rn(__dsub_rn(last, first), (double)nbins);
+  e.ffirst = (float)first;
+  e.flast = (float)last;
+  e.fdelta = __fsub_rn(e.flast, e.ffirst);
+  e.fstep = __fdiv_rn(e.fdelta, (float)nbins);
+  return e;
+}
+
 __device__ __forceinline__ void atomic_min_key(uint32_t* p, uint32_t v) { atomicMin(p, v); }
 __device__ __forceinline__ void atomic_max_key(uint32_t* p, uint32_t v) { atomicMax(p, v); }
 __device__ __forceinline__ void atomic_min_key(uint64_t* p, uint64_t v) {

@@ -128,6 +128,23 @@ __global__ void __launch_bounds__(1024) k_cosine_mean(double* __restrict__ out, 
   }
 }
 
+// a device-sized copy: `*count` words (at most cap) from device memory to mapped pinned host memory
+// (or anywhere else) with a handful of CTAs - 128-bit coalesced stores, posted over PCIe - so that
+// the copy neither needs the size on the host nor takes SMs from the detections in flight
+__global__ void __launch_bounds__(256) k_copy_words(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                    const uint32_t* __restrict__ count, uint32_t cap,
+                                                    uint32_t* __restrict__ count_out) {
+  uint32_t n = *count;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && count_out) *count_out = n;
+  if (n > cap) n = cap;
+  const uint32_t n4 = n >> 2;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) d4[i] = s4[i];
+  for (uint32_t i = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
 // ------------------------------------------------------------------ sparse result map
 // The level-encoded result `keep` is T ("in no map") on ~97 % of a 4096^2 image; only the
 // pixels with keep < T are worth a device -> host copy.  entry = (pixel index << 6) | keep.
@@ -210,6 +227,24 @@ extern "C" int chips_row_cosine(const void* map, const void* map0, int H, int W,
   return CHIPS_OK;
 }
 
+namespace chips {
+// more entries than `cap` words: the words buffer receives the dense map instead (H * W bytes fit
+// when cap >= H * W / 4); *count > cap tells the reader which of the two it holds
+__global__ void __launch_bounds__(256) k_keep_dense_if_overflow(const uint8_t* __restrict__ keep, size_t nbytes,
+                                                                uint32_t* __restrict__ words, uint32_t cap,
+                                                                const uint32_t* __restrict__ count) {
+  if (*count <= cap) return;
+  const uint4* s = reinterpret_cast<const uint4*>(keep);
+  uint4* d = reinterpret_cast<uint4*>(words);
+  const size_t n16 = nbytes >> 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+    d[i] = s[i];
+  for (size_t i = (n16 << 4) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes;
+       i += (size_t)gridDim.x * blockDim.x)
+    reinterpret_cast<uint8_t*>(words)[i] = keep[i];
+}
+}  // namespace chips
+
 extern "C" int chips_pack_keep(const chips_plan* plan, uint32_t* entries, uint32_t cap, uint32_t* count,
                                void* ws, void* stream) {
   if (!plan || !entries || !count || !ws) return CHIPS_E_ARG;
@@ -219,6 +254,22 @@ extern "C" int chips_pack_keep(const chips_plan* plan, uint32_t* entries, uint32
   const uint8_t* keep = (const uint8_t*)ws + plan->off_keep;
   k_pack_keep<<<4 * chips::kNumSM, 256, 0, st>>>(keep, plan->W, plan->roi_x0, plan->roi_y0, plan->roi_w,
                                                 plan->roi_h, plan->T, entries, cap, count);
+  CHIPS_CHECK_LAUNCH();
+  chips::count_launch();
+  const size_t nbytes = (size_t)plan->H * plan->W;
+  if ((size_t)cap * 4 >= nbytes && !(((uintptr_t)entries) & 15)) {
+    chips::k_keep_dense_if_overflow<<<4 * chips::kNumSM, 256, 0, st>>>(keep, nbytes, entries, cap, count);
+    CHIPS_CHECK_LAUNCH();
+    chips::count_launch();
+  }
+  return CHIPS_OK;
+}
+
+extern "C" int chips_copy_words(const uint32_t* src, uint32_t* dst, const uint32_t* count, uint32_t cap,
+                                uint32_t* count_out, void* stream) {
+  if (!src || !dst || !count) return CHIPS_E_ARG;
+  if (((uintptr_t)src | (uintptr_t)dst) & 15) return CHIPS_E_ARG;
+  chips::k_copy_words<<<8, 256, 0, (cudaStream_t)stream>>>(src, dst, count, cap, count_out);
   CHIPS_CHECK_LAUNCH();
   chips::count_launch();
   return CHIPS_OK;

@@ -20,7 +20,7 @@ extern "C" int chips_plan_init(chips_plan* p, int H, int W, int k, int h_bins, i
   if (h_bins < 1 || T < 1 || T > CHIPS_MAX_T || (elem != 4 && elem != 8)) return CHIPS_E_ARG;
   if ((long long)H * W >= (1LL << 31)) return CHIPS_E_ARG;
   p->H = H; p->W = W; p->k = k; p->h_bins = h_bins; p->T = T; p->elem = elem;
-  p->masked = r >= 0; p->pad_ = 0;
+  p->masked = r >= 0; p->f32_math = 0;
   if (r >= 0) {
     int x0 = cx - r, x1 = cx + r + 1, y0 = cy - r, y1 = cy + r + 1;
     if (x0 < 0) x0 = 0;

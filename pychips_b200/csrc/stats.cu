@@ -56,12 +56,11 @@ __global__ void __launch_bounds__(256) k_minmax(const T* __restrict__ filt, int 
 // linspace edges.  Since that guess is within one bin of the bin whose edges bracket v, the
 // result IS the bracketing bin; we reach the same bin from a cheap fp32 guess and exact fp64
 // edge comparisons (no fp64 divide per pixel).
-__device__ __forceinline__ int hist_bin(double v, int nbins, double first, double last, double step,
-                                        float first_f, float scale_f) {
+__device__ __forceinline__ int hist_bin(double v, int nbins, const Edges& E, float first_f, float scale_f) {
   int g = (int)(((float)v - first_f) * scale_f);
   g = min(max(g, 0), nbins - 1);
-  while (g > 0 && v < linspace_edge(g, nbins, first, last, step)) --g;
-  while (g < nbins - 1 && v >= linspace_edge(g + 1, nbins, first, last, step)) ++g;
+  while (g > 0 && v < E(g)) --g;
+  while (g < nbins - 1 && v >= E(g + 1)) ++g;
   return g;
 }
 
@@ -84,37 +83,24 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_hist(const T* __restrict__ filt, int W, int rx0, int ry0,
                                               int rw, int rh, int cx, int cy, int r,
                                               const typename Key<T>::type* __restrict__ minmax,
-                                              int nbins, int copies, int use_table,
+                                              int nbins, int copies, int use_table, int f32_math,
                                               unsigned long long* __restrict__ counts,
                                               chips_result* __restrict__ res) {
   extern __shared__ __align__(16) uint32_t sh[];
   for (int i = threadIdx.x; i < copies * nbins; i += blockDim.x) sh[i] = 0;
-  double first, last;
-  {
-    typename Key<T>::type k0 = minmax[0], k1 = minmax[1];
-    if (k0 > k1) {          // empty selection: np.histogram uses the range (0, 1)
-      first = 0.0;
-      last = 1.0;
-    } else {
-      first = (double)Key<T>::dec(k0);
-      last = (double)Key<T>::dec(k1);
-    }
-    if (first == last) {
-      first = first - 0.5;
-      last = last + 0.5;
-    }
-  }
+  const typename Key<T>::type k0 = minmax[0], k1 = minmax[1];
+  const Edges edge = make_edges((double)Key<T>::dec(k0), (double)Key<T>::dec(k1), k0 > k1, nbins, f32_math);
+  const double first = edge.first, last = edge.last;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     res->first_edge = first;
     res->last_edge = last;
   }
   const double denom = __dsub_rn(last, first);
-  const double step = __ddiv_rn(denom, (double)nbins);
   const float first_f = (float)first, scale_f = (float)((double)nbins / denom);
   // edge table behind the sub-histograms (8-byte aligned: copies * nbins is rounded up to even)
   double* E = reinterpret_cast<double*>(sh + ((copies * nbins + 1) & ~1));
   if (use_table)
-    for (int i = threadIdx.x; i <= nbins; i += blockDim.x) E[i] = linspace_edge(i, nbins, first, last, step);
+    for (int i = threadIdx.x; i <= nbins; i += blockDim.x) E[i] = edge(i);
   __syncthreads();
   uint32_t* mine = sh + ((threadIdx.x >> 5) % copies) * nbins;
   for (int y = ry0 + blockIdx.x; y < ry0 + rh; y += gridDim.x) {
@@ -129,7 +115,7 @@ __global__ void __launch_bounds__(256) k_hist(const T* __restrict__ filt, int W,
         idx[i] = -1;
         if (xi >= xa && xi < xb)
           idx[i] = use_table ? hist_bin_tab((double)row[xi], nbins, E, first_f, scale_f)
-                             : hist_bin((double)row[xi], nbins, first, last, step, first_f, scale_f);
+                             : hist_bin((double)row[xi], nbins, edge, first_f, scale_f);
       }
       // neighbouring pixels of the median-filtered image mostly share a bin: merge first
 #pragma unroll
@@ -161,7 +147,7 @@ struct ThresholdOffsets {   // np.arange(threshold_range[0], threshold_range[1])
 
 __global__ void __launch_bounds__(1024) k_select(const long long* __restrict__ counts, int nbins,
                                                  double ratio, double h_thresh_in,
-                                                 const ThresholdOffsets offs, int T,
+                                                 const ThresholdOffsets offs, int T, int f32_math,
                                                  double* __restrict__ density,
                                                  double* __restrict__ edges,
                                                  double* __restrict__ bound, int* __restrict__ peaks,
@@ -172,8 +158,7 @@ __global__ void __launch_bounds__(1024) k_select(const long long* __restrict__ c
   __shared__ long long total_s;
   __shared__ double hthr_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const double first = res->first_edge, last = res->last_edge;
-  const double step = __ddiv_rn(__dsub_rn(last, first), (double)nbins);
+  const Edges edge = make_edges(res->first_edge, res->last_edge, false, nbins, f32_math);
 
   long long part = 0;
   for (int i = tid; i < nbins; i += blockDim.x) part += counts[i];
@@ -190,14 +175,14 @@ __global__ void __launch_bounds__(1024) k_select(const long long* __restrict__ c
 
   double dmax = -INFINITY;
   for (int i = tid; i <= nbins; i += blockDim.x) {
-    double e0 = linspace_edge(i, nbins, first, last, step);
+    double e0 = edge(i);
     edges[i] = e0;
     if (i < nbins) {
-      double e1 = linspace_edge(i + 1, nbins, first, last, step);
-      double db = __dsub_rn(e1, e0);
+      double e1 = edge(i + 1);
+      double db = edge.width(e0, e1);
       double d = __ddiv_rn(__ddiv_rn((double)counts[i], db), total);   // n / db / n.sum()
       density[i] = d;
-      bound[i] = __dadd_rn(e0, db);                                     // be[:-1] + diff(be)
+      bound[i] = edge.upper(e0, db);                                    // be[:-1] + diff(be)
       dmax = fmax(dmax, d);
     }
   }
@@ -279,7 +264,7 @@ __constant__ double kProbCut[20] = {
 template <typename T>
 __global__ void __launch_bounds__(256) k_threshold_prob(const T* __restrict__ filt, int W, int rx0,
                                                         int ry0, int rw, int rh, int cx, int cy,
-                                                        int r, const chips_result* __restrict__ res,
+                                                        int r, int f32_math, const chips_result* __restrict__ res,
                                                         uint8_t* __restrict__ lev,
                                                         uint32_t* __restrict__ probtab) {
   __shared__ double slim[CHIPS_MAX_T];
@@ -311,10 +296,23 @@ __global__ void __launch_bounds__(256) k_threshold_prob(const T* __restrict__ fi
           if (v <= top) {
             level = 0;
             for (int t = 0; t < nT; ++t) level += (slim[t] < v) ? 1 : 0;   // first t with v <= lim_t
-            double d = __dsub_rn(v, limit_0);
             int bin = 0;
+            if (f32_math) {
+              // float32 data: numpy evaluates 1/(1 + exp(data - limit_0).round(4)) in float32
+              // (chips.py:446) and bins it against float64 edges j/20.  expf here and numpy's SIMD
+              // float32 exp may differ in the last bit: a pixel on a rounding boundary may land in
+              // the neighbouring bin (probabilities agree to ~1e-7, the stated tolerance is 1e-5).
+              const float e = expf(__fsub_rn((float)v, (float)limit_0));
+              const float rr = __fdiv_rn(rintf(__fmul_rn(e, 10000.0f)), 10000.0f);
+              const double ps = (double)__fdiv_rn(1.0f, __fadd_rn(1.0f, rr));
 #pragma unroll
-            for (int j = 1; j < CHIPS_PROB_BINS; ++j) bin += (d <= kProbCut[j]) ? 1 : 0;
+              for (int j = 1; j < CHIPS_PROB_BINS; ++j)
+                bin += (ps >= __dadd_rn(__dmul_rn((double)j, __ddiv_rn(1.0, 20.0)), 0.0)) ? 1 : 0;
+            } else {
+              const double d = __dsub_rn(v, limit_0);
+#pragma unroll
+              for (int j = 1; j < CHIPS_PROB_BINS; ++j) bin += (d <= kProbCut[j]) ? 1 : 0;
+            }
             atomicAdd(&tab[level * CHIPS_PROB_BINS + bin], 1u);
             level = max(level, t_inv);             // chips.py:372-374: lim < -1 wipes the mask
           }
@@ -457,7 +455,7 @@ static int hist_impl(const T* filt, const chips_plan* p, int cx, int cy, int r, 
   int grid = min(p->roi_h, per_sm * kNumSM);
   k_hist<T><<<grid, 256, smem, st>>>(filt, p->W, p->roi_x0, p->roi_y0, p->roi_w, p->roi_h, cx, cy, r,
                                      reinterpret_cast<const K*>(ws + p->off_minmax), nbins, copies, use_table,
-                                     counts, reinterpret_cast<chips_result*>(ws + p->off_result));
+                                     p->f32_math && sizeof(T) == 4, counts, reinterpret_cast<chips_result*>(ws + p->off_result));
   CHIPS_CHECK_LAUNCH();
   count_launch();
   return CHIPS_OK;
@@ -473,7 +471,7 @@ static int thr_impl(const T* filt, const chips_plan* p, int cx, int cy, int r, d
   CHIPS_CUDA(cudaMemsetAsync(tab, 0, (size_t)(p->T + 1) * CHIPS_PROB_BINS * sizeof(uint32_t), st));
   int grid = min(p->roi_h, 8 * kNumSM);
   k_threshold_prob<T><<<grid, 256, 0, st>>>(filt, p->W, p->roi_x0, p->roi_y0, p->roi_w, p->roi_h, cx,
-                                            cy, r, res, lev, tab);
+                                            cy, r, p->f32_math && sizeof(T) == 4, res, lev, tab);
   CHIPS_CHECK_LAUNCH();
   k_prob_epilogue<<<1, CHIPS_MAX_T, 0, st>>>(tab, porb, res);
   CHIPS_CHECK_LAUNCH();
@@ -530,36 +528,19 @@ __global__ void __launch_bounds__(256) k_win_minmax(const T* __restrict__ filt, 
   }
 }
 
-// np.histogram's outer edges of a selection with ordered min / max keys k0, k1
-template <typename T>
-__device__ __forceinline__ void outer_edges(typename Key<T>::type k0, typename Key<T>::type k1, double& first,
-                                            double& last) {
-  if (k0 > k1) {          // empty selection: np.histogram uses the range (0, 1)
-    first = 0.0;
-    last = 1.0;
-  } else {
-    first = (double)Key<T>::dec(k0);
-    last = (double)Key<T>::dec(k1);
-  }
-  if (first == last) {
-    first = first - 0.5;
-    last = last + 0.5;
-  }
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256) k_win_hist(const T* __restrict__ filt, int W, const WinRect* __restrict__ rects,
                                                   int cx, int cy, int r,
                                                   const typename Key<T>::type* __restrict__ minmax, int nbins,
-                                                  int copies, unsigned long long* __restrict__ counts) {
+                                                  int copies, int f32_math,
+                                                  unsigned long long* __restrict__ counts) {
   extern __shared__ __align__(16) uint32_t sh[];
   const WinRect q = rects[blockIdx.y];
   for (int i = threadIdx.x; i < copies * nbins; i += blockDim.x) sh[i] = 0;
-  double first, last;
-  outer_edges<T>(minmax[2 * blockIdx.y], minmax[2 * blockIdx.y + 1], first, last);
-  const double denom = __dsub_rn(last, first);
-  const double step = __ddiv_rn(denom, (double)nbins);
-  const float first_f = (float)first, scale_f = (float)((double)nbins / denom);
+  const typename Key<T>::type k0 = minmax[2 * blockIdx.y], k1 = minmax[2 * blockIdx.y + 1];
+  const Edges edge = make_edges((double)Key<T>::dec(k0), (double)Key<T>::dec(k1), k0 > k1, nbins, f32_math);
+  const double denom = __dsub_rn(edge.last, edge.first);
+  const float first_f = (float)edge.first, scale_f = (float)((double)nbins / denom);
   __syncthreads();
   uint32_t* mine = sh + ((threadIdx.x >> 5) % copies) * nbins;      // warp-private bins
   for (int y = q.y0 + blockIdx.x; y < q.y1; y += gridDim.x) {
@@ -569,7 +550,7 @@ __global__ void __launch_bounds__(256) k_win_hist(const T* __restrict__ filt, in
     for (int x0 = xa; x0 < xb; x0 += blockDim.x) {
       const int x = x0 + threadIdx.x;
       int bin = -1;
-      if (x < xb) bin = hist_bin((double)row[x], nbins, first, last, step, first_f, scale_f);
+      if (x < xb) bin = hist_bin((double)row[x], nbins, edge, first_f, scale_f);
       // neighbouring pixels of the filtered image mostly share a bin: one shared-memory add per
       // run of equal bins inside the warp (shuffle with the left neighbour, ballot of run starts)
       const int left = __shfl_up_sync(0xFFFFFFFFu, bin, 1);
@@ -598,7 +579,7 @@ __global__ void __launch_bounds__(256) k_win_hist(const T* __restrict__ filt, in
 template <typename T>
 __global__ void __launch_bounds__(128) k_win_select(const unsigned long long* __restrict__ counts,
                                                     const typename Key<T>::type* __restrict__ minmax, int nwin,
-                                                    int nbins, double ratio, double h_thresh_in,
+                                                    int nbins, double ratio, double h_thresh_in, int f32_math,
                                                     double* __restrict__ density, double* __restrict__ bound,
                                                     int* __restrict__ peaks, chips_window_rec* __restrict__ recs) {
   const int lane = threadIdx.x & 31;
@@ -606,8 +587,10 @@ __global__ void __launch_bounds__(128) k_win_select(const unsigned long long* __
   if (w >= nwin) return;
   // density of window `v` into `dst` (or nowhere); returns max density and the sample count
   auto fill = [&](int v, double* dst, double* bnd, double& first, double& last, long long& total) {
-    outer_edges<T>(minmax[2 * v], minmax[2 * v + 1], first, last);
-    const double step = __ddiv_rn(__dsub_rn(last, first), (double)nbins);
+    const typename Key<T>::type k0 = minmax[2 * v], k1 = minmax[2 * v + 1];
+    const Edges edge = make_edges((double)Key<T>::dec(k0), (double)Key<T>::dec(k1), k0 > k1, nbins, f32_math);
+    first = edge.first;
+    last = edge.last;
     const unsigned long long* c = counts + (size_t)v * nbins;
     long long part = 0;
     for (int i = lane; i < nbins; i += 32) part += (long long)c[i];
@@ -615,13 +598,12 @@ __global__ void __launch_bounds__(128) k_win_select(const unsigned long long* __
     total = part;
     double dmax = -INFINITY;
     for (int i = lane; i < nbins; i += 32) {
-      const double e0 = linspace_edge(i, nbins, first, last, step);
-      const double e1 = linspace_edge(i + 1, nbins, first, last, step);
-      const double db = __dsub_rn(e1, e0);
+      const double e0 = edge(i), e1 = edge(i + 1);
+      const double db = edge.width(e0, e1);
       const double d = __ddiv_rn(__ddiv_rn((double)c[i], db), (double)part);   // n / db / n.sum()
       if (dst) {
         dst[i] = d;
-        bnd[i] = __dadd_rn(e0, db);                                             // be[:-1] + diff(be)
+        bnd[i] = edge.upper(e0, db);                                            // be[:-1] + diff(be)
       }
       dmax = fmax(dmax, d);          // NaN densities (empty window: 0 / 0) are skipped, as np.max would not
     }
@@ -671,7 +653,8 @@ __global__ void __launch_bounds__(128) k_win_select(const unsigned long long* __
 }
 
 template <typename T>
-static int windows_impl(const T* filt, int H, int W, int cx, int cy, int r, int nwin, const int32_t* rects_host,
+static int windows_impl(const T* filt, int H, int W, int f32_math, int cx, int cy, int r, int nwin,
+                        const int32_t* rects_host,
                         int nbins, double ratio, double h_in, unsigned long long* counts, double* density,
                         double* bound, int32_t* peaks, chips_window_rec* recs, unsigned char* ws, cudaStream_t st) {
   using K = typename Key<T>::type;
@@ -695,10 +678,10 @@ static int windows_impl(const T* filt, int H, int W, int cx, int cy, int r, int 
   k_win_minmax<T><<<grid, 256, 0, st>>>(filt, W, rects, cx, cy, r, minmax);
   CHIPS_CHECK_LAUNCH();
   CHIPS_CUDA(cudaFuncSetAttribute(k_win_hist<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_win_hist<T><<<grid, 256, smem, st>>>(filt, W, rects, cx, cy, r, minmax, nbins, copies, counts);
+  k_win_hist<T><<<grid, 256, smem, st>>>(filt, W, rects, cx, cy, r, minmax, nbins, copies, f32_math, counts);
   CHIPS_CHECK_LAUNCH();
-  k_win_select<T><<<(nwin + 3) / 4, 128, 0, st>>>(counts, minmax, nwin, nbins, ratio, h_in, density, bound, peaks,
-                                                  recs);
+  k_win_select<T><<<(nwin + 3) / 4, 128, 0, st>>>(counts, minmax, nwin, nbins, ratio, h_in, f32_math, density, bound,
+                                                  peaks, recs);
   CHIPS_CHECK_LAUNCH();
   count_launch(4);
   return CHIPS_OK;
@@ -710,18 +693,19 @@ using namespace chips;
 
 extern "C" size_t chips_window_workspace_bytes(int nwin) { return (size_t)(nwin > 0 ? nwin : 0) * 32 + 256; }
 
-extern "C" int chips_window_histograms(const void* filt, int H, int W, int elem, int cx, int cy, int r, int nwin,
-                                       const int32_t* rects, int h_bins, double ht_peak_ratio, double h_thresh_in,
+extern "C" int chips_window_histograms(const void* filt, int H, int W, int elem, int f32_math, int cx, int cy,
+                                       int r, int nwin, const int32_t* rects, int h_bins, double ht_peak_ratio,
+                                       double h_thresh_in,
                                        long long* counts, double* density, double* bound, int32_t* peaks,
                                        chips_window_rec* recs, void* ws, void* stream) {
   if (!filt || !rects || !counts || !density || !bound || !peaks || !recs || !ws) return CHIPS_E_ARG;
   if (H < 1 || W < 1 || nwin < 1 || nwin > 65535 || h_bins < 1) return CHIPS_E_ARG;
   unsigned long long* c = reinterpret_cast<unsigned long long*>(counts);
   if (elem == 4)
-    return windows_impl<float>((const float*)filt, H, W, cx, cy, r, nwin, rects, h_bins, ht_peak_ratio, h_thresh_in,
+    return windows_impl<float>((const float*)filt, H, W, f32_math != 0, cx, cy, r, nwin, rects, h_bins, ht_peak_ratio, h_thresh_in,
                                c, density, bound, peaks, recs, (unsigned char*)ws, (cudaStream_t)stream);
   if (elem == 8)
-    return windows_impl<double>((const double*)filt, H, W, cx, cy, r, nwin, rects, h_bins, ht_peak_ratio,
+    return windows_impl<double>((const double*)filt, H, W, 0, cx, cy, r, nwin, rects, h_bins, ht_peak_ratio,
                                 h_thresh_in, c, density, bound, peaks, recs, (unsigned char*)ws, (cudaStream_t)stream);
   return CHIPS_E_ARG;
 }
@@ -752,7 +736,7 @@ extern "C" int chips_select_threshold(const chips_plan* plan, double ht_peak_rat
   unsigned char* w = (unsigned char*)ws;
   k_select<<<1, 1024, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const long long*>(w + plan->off_counts), plan->h_bins, ht_peak_ratio,
-      h_thresh_in, offs, T, reinterpret_cast<double*>(w + plan->off_density),
+      h_thresh_in, offs, T, plan->f32_math, reinterpret_cast<double*>(w + plan->off_density),
       reinterpret_cast<double*>(w + plan->off_edges), reinterpret_cast<double*>(w + plan->off_bound),
       reinterpret_cast<int*>(w + plan->off_peaks), reinterpret_cast<chips_result*>(w + plan->off_result));
   CHIPS_CHECK_LAUNCH();

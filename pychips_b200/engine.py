@@ -55,7 +55,7 @@ class Detector:
     """
 
     def __init__(self, geom: Geometry, k: int, h_bins: int, t0, t1, elem: int = 4,
-                 device=None, ws: torch.Tensor | None = None):
+                 device=None, ws: torch.Tensor | None = None, f32_math: bool = False):
         self.lib = _lib.load()
         self.device = require_cuda(device)
         self.geom = geom
@@ -70,6 +70,11 @@ class Detector:
         self.plan = Plan()
         _lib.check(self.lib.chips_plan_init(C.byref(self.plan), geom.H, geom.W, self.k, self.h_bins,
                                             self.T, elem, geom.cx, geom.cy, geom.r), "chips_plan_init")
+        # float32 caller arrays: numpy keeps float32 for the bin edges, bound / limit_0 and the
+        # sigmoid of calculate_prob (np.histogram's bin_type = result_type(a)); everything else is
+        # float64 arithmetic on the widened values
+        self.f32_math = bool(f32_math) and elem == 4
+        self.plan.f32_math = int(self.f32_math)
         # scratch tail behind the plan's workspace: outputs of the regional histograms
         # (`region_histogram`), so that they never overwrite the detection's own record
         self._tail = {}
@@ -236,7 +241,8 @@ class Detector:
         ws = torch.empty(int(self.lib.chips_window_workspace_bytes(n)), dtype=torch.uint8, device=dev)
         h_in = float("nan") if h_thresh is None else float(h_thresh)
         _lib.check(self.lib.chips_window_histograms(
-            _ptr(self.filt), self.geom.H, self.geom.W, self.elem, *self._g(), n, rects.ctypes.data, hb,
+            _ptr(self.filt), self.geom.H, self.geom.W, self.elem, int(self.f32_math), *self._g(), n,
+            rects.ctypes.data, hb,
             float(ht_peak_ratio), h_in, _ptr(counts), _ptr(density), _ptr(bound), _ptr(peaks), _ptr(recs),
             _ptr(ws), _stream_ptr()), "chips_window_histograms")
         rec_host = recs.cpu().numpy()

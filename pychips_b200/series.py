@@ -61,12 +61,16 @@ class SparseKeepList:
     def __len__(self):
         return len(self._e)
 
+    def is_dense(self, i) -> bool:
+        """More pixels in some map than the buffer has words: it holds the dense map instead."""
+        return int(self._c[i]) > self._e[i].numel()
+
     def packed(self, i) -> np.ndarray:
-        n = int(self._c[i])
-        if n > self._e[i].numel():
-            raise _lib.ChipsNativeError(f"sparse result map of image {i} overflowed ({n} entries): "
-                                        "use SeriesRunner(sparse_keep=False)")
-        return self._e[i].numpy()[:n].view(np.uint32)
+        """The words of image i (or, for `is_dense(i)`, the dense map as H*W bytes)."""
+        if self.is_dense(i):
+            H, W = self._shape
+            return self._e[i].numpy().view(np.uint8)[:H * W]
+        return self._e[i].numpy()[:int(self._c[i])].view(np.uint32)
 
     def __getitem__(self, i):
         if isinstance(i, slice):
@@ -74,7 +78,8 @@ class SparseKeepList:
         if i < 0:
             i += len(self)
         if i not in self._cache:
-            self._cache[i] = decode_keep(self.packed(i), *self._shape, self._T)
+            self._cache[i] = (self.packed(i).reshape(self._shape).copy() if self.is_dense(i)
+                              else decode_keep(self.packed(i), *self._shape, self._T))
         return self._cache[i]
 
     def __iter__(self):
@@ -88,7 +93,7 @@ class SeriesRunner:
                  threshold_range=(0, 20), ht_peak_ratio=5, porb_threshold=0.8,
                  area_threshold=1e-3, masked: bool = True, device=None, n_streams: int = 2,
                  elem: int = 4, want_keep: bool = True, want_prob_map: bool = True,
-                 want_maps: bool = False, sparse_keep: bool = True):
+                 want_maps: bool = False, sparse_keep: bool = True, f32_math: bool = False):
         self.device = engine.require_cuda(device)
         self.H, self.W = int(H), int(W)
         self.k, self.h_bins = int(medfilt_kernel), int(h_bins)
@@ -97,12 +102,17 @@ class SeriesRunner:
         self.ratio, self.porb, self.area_thr = ht_peak_ratio, porb_threshold, area_threshold
         self.masked = masked
         self.elem = elem
+        # float32 images are a storage format here: the arithmetic is float64 on the widened values
+        # (what the reference does with float64 arrays of the same values).  f32_math=True gives
+        # what the reference does when it is handed float32 arrays (numpy's float32 histogram)
+        self.f32_math = bool(f32_math) and elem == 4
         self.want_keep, self.want_prob_map, self.want_maps = want_keep, want_prob_map, want_maps
         # the result map travels as one word per pixel that is in some map (~3 % of a disk image)
         # instead of H*W bytes; needs the word format of chips_pack_keep
         self.sparse_keep = bool(sparse_keep and want_keep and self.H * self.W <= (1 << 26)
                                 and self.T <= 64 and self.W % 4 == 0)
-        self.sparse_cap = max(4096, self.H * self.W // 8)
+        # H*W/4 words: if more pixels than that are in some map the buffer takes the dense map
+        self.sparse_cap = (self.H * self.W + 3) // 4
         self.dtype = torch.float32 if elem == 4 else torch.float64
         self.n_streams = n_streams
         self._slots = {}
@@ -133,7 +143,8 @@ class SeriesRunner:
                                self.t0, self.t1, self.elem, self.device)
                 ws = self._slot_ws[slot] = big.ws
             g = Geometry(self.H, self.W, c, c, int(r) if self.masked else -1)
-            det = Detector(g, self.k, self.h_bins, self.t0, self.t1, self.elem, self.device, ws=ws)
+            det = Detector(g, self.k, self.h_bins, self.t0, self.t1, self.elem, self.device, ws=ws,
+                           f32_math=self.f32_math)
             self._slot_ws.setdefault(slot, det.ws)
             self._slots[key] = det
         return det
@@ -221,8 +232,8 @@ class SeriesRunner:
                     # does not wait for the device -> host copy
                     st.wait_event(self._stage_free[slot])
                     self._stage_rec[slot].copy_(det.result_bytes(), non_blocking=True)
-                    if self.sparse_keep:
-                        det.pack_keep(keep_host[i], self._stage_cnt[slot])
+                    if self.sparse_keep:      # packed on the device; the copy stream moves the words
+                        det.pack_keep(self._stage_sparse[slot], self._stage_cnt[slot])
                     elif self.want_keep:
                         self._stage_keep[slot].copy_(det.keep, non_blocking=True)
                     self._snap[slot].record(st)
@@ -230,7 +241,12 @@ class SeriesRunner:
                     self._d2h.wait_event(self._snap[slot])
                     rec_host[i].copy_(self._stage_rec[slot], non_blocking=True)
                     if self.sparse_keep:
-                        cnt_host[i:i + 1].copy_(self._stage_cnt[slot], non_blocking=True)
+                        # a copy whose size only the device knows: 8 CTAs store the words (and their
+                        # number) into the pinned buffers through the mapping
+                        _lib.check(self._lib.chips_copy_words(
+                            self._stage_sparse[slot].data_ptr(), keep_host[i].data_ptr(),
+                            self._stage_cnt[slot].data_ptr(), self.sparse_cap,
+                            cnt_host[i:i + 1].data_ptr(), engine._stream_ptr()), "chips_copy_words")
                     elif self.want_keep:
                         keep_host[i].copy_(self._stage_keep[slot], non_blocking=True)
                     self._stage_free[slot].record(self._d2h)
@@ -268,6 +284,9 @@ class SeriesRunner:
         self._stage_keep = [torch.empty((self.H, self.W), dtype=torch.uint8, device=dev)
                             if self.want_keep and not self.sparse_keep else None for _ in range(ns)]
         self._stage_cnt = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in range(ns)]
+        self._stage_sparse = [torch.empty(self.sparse_cap, dtype=torch.int32, device=dev)
+                              if self.sparse_keep else None for _ in range(ns)]
+        self._lib = _lib.load()
         cur = torch.cuda.current_stream()
         for s in range(ns):                      # events start "signalled"
             for p in range(2):

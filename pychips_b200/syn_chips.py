@@ -74,7 +74,8 @@ class SynopticChips(object):
                     t0, t1 = 0, 1
                 H, W = data.shape
                 self._det = Detector(Geometry(int(H), int(W), 0, 0, -1), self.medfilt_kernel,
-                                     self.h_bins, t0, t1, elem, self.device)
+                                     self.h_bins, t0, t1, elem, self.device,
+                                     f32_math=data.dtype == np.float32)     # numpy's float32 histogram
                 self._det.state = set()
             self._img = img
         return self._det
@@ -107,7 +108,7 @@ class SynopticChips(object):
                     self.h_thresh = np.float64(res.h_thresh)
                 npk = int(res.n_peaks)
                 pidx = det.peak_index[:npk].cpu().numpy()
-                bound = det.bound.cpu().numpy()
+                bound = det.bound.cpu().numpy().astype(np.float32 if det.f32_math else np.float64, copy=False)
             peaks = [bound[p] for p in pidx]
             synoptic_map.set_value("histogram", LazyNamespace(
                 _lazy=dict(hbase=lambda: det.density.cpu().numpy(),
@@ -147,7 +148,7 @@ class SynopticChips(object):
                     det.state.add("maps")
                     res = det.result()
                 engine._lib.check_record(res)
-                limit_0 = np.float64(res.limit_0)
+                limit_0 = (np.float32 if det.f32_math else np.float64)(res.limit_0)
                 dtmp_map = {}
                 for t in range(det.T):
                     lim = np.float64(res.limits[t])

@@ -31,6 +31,15 @@ DISK_CASES = {
     # List[float] threshold_range (chips.py:56): np.arange(-2.5, 6.25) = -2.5, -1.5, ..., 5.5
     "disk_n192_k11_frange": (192, 6, 1.0, dict(medfilt_kernel=11, h_bins=500, threshold_range=[-2.5, 6.25])),
 }
+# float32 raw / normalized arrays: numpy keeps float32 bin edges (np.histogram's bin_type), bound,
+# limit_0 and the sigmoid of calculate_prob - the dtype real synoptic FITS maps come in
+F32_DISK_CASES = {
+    "disk_n256_k11_f32": (256, 7, 1.0, dict(medfilt_kernel=11, h_bins=500, threshold_range=[0, 20])),
+    "disk_n192_k31_f32": (192, 8, 1.0, dict(medfilt_kernel=31, h_bins=5000, threshold_range=[-3, 11])),
+}
+F32_SYN_CASES = {
+    "syn_180x360_k3_f32": (180, 360, 3, dict(medfilt_kernel=3, h_bins=5000, threshold_range=[-5, 20])),
+}
 SYN_CASES = {
     "syn_180x360_k3": (180, 360, 0, dict(medfilt_kernel=3, h_bins=5000, threshold_range=[-5, 20])),
     "syn_96x240_k11": (96, 240, 1, dict(medfilt_kernel=11, h_bins=500, threshold_range=[-5, 20])),
@@ -42,13 +51,14 @@ def _same(a, b):
     return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
 
 
-def make_disk(name, n, seed, scale, kw):
+def make_disk(name, n, seed, scale, kw, dtype=np.float64):
     img, r = synth.synthetic_disk(n, seed)
     img = (img * np.float32(scale)).astype(np.float32)
-    d_ref = synth.FakeDisk(img.astype(np.float64), r)
+    d_ref = synth.FakeDisk(img.astype(dtype), r)
     rh.run_disk(d_ref, synth.FakeAIA(d_ref), **kw)
-    d_or = synth.FakeDisk(img.astype(np.float64), r)
+    d_or = synth.FakeDisk(img.astype(dtype), r)
     co.OracleChips(**kw).run(d_or)
+    assert d_ref.histogram.hbins.dtype == dtype and d_ref.solar_filter.filt_disk.dtype == dtype
     assert _same(d_ref.solar_mask.n_mask, d_or.solar_mask.n_mask)
     assert _same(d_ref.solar_filter.filt_disk, d_or.solar_filter.filt_disk)
     assert _same(d_ref.solar_filter.solar_disk, d_or.solar_filter.solar_disk)
@@ -59,9 +69,9 @@ def make_disk(name, n, seed, scale, kw):
                filt_disk=d_ref.solar_filter.filt_disk.astype(np.float32),
                hbase=d_ref.histogram.hbase, hbins=d_ref.histogram.hbins,
                bound=d_ref.histogram.bound, h_thresh=d_ref.histogram.h_thresh,
-               peaks=np.array(d_ref.histogram.peaks, dtype=np.float64),
+               peaks=np.array(d_ref.histogram.peaks, dtype=dtype),
                kw_medfilt_kernel=kw["medfilt_kernel"], kw_h_bins=kw["h_bins"],
-               kw_threshold_range=np.array(kw["threshold_range"]))
+               kw_threshold_range=np.array(kw["threshold_range"]), input_dtype=np.dtype(dtype).name)
     assert _same(out["filt_disk"].astype(np.float64), d_ref.solar_filter.filt_disk)
     has = hasattr(d_ref, "solar_ch_regions")
     assert has == hasattr(d_or, "solar_ch_regions")
@@ -90,12 +100,13 @@ def make_disk(name, n, seed, scale, kw):
     print(name, "peaks", len(out["peaks"]), "regions", has, "T", len(out.get("limits", [])))
 
 
-def make_syn(name, h, w, seed, kw):
+def make_syn(name, h, w, seed, kw, dtype=np.float64):
     img = synth.synthetic_synoptic(h, w, seed)
-    s_ref = synth.FakeSynoptic(img.astype(np.float64))
+    s_ref = synth.FakeSynoptic(img.astype(dtype))
     rh.run_synoptic(s_ref, **kw)
-    s_or = synth.FakeSynoptic(img.astype(np.float64))
+    s_or = synth.FakeSynoptic(img.astype(dtype))
     co.OracleSynopticChips(**kw).run(s_or)
+    assert s_ref.histogram.bound.dtype == dtype
     assert _same(s_ref.solar_filter, s_or.solar_filter)
     for f in ("hbase", "bound", "h_thresh"):
         assert _same(getattr(s_ref.histogram, f), getattr(s_or.histogram, f)), f
@@ -112,7 +123,8 @@ def make_syn(name, h, w, seed, kw):
         peaks=np.array(s_ref.histogram.peaks), keys=np.array(keys), limits=np.array(lims),
         probs=np.array(probs), limit_0=s_ref.solar_ch_regions.__dict__[keys[0]].limit_0,
         maps=np.packbits(np.array(maps)), kw_medfilt_kernel=kw["medfilt_kernel"],
-        kw_h_bins=kw["h_bins"], kw_threshold_range=np.array(kw["threshold_range"]))
+        kw_h_bins=kw["h_bins"], kw_threshold_range=np.array(kw["threshold_range"]),
+        input_dtype=np.dtype(dtype).name)
     print(name, "peaks", len(s_ref.histogram.peaks), "T", len(keys))
 
 
@@ -216,3 +228,9 @@ if __name__ == "__main__":
     for name, (n, seed, kw) in FL_CASES.items():
         if not only or name in only:
             make_fl(name, n, seed, kw)
+    for name, (n, seed, scale, kw) in F32_DISK_CASES.items():
+        if not only or name in only:
+            make_disk(name, n, seed, scale, kw, np.float32)
+    for name, (h, w, seed, kw) in F32_SYN_CASES.items():
+        if not only or name in only:
+            make_syn(name, h, w, seed, kw, np.float32)

@@ -211,6 +211,11 @@ def test_median_quantised_full_size_is_not_slower():
 
 
 # ----------------------------------------------------------------------------- full pipeline
+def in_dtype(g):
+    """dtype of the arrays the reference was given (float32 goldens: numpy's float32 histogram)."""
+    return np.dtype(str(g["input_dtype"])) if "input_dtype" in g else np.dtype(np.float64)
+
+
 def run_gpu_disk(img, r, dtype=np.float64, **kw):
     from pychips_b200 import Chips
     d = synth.FakeDisk(img.astype(dtype), r)
@@ -245,11 +250,15 @@ def compare_disk(d, g_filt, g_hbase, g_hbins, g_bound, g_peaks, g_lims, g_probs,
 
 
 @pytest.mark.parametrize("name", ["disk_n256_k11", "disk_n256_k31_211", "disk_n192_k51",
-                                  "disk_n256_k5_t28", "disk_n200_k7_wiped", "disk_n192_k11_frange"])
+                                  "disk_n256_k5_t28", "disk_n200_k7_wiped", "disk_n192_k11_frange",
+                                  "disk_n256_k11_f32", "disk_n192_k31_f32"])
 def test_disk_pipeline_vs_reference_golden(name):
+    """(the *_f32 goldens: the reference ran on float32 raw / normalized arrays, where numpy keeps
+    float32 bin edges, bound, limit_0 and sigmoid; edges, counts, peaks, limits and maps are compared
+    exactly, the probabilities to 1e-5 - a float32 exp differs between implementations in the last bit)"""
     g = load_golden(name)
     n = g["image"].shape[0]
-    c, d = run_gpu_disk(g["image"], int(g["pixel_radius"]),
+    c, d = run_gpu_disk(g["image"], int(g["pixel_radius"]), dtype=in_dtype(g),
                         medfilt_kernel=int(g["kw_medfilt_kernel"]), h_bins=int(g["kw_h_bins"]),
                         threshold_range=[v.item() for v in g["kw_threshold_range"]])
     T = len(g["limits"])
@@ -261,6 +270,11 @@ def test_disk_pipeline_vs_reference_golden(name):
     compare_disk(d, g["filt_disk"].astype(np.float64), g["hbase"], g["hbins"], g["bound"], g["peaks"],
                  g["limits"], g["probs"], raw, maps, g.get("stack"), c)
     assert c.h_thresh == g["h_thresh"]
+    assert d.histogram.hbins.dtype == d.histogram.bound.dtype == in_dtype(g)
+    assert d.solar_filter.filt_disk.dtype == in_dtype(g)
+    reg0 = list(d.solar_ch_regions.__dict__.values())[0]
+    assert type(reg0.limit_0) is type(d.histogram.peaks[0]) and reg0.limit_0 == g["limit_0"]
+    assert type(reg0.limit_0) is (np.float32 if in_dtype(g) == np.float32 else np.float64)
 
 
 @pytest.mark.parametrize("n,k,hb,tr,seed", [(512, 11, 500, [0, 20], 7), (384, 31, 1000, [-3, 11], 8),
@@ -335,13 +349,14 @@ def test_float64_storage_path_not_f32_representable():
                  [x.map.astype(np.uint8) for x in regs])
 
 
-@pytest.mark.parametrize("name", ["syn_180x360_k3", "syn_96x240_k11", "syn_90x200_k5_frange"])
+@pytest.mark.parametrize("name", ["syn_180x360_k3", "syn_96x240_k11", "syn_90x200_k5_frange",
+                                  "syn_180x360_k3_f32"])
 def test_synoptic_pipeline_vs_reference_golden(name):
     from pychips_b200 import SynopticChips
     g = load_golden(name)
     img = g["image"]
     H, W = img.shape
-    s = synth.FakeSynoptic(img.astype(np.float64))
+    s = synth.FakeSynoptic(img.astype(in_dtype(g)))
     sc = SynopticChips(s, base_folder="/tmp/chips_b200_test/", medfilt_kernel=int(g["kw_medfilt_kernel"]),
                        h_bins=int(g["kw_h_bins"]),
                        threshold_range=[v.item() for v in g["kw_threshold_range"]])
@@ -357,7 +372,12 @@ def test_synoptic_pipeline_vs_reference_golden(name):
     for t, k in enumerate(keys):
         reg = s.solar_ch_regions.__dict__[k]
         assert np.array_equal(reg.map.astype(np.uint8), maps[t]), t
-        assert np.array_equal(reg.prob, g["probs"][t], equal_nan=True)
+        gp = g["probs"][t]
+        if in_dtype(g) == np.float32:      # float32 exp: last-bit differences between implementations
+            assert (np.isnan(gp) and np.isnan(reg.prob)) or abs(reg.prob - gp) <= REL * abs(gp)
+        else:
+            assert np.array_equal(reg.prob, gp, equal_nan=True)
+    assert s.histogram.bound.dtype == in_dtype(g) and s.solar_filter.dtype == in_dtype(g)
 
 
 # ----------------------------------------------------------------------------- stage level
@@ -461,14 +481,20 @@ def test_full_size_4096_properties():
     on = fp.circle_mask(n, n, n // 2, n // 2, r)
     assert res.n_samples == int(on.sum())
     filt = det.filt.cpu().numpy()
-    # histogram: counts of the GPU == numpy on the GPU-filtered data; first peak -> limit_0
-    cn, en = np.histogram(filt[on].astype(np.float64), bins=500)
-    assert np.array_equal(det.counts.cpu().numpy(), cn)
-    hn, _ = np.histogram(filt[on].astype(np.float64), bins=500, density=True)
+    # histogram: counts of the GPU == numpy on the GPU-filtered data; first peak -> limit_0.  The
+    # arrays are float32 here, so numpy keeps float32 bin edges, bound and limit_0 (bin_type =
+    # result_type(a)) and so does the device (plan.f32_math)
+    assert filt.dtype == np.float32 and det.f32_math
+    cn, en = np.histogram(filt[on], bins=500)
+    assert en.dtype == np.float32 and np.array_equal(det.counts.cpu().numpy(), cn)
+    assert np.array_equal(det.edges.cpu().numpy(), en.astype(np.float64))
+    hn, _ = np.histogram(filt[on], bins=500, density=True)
+    assert np.array_equal(det.density.cpu().numpy(), hn)
     pk, _ = signal.find_peaks(hn, height=np.max(hn) / 5)
-    assert res.limit_0 == (en[:-1] + np.diff(en))[pk[0]]
+    l0 = (en[:-1] + np.diff(en))[pk[0]]
+    assert l0.dtype == np.float32 and res.limit_0 == l0
     lims = np.array(res.limits[:det.T])
-    assert np.array_equal(lims, np.round(res.limit_0 + np.arange(0, 20), 4))
+    assert np.array_equal(lims, np.round(l0 + np.arange(0, 20), 4))
     lev = det.level.cpu().numpy()
     assert np.array_equal(lev, fp.level_image(filt, on, lims))
     W = det.fill.cpu().numpy()
@@ -613,7 +639,7 @@ def test_config3_time_series_runner_matches_single_image_path():
     res = runner.run([torch.from_numpy(im).pin_memory() for im in imgs], radii)
     total = np.zeros((n, n))
     for i, (im, r) in enumerate(zip(imgs, radii)):
-        c, d = run_gpu_disk(im, r, dtype=np.float32, medfilt_kernel=k)
+        c, d = run_gpu_disk(im, r, medfilt_kernel=k)        # float64 arrays: float64 arithmetic, as the runner's default
         regs = list(d.solar_ch_regions.__dict__.values())
         assert np.array_equal(res.limits[i], [x.lim for x in regs])
         assert np.array_equal(res.probs[i], [x.prob for x in regs], equal_nan=True)
@@ -631,6 +657,15 @@ def test_config3_time_series_runner_matches_single_image_path():
     rd = dense.run([torch.from_numpy(im).pin_memory() for im in imgs], radii)
     for i in range(len(imgs)):
         assert np.array_equal(rd.keep[i], res.keep[i])
+    # a buffer too small for the words of an image receives the dense map instead
+    tiny = series.SeriesRunner(n, n, k, 500, (0, 20), n_streams=2, want_maps=False)
+    assert tiny.sparse_cap * 4 >= n * n
+    dark = [np.minimum(im, np.float32(np.percentile(im, 30))) for im in imgs[:2]]   # most of the disk is "hole"
+    rt = tiny.run([torch.from_numpy(im).pin_memory() for im in dark], radii[:2])
+    rdd = dense.run([torch.from_numpy(im).pin_memory() for im in dark], radii[:2])
+    assert any(rt.keep.is_dense(i) for i in range(2))
+    for i in range(2):
+        assert np.array_equal(rt.keep[i], rdd.keep[i])
     # three radii on two stream slots: one workspace per slot, shared by the per-radius plans
     assert len(runner._slots) > 2
     assert len({d.ws.data_ptr() for d in runner._slots.values()}) == 2

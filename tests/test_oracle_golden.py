@@ -8,8 +8,13 @@ from oracle import chips_oracle as co
 from pychips_b200 import synth
 
 DISK = ["disk_n256_k11", "disk_n256_k31_211", "disk_n192_k51", "disk_n256_k5_t28",
-        "disk_n200_k7_wiped", "disk_n192_k11_frange"]
-SYN = ["syn_180x360_k3", "syn_96x240_k11", "syn_90x200_k5_frange"]
+        "disk_n200_k7_wiped", "disk_n192_k11_frange", "disk_n256_k11_f32", "disk_n192_k31_f32"]
+SYN = ["syn_180x360_k3", "syn_96x240_k11", "syn_90x200_k5_frange", "syn_180x360_k3_f32"]
+
+
+def in_dtype(g):
+    """dtype of the arrays the reference was given (float32 goldens: numpy's float32 histogram)."""
+    return np.dtype(str(g["input_dtype"])) if "input_dtype" in g else np.dtype(np.float64)
 
 
 def unpack(bits, T, H, W):
@@ -21,10 +26,11 @@ def test_disk_oracle_matches_reference_golden(name):
     g = load_golden(name)
     img = g["image"]
     n = img.shape[0]
-    d = synth.FakeDisk(img.astype(np.float64), int(g["pixel_radius"]))
+    d = synth.FakeDisk(img.astype(in_dtype(g)), int(g["pixel_radius"]))
     o = co.OracleChips(medfilt_kernel=int(g["kw_medfilt_kernel"]), h_bins=int(g["kw_h_bins"]),
                        threshold_range=list(g["kw_threshold_range"]))
     o.run(d)
+    assert d.histogram.hbins.dtype == g["hbins"].dtype == in_dtype(g)
     assert np.array_equal(np.unpackbits(g["i_mask"])[:n * n].reshape(n, n),
                           d.solar_mask.i_mask.astype(np.uint8))
     assert np.array_equal(g["filt_disk"].astype(np.float64), d.solar_filter.filt_disk)
@@ -51,7 +57,7 @@ def test_disk_oracle_matches_reference_golden(name):
 def test_synoptic_oracle_matches_reference_golden(name):
     g = load_golden(name)
     img = g["image"]
-    s = synth.FakeSynoptic(img.astype(np.float64))
+    s = synth.FakeSynoptic(img.astype(in_dtype(g)))
     o = co.OracleSynopticChips(medfilt_kernel=int(g["kw_medfilt_kernel"]),
                                h_bins=int(g["kw_h_bins"]),
                                threshold_range=list(g["kw_threshold_range"]))
