@@ -332,9 +332,9 @@ def run_b200(a):
             down_note = "per image the 1.6 kB record and the dense level-encoded result map"
         e2e = {"value": world * a.batch * a.steps / (ms_e / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": up_per_step * world,
-               "h2d_note": "only the rectangle of each pinned host image that the kernels read is uploaded "
-                           f"(disk bounding box + median blocks and halo): {up_per_step / in_bytes:.0%} of "
-                           f"the {in_bytes} bytes of the batch",
+               "h2d_note": "only the row intervals of each pinned host image that the kernels read are uploaded "
+                           f"(the on-disk median blocks with their halo, chips_input_spans): "
+                           f"{up_per_step / in_bytes:.0%} of the {in_bytes} bytes of the batch",
                "d2h_bytes_per_step": world * down, "d2h_note": down_note,
                "host_dtype": "float32 (pinned)", "ms_per_step": ms_e / a.steps}
         assert int(res.n_peaks.min()) > 0

@@ -107,6 +107,7 @@ SIGNATURES = {
     "chips_pack_cube": ([_PP, _i, _vp, _vp, _vp], C.c_int),
     "chips_row_cosine": ([_vp, _vp, _i, _i, _i, _vp, _vp], C.c_int),
     "chips_input_rect": ([_PP, _vp], C.c_int),
+    "chips_input_spans": ([_PP, _i, _i, _i, _vp, _i], C.c_int),
     "chips_copy_rect": ([_vp, _vp, _sz, _sz, _i, _sz, _i, _i, _vp], C.c_int),
     "chips_contours_workspace_bytes": ([_i, _i, C.c_longlong], C.c_size_t),
     "chips_contours": ([_vp, _i, _i, _i, _i, _i, C.c_longlong, _i, _vp, C.c_longlong, _vp, C.c_longlong,

@@ -27,6 +27,7 @@ struct Slot {
   cudaGraphExec_t exec = nullptr;
   double key[4] = {0, 0, 0, 0};   // ht_peak_ratio, h_thresh_in, porb, area of the captured graph
   std::vector<double> offsets;
+  std::vector<int32_t> spans;     // chips_input_spans of the captured geometry
   cudaEvent_t detected = nullptr; // detection of the slot's current image has finished
   cudaEvent_t summed = nullptr;   // ... and its probability map is in the sum
   int pending = -1;               // batch index whose results are still on the device
@@ -161,19 +162,24 @@ extern "C" int chips_detect_batch(void* handle, int B, const void* const* images
       const cudaError_t ci = cudaGraphInstantiate(&s.exec, graph, 0);
       cudaGraphDestroy(graph);
       if (ci != cudaSuccess) return CHIPS_E_CUDA;
+      s.spans.assign(4 * 4096, 0);
+      const int ns = chips_input_spans(&s.plan, cx[i], cy[i], r[i], s.spans.data(), 4096);
+      if (ns < 1) return ns < 0 ? ns : CHIPS_E_ARG;
+      s.spans.resize((size_t)4 * ns);
       s.cx = cx[i]; s.cy = cy[i]; s.r = r[i];
       for (int j = 0; j < 4; ++j) s.key[j] = key[j];
       for (int j = 0; j < b->T; ++j) s.offsets[(size_t)j] = offsets[j];
       s.has_graph = true;
     }
-    // upload the rectangle the kernels read
-    int32_t rect[4];
-    chips_input_rect(&s.plan, rect);
-    const size_t off = (size_t)rect[1] * pitch + (size_t)rect[0] * b->elem;
-    CHIPS_CUDA(cudaMemcpy2DAsync(static_cast<char*>(s.image) + off, pitch,
-                                 static_cast<const char*>(images[i]) + off, pitch,
-                                 (size_t)(rect[2] - rect[0]) * b->elem, (size_t)(rect[3] - rect[1]),
-                                 images_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s.stream));
+    // upload the row intervals the kernels read (chips_input_spans)
+    for (size_t q = 0; q + 3 < s.spans.size(); q += 4) {
+      const int y0 = s.spans[q], y1 = s.spans[q + 1], x0 = s.spans[q + 2], x1 = s.spans[q + 3];
+      const size_t off = (size_t)y0 * pitch + (size_t)x0 * b->elem;
+      CHIPS_CUDA(cudaMemcpy2DAsync(static_cast<char*>(s.image) + off, pitch,
+                                   static_cast<const char*>(images[i]) + off, pitch,
+                                   (size_t)(x1 - x0) * b->elem, (size_t)(y1 - y0),
+                                   images_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s.stream));
+    }
     CHIPS_CUDA(cudaGraphLaunch(s.exec, s.stream));
     chips::count_launch(0);
     CHIPS_CUDA(cudaEventRecord(s.detected, s.stream));

@@ -159,6 +159,76 @@ extern "C" int chips_input_rect(const chips_plan* plan, int32_t* rect) {
   return CHIPS_OK;
 }
 
+// The same, tighter: row intervals [y0, y1) with their own column range [x0, x1).  Only the
+// halo-extended regions of the blocks that hold an on-disk pixel are read (k_block_sort, and the
+// medians k_rank_select fetches from them): per band of blk_rows rows the on-disk blocks are a
+// contiguous run, so the union is one column range per row interval - 52 % of a 4096^2 image at
+// r = 1577, k = 51 against 63 % for the rectangle.  Returns the number of spans (<= max_spans), or
+// a negative error; spans are disjoint and ascending in y.
+static bool host_rect_on_disk(int x0, int y0, int w, int h, int cx, int cy, int r) {   // median.cu rect_on_disk
+  if (r < 0) return true;
+  const long long nx = cx < x0 ? x0 : (cx > x0 + w - 1 ? x0 + w - 1 : cx);
+  const long long ny = cy < y0 ? y0 : (cy > y0 + h - 1 ? y0 + h - 1 : cy);
+  return (nx - cx) * (nx - cx) + (ny - cy) * (ny - cy) <= (long long)r * r;
+}
+
+extern "C" int chips_input_spans(const chips_plan* plan, int cx, int cy, int r, int32_t* spans, int max_spans) {
+  if (!plan || !spans || max_spans < 1) return CHIPS_E_ARG;
+  int32_t rect[4];
+  chips_input_rect(plan, rect);
+  const int half = plan->k / 2, L = plan->blk_rows;
+  if (!plan->masked || plan->k <= 5 || r < 0) {          // whole rectangle (the k <= 5 kernels read windows, not blocks)
+    spans[0] = rect[1]; spans[1] = rect[3]; spans[2] = rect[0]; spans[3] = rect[2];
+    return 1;
+  }
+  // column range of every band, then the union over the (at most two or three) bands a row belongs to
+  const int nby = plan->blk_nby, nbx = plan->blk_nbx;
+  if (nby > 4096) return CHIPS_E_ARG;
+  static thread_local int band_xa[4096], band_xb[4096];
+  for (int by = 0; by < nby; ++by) {
+    const int Y = plan->roi_y0 + L * by;
+    band_xa[by] = 1 << 30;
+    band_xb[by] = -1;
+    for (int bx = 0; bx < nbx; ++bx) {
+      const int X = plan->roi_x0 + 128 * bx;
+      if (!host_rect_on_disk(X, Y, 128, L, cx, cy, r)) continue;
+      if (X - half < band_xa[by]) band_xa[by] = X - half;
+      if (X + 128 + half > band_xb[by]) band_xb[by] = X + 128 + half;
+    }
+  }
+  int n = 0;
+  int cur_x0 = 0, cur_x1 = 0, cur_y0 = 0;
+  bool open = false;
+  for (int y = rect[1]; y <= rect[3]; ++y) {
+    int xa = 1 << 30, xb = -1;
+    if (y < rect[3]) {
+      int b0 = (y - half - plan->roi_y0) / L - 1, b1 = (y + half - plan->roi_y0) / L + 1;
+      if (b0 < 0) b0 = 0;
+      if (b1 >= nby) b1 = nby - 1;
+      for (int by = b0; by <= b1; ++by) {
+        const int Y = plan->roi_y0 + L * by;
+        if (y < Y - half || y >= Y + L + half || band_xb[by] < 0) continue;
+        if (band_xa[by] < xa) xa = band_xa[by];
+        if (band_xb[by] > xb) xb = band_xb[by];
+      }
+      if (xa < rect[0]) xa = rect[0];
+      if (xb > rect[2]) xb = rect[2];
+    }
+    const bool has = xb > xa;
+    if (open && (!has || xa != cur_x0 || xb != cur_x1)) {
+      if (n >= max_spans) return CHIPS_E_WS;
+      spans[4 * n + 0] = cur_y0; spans[4 * n + 1] = y; spans[4 * n + 2] = cur_x0; spans[4 * n + 3] = cur_x1;
+      ++n;
+      open = false;
+    }
+    if (has && !open) {
+      open = true;
+      cur_y0 = y; cur_x0 = xa; cur_x1 = xb;
+    }
+  }
+  return n;
+}
+
 extern "C" int chips_copy_rect(void* dst, const void* src, size_t pitch_bytes, size_t x0_bytes, int y0,
                                size_t width_bytes, int rows, int to_device, void* stream) {
   if (!dst || !src || rows < 1 || y0 < 0 || width_bytes < 1 || x0_bytes + width_bytes > pitch_bytes)

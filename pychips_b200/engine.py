@@ -94,12 +94,19 @@ class Detector:
         rect = (C.c_int32 * 4)()
         _lib.check(self.lib.chips_input_rect(self._pp, rect), "chips_input_rect")
         self.input_rect = tuple(int(v) for v in rect)     # x0, y0, x1, y1: all a detection reads of its input
+        sp = (C.c_int32 * (4 * 4096))()
+        ns = int(self.lib.chips_input_spans(self._pp, geom.cx, geom.cy, geom.r, sp, 4096))
+        if ns < 1:
+            raise _lib.ChipsNativeError(f"chips_input_spans failed with code {ns}")
+        # (y0, y1, x0, x1) row intervals inside input_rect that hold everything a detection reads
+        self.input_spans = [tuple(int(sp[4 * i + j]) for j in range(4)) for i in range(ns)]
         self.dtype = torch.float32 if elem == 4 else torch.float64
         self.graph_launches = 0        # kernels launched through CUDA-graph replays (not seen by the library counter)
 
     def upload(self, dst: torch.Tensor, src: torch.Tensor) -> int:
-        """Host image -> device image, only `input_rect` (the rest of `dst` is never read by a
-        detection with this plan).  Enqueued on the current stream; returns the bytes copied."""
+        """Host image -> device image, only `input_spans` (row intervals inside `input_rect`; the
+        rest of `dst` is never read by a detection with this plan).  Enqueued on the current
+        stream; returns the bytes copied."""
         x0, y0, x1, y1 = self.input_rect
         H, W = self.geom.H, self.geom.W
         if (src.dtype != dst.dtype or tuple(src.shape) != (H, W) or tuple(dst.shape) != (H, W)
@@ -107,9 +114,12 @@ class Detector:
             dst.copy_(src, non_blocking=True)
             return src.numel() * src.element_size()
         e = src.element_size()
-        _lib.check(self.lib.chips_copy_rect(_ptr(dst), C.c_void_p(src.data_ptr()), W * e, x0 * e, y0,
-                                            (x1 - x0) * e, y1 - y0, 1, _stream_ptr()), "chips_copy_rect")
-        return (x1 - x0) * e * (y1 - y0)
+        total = 0
+        for (sy0, sy1, sx0, sx1) in self.input_spans:      # ~26 two-dimensional copies at 4096^2
+            _lib.check(self.lib.chips_copy_rect(_ptr(dst), C.c_void_p(src.data_ptr()), W * e, sx0 * e, sy0,
+                                                (sx1 - sx0) * e, sy1 - sy0, 1, _stream_ptr()), "chips_copy_rect")
+            total += (sx1 - sx0) * e * (sy1 - sy0)
+        return total
 
     # ------------------------------------------------------------------ workspace views
     def view(self, name: str, dtype, shape) -> torch.Tensor:

@@ -163,6 +163,38 @@ def test_input_rect_covers_the_median_blocks():
     assert lib.chips_plan_init(C.byref(p), 100, 100, 5, 10, 3, 8, 50, 50, 80) == 0         # clipped disk
     assert lib.chips_input_rect(C.byref(p), rect) == 0 and tuple(rect) == (0, 0, 100, 100)
     assert lib.chips_input_rect(None, rect) == -1
+    # the spans: disjoint ascending row intervals inside the rectangle that cover every on-disk
+    # block with its halo (recomputed here from the plan) and, at 4096^2, 52 % of the image
+    for (n, k, r) in ((4096, 51, 1577), (1024, 11, 394), (256, 31, 120), (200, 7, 140)):
+        c = n // 2
+        assert lib.chips_plan_init(C.byref(p), n, n, k, 500, 20, 4, c, c, r) == 0
+        assert lib.chips_input_rect(C.byref(p), rect) == 0
+        sp = (C.c_int32 * (4 * 4096))()
+        ns = lib.chips_input_spans(C.byref(p), c, c, r, sp, 4096)
+        assert 1 <= ns <= 200
+        spans = [tuple(sp[4 * i:4 * i + 4]) for i in range(ns)]
+        import numpy as np
+        cover = np.zeros((n, n), bool)
+        prev = -1
+        for (y0, y1, x0, x1) in spans:
+            assert prev <= y0 < y1 and rect[1] <= y0 and y1 <= rect[3] and rect[0] <= x0 < x1 <= rect[2]
+            prev = y1
+            cover[y0:y1, x0:x1] = True
+        half = k // 2
+        need = np.zeros((n, n), bool)
+        for by in range(p.blk_nby):
+            for bx in range(p.blk_nbx):
+                X, Y = p.roi_x0 + 128 * bx, p.roi_y0 + p.blk_rows * by
+                nx, ny = min(max(c, X), X + 127), min(max(c, Y), Y + p.blk_rows - 1)
+                if (nx - c) ** 2 + (ny - c) ** 2 <= r * r:
+                    need[max(0, Y - half):Y + p.blk_rows + half, max(0, X - half):X + 128 + half] = True
+        assert not (need & ~cover).any()
+        if n == 4096:
+            assert 0.50 < cover.mean() < 0.53
+    assert lib.chips_plan_init(C.byref(p), 1024, 1024, 11, 500, 20, 4, 512, 512, 394) == 0
+    assert lib.chips_input_spans(C.byref(p), 512, 512, 394, sp, 1) == -3
+    assert lib.chips_plan_init(C.byref(p), 1440, 3600, 3, 5000, 25, 4, 0, 0, -1) == 0
+    assert lib.chips_input_spans(C.byref(p), 0, 0, -1, sp, 8) == 1 and tuple(sp[0:4]) == (0, 1440, 0, 3600)
     one = C.c_void_p(256)
     assert lib.chips_copy_rect(one, one, 64, 60, 0, 8, 1, 1, None) == -1      # runs past the pitch
     assert lib.chips_copy_rect(None, one, 64, 0, 0, 8, 1, 1, None) == -1

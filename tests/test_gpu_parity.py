@@ -1354,10 +1354,13 @@ def test_series_uploads_only_the_rectangle_the_kernels_read(n, k, rfrac):
                 buf.fill_(float("nan"))
         torch.cuda.synchronize()
         res = runner.run(pinned, [r] * 3)
-        out.append((res, runner.h2d_bytes, next(iter(runner._slots.values())).input_rect))
-    (a, bytes_full, _), (b, bytes_roi, rect) = out
+        det0 = next(iter(runner._slots.values()))
+        out.append((res, runner.h2d_bytes, det0.input_rect, det0.input_spans))
+    (a, bytes_full, _, _), (b, bytes_roi, rect, spans) = out
     x0, y0, x1, y1 = rect
-    assert bytes_full == 3 * n * n * 4 and bytes_roi == 3 * (x1 - x0) * (y1 - y0) * 4
+    assert bytes_full == 3 * n * n * 4
+    assert bytes_roi == 3 * 4 * sum((sy1 - sy0) * (sx1 - sx0) for (sy0, sy1, sx0, sx1) in spans)
+    assert bytes_roi <= 3 * (x1 - x0) * (y1 - y0) * 4
     assert bytes_roi < bytes_full or r > n // 2
     assert int(a.n_peaks.min()) > 0
     for i in range(3):
