@@ -119,7 +119,10 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
   const int ncap = NT * ((((n + NT - 1) / NT) + VEC - 1) / VEC * VEC);      // slots of one order
   uint16_t* ia = reinterpret_cast<uint16_t*>(keys + npad);
   uint16_t* ib = ia + ncap;
-  uint16_t* mycnt = s_cnt + tid;
+  // my counter of digit d: s_cnt[d * NT + slot], slot = 2 * lane + (warp & 1) + 64 * (warp >> 1): lane l
+  // of every warp addresses bank l whatever the digit (with slot = tid, lanes 2j and 2j+1 share a
+  // bank and differ in the digit row: a 2-way conflict on every counter access)
+  uint16_t* mycnt = s_cnt + (2 * lane + (warp & 1) + 64 * (warp >> 1));
 
   // ---- load the region as ordered keys (coalesced rows), identity order, key range
   K lmin = Key<T>::kMax, lmax = 0;
