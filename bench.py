@@ -323,7 +323,7 @@ def run_b200(a):
         if runner.sparse_keep:     # one word per pixel that is in some map + the count, written by the kernel
             down = sum(int(res.keep.packed(i).nbytes) + 4 + rec for i in range(a.batch))
             down_note = ("per image the 1.6 kB record and the result map as one 32-bit word per pixel that is in "
-                         "some map (chips_pack_keep writes them through the pinned mapping; "
+                         "some map (chips_pack_keep on the device, chips_copy_words stores them through the pinned mapping; "
                          f"{down / a.batch / 1e6:.2f} MB per image instead of {n * n / 1e6:.1f} MB dense)")
             assert not res.keep.is_dense(0) and np.array_equal(
                 res.keep[0], series.decode_keep(res.keep.packed(0), n, n, T))
