@@ -57,8 +57,10 @@ struct Roi {
     return x >= x0 && x < x0 + w && y >= y0 && y < y0 + h && on_disk(x, y, cx, cy, r);
   }
   __device__ __forceinline__ uint32_t li(int x, int y) const {
+    CHIPS_BOUNDS(x >= x0 && x < x0 + w && y >= y0 && y < y0 + h);
     return (uint32_t)((y - y0) * w + (x - x0));
   }
+  __device__ __forceinline__ uint32_t npix() const { return (uint32_t)w * (uint32_t)h; }
 };
 
 // ------------------------------------------------------------------ phase B
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(256) k_fill_bulk_link(Roi g, const uint8_t* __
     return on_disk(xx, yy, g.cx, g.cy, g.r) && lev[(size_t)yy * g.W + xx] == T;
   });
   if (!valid) return;
+  CHIPS_BOUNDS(me <= g.npix() && tgt <= me);
   parent[me] = tgt;
   Wimg[(size_t)y * g.W + x] = on_disk(x, y, g.cx, g.cy, g.r) ? 0 : (uint8_t)T;
 }
@@ -211,6 +214,7 @@ __global__ void __launch_bounds__(256) k_fill_pending(Roi g, const uint8_t* __re
     if (scnt[i]) atomicAdd(&lvl_count[i], scnt[i]);
   if (threadIdx.x == 0 && s_total) s_base = atomicAdd(total, s_total);
   __syncthreads();
+  CHIPS_BOUNDS(mylev < 0 || s_base + woff + __popc(act & ((1u << lane_) - 1u)) < g.npix());
   if (mylev >= 0) unsorted[s_base + woff + __popc(act & ((1u << lane_) - 1u))] = g.li(x, y);
 }
 
@@ -246,6 +250,7 @@ __global__ void __launch_bounds__(256) k_list_scatter(Roi g, const uint8_t* __re
       uint32_t base = 0;
       if (lane == leader) base = atomicAdd(&cursor[level], (uint32_t)__popc(peers));
       base = __shfl_sync(peers, base, leader);
+      CHIPS_BOUNDS(base + __popc(peers & ((1u << lane) - 1u)) < g.npix() && li < g.npix());
       out[base + __popc(peers & ((1u << lane) - 1u))] = li;
     }
   }
@@ -276,6 +281,7 @@ __global__ void __launch_bounds__(256) k_fill_round_union(Roi g, const uint8_t* 
   const uint32_t beg = lvl_offset[lv], end = lvl_offset[lv + 1];
   for (uint32_t i = beg + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
     uint32_t li = pending[i];
+    CHIPS_BOUNDS(i < g.npix() && li < g.npix());
     int y = g.y0 + (int)(li / (uint32_t)g.w), x = g.x0 + (int)(li % (uint32_t)g.w);
     uint32_t me = li + 1;
     int l_l = level_at(g, lev, x - 1, y), l_r = level_at(g, lev, x + 1, y);
@@ -315,6 +321,7 @@ __global__ void __launch_bounds__(256) k_fill_round_assign(Roi g, int t, int T,
   const uint32_t beg = lvl_offset[t + 1], end = lvl_offset[T + 1];
   for (uint32_t i = beg + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
     uint32_t li = pending[i];
+    CHIPS_BOUNDS(i < g.npix() && li < g.npix());
     int y = g.y0 + (int)(li / (uint32_t)g.w), x = g.x0 + (int)(li % (uint32_t)g.w);
     size_t o = (size_t)y * g.W + x;
     if (Wimg[o] != 0) continue;
@@ -350,6 +357,7 @@ struct Tree {
   uint32_t* hooked;    // hooked old roots in hook order
   uint32_t* offset;    // [T+2] list offsets by W (lvl_offset)
   uint32_t* ctr;       // [1] hook cursor, [2] kept components, [3] components, [8+t] hook cursor after level t
+  uint32_t npix;       // ROI pixels = capacity of every array above
 };
 
 __device__ __forceinline__ int wl_at(const Roi& g, const uint8_t* __restrict__ wl, int lx, int ly) {
@@ -368,7 +376,11 @@ __device__ __forceinline__ void uf_unite_rec(const Tree& tr, int t, uint32_t a, 
     }                            // a > b : hook a under b
     uint32_t old = atomicMin(&parent[a], b);
     if (old == a) {              // a was a root until now: it is hooked exactly once
-      if (tr.wl[a] != t) tr.hooked[atomicAdd(&tr.ctr[1], 1u)] = a;   // an older component merges
+      if (tr.wl[a] != t) {                                           // an older component merges
+        const uint32_t slot = atomicAdd(&tr.ctr[1], 1u);
+        CHIPS_BOUNDS(slot < tr.npix && a < tr.npix);
+        tr.hooked[slot] = a;
+      }
       a = b;
     } else {
       a = old;                   // hooked by somebody else in this level: go on with its parent
@@ -437,6 +449,7 @@ __global__ void __launch_bounds__(256) k_tree_union(Roi g, int t, Tree tr, uint3
   const uint8_t* __restrict__ wl = tr.wl;
   for (uint32_t i = beg + gtid; i < end; i += nthreads) {
     const uint32_t me = tr.plist[i];
+    CHIPS_BOUNDS(i < tr.npix && me < tr.npix);
     const int ly = (int)(me / (uint32_t)g.w), lx = (int)(me - (uint32_t)ly * (uint32_t)g.w);
     const int w_l = wl_at(g, wl, lx - 1, ly), w_r = wl_at(g, wl, lx + 1, ly);
     const int w_u = wl_at(g, wl, lx, ly - 1), w_d = wl_at(g, wl, lx, ly + 1);
@@ -472,6 +485,7 @@ __global__ void __launch_bounds__(256) k_tree_merge(Roi g, int t, Tree tr, uint3
   int dk = 0, dc = 0;                             // change of the kept / total component counts
   for (uint32_t i = hook_begin + gtid; i < hook_end; i += nthreads) {
     const uint32_t a = tr.hooked[i];
+    CHIPS_BOUNDS(i < tr.npix && a < tr.npix);
     const uint32_t r = uf_find(tr.parent, a);
     tr.mparent[a] = r;
     tr.mlevel[a] = (uint8_t)t;
@@ -490,6 +504,7 @@ __global__ void __launch_bounds__(256) k_tree_merge(Roi g, int t, Tree tr, uint3
   const uint8_t* __restrict__ wl = tr.wl;
   for (uint32_t i = beg + gtid; i < end; i += nthreads) {
     const uint32_t me = tr.plist[i];
+    CHIPS_BOUNDS(i < tr.npix && me < tr.npix);
     const int ly = (int)(me / (uint32_t)g.w), lx = (int)(me - (uint32_t)ly * (uint32_t)g.w);
     int wn[3][3];
 #pragma unroll
@@ -551,6 +566,7 @@ __global__ void __launch_bounds__(256) k_tree_keep(Roi g, int T, Tree tr, uint32
   const uint32_t total = tr.offset[T];
   for (uint32_t i = gtid; i < total; i += nthreads) {
     const uint32_t me = tr.plist[i];
+    CHIPS_BOUNDS(i < tr.npix && me < tr.npix);
     const int ly = (int)(me / (uint32_t)g.w), lx = (int)(me - (uint32_t)ly * (uint32_t)g.w);
     int tjoin = tr.wl[me], kk = T;
     uint32_t n = me;
@@ -732,6 +748,7 @@ static Tree make_tree(const chips_plan* p, unsigned char* w) {
   uint32_t* lvl = reinterpret_cast<uint32_t*>(w + p->off_lvl);
   t.offset = lvl + 128;
   t.ctr = lvl + 384;
+  t.npix = (uint32_t)nr;
   return t;
 }
 

@@ -17,6 +17,23 @@
     if (e__ != cudaSuccess) return CHIPS_E_CUDA;               \
   } while (0)
 
+// -DCHIPS_DEBUG_BOUNDS (python -m pychips_b200.build with CHIPS_EXTRA_NVCC_FLAGS): index asserts on the
+// union-find, list and candidate buffers; a violation prints the site and traps (the call then
+// fails with a CUDA error).  compute-sanitizer is not available on this pool: the full GPU suite
+// is run once against such a build instead (profiles/r02_debug_bounds.txt).
+#ifdef CHIPS_DEBUG_BOUNDS
+#include <stdio.h>
+#define CHIPS_BOUNDS(cond)                                                                   \
+  do {                                                                                       \
+    if (!(cond)) {                                                                           \
+      printf("CHIPS_BOUNDS failed: %s  (%s:%d)\n", #cond, __FILE__, __LINE__);               \
+      __trap();                                                                              \
+    }                                                                                        \
+  } while (0)
+#else
+#define CHIPS_BOUNDS(cond) do { } while (0)
+#endif
+
 namespace chips {
 
 // number of kernels this library has launched (bench.py reports it as gpu_launches)

@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
         for (int u = 0; u < VEC; ++u) {
           const int j = VEC * jv + u;
           const uint32_t e = item[j];
+          CHIPS_BOUNDS(e < (uint32_t)ncap);
           const uint32_t d = (uint32_t)((keys[e] - kmin) >> shift) & (uint32_t)(ND - 1);      // (e >= n reads slack)
           item[j] = e | ((e < (uint32_t)n ? d : (uint32_t)(ND - 1)) << 16);
         }
@@ -293,7 +294,10 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
     for (int jv = 0; jv < IT / VEC; ++jv) {
       if (VEC * jv < chunk) {
 #pragma unroll
-        for (int u = 0; u < VEC; ++u) out[item[VEC * jv + u] >> 16] = (uint16_t)(item[VEC * jv + u] & 0xFFFFu);
+        for (int u = 0; u < VEC; ++u) {
+          CHIPS_BOUNDS((item[VEC * jv + u] >> 16) < (uint32_t)ncap);
+          out[item[VEC * jv + u] >> 16] = (uint16_t)(item[VEC * jv + u] & 0xFFFFu);
+        }
       }
     }
     __syncthreads();   // `out` is complete; s_wtot and the counters are free again
@@ -318,7 +322,9 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
     const uint32_t magic = 0xFFFFFFFFu / (uint32_t)ew + 1u, magic_s = 0xFFFFFFFFu / (uint32_t)S + 1u;
     for (int i = tid; i < n; i += NT) {
       const uint32_t e = in[i];
+      CHIPS_BOUNDS(e < (uint32_t)n);                                  // the virtual elements sort last
       const uint32_t ly = __umulhi(e, magic), lx = e - ly * ew;
+      CHIPS_BOUNDS(ly == e / (uint32_t)ew && ly < (uint32_t)eh && __umulhi((uint32_t)i, magic_s) == (uint32_t)i / (uint32_t)S);
       ord[i] = (uint16_t)((ly << 8) | lx);
       bkt[e] = (uint8_t)__umulhi((uint32_t)i, magic_s);
     }
@@ -563,6 +569,7 @@ __global__ void __launch_bounds__(32 * kH4Warps) k_huang4(const uint8_t* __restr
         ++P;
       }
       const size_t o = (size_t)y * W + (x0 + j);
+      CHIPS_BOUNDS(P >= 0 && P < kBuckets && c > 0 && R - lt >= 0 && R - lt < c);
       bstar[o] = (uint8_t)P;
       rres[o] = (uint32_t)(R - lt) | ((uint32_t)c << 16);   // residual rank | bucket population
     }
@@ -662,6 +669,7 @@ __global__ void __launch_bounds__(kTile* kTile, 8) k_rank_select(
     //         still in key order)
     for (int o = o0 + warp; o < o1; o += NW) {
       const int b = blist[o];
+      CHIPS_BOUNDS(o < kBuckets && b < kBuckets && b * S < nelem);
       const int rb = b * S, re = min(rb + S, nelem);
       uint16_t* dst = cand + (o - o0) * S;
       int nout = 0;
@@ -679,6 +687,8 @@ __global__ void __launch_bounds__(kTile* kTile, 8) k_rank_select(
         const uint32_t ma = __ballot_sync(0xFFFFFFFFu, ha), mb = __ballot_sync(0xFFFFFFFFu, hb);
         // key order: a0 b0 a1 b1 ...: before my a come the a's and b's of the lower lanes
         const int before = __popc(ma & lt_mask) + __popc(mb & lt_mask);
+        CHIPS_BOUNDS((!ha || (o - o0) * S + nout + before < kSelSlots) &&
+                     (!hb || (o - o0) * S + nout + before + (ha ? 1 : 0) < kSelSlots));
         if (ha) dst[nout + before] = (uint16_t)ta;
         if (hb) dst[nout + before + (ha ? 1 : 0)] = (uint16_t)tb;
         nout += __popc(ma) + __popc(mb);
@@ -690,6 +700,7 @@ __global__ void __launch_bounds__(kTile* kTile, 8) k_rank_select(
     if (active && myord >= o0 && myord < o1) {
       const uint16_t* spos = cand + (myord - o0) * S;
       const int end = ncand[myord - o0];
+      CHIPS_BOUNDS(end <= S && (myord - o0 + 1) * S <= kSelSlots && rr < mpop && mpop <= end);
       const bool fwd = 2 * rr < mpop;
       const int want = fwd ? rr : mpop - 1 - rr;     // in-window candidates to skip
       const int step = fwd ? 1 : -1;

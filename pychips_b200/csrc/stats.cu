@@ -61,6 +61,7 @@ __device__ __forceinline__ int hist_bin(double v, int nbins, const Edges& E, flo
   g = min(max(g, 0), nbins - 1);
   while (g > 0 && v < E(g)) --g;
   while (g < nbins - 1 && v >= E(g + 1)) ++g;
+  CHIPS_BOUNDS(g >= 0 && g < nbins && v >= E(g) && (g == nbins - 1 || v < E(g + 1)));
   return g;
 }
 
