@@ -425,7 +425,7 @@ class Chips(object):
 
     # ---- plots.py:305-322 (the arithmetic only)
     def probability_map(self, disk, prob_lower_lim: float = 0.0) -> np.ndarray:
-        det = self._detector(disk)
+        det = self._device_results(disk)
         with torch.cuda.device(self.device):
             return det.prob_stack(prob_lower_lim).cpu().numpy()
 

@@ -40,7 +40,20 @@ namespace chips {
 extern std::atomic<long long> g_launches;
 static inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-constexpr int kNumSM = 148;   // B200: 2 dies x 74 SMs
+// SMs of the current device (148 on B200: 2 dies x 74), queried once per thread; grids of the
+// grid-stride kernels are multiples of it
+static inline int num_sms() {
+  static thread_local int cached = 0;
+  if (cached <= 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached = n;
+  }
+  return cached;
+}
+#define kNumSM (::chips::num_sms())
 
 // ---- order-preserving integer keys of IEEE floats (NaN-free input: the median's input pass
 //      counts non-finite pixels in chips_result.n_nonfinite and the host classes raise) ----------

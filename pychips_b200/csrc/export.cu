@@ -252,13 +252,13 @@ extern "C" int chips_pack_keep(const chips_plan* plan, uint32_t* entries, uint32
   cudaStream_t st = (cudaStream_t)stream;
   CHIPS_CUDA(cudaMemsetAsync(count, 0, sizeof(uint32_t), st));
   const uint8_t* keep = (const uint8_t*)ws + plan->off_keep;
-  k_pack_keep<<<4 * chips::kNumSM, 256, 0, st>>>(keep, plan->W, plan->roi_x0, plan->roi_y0, plan->roi_w,
+  k_pack_keep<<<4 * kNumSM, 256, 0, st>>>(keep, plan->W, plan->roi_x0, plan->roi_y0, plan->roi_w,
                                                 plan->roi_h, plan->T, entries, cap, count);
   CHIPS_CHECK_LAUNCH();
   chips::count_launch();
   const size_t nbytes = (size_t)plan->H * plan->W;
   if ((size_t)cap * 4 >= nbytes && !(((uintptr_t)entries) & 15)) {
-    chips::k_keep_dense_if_overflow<<<4 * chips::kNumSM, 256, 0, st>>>(keep, nbytes, entries, cap, count);
+    chips::k_keep_dense_if_overflow<<<4 * kNumSM, 256, 0, st>>>(keep, nbytes, entries, cap, count);
     CHIPS_CHECK_LAUNCH();
     chips::count_launch();
   }

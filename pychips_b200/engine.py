@@ -328,6 +328,8 @@ class Detector:
                 gc.enable()
         nodes = int(self.lib.chips_launch_count() - n0)   # counted while capturing, not executed
         cur.wait_stream(cap)
+        if len(graphs) >= 16:                         # (buffer, parameters) keys seen so far: keep the 16 newest
+            graphs.pop(next(iter(graphs)))
         graphs[key] = (g, nodes)
         self.graph_launches -= nodes                  # undo the capture's count in the library total
 
