@@ -64,44 +64,46 @@ struct Roi {
 };
 
 // ------------------------------------------------------------------ phase B
-// Row-run linking for the pixels of one level set (`sel`): every pixel points at the start
-// of its run inside the warp's 32-pixel span, a run that continues across the span boundary
-// points at the last pixel of the previous span (chains hop 32 pixels at a time).  Returns
-// the link target (or `me` when not selected).  Must be called by all 32 lanes; lanes of a
-// warp hold 32 consecutive pixels of one row.
-template <typename Sel>
-__device__ __forceinline__ uint32_t row_run_target(const Roi& g, int x, int y, bool valid,
-                                                   uint32_t me, Sel sel) {
-  int lane = threadIdx.x & 31;
-  bool act = valid && sel(x, y);
-  unsigned m = __ballot_sync(0xFFFFFFFFu, act);
-  bool left_act = false;
-  if (lane == 0 && act) left_act = (x - 1 >= g.x0) && sel(x - 1, y);
-  left_act = __shfl_sync(0xFFFFFFFFu, left_act, 0);
-  if (!act) return me;
-  unsigned z = ~m & ((1u << lane) - 1u);
-  int s = z ? (32 - __clz(z)) : 0;
-  if (s == 0 && left_act) return me - (uint32_t)lane - 1u;   // last pixel of previous span
-  return me - (uint32_t)(lane - s);
-}
-
-// B1: parent init for every ROI pixel (run links for the bulk background = pixels in no
-// mask at all, self otherwise) and W = 0 on-disk / T off-disk.
+// B1: parent init for every ROI pixel, one CTA per ROI row.  A bulk-background pixel (on the disk,
+// in no mask at all) points at the FIRST pixel of its row run - warp ballots, the masks of the
+// CTA's eight warps and a carry across the 256-pixel chunks of the row - so every later find on
+// a bulk pixel is one hop to its run start; everything else is a singleton.  (Round 1 linked runs
+// inside 32-pixel spans only: a 3000-pixel run of quiet Sun was a chain of ~100 dependent hops.)
 __global__ void __launch_bounds__(256) k_fill_bulk_link(Roi g, const uint8_t* __restrict__ lev, int T,
-                                                        uint8_t* __restrict__ Wimg,
                                                         uint32_t* __restrict__ parent) {
-  int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
-  int y = g.y0 + blockIdx.y;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) parent[0] = kBorder;
-  bool valid = x < g.x0 + g.w;
-  uint32_t me = valid ? g.li(x, y) + 1u : 0u;
-  uint32_t tgt = row_run_target(g, x, y, valid, me, [&](int xx, int yy) {
-    return on_disk(xx, yy, g.cx, g.cy, g.r) && lev[(size_t)yy * g.W + xx] == T;
-  });
-  if (!valid) return;
-  CHIPS_BOUNDS(me <= g.npix() && tgt <= me);
-  parent[me] = tgt;
-  Wimg[(size_t)y * g.W + x] = on_disk(x, y, g.cx, g.cy, g.r) ? 0 : (uint8_t)T;
+  __shared__ uint32_t s_mask[2][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int y = g.y0 + blockIdx.x;
+  if (blockIdx.x == 0 && tid == 0) parent[0] = kBorder;
+  int xa, xb;                                           // on-disk columns of this row
+  if (!row_chord(y, g.cx, g.cy, g.r, g.x0, g.w, xa, xb)) xa = xb = g.x0;
+  const int la = xa - g.x0, lb = xb - g.x0;
+  const uint8_t* __restrict__ row = lev + (size_t)y * g.W + g.x0;
+  const uint32_t node0 = (uint32_t)blockIdx.x * (uint32_t)g.w + 1u;      // node of local column 0
+  int carry = 0;                 // local column after the last non-bulk pixel left of this chunk
+  for (int base = 0, it = 0; base < g.w; base += 256, ++it) {
+    const int lx = base + tid;
+    const bool valid = lx < g.w;
+    const bool act = valid && lx >= la && lx < lb && row[lx] == T;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, act);
+    uint32_t* sm = s_mask[it & 1];
+    if (lane == 0) sm[warp] = m;
+    __syncthreads();
+    const unsigned z = ~m & ((1u << lane) - 1u);
+    int start;
+    if (z) {
+      start = base + 32 * warp + (32 - __clz(z));
+    } else {                     // the run covers the start of my warp's span
+      int wv = warp - 1;
+      while (wv >= 0 && sm[wv] == 0xFFFFFFFFu) --wv;
+      start = wv >= 0 ? base + 32 * wv + (32 - __clz(~sm[wv])) : carry;
+    }
+    CHIPS_BOUNDS(!act || (start >= 0 && start <= lx));
+    if (valid) parent[node0 + (uint32_t)lx] = node0 + (uint32_t)(act ? start : lx);
+    int wl = 7;
+    while (wl >= 0 && sm[wl] == 0xFFFFFFFFu) --wl;
+    if (wl >= 0) carry = base + 32 * wl + (32 - __clz(~sm[wl]));
+  }
 }
 
 __device__ __forceinline__ int level_at(const Roi& g, const uint8_t* __restrict__ lev, int xx, int yy) {
@@ -171,8 +173,9 @@ __global__ void __launch_bounds__(256) k_fill_pending(Roi g, const uint8_t* __re
   int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
   int y = g.y0 + blockIdx.y;
   int mylev = -1;
-  bool bulk = false;
+  bool bulk = false, disk = false;
   if (x < g.x0 + g.w && on_disk(x, y, g.cx, g.cy, g.r)) {
+    disk = true;
     size_t o = (size_t)y * g.W + x;
     int l = lev[o];
     if (l == T) bulk = true;
@@ -180,20 +183,23 @@ __global__ void __launch_bounds__(256) k_fill_pending(Roi g, const uint8_t* __re
   }
   if (PASS == 0) {
     // bulk pixels of one row run share their root: the first lane of each run inside the warp's
-    // span finds it, the others copy it.  Everybody is flattened (later finds are one hop).
+    // span finds it (and is flattened), the others copy it.  Their own parents keep pointing at the
+    // run start, which is flat: later finds on them are two hops, and no parent is rewritten here.
     const int lane = threadIdx.x & 31;
     const unsigned mb = __ballot_sync(0xFFFFFFFFu, bulk);
     const unsigned z = ~mb & ((1u << lane) - 1u);
     const int s = bulk ? (z ? (32 - __clz(z)) : 0) : lane;
     uint32_t root = 0;
     const uint32_t me = bulk ? g.li(x, y) + 1 : 0u;
-    if (bulk && s == lane) root = uf_find(parent, me);
-    root = __shfl_sync(0xFFFFFFFFu, root, s);
-    if (bulk) {
+    if (bulk && s == lane) {
+      root = uf_find(parent, me);
       if (root != me) parent[me] = root;
-      if (root == kBorder) Wimg[(size_t)y * g.W + x] = (uint8_t)T;
-      else mylev = T;
     }
+    root = __shfl_sync(0xFFFFFFFFu, root, s);
+    if (bulk && root != kBorder) mylev = T;
+    // W: T for the bulk background that reaches the border (and off the disk: the memset), 0 = not
+    // assigned yet for every other on-disk pixel
+    if (disk) Wimg[(size_t)y * g.W + x] = (bulk && root == kBorder) ? (uint8_t)T : (uint8_t)0;
   }
   // per-level counts, and the pending pixels appended (in no particular order) to `unsorted`:
   // one shared atomic per warp, one global atomic per CTA
@@ -780,7 +786,7 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
   CHIPS_CUDA(cudaMemsetAsync(keep, T, n_img, st));
   k_cleanup_reset<<<1, 128, 0, st>>>(res, lvl_count, ctr);
   // round T-1: the bulk background (pixels in no mask at all)
-  k_fill_bulk_link<<<grid, blk, 0, st>>>(g, lev, T, Wimg, parent_b);
+  k_fill_bulk_link<<<g.h, blk, 0, st>>>(g, lev, T, parent_b);
   dim3 grid4((g.w / 4 + 2 + 255) / 256, g.h);
   k_fill_bulk_union<<<grid4, blk, 0, st>>>(g, lev, T, parent_b);
   uint32_t* list2 = reinterpret_cast<uint32_t*>(w + plan->off_list2);
