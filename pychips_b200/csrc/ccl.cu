@@ -81,28 +81,41 @@ __global__ void __launch_bounds__(256) k_fill_bulk_link(Roi g, const uint8_t* __
   const uint8_t* __restrict__ row = lev + (size_t)y * g.W + g.x0;
   const uint32_t node0 = (uint32_t)blockIdx.x * (uint32_t)g.w + 1u;      // node of local column 0
   int carry = 0;                 // local column after the last non-bulk pixel left of this chunk
-  for (int base = 0, it = 0; base < g.w; base += 256, ++it) {
-    const int lx = base + tid;
-    const bool valid = lx < g.w;
-    const bool act = valid && lx >= la && lx < lb && row[lx] == T;
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, act);
-    uint32_t* sm = s_mask[it & 1];
-    if (lane == 0) sm[warp] = m;
-    __syncthreads();
-    const unsigned z = ~m & ((1u << lane) - 1u);
-    int start;
-    if (z) {
-      start = base + 32 * warp + (32 - __clz(z));
-    } else {                     // the run covers the start of my warp's span
-      int wv = warp - 1;
-      while (wv >= 0 && sm[wv] == 0xFFFFFFFFu) --wv;
-      start = wv >= 0 ? base + 32 * wv + (32 - __clz(~sm[wv])) : carry;
+  constexpr int U = 8;           // chunks whose loads are in flight together
+  int it = 0;
+  for (int base0 = 0; base0 < g.w; base0 += 256 * U) {
+    int v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int lx = base0 + 256 * u + tid;
+      v[u] = (lx >= la && lx < lb) ? (int)row[lx] : 255;       // [la, lb) lies inside [0, g.w)
     }
-    CHIPS_BOUNDS(!act || (start >= 0 && start <= lx));
-    if (valid) parent[node0 + (uint32_t)lx] = node0 + (uint32_t)(act ? start : lx);
-    int wl = 7;
-    while (wl >= 0 && sm[wl] == 0xFFFFFFFFu) --wl;
-    if (wl >= 0) carry = base + 32 * wl + (32 - __clz(~sm[wl]));
+#pragma unroll
+    for (int u = 0; u < U; ++u, ++it) {
+      const int base = base0 + 256 * u;
+      if (base >= g.w) break;
+      const int lx = base + tid;
+      const bool valid = lx < g.w;
+      const bool act = v[u] == T;
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, act);
+      uint32_t* sm = s_mask[it & 1];
+      if (lane == 0) sm[warp] = m;
+      __syncthreads();
+      const unsigned z = ~m & ((1u << lane) - 1u);
+      int start;
+      if (z) {
+        start = base + 32 * warp + (32 - __clz(z));
+      } else {                     // the run covers the start of my warp's span
+        int wv = warp - 1;
+        while (wv >= 0 && sm[wv] == 0xFFFFFFFFu) --wv;
+        start = wv >= 0 ? base + 32 * wv + (32 - __clz(~sm[wv])) : carry;
+      }
+      CHIPS_BOUNDS(!act || (start >= 0 && start <= lx));
+      if (valid) parent[node0 + (uint32_t)lx] = node0 + (uint32_t)(act ? start : lx);
+      int wl = 7;
+      while (wl >= 0 && sm[wl] == 0xFFFFFFFFu) --wl;
+      if (wl >= 0) carry = base + 32 * wl + (32 - __clz(~sm[wl]));
+    }
   }
 }
 
@@ -152,76 +165,126 @@ __global__ void __launch_bounds__(256) k_fill_bulk_union(Roi g, const uint8_t* _
   }
 }
 
-// B3/B5: bulk pixels that reached the border get W = T; everything else on the disk (pixels
-// of some mask, and bulk pixels enclosed by masks) is "pending".  PASS 0 counts pending pixels
-// per level, PASS 1 scatters their ROI-local indices into a list grouped by level.
-template <int PASS>
+// B3: bulk pixels that reached the border get W = T; everything else on the disk (pixels of some
+// mask, and bulk pixels enclosed by masks) is "pending": W = 0, counted per level and appended (in
+// no particular order) to `unsorted`.  Four pixels per thread, 1024 per CTA.  A bulk pixel's parent
+// is the start of its row run (k_fill_bulk_link), so its root is two cached hops away: no leader
+// election, the four chases of a thread are independent; the run starts themselves are flattened,
+// other parents are not rewritten.
 __global__ void __launch_bounds__(256) k_fill_pending(Roi g, const uint8_t* __restrict__ lev, int T,
                                                       uint8_t* __restrict__ Wimg,
                                                       uint32_t* __restrict__ parent,
                                                       uint32_t* __restrict__ lvl_count,
                                                       uint32_t* __restrict__ total,
                                                       uint32_t* __restrict__ unsorted) {
-  static_assert(PASS == 0, "the scatter pass is k_list_scatter");
   __shared__ uint32_t scnt[CHIPS_MAX_T + 1];
   __shared__ uint32_t s_total, s_base;
-  if (PASS == 0) {
-    for (int i = threadIdx.x; i <= T; i += blockDim.x) scnt[i] = 0;
-    if (threadIdx.x == 0) s_total = 0;
-    __syncthreads();
+  __shared__ int s_xa, s_xb;
+  const int y = g.y0 + blockIdx.y;
+  for (int i = threadIdx.x; i <= T; i += blockDim.x) scnt[i] = 0;
+  if (threadIdx.x == 0) {
+    s_total = 0;
+    int xa, xb;
+    if (!row_chord(y, g.cx, g.cy, g.r, g.x0, g.w, xa, xb)) xa = xb = g.x0;
+    s_xa = xa;
+    s_xb = xb;
   }
-  int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x;
-  int y = g.y0 + blockIdx.y;
-  int mylev = -1;
-  bool bulk = false, disk = false;
-  if (x < g.x0 + g.w && on_disk(x, y, g.cx, g.cy, g.r)) {
-    disk = true;
-    size_t o = (size_t)y * g.W + x;
-    int l = lev[o];
-    if (l == T) bulk = true;
-    else mylev = l;
-  }
-  if (PASS == 0) {
-    // bulk pixels of one row run share their root: the first lane of each run inside the warp's
-    // span finds it (and is flattened), the others copy it.  Their own parents keep pointing at the
-    // run start, which is flat: later finds on them are two hops, and no parent is rewritten here.
-    const int lane = threadIdx.x & 31;
-    const unsigned mb = __ballot_sync(0xFFFFFFFFu, bulk);
-    const unsigned z = ~mb & ((1u << lane) - 1u);
-    const int s = bulk ? (z ? (32 - __clz(z)) : 0) : lane;
-    uint32_t root = 0;
-    const uint32_t me = bulk ? g.li(x, y) + 1 : 0u;
-    if (bulk && s == lane) {
-      root = uf_find(parent, me);
-      if (root != me) parent[me] = root;
+  __syncthreads();
+  const int xa = s_xa, xb = s_xb;
+  const int x4 = (g.x0 & ~3) + 4 * (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  const int lane = threadIdx.x & 31;
+  const uint8_t* __restrict__ row = lev + (size_t)y * g.W;
+  uint8_t* __restrict__ wrow = Wimg + (size_t)y * g.W;
+  const bool some = x4 + 4 > xa && x4 < xb;           // the group holds an on-disk pixel
+  const bool vec = (g.W & 3) == 0 && x4 + 4 <= g.W;    // x4 >= 0 is a multiple of 4
+  uint32_t lw = 0;
+  int lleft = -1;
+  if (some) {
+    if (vec) {
+      lw = *reinterpret_cast<const uint32_t*>(row + x4);
+    } else {
+      for (int i = 0; i < 4; ++i)
+        if (x4 + i < g.W) lw |= (uint32_t)row[x4 + i] << (8 * i);
     }
-    root = __shfl_sync(0xFFFFFFFFu, root, s);
-    if (bulk && root != kBorder) mylev = T;
-    // W: T for the bulk background that reaches the border (and off the disk: the memset), 0 = not
-    // assigned yet for every other on-disk pixel
-    if (disk) Wimg[(size_t)y * g.W + x] = (bulk && root == kBorder) ? (uint8_t)T : (uint8_t)0;
+    if (x4 - 1 >= xa) lleft = row[x4 - 1];
   }
-  // per-level counts, and the pending pixels appended (in no particular order) to `unsorted`:
-  // one shared atomic per warp, one global atomic per CTA
-  const int lane_ = threadIdx.x & 31;
-  const unsigned act = __ballot_sync(0xFFFFFFFFu, mylev >= 0);
-  uint32_t woff = 0;
-  if (act) {
-    const int first = __ffs(act) - 1;
-    if (lane_ == first) woff = atomicAdd(&s_total, (uint32_t)__popc(act));
-    woff = __shfl_sync(0xFFFFFFFFu, woff, first);
+  bool disk[4], bulk[4], start[4];
+  uint32_t me[4], s0[4], sp[4], rp[4];
+  int mylev[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int x = x4 + i;
+    const int l = (int)((lw >> (8 * i)) & 255u);
+    disk[i] = some && x >= xa && x < xb;
+    bulk[i] = disk[i] && l == T;
+    const int left = i ? (int)((lw >> (8 * (i - 1))) & 255u) : lleft;
+    start[i] = bulk[i] && !(x - 1 >= xa && left == T);
+    me[i] = bulk[i] ? g.li(x, y) + 1u : 0u;
+    mylev[i] = (disk[i] && !bulk[i]) ? l : -1;
   }
-  if (mylev >= 0) {
-    unsigned peers = __match_any_sync(act, mylev);
-    if (lane_ == __ffs(peers) - 1) atomicAdd(&scnt[mylev], __popc(peers));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s0[i] = sp[i] = bulk[i] ? parent[me[i]] : 0u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rp[i] = parent[sp[i]];          // (node 0 is its own parent)
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    while (rp[i] != sp[i]) {
+      sp[i] = rp[i];
+      rp[i] = parent[sp[i]];
+    }
+    if (start[i] && rp[i] != s0[i]) parent[me[i]] = rp[i];
+    if (bulk[i] && rp[i] != kBorder) mylev[i] = T;
+  }
+  // W: T for the bulk background that reaches the border (and off the disk: the memset), 0 = not
+  // assigned yet for every other on-disk pixel
+  if (some) {
+    uint32_t ww = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ww |= (uint32_t)((!disk[i] || (bulk[i] && rp[i] == kBorder)) ? T : 0) << (8 * i);
+    if (vec) {
+      *reinterpret_cast<uint32_t*>(wrow + x4) = ww;           // (off-disk bytes of the group: T as before)
+    } else {
+      for (int i = 0; i < 4; ++i)
+        if (disk[i]) wrow[x4 + i] = (uint8_t)(ww >> (8 * i));
+    }
+  }
+  // per-level counts and list slots: one shared atomic per warp, one global atomic per CTA
+  const int np = (mylev[0] >= 0) + (mylev[1] >= 0) + (mylev[2] >= 0) + (mylev[3] >= 0);
+  uint32_t slot = 0;
+  if (__ballot_sync(0xFFFFFFFFu, np > 0)) {
+    uint32_t incl = (uint32_t)np;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    uint32_t woff = 0;
+    if (lane == 31) woff = atomicAdd(&s_total, incl);
+    woff = __shfl_sync(0xFFFFFFFFu, woff, 31);
+    slot = woff + incl - (uint32_t)np;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const unsigned act = __ballot_sync(0xFFFFFFFFu, mylev[i] >= 0);
+      if (mylev[i] >= 0) {
+        const unsigned peers = __match_any_sync(act, mylev[i]);
+        if (lane == __ffs(peers) - 1) atomicAdd(&scnt[mylev[i]], __popc(peers));
+      }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i <= T; i += blockDim.x)
     if (scnt[i]) atomicAdd(&lvl_count[i], scnt[i]);
   if (threadIdx.x == 0 && s_total) s_base = atomicAdd(total, s_total);
   __syncthreads();
-  CHIPS_BOUNDS(mylev < 0 || s_base + woff + __popc(act & ((1u << lane_) - 1u)) < g.npix());
-  if (mylev >= 0) unsorted[s_base + woff + __popc(act & ((1u << lane_) - 1u))] = g.li(x, y);
+  if (np) {
+    slot += s_base;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (mylev[i] >= 0) {
+        CHIPS_BOUNDS(slot < g.npix());
+        unsorted[slot++] = g.li(x4 + i, y);
+      }
+  }
 }
 
 // B5 / C1b: regroup a pixel list by level: entry -> slot of its level's segment (cursor[] starts
@@ -394,38 +457,43 @@ __device__ __forceinline__ void uf_unite_rec(const Tree& tr, int t, uint32_t a, 
   }
 }
 
-// C1: ROI-local W, per-level counts of the foreground pixels and singleton initialisation
-// (PASS 0); the list grouped by W (PASS 1).
-template <int PASS>      // (only PASS 0; the list itself is regrouped from phase B's by k_list_scatter)
+// C1: ROI-local W, per-level counts of the foreground pixels and singleton initialisation (the
+// list itself is regrouped from phase B's by k_list_scatter).  A CTA covers 1024 pixels of a row
+// in four 256-pixel chunks whose W bytes are loaded together.
 __global__ void __launch_bounds__(256) k_tree_list(Roi g, const uint8_t* __restrict__ Wimg, int T, Tree tr,
-                                                   uint32_t thr2, uint32_t* __restrict__ lvl_count,
-                                                   uint32_t* __restrict__ lvl_cursor) {
+                                                   uint32_t thr2, uint32_t* __restrict__ lvl_count) {
   __shared__ uint32_t scnt[CHIPS_MAX_T + 1];
-  if (PASS == 0) {
-    for (int i = threadIdx.x; i <= T; i += blockDim.x) scnt[i] = 0;
-    __syncthreads();
+  for (int i = threadIdx.x; i <= T; i += blockDim.x) scnt[i] = 0;
+  __syncthreads();
+  const int y = g.y0 + blockIdx.y;
+  const uint8_t* __restrict__ wrow = Wimg + (size_t)y * g.W;
+  const int lane = threadIdx.x & 31;
+  int vv[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int x = g.x0 + (4 * (int)blockIdx.x + c) * 256 + (int)threadIdx.x;
+    vv[c] = x < g.x0 + g.w ? (int)wrow[x] : 255;
   }
-  const int x = g.x0 + blockIdx.x * blockDim.x + threadIdx.x, y = g.y0 + blockIdx.y;
-  int w = -1;
-  if (x < g.x0 + g.w) {
-    const int v = Wimg[(size_t)y * g.W + x];
-    if (v < T) w = v;
-    if (PASS == 0) tr.wl[g.li(x, y)] = (uint8_t)(v < T ? v : 255);
-  }
-  const unsigned act = __ballot_sync(0xFFFFFFFFu, w >= 0);
-  if (w >= 0) {
-    const uint32_t me = g.li(x, y);
-    const unsigned peers = __match_any_sync(act, w);
-    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-    const int lane_x0 = x - lane;                  // image column of lane 0 of this warp
-    if (PASS == 0) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int x = g.x0 + (4 * (int)blockIdx.x + c) * 256 + (int)threadIdx.x;
+    if (x - (int)threadIdx.x >= g.x0 + g.w) break;            // the whole chunk lies right of the ROI
+    const int v = vv[c];
+    const int w = (x < g.x0 + g.w && v < T) ? v : -1;
+    if (x < g.x0 + g.w) tr.wl[g.li(x, y)] = (uint8_t)(v < T ? v : 255);
+    const unsigned act = __ballot_sync(0xFFFFFFFFu, w >= 0);
+    if (w >= 0) {
+      const uint32_t me = g.li(x, y);
+      const unsigned peers = __match_any_sync(act, w);
+      const int leader = __ffs(peers) - 1;
+      const int lane_x0 = x - lane;                  // image column of lane 0 of this warp
       // pixels of one row run that appear at the same level belong to one component from that
       // level on: link each to the start of its run inside the warp's 32-pixel span (a run that
       // continues across the span boundary points at the last pixel of the previous span)
       const unsigned z = ~peers & ((1u << lane) - 1u);
       const int s = z ? (32 - __clz(z)) : 0;
       uint32_t tgt = me - (uint32_t)(lane - s);
-      if (s == 0 && lane_x0 > g.x0 && Wimg[(size_t)y * g.W + lane_x0 - 1] == w) tgt = me - (uint32_t)lane - 1u;
+      if (s == 0 && lane_x0 > g.x0 && wrow[lane_x0 - 1] == w) tgt = me - (uint32_t)lane - 1u;
       tr.parent[me] = tgt;
       tr.area[me] = 0;
       tr.mlevel[me] = 255;
@@ -433,11 +501,9 @@ __global__ void __launch_bounds__(256) k_tree_list(Roi g, const uint8_t* __restr
       if (lane == leader) atomicAdd(&scnt[w], __popc(peers));
     }
   }
-  if (PASS == 0) {
-    __syncthreads();
-    for (int i = threadIdx.x; i <= T; i += blockDim.x)
-      if (scnt[i]) atomicAdd(&lvl_count[i], scnt[i]);
-  }
+  __syncthreads();
+  for (int i = threadIdx.x; i <= T; i += blockDim.x)
+    if (scnt[i]) atomicAdd(&lvl_count[i], scnt[i]);
 }
 
 __device__ __forceinline__ void tree_stats(const Tree& tr, int t, uint32_t thr2, chips_result* res) {
@@ -790,7 +856,7 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
   dim3 grid4((g.w / 4 + 2 + 255) / 256, g.h);
   k_fill_bulk_union<<<grid4, blk, 0, st>>>(g, lev, T, parent_b);
   uint32_t* list2 = reinterpret_cast<uint32_t*>(w + plan->off_list2);
-  k_fill_pending<0><<<grid, blk, 0, st>>>(g, lev, T, Wimg, parent_b, lvl_count, &ctr[4], list2);
+  k_fill_pending<<<grid4, blk, 0, st>>>(g, lev, T, Wimg, parent_b, lvl_count, &ctr[4], list2);
   k_fill_offsets<<<1, 32, 0, st>>>(T, lvl_count, lvl_offset, lvl_cursor);
   k_list_scatter<<<4 * kNumSM, blk, 0, st>>>(g, lev, 0, list2, &ctr[4], lvl_cursor, pending);
   CHIPS_CHECK_LAUNCH();
@@ -817,7 +883,7 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
     }                                          // NaN / huge threshold: nothing is ever kept
   }
   k_zero_counts<<<1, 128, 0, st>>>(lvl_count);
-  k_tree_list<0><<<grid, blk, 0, st>>>(g, Wimg, T, tr, thr2, lvl_count, lvl_cursor);
+  k_tree_list<<<dim3((g.w + 1023) / 1024, g.h), blk, 0, st>>>(g, Wimg, T, tr, thr2, lvl_count);
   k_fill_offsets<<<1, 32, 0, st>>>(T, lvl_count, lvl_offset, lvl_cursor);
   // the foreground pixels are exactly phase B's pending pixels: regroup that list by W
   k_list_scatter<<<4 * kNumSM, blk, 0, st>>>(g, tr.wl, 1, pending, &ctr[4], lvl_cursor, list2);
