@@ -33,6 +33,7 @@
 //
 // k_median_brute is an independent per-thread radix-select used only as the at-scale
 // checker in the tests.
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -88,20 +89,21 @@ template <typename T> static int sort_chunk(int n) {
 }
 
 template <typename T>
-static size_t block_sort_smem(int n) {   // keys[n] + two orders of NT * chunk slots
+static size_t block_sort_smem(int n) {   // keys[n] (padded to 128 bytes: the orders double as the TMA landing area) + two orders of NT * chunk slots
   const size_t npad = ((size_t)n + 15) & ~(size_t)7;
-  return npad * sizeof(T) + (size_t)4 * SortCfg<T>::NT * sort_chunk<T>(n);
+  return ((npad * sizeof(T) + 127) & ~(size_t)127) + (size_t)4 * SortCfg<T>::NT * sort_chunk<T>(n);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
     const T* __restrict__ img, int H, int W, BlockGeom g, int cx, int cy, int r, int S,
     uint16_t* __restrict__ Ord, uint8_t* __restrict__ Bp, typename Key<T>::type* __restrict__ minmax,
-    int* __restrict__ n_nonfinite) {
+    int* __restrict__ n_nonfinite, const int tma_boxw, const __grid_constant__ CUtensorMap tm_img) {
   using K = typename Key<T>::type;
   constexpr int NT = SortCfg<T>::NT, IT = SortCfg<T>::IT, VEC = SortCfg<T>::VEC, NW = NT / 32;
   constexpr int DB = SortCfg<T>::DB, ND = 1 << DB;
-  extern __shared__ __align__(16) unsigned char sort_smem[];
+  extern __shared__ __align__(128) unsigned char sort_smem[];
+  __shared__ __align__(8) uint64_t tma_bar;
   __shared__ K s_min[NW], s_max[NW];
   __shared__ uint16_t s_wtot[ND * NW];          // [digit][warp] totals, then exclusive starts
   __shared__ uint16_t s_cnt[ND * NT];           // [digit][thread] counts, then start offsets
@@ -117,30 +119,76 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
   const int npad = (n + 15) & ~7;
   K* keys = reinterpret_cast<K*>(sort_smem);
   const int ncap = NT * ((((n + NT - 1) / NT) + VEC - 1) / VEC * VEC);      // slots of one order
-  uint16_t* ia = reinterpret_cast<uint16_t*>(keys + npad);
+  uint16_t* ia = reinterpret_cast<uint16_t*>(sort_smem + (((size_t)npad * sizeof(K) + 127) & ~(size_t)127));
   uint16_t* ib = ia + ncap;
   // my counter of digit d: s_cnt[d * NT + slot], slot = 2 * lane + (warp & 1) + 64 * (warp >> 1): lane l
   // of every warp addresses bank l whatever the digit (with slot = tid, lanes 2j and 2j+1 share a
   // bank and differ in the digit row: a 2-way conflict on every counter access)
   uint16_t* mycnt = s_cnt + (2 * lane + (warp & 1) + 64 * (warp >> 1));
 
-  // ---- load the region as ordered keys (coalesced rows), identity order, key range
+  // ---- load the region as ordered keys, identity order, key range.
+  //      TMA path (tma_boxw > 0): ONE 2-D tensor-tile load (cp.async.bulk.tensor, tracked by an
+  //      mbarrier) lands the whole halo-extended region in the area of the two order arrays; the
+  //      TMA unit zero-fills coordinates outside the image, which IS medfilt2d's zero padding.  The
+  //      box starts at the 16-byte aligned column at or left of the region (`vmis` columns early).
+  //      Fallback (unaligned rows, tiny images, no room for the box): coalesced row loads.
   K lmin = Key<T>::kMax, lmax = 0;
   bool bad_value = false;
-  for (int row = warp; row < eh; row += NW) {
-    const int y = Y - g.half + row;
-    const bool yin = y >= 0 && y < H;
-    const T* irow = img + (size_t)(yin ? y : 0) * W;
-    for (int lx = lane; lx < ew; lx += 32) {
-      const int x = X - g.half + lx;
-      const T v = (yin && x >= 0 && x < W) ? __ldg(irow + x) : (T)0;   // medfilt2d zero padding
-      bad_value |= nonfinite(v);
-      const K key = Key<T>::enc(v);
-      const int e = row * ew + lx;
-      keys[e] = key;
-      ia[e] = (uint16_t)e;
-      lmin = key < lmin ? key : lmin;
-      lmax = key > lmax ? key : lmax;
+  if (tma_boxw > 0) {
+    constexpr int EPA = 16 / (int)sizeof(T);
+    const int vx0 = (X - g.half) & ~(EPA - 1);          // (& on a negative rounds down)
+    const int vmis = (X - g.half) - vx0;
+    const T* sraw = reinterpret_cast<const T*>(ia);
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&tma_bar);
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)(tma_boxw * eh * (int)sizeof(T));
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+          "[%0], [%1, {%2, %3}], [%4];" ::"r"((uint32_t)__cvta_generic_to_shared(ia)),
+          "l"(reinterpret_cast<uint64_t>(&tm_img)), "r"(vx0), "r"(Y - g.half), "r"(bar)
+          : "memory");
+    }
+    uint32_t ok = 0;
+    for (int spin = 0; !ok && spin < (1 << 22); ++spin) {      // bounded: a bad descriptor must not hang
+      asm volatile(
+          "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+          : "=r"(ok) : "r"(bar) : "memory");
+    }
+    if (!ok) bad_value = true;                                 // reported as non-finite input: the host raises
+    for (int row = warp; row < eh; row += NW) {
+      for (int lx = lane; lx < ew; lx += 32) {
+        const T v = sraw[row * tma_boxw + vmis + lx];
+        bad_value |= nonfinite(v);
+        const K key = Key<T>::enc(v);
+        keys[row * ew + lx] = key;
+        lmin = key < lmin ? key : lmin;
+        lmax = key > lmax ? key : lmax;
+      }
+    }
+    __syncthreads();                                           // the landing area becomes the order array
+    for (int e = tid; e < n; e += NT) ia[e] = (uint16_t)e;
+  } else {
+    for (int row = warp; row < eh; row += NW) {
+      const int y = Y - g.half + row;
+      const bool yin = y >= 0 && y < H;
+      const T* irow = img + (size_t)(yin ? y : 0) * W;
+      for (int lx = lane; lx < ew; lx += 32) {
+        const int x = X - g.half + lx;
+        const T v = (yin && x >= 0 && x < W) ? __ldg(irow + x) : (T)0;   // medfilt2d zero padding
+        bad_value |= nonfinite(v);
+        const K key = Key<T>::enc(v);
+        const int e = row * ew + lx;
+        keys[e] = key;
+        ia[e] = (uint16_t)e;
+        lmin = key < lmin ? key : lmin;
+        lmax = key > lmax ? key : lmax;
+      }
     }
   }
 #pragma unroll
@@ -313,30 +361,50 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
   __syncthreads();
   drop = 0;
   }
-  // ---- outputs: the block's pixels in key order as (ly << 8 | lx) (coalesced), and the bucket
-  //      image: bucket = rank / S by position (scattered in shared memory, copied out by rows)
+  // ---- outputs: the block's pixels in key order as (ly << 8 | lx), and the bucket image: bucket =
+  //      rank / S by position.  Both are assembled in shared memory (the order array in place, the
+  //      bucket image at its global pitch in the other order array) and leave the SM as two bulk
+  //      asynchronous copies (cp.async.bulk shared -> global) issued by one thread.
   {
     uint16_t* ord = Ord + (size_t)blk * ((n + 7) & ~7);
-    uint8_t* bkt = reinterpret_cast<uint8_t*>(out);          // [n] bucket by position
+    uint8_t* bkt = reinterpret_cast<uint8_t*>(out);          // [eh][LP] bucket by position
+    uint8_t* bp = Bp + (size_t)blk * g.LR * g.LP;
     // e / ew == umulhi(e, magic) for e < 2^16 (ew, S < 2^16)
     const uint32_t magic = 0xFFFFFFFFu / (uint32_t)ew + 1u, magic_s = 0xFFFFFFFFu / (uint32_t)S + 1u;
+    const bool bulk = (size_t)eh * g.LP <= (size_t)2 * ncap;  // the pitched bucket image fits the spare order array
+    const int bpitch = bulk ? g.LP : ew;
     for (int i = tid; i < n; i += NT) {
       const uint32_t e = in[i];
       CHIPS_BOUNDS(e < (uint32_t)n);                                  // the virtual elements sort last
       const uint32_t ly = __umulhi(e, magic), lx = e - ly * ew;
       CHIPS_BOUNDS(ly == e / (uint32_t)ew && ly < (uint32_t)eh && __umulhi((uint32_t)i, magic_s) == (uint32_t)i / (uint32_t)S);
-      ord[i] = (uint16_t)((ly << 8) | lx);
-      bkt[e] = (uint8_t)__umulhi((uint32_t)i, magic_s);
+      const uint16_t pos = (uint16_t)((ly << 8) | lx);
+      if (bulk) in[i] = pos;
+      else ord[i] = pos;
+      bkt[ly * bpitch + lx] = (uint8_t)__umulhi((uint32_t)i, magic_s);
     }
-    __syncthreads();
-    uint8_t* bp = Bp + (size_t)blk * g.LR * g.LP;
-    const int groups = (ew + 3) >> 2;
-    for (int row = warp; row < eh; row += NW) {
-      for (int gq = lane; gq < groups; gq += 32) {
-        const int lx = 4 * gq;
-        const uint8_t* src = bkt + row * ew + lx;                // (reads <= 3 bytes past a row: slack columns)
-        *reinterpret_cast<uint32_t*>(bp + (size_t)row * g.LP + lx) =
-            (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24);
+    if (bulk) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy reads
+      __syncthreads();
+      if (tid == 0) {
+        const uint32_t nb_ord = (uint32_t)(((n + 7) & ~7) * 2), nb_bkt = (uint32_t)(eh * g.LP);
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(ord),
+                     "r"((uint32_t)__cvta_generic_to_shared(in)), "r"(nb_ord) : "memory");
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(bp),
+                     "r"((uint32_t)__cvta_generic_to_shared(bkt)), "r"(nb_bkt) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory must outlive the reads
+      }
+    } else {
+      __syncthreads();
+      const int groups = (ew + 3) >> 2;
+      for (int row = warp; row < eh; row += NW) {
+        for (int gq = lane; gq < groups; gq += 32) {
+          const int lx = 4 * gq;
+          const uint8_t* src = bkt + row * ew + lx;                // (reads <= 3 bytes past a row: slack columns)
+          *reinterpret_cast<uint32_t*>(bp + (size_t)row * g.LP + lx) =
+              (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24);
+        }
       }
     }
   }
@@ -880,6 +948,49 @@ __global__ void k_copy_masked(const T* __restrict__ in, T* __restrict__ out, int
   out[i] = v;
 }
 
+// ------------------------------------------------------------------ TMA descriptor (host)
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D row-major image [rows][cols] of `elem`-byte words, box [box_rows][box_cols], out of bounds -> 0.
+// false: the image cannot be described (rows not 16-byte aligned, a box larger than the image -
+// which faults on sm_100a -, no driver entry point, CHIPS_NO_TMA=1 for A/B timing): the caller falls
+// back to plain loads.
+static bool make_tile_map(CUtensorMap* tm, const void* base, int elem, long long cols, long long rows,
+                          int box_cols, int box_rows) {
+  static const bool disabled = getenv("CHIPS_NO_TMA") != nullptr;
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || disabled) return false;
+  const long long row_bytes = cols * elem;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) || (row_bytes & 15) || ((box_cols * elem) & 15) ||
+      box_cols > 256 || box_rows > 256 || box_cols > cols || box_rows > rows)
+    return false;
+  const CUtensorMapDataType dt = elem == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT64;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)row_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // ------------------------------------------------------------------ host-side launchers
 template <typename T>
 static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy, int r,
@@ -931,7 +1042,18 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
       if (sort_chunk<T>(nelem) > SortCfg<T>::IT || smem + kStatic > 227 * 1024) return CHIPS_E_ARG;
     }
     CHIPS_CUDA(cudaFuncSetAttribute(k_block_sort<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_block_sort<T><<<nblocks, SortCfg<T>::NT, smem, st>>>(in, H, W, g, cx, cy, r, S, Ord, Bp, minmax, err + 1);
+    // the region of a block as one TMA box, landed in the two order arrays (4 * NT * chunk bytes):
+    // ew columns + the 16-byte alignment of the box start, rounded to whole 16-byte groups
+    CUtensorMap tm_img;
+    memset(&tm_img, 0, sizeof(tm_img));
+    constexpr int EPA = 16 / (int)sizeof(T);
+    const int ew = kHuangThreads + 2 * half;
+    int boxw = (ew + 2 * EPA - 2) & ~(EPA - 1);
+    if ((size_t)boxw * p->bp_rows * sizeof(T) > (size_t)4 * SortCfg<T>::NT * sort_chunk<T>(nelem) ||
+        !make_tile_map(&tm_img, in, (int)sizeof(T), W, H, boxw, p->bp_rows))
+      boxw = 0;
+    k_block_sort<T><<<nblocks, SortCfg<T>::NT, smem, st>>>(in, H, W, g, cx, cy, r, S, Ord, Bp, minmax, err + 1, boxw,
+                                                           tm_img);
     CHIPS_CHECK_LAUNCH();
     count_launch();
   }
