@@ -101,20 +101,22 @@ __global__ void __launch_bounds__(256) k_fill_bulk_link(Roi g, const uint8_t* __
       uint32_t* sm = s_mask[it & 1];
       if (lane == 0) sm[warp] = m;
       __syncthreads();
+      // the eight masks, one per lane (replicated four times): which warps hold a non-bulk pixel,
+      // the last one before mine (my run starts behind its last non-bulk pixel) and the last one
+      // of the chunk (the carry), without a loop over the masks
+      const uint32_t mq = sm[lane & 7];
+      const unsigned nf = __ballot_sync(0xFFFFFFFFu, mq != 0xFFFFFFFFu) & 0xFFu;
+      const unsigned below = nf & ((1u << warp) - 1u);
+      const int wv = below ? 31 - __clz(below) : 0;
+      const uint32_t mv = __shfl_sync(0xFFFFFFFFu, mq, wv);
+      const int wl = nf ? 31 - __clz(nf) : 0;
+      const uint32_t ml = __shfl_sync(0xFFFFFFFFu, mq, wl);
       const unsigned z = ~m & ((1u << lane) - 1u);
-      int start;
-      if (z) {
-        start = base + 32 * warp + (32 - __clz(z));
-      } else {                     // the run covers the start of my warp's span
-        int wv = warp - 1;
-        while (wv >= 0 && sm[wv] == 0xFFFFFFFFu) --wv;
-        start = wv >= 0 ? base + 32 * wv + (32 - __clz(~sm[wv])) : carry;
-      }
+      const int start = z ? base + 32 * warp + (32 - __clz(z))
+                          : (below ? base + 32 * wv + (32 - __clz(~mv)) : carry);
       CHIPS_BOUNDS(!act || (start >= 0 && start <= lx));
       if (valid) parent[node0 + (uint32_t)lx] = node0 + (uint32_t)(act ? start : lx);
-      int wl = 7;
-      while (wl >= 0 && sm[wl] == 0xFFFFFFFFu) --wl;
-      if (wl >= 0) carry = base + 32 * wl + (32 - __clz(~sm[wl]));
+      if (nf) carry = base + 32 * wl + (32 - __clz(~ml));
     }
   }
 }
@@ -147,7 +149,8 @@ __global__ void __launch_bounds__(256) k_fill_bulk_union(Roi g, const uint8_t* _
   const int y = g.y0 + blockIdx.y;
   if (x4 >= g.x0 + g.w) return;
   if ((g.W & 3) == 0 && x4 >= g.x0 + 1 && x4 + 5 <= g.x0 + g.w && y > g.y0 && y + 1 < g.y0 + g.h) {
-    // the disk is convex: its 4 corners on-disk => the whole 6x3 box is
+    // the disk is convex: its 4 corners on-disk => the whole 6x3 box is, no pixel of the group
+    // touches the border and every neighbour level is in the three row words + three bytes
     if (on_disk(x4 - 1, y - 1, g.cx, g.cy, g.r) && on_disk(x4 + 4, y - 1, g.cx, g.cy, g.r) &&
         on_disk(x4 - 1, y + 1, g.cx, g.cy, g.r) && on_disk(x4 + 4, y + 1, g.cx, g.cy, g.r)) {
       const uint32_t T4 = (uint32_t)T * 0x01010101u;
@@ -155,7 +158,17 @@ __global__ void __launch_bounds__(256) k_fill_bulk_union(Roi g, const uint8_t* _
       const uint32_t cur = *reinterpret_cast<const uint32_t*>(c);
       const uint32_t up = *reinterpret_cast<const uint32_t*>(c - g.W);
       const uint32_t dn = *reinterpret_cast<const uint32_t*>(c + g.W);
-      if (cur == T4 && up == T4 && dn == T4 && c[-1] == T && c[4] == T && c[-g.W - 1] == T) return;
+      const uint32_t cl = c[-1], ul0 = c[-g.W - 1];
+      if (cur == T4 && up == T4 && dn == T4 && cl == (uint32_t)T && c[4] == T && ul0 == (uint32_t)T) return;
+      const uint32_t me0 = g.li(x4, y) + 1u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (((cur >> (8 * i)) & 255u) != (uint32_t)T || ((up >> (8 * i)) & 255u) != (uint32_t)T) continue;
+        const uint32_t l_l = i ? (cur >> (8 * (i - 1))) & 255u : cl;
+        const uint32_t l_ul = i ? (up >> (8 * (i - 1))) & 255u : ul0;
+        if (!(l_l == (uint32_t)T && l_ul == (uint32_t)T)) uf_unite(parent, me0 + (uint32_t)i, me0 + (uint32_t)i - (uint32_t)g.w);
+      }
+      return;
     }
   }
 #pragma unroll
@@ -858,7 +871,7 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
   uint32_t* list2 = reinterpret_cast<uint32_t*>(w + plan->off_list2);
   k_fill_pending<<<grid4, blk, 0, st>>>(g, lev, T, Wimg, parent_b, lvl_count, &ctr[4], list2);
   k_fill_offsets<<<1, 32, 0, st>>>(T, lvl_count, lvl_offset, lvl_cursor);
-  k_list_scatter<<<4 * kNumSM, blk, 0, st>>>(g, lev, 0, list2, &ctr[4], lvl_cursor, pending);
+  k_list_scatter<<<16 * kNumSM, blk, 0, st>>>(g, lev, 0, list2, &ctr[4], lvl_cursor, pending);
   CHIPS_CHECK_LAUNCH();
   // the bulk pixels that did not reach the border in round T-1 stay pending at level T and
   // are re-examined by every later round (suffix of the list)
@@ -886,13 +899,13 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
   k_tree_list<<<dim3((g.w + 1023) / 1024, g.h), blk, 0, st>>>(g, Wimg, T, tr, thr2, lvl_count);
   k_fill_offsets<<<1, 32, 0, st>>>(T, lvl_count, lvl_offset, lvl_cursor);
   // the foreground pixels are exactly phase B's pending pixels: regroup that list by W
-  k_list_scatter<<<4 * kNumSM, blk, 0, st>>>(g, tr.wl, 1, pending, &ctr[4], lvl_cursor, list2);
+  k_list_scatter<<<16 * kNumSM, blk, 0, st>>>(g, tr.wl, 1, pending, &ctr[4], lvl_cursor, list2);
   CHIPS_CHECK_LAUNCH();
   for (int t = 0; t < T; ++t) {
     k_tree_union<<<gl, blk, 0, st>>>(g, t, tr, thr2, res);
     k_tree_merge<<<gl, blk, 0, st>>>(g, t, tr, thr2);
   }
-  k_tree_keep<<<4 * kNumSM, blk, 0, st>>>(g, T, tr, thr2, res, keep);
+  k_tree_keep<<<16 * kNumSM, blk, 0, st>>>(g, T, tr, thr2, res, keep);
   CHIPS_CHECK_LAUNCH();
   count_launch(6 + 2 * (T - 1) + 5 + 2 * T);
   return CHIPS_OK;

@@ -68,6 +68,32 @@ def test_median_fast_vs_scipy_unmasked(k, dtype):
     assert bad.size == 0, (len(bad), bad[:5], got[tuple(bad[0])], ref[tuple(bad[0])])
 
 
+@pytest.mark.parametrize("k", [11, 31, 51])
+def test_median_tma_tile_loads_and_plain_load_fallback_vs_scipy(k):
+    # W % 4 == 0, a 16-byte aligned base and an image larger than a block's box: k_block_sort stages
+    # every region with one TMA tile load whose out-of-image zero fill is medfilt2d's padding (all
+    # four borders are met).  The same pixels at a base address that is NOT 16-byte aligned cannot be
+    # described by a tensor map and take the plain-load path.
+    eng = _engine()
+    dev = eng.require_cuda()
+    rng = np.random.default_rng(900 + k)
+    H, W = 300, 512
+    img = rng.gamma(2.0, 30.0, size=(H, W)).astype(np.float32)
+    img[:40, :60] = 0.0                       # ties with the zero padding in a corner
+    img[250:, 400:] = -3.0                    # negatives against the padding
+    ref = signal.medfilt2d(img, k)
+    got, res = gpu_medfilt(img, k)
+    assert res.median_errors == 0 and np.array_equal(got, ref)
+    flat = torch.empty(H * W + 1, dtype=torch.float32, device=dev)
+    t = flat[1:].view(H, W)
+    t.copy_(torch.from_numpy(img))
+    assert t.data_ptr() % 16 != 0
+    out = torch.full((H, W), -777.0, dtype=torch.float32, device=dev)
+    det = eng.Detector(eng.Geometry(H, W, 0, 0, -1), k, 8, 0, 1, 4, dev)
+    det.medfilt(t, out)
+    assert det.result().median_errors == 0 and np.array_equal(out.cpu().numpy(), ref)
+
+
 @pytest.mark.parametrize("shape,k", [((20, 20), 31), ((9, 300), 11), ((300, 9), 11), ((1, 1), 3),
                                      ((64, 64), 51), ((17, 33), 5)])
 def test_median_fast_ragged_shapes(shape, k):
