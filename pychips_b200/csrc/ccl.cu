@@ -303,18 +303,23 @@ __global__ void __launch_bounds__(256) k_fill_pending(Roi g, const uint8_t* __re
 // B5 / C1b: regroup a pixel list by level: entry -> slot of its level's segment (cursor[] starts
 // at the segment offsets).  `mode` 0: level = lev image value (phase B: pending pixels by lev),
 // 1: level = ROI-local W (phase C: foreground pixels by W; 255 = not foreground, skipped).
-__global__ void __launch_bounds__(256) k_list_scatter(Roi g, const uint8_t* __restrict__ levsrc, int mode,
-                                                      const uint32_t* __restrict__ in,
-                                                      const uint32_t* __restrict__ n_ptr,
-                                                      uint32_t* __restrict__ cursor,
-                                                      uint32_t* __restrict__ out) {
+// A CTA ranks the 512 entries of a tile per level in shared memory and reserves each level's
+// slots with ONE global atomic (per-warp atomics on the ~20 cursors serialised in L2: 16 us).
+constexpr int kScatterThreads = 512;
+__global__ void __launch_bounds__(kScatterThreads) k_list_scatter(Roi g, const uint8_t* __restrict__ levsrc, int mode,
+                                                                  const uint32_t* __restrict__ in,
+                                                                  const uint32_t* __restrict__ n_ptr,
+                                                                  uint32_t* __restrict__ cursor,
+                                                                  uint32_t* __restrict__ out) {
+  __shared__ uint32_t scnt[CHIPS_MAX_T + 1], sbase[CHIPS_MAX_T + 1];
   const uint32_t n = *n_ptr;
-  const uint32_t nthreads = gridDim.x * blockDim.x;
   const int lane = threadIdx.x & 31;
-  for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; i0 < n; i0 += nthreads) {
-    const uint32_t i = i0 + lane;
+  for (uint32_t t0 = blockIdx.x * kScatterThreads; t0 < n; t0 += gridDim.x * kScatterThreads) {
+    if (threadIdx.x <= CHIPS_MAX_T) scnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t i = t0 + threadIdx.x;
     int level = -1;
-    uint32_t li = 0;
+    uint32_t li = 0, rank = 0;
     if (i < n) {
       li = in[i];
       if (mode == 0) {
@@ -325,15 +330,20 @@ __global__ void __launch_bounds__(256) k_list_scatter(Roi g, const uint8_t* __re
         level = w == 255 ? -1 : w;
       }
     }
+    CHIPS_BOUNDS(level <= CHIPS_MAX_T);
     const unsigned act = __ballot_sync(0xFFFFFFFFu, level >= 0);
     if (level >= 0) {
       const unsigned peers = __match_any_sync(act, level);
       const int leader = __ffs(peers) - 1;
-      uint32_t base = 0;
-      if (lane == leader) base = atomicAdd(&cursor[level], (uint32_t)__popc(peers));
-      base = __shfl_sync(peers, base, leader);
-      CHIPS_BOUNDS(base + __popc(peers & ((1u << lane) - 1u)) < g.npix() && li < g.npix());
-      out[base + __popc(peers & ((1u << lane) - 1u))] = li;
+      if (lane == leader) rank = atomicAdd(&scnt[level], (uint32_t)__popc(peers));
+      rank = __shfl_sync(peers, rank, leader) + __popc(peers & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    if (threadIdx.x <= CHIPS_MAX_T && scnt[threadIdx.x]) sbase[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], scnt[threadIdx.x]);
+    __syncthreads();
+    if (level >= 0) {
+      CHIPS_BOUNDS(sbase[level] + rank < g.npix() && li < g.npix());
+      out[sbase[level] + rank] = li;
     }
   }
 }
@@ -871,7 +881,7 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
   uint32_t* list2 = reinterpret_cast<uint32_t*>(w + plan->off_list2);
   k_fill_pending<<<grid4, blk, 0, st>>>(g, lev, T, Wimg, parent_b, lvl_count, &ctr[4], list2);
   k_fill_offsets<<<1, 32, 0, st>>>(T, lvl_count, lvl_offset, lvl_cursor);
-  k_list_scatter<<<16 * kNumSM, blk, 0, st>>>(g, lev, 0, list2, &ctr[4], lvl_cursor, pending);
+  k_list_scatter<<<8 * kNumSM, kScatterThreads, 0, st>>>(g, lev, 0, list2, &ctr[4], lvl_cursor, pending);
   CHIPS_CHECK_LAUNCH();
   // the bulk pixels that did not reach the border in round T-1 stay pending at level T and
   // are re-examined by every later round (suffix of the list)
@@ -899,7 +909,7 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
   k_tree_list<<<dim3((g.w + 1023) / 1024, g.h), blk, 0, st>>>(g, Wimg, T, tr, thr2, lvl_count);
   k_fill_offsets<<<1, 32, 0, st>>>(T, lvl_count, lvl_offset, lvl_cursor);
   // the foreground pixels are exactly phase B's pending pixels: regroup that list by W
-  k_list_scatter<<<16 * kNumSM, blk, 0, st>>>(g, tr.wl, 1, pending, &ctr[4], lvl_cursor, list2);
+  k_list_scatter<<<8 * kNumSM, kScatterThreads, 0, st>>>(g, tr.wl, 1, pending, &ctr[4], lvl_cursor, list2);
   CHIPS_CHECK_LAUNCH();
   for (int t = 0; t < T; ++t) {
     k_tree_union<<<gl, blk, 0, st>>>(g, t, tr, thr2, res);
