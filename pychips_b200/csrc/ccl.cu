@@ -235,18 +235,41 @@ __global__ void __launch_bounds__(256) k_fill_pending(Roi g, const uint8_t* __re
     me[i] = bulk[i] ? g.li(x, y) + 1u : 0u;
     mylev[i] = (disk[i] && !bulk[i]) ? l : -1;
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) s0[i] = sp[i] = bulk[i] ? parent[me[i]] : 0u;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) rp[i] = parent[sp[i]];          // (node 0 is its own parent)
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    while (rp[i] != sp[i]) {
-      sp[i] = rp[i];
-      rp[i] = parent[sp[i]];
+  // quiet Sun: all 128 pixels of the warp are bulk, i.e. one piece of one row run - lane 0 chases
+  // its root for everybody
+  const bool wfull = __all_sync(0xFFFFFFFFu, bulk[0] && bulk[1] && bulk[2] && bulk[3]);
+  if (wfull) {
+    uint32_t root = 0;
+    if (lane == 0) {
+      const uint32_t first = parent[me[0]];
+      uint32_t sp0 = first, rp0 = parent[sp0];
+      while (rp0 != sp0) {
+        sp0 = rp0;
+        rp0 = parent[sp0];
+      }
+      if (start[0] && rp0 != first) parent[me[0]] = rp0;
+      root = rp0;
     }
-    if (start[i] && rp[i] != s0[i]) parent[me[i]] = rp[i];
-    if (bulk[i] && rp[i] != kBorder) mylev[i] = T;
+    root = __shfl_sync(0xFFFFFFFFu, root, 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      rp[i] = root;
+      if (root != kBorder) mylev[i] = T;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s0[i] = sp[i] = bulk[i] ? parent[me[i]] : 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rp[i] = parent[sp[i]];          // (node 0 is its own parent)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      while (rp[i] != sp[i]) {
+        sp[i] = rp[i];
+        rp[i] = parent[sp[i]];
+      }
+      if (start[i] && rp[i] != s0[i]) parent[me[i]] = rp[i];
+      if (bulk[i] && rp[i] != kBorder) mylev[i] = T;
+    }
   }
   // W: T for the bulk background that reaches the border (and off the disk: the memset), 0 = not
   // assigned yet for every other on-disk pixel
