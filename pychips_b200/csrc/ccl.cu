@@ -908,7 +908,7 @@ extern "C" int chips_cleanup(const chips_plan* plan, int cx, int cy, int r, doub
   CHIPS_CHECK_LAUNCH();
   // the bulk pixels that did not reach the border in round T-1 stay pending at level T and
   // are re-examined by every later round (suffix of the list)
-  const int gl = 2 * kNumSM;
+  const int gl = kNumSM;      // (2 x SMs: 4 % shorter alone, 1.5 % less throughput with 16 detections in flight)
   for (int t = T - 2; t >= 0; --t) {
     k_fill_round_union<<<gl, blk, 0, st>>>(g, lev, t, lvl_offset, pending, parent_b);
     k_fill_round_assign<<<gl, blk, 0, st>>>(g, t, T, lvl_offset, pending, Wimg, parent_b);
