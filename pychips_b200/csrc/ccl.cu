@@ -75,8 +75,8 @@ __global__ void __launch_bounds__(256) k_fill_bulk_link(Roi g, const uint8_t* __
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int y = g.y0 + blockIdx.x;
   if (blockIdx.x == 0 && tid == 0) parent[0] = kBorder;
-  int xa, xb;                                           // on-disk columns of this row
-  if (!row_chord(y, g.cx, g.cy, g.r, g.x0, g.w, xa, xb)) xa = xb = g.x0;
+  int xa, xb;                                           // on-disk columns of this row (xa = xb: none)
+  warp_row_chord(y, g.cx, g.cy, g.r, g.x0, g.w, xa, xb);
   const int la = xa - g.x0, lb = xb - g.x0;
   const uint8_t* __restrict__ row = lev + (size_t)y * g.W + g.x0;
   const uint32_t node0 = (uint32_t)blockIdx.x * (uint32_t)g.w + 1u;      // node of local column 0
@@ -192,18 +192,12 @@ __global__ void __launch_bounds__(256) k_fill_pending(Roi g, const uint8_t* __re
                                                       uint32_t* __restrict__ unsorted) {
   __shared__ uint32_t scnt[CHIPS_MAX_T + 1];
   __shared__ uint32_t s_total, s_base;
-  __shared__ int s_xa, s_xb;
   const int y = g.y0 + blockIdx.y;
   for (int i = threadIdx.x; i <= T; i += blockDim.x) scnt[i] = 0;
-  if (threadIdx.x == 0) {
-    s_total = 0;
-    int xa, xb;
-    if (!row_chord(y, g.cx, g.cy, g.r, g.x0, g.w, xa, xb)) xa = xb = g.x0;
-    s_xa = xa;
-    s_xb = xb;
-  }
+  if (threadIdx.x == 0) s_total = 0;
+  int xa, xb;                                           // on-disk columns of this row, per warp (no
+  warp_row_chord(y, g.cx, g.cy, g.r, g.x0, g.w, xa, xb);   // CTA waits on one thread's square root)
   __syncthreads();
-  const int xa = s_xa, xb = s_xb;
   const int x4 = (g.x0 & ~3) + 4 * (int)(blockIdx.x * blockDim.x + threadIdx.x);
   const int lane = threadIdx.x & 31;
   const uint8_t* __restrict__ row = lev + (size_t)y * g.W;

@@ -116,6 +116,16 @@ __device__ __forceinline__ bool row_chord(int y, int cx, int cy, int r, int rx0,
   return xa < xb;
 }
 
+// on-disk columns [xa, xb) of row y, computed by lane 0 of the warp (an fp64 square root) and
+// broadcast; xa = xb when the row misses the disk
+__device__ __forceinline__ void warp_row_chord(int y, int cx, int cy, int r, int rx0, int rw, int& xa, int& xb) {
+  xa = 0;
+  xb = 0;
+  if ((threadIdx.x & 31) == 0 && !row_chord(y, cx, cy, r, rx0, rw, xa, xb)) xa = xb = 0;
+  xa = __shfl_sync(0xFFFFFFFFu, xa, 0);
+  xb = __shfl_sync(0xFFFFFFFFu, xb, 0);
+}
+
 // np.linspace edge i (fp64, multiply THEN add, never fused), last edge forced to `last`
 __device__ __forceinline__ double linspace_edge(int i, int nbins, double first, double last,
                                                 double step) {

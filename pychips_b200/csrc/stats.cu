@@ -119,16 +119,6 @@ __device__ __forceinline__ void load4(const T* __restrict__ row, int x, int W, b
   }
 }
 
-// on-disk columns [xa, xb) of row y, computed by lane 0 of the warp (an fp64 square root) and
-// broadcast; xa = xb when the row misses the disk
-__device__ __forceinline__ void warp_row_chord(int y, int cx, int cy, int r, int rx0, int rw, int& xa, int& xb) {
-  xa = 0;
-  xb = 0;
-  if ((threadIdx.x & 31) == 0 && !row_chord(y, cx, cy, r, rx0, rw, xa, xb)) xa = xb = 0;
-  xa = __shfl_sync(0xFFFFFFFFu, xa, 0);
-  xb = __shfl_sync(0xFFFFFFFFu, xb, 0);
-}
-
 template <typename T>
 __global__ void __launch_bounds__(256, 4) k_hist(const T* __restrict__ filt, int W, int rx0, int ry0,
                                               int rw, int rh, int cx, int cy, int r,
