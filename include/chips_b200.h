@@ -113,11 +113,14 @@ int chips_disk_mask(void* n_mask, void* i_mask, int H, int W, int elem, int cx, 
  *             scipy.signal.medfilt2d(raw, k), syn_chips.py:106.
  * Zero-padded k x k median (rank (k*k-1)/2), bit-exact; with r >= 0 the output is the
  * median on-disk and 0 off-disk, and min/max keys of the on-disk output are left at
- * plan->off_minmax.  `out` may be ws + plan->off_filt. */
+ * plan->off_minmax.  `out` may be ws + plan->off_filt.
+ * Fast path of the float32 block sort: `in` 16-byte aligned and W a multiple of 4 (any cudaMalloc'd
+ * image of an even-sized instrument frame) - the kernel then stages each block with one TMA tensor
+ * tile load; anything else takes plain loads, same result (CHIPS_NO_TMA=1 forces them: A/B timing). */
 int chips_medfilt2d(const void* in, void* out, const chips_plan* plan, int cx, int cy, int r,
                     void* ws, void* stream);
-/* the same, restricted to a subset of its four kernels (bit 0 boundaries, 1 bucket image,
- * 2 tier-1 sliding histograms, 3 tier-2 tile refine) so a caller can time each one */
+/* the same, restricted to a subset of its kernels (bit 0 block sort, 2 tier-1 sliding
+ * histograms, 3 tier-2 rank select; bit 1 unused) so a caller can time each one */
 int chips_medfilt2d_stages(const void* in, void* out, const chips_plan* plan, int cx, int cy,
                            int r, void* ws, void* stream, int stages);
 /* brute-force radix-select reference of the same filter (tests / at-scale checker) */
