@@ -654,13 +654,6 @@ __global__ void __launch_bounds__(32 * kH4Warps) k_huang4(const uint8_t* __restr
 }
 
 // ------------------------------------------------------------------ 3. tier 2: select
-__device__ __forceinline__ bool in_window(unsigned p, unsigned bias, unsigned win) {
-  // p = (ry << 8) | rx, bias = (ty << 8) | tx.  A borrow out of the low byte (rx < tx) leaves a
-  // low byte >= 256 - 15 > win, a negative row difference wraps the whole word: both rejected.
-  unsigned t = p - bias;
-  return ((t >> 8) <= win) & ((t & 255u) <= win);
-}
-
 constexpr int kSelSlots = 8192;   // candidate slots per round (16 KB per CTA)
 
 template <typename T, int KT>      // KT: compile-time window size (0 = run time)
@@ -672,7 +665,7 @@ __global__ void __launch_bounds__(kTile* kTile, 8) k_rank_select(
   using K = typename Key<T>::type;
   constexpr int NT = kTile * kTile;
   constexpr int NW = NT / 32;
-  __shared__ uint16_t cand[kSelSlots];          // [needed bucket of this round][S] candidates in key order
+  __shared__ __align__(16) uint16_t cand[kSelSlots];   // [needed bucket of this round][Sp] candidates in key order
   __shared__ uint16_t ncand[kBuckets];          // candidates per needed bucket of this round
   __shared__ uint8_t blist[kBuckets];           // the needed buckets, ascending
   __shared__ uint32_t need[4];
@@ -728,6 +721,14 @@ __global__ void __launch_bounds__(kTile* kTile, 8) k_rank_select(
   const unsigned RSm1 = (unsigned)(kTile + 2 * half - 1);
   const unsigned win = 2u * (unsigned)half;
   const unsigned bias = ((unsigned)ty << 8) | (unsigned)tx;
+  // A slice of the candidate buffer holds S entries + a sentinel, at an even stride: the walk reads
+  // two u16 candidates per 32-bit word.  Region coordinates are < 128 (k <= 73), so bits 7 and 15 of
+  // an entry are free guard bits: four fields per word are tested against [b, b + win] by two
+  // borrow-free subtractions (SWAR) instead of two compares per field.
+  const int Sp = (S + 2) & ~1;
+  const uint32_t kG = 0x80808080u;
+  const uint32_t B2 = bias | (bias << 16);
+  const uint32_t BH = (B2 + win * 0x01010101u) | kG;      // b + win <= 15 + 72: no carry between fields
   unsigned found = 0xFFFFFFFFu;
   for (int o0 = 0; o0 < nneeded; o0 += per_round) {
     const int o1 = min(o0 + per_round, nneeded);
@@ -739,7 +740,7 @@ __global__ void __launch_bounds__(kTile* kTile, 8) k_rank_select(
       const int b = blist[o];
       CHIPS_BOUNDS(o < kBuckets && b < kBuckets && b * S < nelem);
       const int rb = b * S, re = min(rb + S, nelem);
-      uint16_t* dst = cand + (o - o0) * S;
+      uint16_t* dst = cand + (o - o0) * Sp;
       int nout = 0;
       for (int i0 = rb & ~1; i0 < re; i0 += 64) {
         const int i = i0 + 2 * lane;
@@ -755,57 +756,62 @@ __global__ void __launch_bounds__(kTile* kTile, 8) k_rank_select(
         const uint32_t ma = __ballot_sync(0xFFFFFFFFu, ha), mb = __ballot_sync(0xFFFFFFFFu, hb);
         // key order: a0 b0 a1 b1 ...: before my a come the a's and b's of the lower lanes
         const int before = __popc(ma & lt_mask) + __popc(mb & lt_mask);
-        CHIPS_BOUNDS((!ha || (o - o0) * S + nout + before < kSelSlots) &&
-                     (!hb || (o - o0) * S + nout + before + (ha ? 1 : 0) < kSelSlots));
+        CHIPS_BOUNDS((!ha || (o - o0) * Sp + nout + before < kSelSlots) &&
+                     (!hb || (o - o0) * Sp + nout + before + (ha ? 1 : 0) < kSelSlots));
         if (ha) dst[nout + before] = (uint16_t)ta;
         if (hb) dst[nout + before + (ha ? 1 : 0)] = (uint16_t)tb;
         nout += __popc(ma) + __popc(mb);
       }
-      if (lane == 0) ncand[o - o0] = (uint16_t)nout;
+      if (lane == 0) {
+        ncand[o - o0] = (uint16_t)nout;
+        dst[nout] = 0x7F7Fu;                       // sentinel: in nobody's window (completes the last pair)
+      }
     }
     __syncthreads();
-    // ---- b. walk the candidates of my bucket from the nearer end, counting those inside my window
+    // ---- b. walk the candidates of my bucket from the nearer end, two per 32-bit word, counting
+    //         those inside my window.  Walking backwards the halves of a word are swapped first, so
+    //         "low half, then high half" is the walking order in both directions.
     if (active && myord >= o0 && myord < o1) {
-      const uint16_t* spos = cand + (myord - o0) * S;
+      const uint32_t* sp32 = reinterpret_cast<const uint32_t*>(cand + (myord - o0) * Sp);
       const int end = ncand[myord - o0];
-      CHIPS_BOUNDS(end <= S && (myord - o0 + 1) * S <= kSelSlots && rr < mpop && mpop <= end);
+      CHIPS_BOUNDS(end <= S && (myord - o0 + 1) * Sp <= kSelSlots && rr < mpop && mpop <= end);
       const bool fwd = 2 * rr < mpop;
       const int want = fwd ? rr : mpop - 1 - rr;     // in-window candidates to skip
+      const int npairs = (end + 1) >> 1;
       const int step = fwd ? 1 : -1;
-      int i = fwd ? 0 : end - 1;
-      int left = end;
-      int cnt = 0, fi = -1;
+      const uint32_t sel = fwd ? 0x3210u : 0x1032u;
+      // bit 7 / bit 23 of the result: the low / high candidate of the word lies in my window
+      auto test = [&](uint32_t w) -> uint32_t {
+        const uint32_t ok = ((w | kG) - B2) & (BH - w) & kG;   // per field: f >= b and f <= b + win
+        return ok & (ok >> 8) & 0x00800080u;
+      };
+      int p = fwd ? 0 : npairs - 1;
+      int left = npairs, cnt = 0;
+      uint32_t hit = 0xFFFFFFFFu;
       if (want >= 0) {
-        for (; left >= 4; left -= 4, i += 4 * step) {
-          unsigned p0 = spos[i], p1 = spos[i + step], p2 = spos[i + 2 * step], p3 = spos[i + 3 * step];
-          int c0 = in_window(p0, bias, win), c1 = in_window(p1, bias, win);
-          int c2 = in_window(p2, bias, win), c3 = in_window(p3, bias, win);
-          int c = c0 + c1 + c2 + c3;
-          if (cnt + c > want) {                        // the target is one of these four
-            if (c0 && cnt == want) fi = i;
-            cnt += c0;
-            if (fi < 0 && c1 && cnt == want) fi = i + step;
-            cnt += c1;
-            if (fi < 0 && c2 && cnt == want) fi = i + 2 * step;
-            cnt += c2;
-            if (fi < 0) fi = i + 3 * step;
+        for (; left >= 2; left -= 2, p += 2 * step) {
+          const uint32_t w0 = __byte_perm(sp32[p], 0u, sel), w1 = __byte_perm(sp32[p + step], 0u, sel);
+          const uint32_t m0 = test(w0), m1 = test(w1);
+          const int c0 = __popc(m0), c1 = __popc(m1);
+          if (cnt + c0 + c1 > want) {                  // the target is one of these four
+            uint32_t w = w0, m = m0;
+            if (cnt + c0 <= want) {
+              cnt += c0;
+              w = w1;
+              m = m1;
+            }
+            hit = ((m & 0x80u) && cnt == want) ? (w & 0xFFFFu) : (w >> 16);
             break;
           }
-          cnt += c;
+          cnt += c0 + c1;
         }
-        if (fi < 0) {
-          for (; left > 0; --left, i += step) {
-            if (in_window(spos[i], bias, win)) {
-              if (cnt == want) {
-                fi = i;
-                break;
-              }
-              ++cnt;
-            }
-          }
+        if (hit == 0xFFFFFFFFu && left == 1) {
+          const uint32_t w = __byte_perm(sp32[p], 0u, sel);
+          const uint32_t m = test(w);
+          if (cnt + __popc(m) > want) hit = ((m & 0x80u) && cnt == want) ? (w & 0xFFFFu) : (w >> 16);
         }
       }
-      if (fi >= 0) found = spos[fi];
+      if (hit != 0xFFFFFFFFu) found = hit;
     }
   }
   // ---- epilogue: fetch the one value, mask, min/max of the masked output
@@ -1033,7 +1039,7 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
   }
   const int nelem = (kHuangThreads + 2 * half) * p->bp_rows;
   const int S = p->blk_bucket;
-  if (S < 1 || (nelem + S - 1) / S > kBuckets || nelem > 65535 || S > kSelSlots) return CHIPS_E_ARG;
+  if (S < 1 || (nelem + S - 1) / S > kBuckets || nelem > 65535 || S + 2 > kSelSlots) return CHIPS_E_ARG;
   if (stages & 1) {  // rank + bucket images of every block's halo-extended region
     const size_t smem = block_sort_smem<T>(nelem);
     {   // 227 KB per CTA, minus the kernel's static arrays (counters, warp totals, min/max)
@@ -1080,7 +1086,7 @@ static int medfilt_impl(const T* in, T* out, const chips_plan* p, int cx, int cy
   if (stages & 8) {  // tier 2: one CTA per 16x16 tile
     const dim3 grid((rw + kTile - 1) / kTile, (rh + kTile - 1) / kTile);
 #define CHIPS_LAUNCH_SELECT(KT)                                                                             \
-    k_rank_select<T, KT><<<grid, kTile * kTile, 0, st>>>(in, Ord, g, S, kSelSlots / S,                     \
+    k_rank_select<T, KT><<<grid, kTile * kTile, 0, st>>>(in, Ord, g, S, kSelSlots / ((S + 2) & ~1),                     \
                                                          0xFFFFFFFFu / (uint32_t)p->blk_rows + 1u, bstar, rres, H, W, rw, rh, cx, cy, r, out, \
                                                     minmax, err)
     switch (k) {
