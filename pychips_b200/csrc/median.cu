@@ -7,9 +7,11 @@
 //
 //   0. the ROI is cut into blocks of 128 columns x L rows (L a multiple of the 16-pixel
 //      select tile, chosen by chips_plan_init so that one wave of tier-1 warps covers the ROI).
-//   1. k_block_sort  one CTA per block: the block's halo-extended region (zero padding outside
-//                    the image) is radix-sorted in shared memory (LSD, 4-bit digits over the
-//                    significant bits of key - min, thread-private counters, no atomics).
+//   1. k_block_sort  one CTA per block: the block's halo-extended region arrives as one TMA tensor
+//                    tile (cp.async.bulk.tensor; the unit's zero fill outside the image IS the
+//                    zero padding of medfilt2d) and is radix-sorted in shared memory (LSD, 4-bit
+//                    digits over the significant bits of key - min, thread-private counters, no
+//                    atomics); the two outputs leave as bulk shared -> global copies.
 //                    Output: the block's pixel POSITIONS in key order (u16 list; a pixel's index in
 //                    it is its rank, unique - ties are broken by the sort) and every pixel's bucket
 //                    = rank / S (u8 image, 128 buckets of exactly equal population).  From here on

@@ -185,3 +185,30 @@ def test_first_principles_pipeline_on_golden(name):
             K[maps[t] == 1] = t
         stack, _ = fp.prob_stack_levels(K, pr)
         assert np.array_equal(stack, g["stack"], equal_nan=True)
+
+
+@pytest.mark.parametrize("offset,scale,hb,dtype", [(0.0, 1.0, 500, np.float32), (40.0, 1.0, 5000, np.float32),
+                                                   (-300.0, 0.5, 2000, np.float32), (3.0, 1e-3, 777, np.float64),
+                                                   (1e6, 1.0, 200, np.float64), (0.0, 1.0, 16, np.float32)])
+def test_hist_fast_path_error_bound(offset, scale, hb, dtype):
+    # csrc/stats.cu hist_bin_fast / hist_eps restated in numpy float32: wherever the kernel would take
+    # trunc(t) as the bin without reading an edge (t farther than eps from an integer), that bin is the
+    # one whose float64 np.histogram edges bracket the value; and the actual float32 error of t stays
+    # at least 8x below eps (the margin the kernel's constant claims).
+    rng = np.random.default_rng(hb)
+    x = np.concatenate([rng.normal(28, 3, 60000), rng.normal(130, 15, 90000), np.linspace(20, 180, 10001)])
+    x = (offset + scale * x).astype(dtype)
+    v = x.astype(np.float64)
+    first, last = v.min(), v.max()
+    _, en = np.histogram(v, bins=hb)
+    true = np.clip(np.searchsorted(en, v, side="right") - 1, 0, hb - 1)
+    denom = last - first
+    e = 8.0 * hb * 2.0 ** -24 * (3.0 + 2.0 * max(abs(first), abs(last)) / denom)
+    eps = np.float32(e) * np.float32(1.0001) if e < 0.25 else np.float32(2.0)
+    t = (x.astype(np.float32) - np.float32(first)) * np.float32(hb / denom)
+    fl = np.floor(t)
+    fr = t - fl
+    fast = (fr >= eps) & (fr <= np.float32(1.0) - eps) & (fl >= 0) & (fl < hb)
+    assert np.array_equal(fl[fast].astype(np.int64), true[fast])
+    err = np.max(np.abs(t.astype(np.float64) - (v - first) / denom * hb))
+    assert err * 8.0 <= e

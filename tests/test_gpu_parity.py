@@ -432,6 +432,33 @@ def test_histogram_stage_vs_numpy(hb):
     assert res.n_samples == img.size
 
 
+@pytest.mark.parametrize("offset,scale,hb,dtype", [(0.0, 1.0, 500, np.float32), (40.0, 1.0, 500, np.float32),
+                                                   (1000.0, 0.004, 500, np.float32), (-300.0, 0.5, 2000, np.float32),
+                                                   (1e6, 1.0, 200, np.float64), (3.0, 1e-3, 777, np.float64),
+                                                   (0.0, 1.0, 16, np.float32)])
+def test_histogram_bin_fast_path_bound_vs_numpy(offset, scale, hb, dtype):
+    # k_hist takes trunc((v - first) * nbins / (last - first)) in float32 as the bin when that value is
+    # farther than a rounding bound from an integer, and the exact float64 edge comparison otherwise.  The
+    # bound grows with |offset| / range: distributions far from zero, narrow ranges, values exactly on bin
+    # edges (a uniform grid) and both storage widths must all give numpy's counts exactly.
+    eng = _engine()
+    dev = eng.require_cuda()
+    rng = np.random.default_rng(int(abs(offset)) + hb)
+    x = np.concatenate([rng.normal(28, 3, 60000), rng.normal(130, 15, 90000),
+                        np.linspace(20.0, 180.0, 10001)])          # the grid puts values ON edges
+    x = (offset + scale * x).astype(dtype)
+    img = np.ascontiguousarray(x[:160000].reshape(400, 400))
+    elem = np.dtype(dtype).itemsize
+    det = eng.Detector(eng.Geometry(400, 400, 0, 0, -1), 1, hb, 0, 4, elem, dev)
+    det.filt.copy_(torch.from_numpy(img).to(dev))
+    det.histogram(recompute_minmax=True)
+    det.select_threshold(5, None)
+    cn, en = np.histogram(img.astype(np.float64).ravel(), bins=hb)
+    assert np.array_equal(det.edges.cpu().numpy(), en)
+    got = det.counts.cpu().numpy()
+    assert np.array_equal(got, cn), np.flatnonzero(got != cn)[:10]
+
+
 def test_histogram_constant_image_and_sticky_threshold():
     eng = _engine()
     dev = eng.require_cuda()
