@@ -173,8 +173,7 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
         lmax = key > lmax ? key : lmax;
       }
     }
-    __syncthreads();                                           // the landing area becomes the order array
-    for (int e = tid; e < n; e += NT) ia[e] = (uint16_t)e;
+    __syncthreads();                                           // the landing area becomes the order arrays
   } else {
     for (int row = warp; row < eh; row += NW) {
       const int y = Y - g.half + row;
@@ -187,7 +186,6 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
         const K key = Key<T>::enc(v);
         const int e = row * ew + lx;
         keys[e] = key;
-        ia[e] = (uint16_t)e;
         lmin = key < lmin ? key : lmin;
         lmax = key > lmax ? key : lmax;
       }
@@ -224,11 +222,10 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
   // digit is always 15: they stay behind every real element (the sort is stable).
   const int chunk = (((n + NT - 1) / NT) + VEC - 1) / VEC * VEC;          // <= IT
   const int beg = tid * chunk;
-  for (int e = n + tid; e < NT * chunk; e += NT) ia[e] = (uint16_t)e;
-  __syncthreads();
   uint16_t *in = ia, *out = ib;
   while (true) {
-  const int npass = (nbits - drop + DB - 1) / DB;
+  // (at least one pass: it creates the order, whatever the keys)
+  const int npass = max(1, (nbits - drop + DB - 1) / DB);
   for (int pass = 0; pass < npass; ++pass) {
     const int shift = drop + DB * pass;
     // 1. my chunk.  All loads first (independent: nothing is stored in between), then the digit
@@ -236,6 +233,20 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
     //    item = element | digit << 16 | my running count << 20.  (Counters packed in registers
     //    cost three times the instructions of the shared-memory read-modify-write.)
     uint32_t item[IT];
+    if (pass == 0) {
+      // The first pass starts from ANY order (LSD only needs the later passes to be stable), so no
+      // order array is read: slot beg + j of the virtual initial order holds element j * NT + tid -
+      // the keys are read in place, consecutive lanes consecutive addresses (no index load, no
+      // bank conflict, no identity array to initialise).
+#pragma unroll
+      for (int j = 0; j < IT; ++j) {
+        if (j < chunk) {
+          const uint32_t e = (uint32_t)(j * NT + tid);
+          const uint32_t d = (uint32_t)((keys[e] - kmin) >> shift) & (uint32_t)(ND - 1);      // (e >= n reads slack)
+          item[j] = e | ((e < (uint32_t)n ? d : (uint32_t)(ND - 1)) << 16);
+        }
+      }
+    } else {
 #pragma unroll
     for (int jv = 0; jv < IT / VEC; ++jv) {
       if (VEC * jv < chunk) {
@@ -264,6 +275,7 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
           item[j] = e | ((e < (uint32_t)n ? d : (uint32_t)(ND - 1)) << 16);
         }
       }
+    }
     }
 #pragma unroll
     for (int d = 0; d < ND; ++d) mycnt[d * NT] = 0;
@@ -359,9 +371,7 @@ __global__ void __launch_bounds__(SortCfg<T>::NT, 1) k_block_sort(
   bool bad = false;                                            // is the order exact on the full keys?
   for (int i = tid; i + 1 < n; i += NT) bad |= keys[in[i]] > keys[in[i + 1]];
   if (!__syncthreads_or(bad)) break;
-  for (int e = tid; e < NT * chunk; e += NT) in[e] = (uint16_t)e;   // again, on every bit
-  __syncthreads();
-  drop = 0;
+  drop = 0;                                                    // again, on every bit
   }
   // ---- outputs: the block's pixels in key order as (ly << 8 | lx), and the bucket image: bucket =
   //      rank / S by position.  Both are assembled in shared memory (the order array in place, the
