@@ -719,19 +719,23 @@ __global__ void k_zero_counts(uint32_t* lvl_count) {
 // ------------------------------------------------------------------ expansion / debugging
 __global__ void __launch_bounds__(256) k_expand_all(const uint8_t* __restrict__ src, size_t n, int T,
                                                     uint8_t* __restrict__ maps) {
-  // 4 pixels per thread, one 32-bit store per plane
-  size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (i4 >= n) return;
-  if (i4 + 4 <= n && (n & 3) == 0) {      // plane stride n keeps the 32-bit stores aligned
-    uint32_t v = *reinterpret_cast<const uint32_t*>(src + i4);
+  // 16 pixels per thread: one 128-bit load, one 128-bit store per plane; map_t = (keep <= t) for
+  // four bytes at a time (SIMD byte compare)
+  size_t i16 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i16 >= n) return;
+  if (i16 + 16 <= n && (n & 15) == 0 && (reinterpret_cast<uintptr_t>(maps) & 15) == 0) {     // aligned 128-bit stores in every plane
+    const uint4 v = *reinterpret_cast<const uint4*>(src + i16);
     for (int t = 0; t < T; ++t) {
-      uint32_t o = 0;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) o |= ((((v >> (8 * b)) & 255u) <= (uint32_t)t) ? 1u : 0u) << (8 * b);
-      *reinterpret_cast<uint32_t*>(maps + (size_t)t * n + i4) = o;
+      const uint32_t t4 = (uint32_t)t * 0x01010101u;
+      uint4 o;
+      o.x = __vcmpleu4(v.x, t4) & 0x01010101u;
+      o.y = __vcmpleu4(v.y, t4) & 0x01010101u;
+      o.z = __vcmpleu4(v.z, t4) & 0x01010101u;
+      o.w = __vcmpleu4(v.w, t4) & 0x01010101u;
+      *reinterpret_cast<uint4*>(maps + (size_t)t * n + i16) = o;
     }
   } else {
-    for (size_t i = i4; i < n && i < i4 + 4; ++i)
+    for (size_t i = i16; i < n && i < i16 + 16; ++i)
       for (int t = 0; t < T; ++t) maps[(size_t)t * n + i] = src[i] <= t;
   }
 }
@@ -946,7 +950,7 @@ extern "C" int chips_expand_maps(const chips_plan* plan, int which, uint8_t* map
                                  void* stream) {
   if (!plan || !maps || !ws) return CHIPS_E_ARG;
   size_t n = (size_t)plan->H * plan->W;
-  unsigned grid = (unsigned)((n / 4 + 256) / 256);
+  unsigned grid = (unsigned)((n / 16 + 256) / 256);
   k_expand_all<<<grid, 256, 0, (cudaStream_t)stream>>>(pick_src(plan, which, (unsigned char*)ws), n,
                                                        plan->T, maps);
   CHIPS_CHECK_LAUNCH();
